@@ -1,0 +1,292 @@
+"""ORACLE — torch-CPU / numpy restatement of the reference's Python hot path.  Test infrastructure only.
+
+This module restates, function by function, what the reference computes on the
+CAM -> pseudo-label -> dense-CRF-loss path, on CPU tensors, without importing anything from
+/root/reference (which does not exist on the GPU box).  It is the checker for the CUDA product in
+``cosa_b200/`` and the CPU leg that ``bench.py`` times; the product never imports it.
+
+Parity pin: ``tests/test_oracle_golden.py`` compares every function here with golden vectors made by
+running the reference's own code (``tests/golden/make_golden.py``, executed in the build container
+where /root/reference is mounted).
+
+Reference map (paths relative to /root/reference):
+  par_forward                  models/PAR.py:39-91 (neighbour order: get_kernel :10-24)
+  normalize_cam                utils/seg_helper.py:264-270
+  cam_validation               utils/seg_helper.py:547-551
+  cam_to_label                 utils/seg_helper.py:515-545
+  refine_cams                  utils/seg_helper.py:787-797
+  cam2mask                     utils/seg_helper.py:721-785
+  dense_energy_function_*      utils/seg_helper.py:864-903  (dup utils/rrm_utils.py:352-391)
+  dense_energy_loss            utils/seg_helper.py:191-208
+  get_energy_loss              utils/seg_helper.py:210-230
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import lattice as _lattice
+
+DEFAULT_DILATIONS = (1, 2, 4, 8, 12, 24)
+# (dy, dx) of the 8 one-hot 3x3 taps in models/PAR.py:10-24, in channel order.
+DIRECTIONS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
+
+
+# ----------------------------------------------------------------------------------------------
+# PAR
+# ----------------------------------------------------------------------------------------------
+def _neighbour_index(h, w, dilations):
+    """Clamped source coordinates of the 8*len(dilations) neighbours (replicate border, PAR.py:44-46)."""
+    ys = torch.arange(h).view(1, h, 1)
+    xs = torch.arange(w).view(1, 1, w)
+    dy = torch.tensor([d * a for d in dilations for (a, _) in DIRECTIONS]).view(-1, 1, 1)
+    dx = torch.tensor([d * b for d in dilations for (_, b) in DIRECTIONS]).view(-1, 1, 1)
+    yy = (ys + dy).clamp_(0, h - 1).expand(-1, h, w)
+    xx = (xs + dx).clamp_(0, w - 1).expand(-1, h, w)
+    return yy, xx
+
+
+def gather_neighbours(x, dilations):
+    """x [b,c,h,w] -> [b,c,8*len(dilations),h,w]; equals pad(replicate)+one-hot dilated conv bit for bit."""
+    h, w = x.shape[-2:]
+    yy, xx = _neighbour_index(h, w, dilations)
+    return x[:, :, yy, xx]
+
+
+def par_position_affinity(dilations, h=16, w=16, w1=0.3):
+    """softmax over neighbours of -(pos/(std(pos)+1e-8)/w1)^2 (PAR.py:51-62,77,82) -> [1,1,ND,h,w].
+
+    The reference evaluates this on the constant vector repeated over (h, w) (PAR.py:73,77,82).  torch's
+    CPU softmax over a non-innermost dim picks its algorithm from the inner size, so to stay bit-identical
+    the oracle evaluates it on the same (h, w) extent (every pixel then holds the same ND values).
+    """
+    ker = torch.ones(8)
+    for m in (0, 2, 5, 7):
+        ker[m] = np.sqrt(2)
+    pos = torch.cat([ker * d for d in dilations]).view(1, 1, -1, 1, 1).expand(1, 1, -1, h, w).contiguous()
+    pos_std = torch.std(pos, dim=2, keepdim=True)
+    pos_aff = -(pos / (pos_std + 1e-8) / w1) ** 2
+    return F.softmax(pos_aff, dim=2)
+
+
+def par_affinity(imgs, dilations=DEFAULT_DILATIONS, w1=0.3, w2=0.01):
+    """Affinity A [b,1,ND,h,w] (PAR.py:69-85).  Sum over ND is 1 + w2, not 1."""
+    nb = gather_neighbours(imgs, dilations)                       # [b,3,ND,h,w]
+    absdiff = torch.abs(nb - imgs.unsqueeze(2))
+    std = torch.std(nb, dim=2, keepdim=True)                      # unbiased over the ND neighbours
+    aff = -(absdiff / (std + 1e-8) / w1) ** 2
+    aff = aff.mean(dim=1, keepdim=True)
+    pos = par_position_affinity(dilations, imgs.shape[-2], imgs.shape[-1], w1)
+    return F.softmax(aff, dim=2) + w2 * pos
+
+
+def par_forward(imgs, masks, dilations=DEFAULT_DILATIONS, num_iter=10):
+    """PAR.forward (PAR.py:64-91) on CPU tensors."""
+    masks = F.interpolate(masks, size=imgs.shape[-2:], mode="bilinear", align_corners=True)
+    aff = par_affinity(imgs, dilations)
+    for _ in range(num_iter):
+        masks = (gather_neighbours(masks, dilations) * aff).sum(2)
+    return masks
+
+
+class ParOracle:
+    """Callable with the reference module's ctor/forward shape, usable as ``refine_model``."""
+
+    def __init__(self, dilations=DEFAULT_DILATIONS, num_iter=10):
+        self.dilations = tuple(dilations)
+        self.num_iter = num_iter
+
+    def __call__(self, imgs, masks):
+        return par_forward(imgs, masks, self.dilations, self.num_iter)
+
+
+# ----------------------------------------------------------------------------------------------
+# CAM normalise / validation / labelling
+# ----------------------------------------------------------------------------------------------
+def normalize_cam(cam_scales):
+    """Sum the per-scale CAMs, subtract the per-(b,c) min, divide by the per-(b,c) max + 1e-5."""
+    cam = torch.sum(torch.stack(list(cam_scales), dim=0), dim=0)
+    cam = cam + (-cam).amax(dim=(2, 3), keepdim=True)
+    return cam / (cam.amax(dim=(2, 3), keepdim=True) + 1e-5)
+
+
+def cam_validation(cam, cls_label):
+    return cls_label[:, :, None, None] * cam
+
+
+def _box_slices(coord, h, w):
+    c = [int(v) for v in coord]
+    return slice(c[0], c[1]), slice(c[2], c[3])
+
+
+def cam_to_label(cam, cls_label, img_box=None, bkg_thre=None, high_thre=None, low_thre=None,
+                 ignore_mid=False, ignore_index=None):
+    b, c, h, w = cam.shape
+    valid_cam = cls_label[:, :, None, None] * cam if cls_label is not None else cam
+    value, idx = valid_cam.max(dim=1)            # first maximal index on ties
+    label = idx + 1
+    label[value <= bkg_thre] = 0
+    if img_box is None:
+        return label
+    if ignore_mid:
+        label[value <= high_thre] = ignore_index
+        label[value <= low_thre] = 0
+    out = torch.full_like(label, ignore_index)
+    for i, coord in enumerate(img_box):
+        ys, xs = _box_slices(coord, h, w)
+        out[i, ys, xs] = label[i, ys, xs]
+    return valid_cam, out
+
+
+def refine_cams(refine_model, images, cams, valid_key, orig_size):
+    refined = refine_model(images, cams) if refine_model else cams
+    refined = F.interpolate(refined, size=orig_size, mode="bilinear", align_corners=False)
+    return valid_key[refined.argmax(dim=1)]
+
+
+def cam2mask(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model=None,
+             ignore_index=255, downscale=2, return_parts=False):
+    b, _, h, w = images.shape
+    if downscale:
+        size = [h // downscale, w // downscale]
+        small = F.interpolate(images, size=size, mode="bilinear", align_corners=False)
+    else:
+        small = images
+    ones = torch.ones((b, 1, h, w))
+    stacks = []
+    for thr in (threshold_high, threshold_low):
+        s = torch.cat([ones * thr, cams], dim=1)
+        if downscale:
+            s = F.interpolate(s, size=size, mode="bilinear", align_corners=False)
+        stacks.append(s)
+    present = torch.cat([torch.ones((b, 1)), cls_labels], dim=1)
+    lab_hi = torch.full((b, h, w), float(ignore_index))
+    lab_lo = lab_hi.clone()
+    for i, coord in enumerate(img_boxes):
+        keys = torch.nonzero(present[i])[:, 0]
+        ys, xs = _box_slices(coord, h, w)
+        for stack, dst in ((stacks[0], lab_hi), (stacks[1], lab_lo)):
+            active = stack[i, keys].unsqueeze(0).softmax(dim=1)
+            lab = refine_cams(refine_model, small[[i]], active, keys, (h, w))
+            dst[i, ys, xs] = lab[0, ys, xs].to(dst.dtype)
+    out = lab_hi.clone()
+    out[lab_hi == 0] = ignore_index
+    out[(lab_hi + lab_lo) == 0] = 0
+    if return_parts:
+        return out, lab_hi, lab_lo
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Dense-CRF energy loss
+# ----------------------------------------------------------------------------------------------
+def dense_energy_function_forward(images, segs, sigma_rgb, sigma_xy, rois, unlabel, filter_fn=None):
+    """DenseEnergyLossFunction.forward.  Returns (loss float32 scalar, gated AS [N,K,H,W], S*ROI)."""
+    filter_fn = filter_fn or _lattice.cpu_bilateralfilter_batch
+    N, K, H, W = segs.shape
+    gate = rois - segs.max(dim=1)[0]
+    gate[unlabel] = 1
+    gate[gate < 0] = 0
+    s = (segs * rois[:, None]).contiguous()
+    s_flat = s.detach().numpy().reshape(-1)
+    AS = np.zeros(s_flat.shape, dtype=np.float32)
+    filter_fn(images.detach().numpy().reshape(-1), s_flat, AS, N, K, H, W, sigma_rgb, sigma_xy)
+    AS = AS * gate[:, None].expand(N, K, H, W).contiguous().numpy().reshape(-1)
+    loss = 0.0
+    loss -= np.dot(s_flat, AS)
+    loss /= N
+    return np.float32(loss), AS.reshape(N, K, H, W), s
+
+
+def dense_energy_function_backward(grad_output, AS, rois, N):
+    """grad wrt segmentations: -2 * g * AS / N * ROI  (seg_helper.py:898-903)."""
+    g = -2 * grad_output * torch.from_numpy(AS) / N
+    return g * rois[:, None]
+
+
+class _EnergyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, segs, sigma_rgb, sigma_xy, rois, unlabel):
+        loss, AS, _ = dense_energy_function_forward(images, segs, sigma_rgb, sigma_xy, rois, unlabel)
+        ctx.AS, ctx.rois, ctx.N = AS, rois, segs.shape[0]
+        return torch.tensor([loss])
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return None, dense_energy_function_backward(grad_output, ctx.AS, ctx.rois, ctx.N), None, None, None, None
+
+
+def dense_energy_loss(images, segs, rois, seg_label, weight=1e-7, sigma_rgb=15.0, sigma_xy=100.0,
+                      scale_factor=0.5, recompute_scale_factor=True):
+    """DenseEnergyLoss.forward (seg_helper.py:199-208; rrm_utils.py:402-410 omits recompute_scale_factor)."""
+    kw = dict(scale_factor=scale_factor)
+    if recompute_scale_factor:
+        kw["recompute_scale_factor"] = True
+    s_img = F.interpolate(images, **kw)
+    s_seg = F.interpolate(segs, mode="bilinear", align_corners=False, **kw)
+    s_roi = F.interpolate(rois.unsqueeze(1), **kw).squeeze(1)
+    s_lab = F.interpolate(seg_label, mode="nearest", **kw)
+    unlabel = (s_lab.long() == 255).squeeze(1)
+    return weight * _EnergyFn.apply(s_img, s_seg, sigma_rgb, sigma_xy * scale_factor, s_roi, unlabel)
+
+
+IMAGENET_MEAN = (123.675, 116.28, 103.53)
+IMAGENET_STD = (58.395, 57.12, 57.375)
+
+
+def get_energy_loss(img, logit, label, img_box, mean=IMAGENET_MEAN, std=IMAGENET_STD, **layer_kw):
+    """get_energy_loss (seg_helper.py:210-230) with the loss layer's ctor arguments in ``layer_kw``."""
+    prob = F.softmax(logit, dim=1)
+    b, _, h, w = prob.shape
+    crop = torch.zeros((b, h, w))
+    for i, coord in enumerate(img_box):
+        ys, xs = _box_slices(coord, h, w)
+        crop[i, ys, xs] = 1
+    raw = torch.zeros_like(img)
+    for c in range(3):
+        raw[:, c] = img[:, c] * std[c] + mean[c]
+    return dense_energy_loss(raw, prob, crop, label.type(torch.uint8).unsqueeze(1), **layer_kw)
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic VOC/COCO-shaped inputs; shared by tests and bench.py so that the
+# CUDA path and the CPU path always see the same tensors.
+# ----------------------------------------------------------------------------------------------
+def synthetic_batch(B, C, H, W, n_fg, seed, noise_sigma=10.0, cam_kind="blobs", box="full"):
+    g = torch.Generator().manual_seed(seed)
+    ys = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    xs = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    cc = torch.arange(3, dtype=torch.float32).view(3, 1, 1)
+    base = 127 + 100 * torch.sin(0.02 * xs + cc) * torch.cos(0.03 * ys)
+    u8 = (base.unsqueeze(0) + noise_sigma * torch.randn((B, 3, H, W), generator=g)).floor().clamp(0, 255)
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    simg = (u8 - mean) / std
+    img_denorm = u8 / 255.0
+    cls_label = torch.zeros((B, C - 1))
+    for b in range(B):
+        cls_label[b, torch.randperm(C - 1, generator=g)[:n_fg]] = 1
+    if cam_kind == "blobs":
+        cams = 0.05 * torch.rand((B, C - 1, H, W), generator=g)
+        for b in range(B):
+            for c in torch.nonzero(cls_label[b])[:, 0].tolist():
+                for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
+                    cy, cx = (torch.rand(2, generator=g) * torch.tensor([H, W])).tolist()
+                    s = float(torch.rand(1, generator=g)) * (60.0 * H / 448) + 30.0 * H / 448
+                    cams[b, c] += torch.exp(-((ys[0] - cy) ** 2 + (xs[0] - cx) ** 2) / (2 * s * s))
+        cams = normalize_cam([cams])
+    else:
+        gh, gw = max(H // 16, 2), max(W // 16, 2)
+        cams = F.interpolate(torch.rand((B, C - 1, gh, gw), generator=g), size=(H, W), mode="bilinear",
+                             align_corners=False)
+    cams = cam_validation(cams, cls_label)
+    gh, gw = max(H // 16, 2), max(W // 16, 2)
+    logits = F.interpolate(3 * torch.randn((B, C, gh, gw), generator=g), size=(H, W), mode="bilinear",
+                           align_corners=False)
+    if box == "full":
+        boxes = torch.tensor([[0, H, 0, W]] * B, dtype=torch.int16)
+    else:
+        boxes = torch.tensor([[H // 28, H - H // 28, W // 14, W]] * B, dtype=torch.int16)
+    return dict(simg=simg.contiguous(), img_denorm=img_denorm.contiguous(), cams=cams.contiguous(),
+                cls_label=cls_label, logits=logits.contiguous(), img_box=boxes)
