@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Headline benchmark: refined pseudo-label images/sec through PAR + labelling + dense-CRF loss.
+
+One "step" is one pass of the hot path over one synthetic VOC-shaped batch per GPU
+(BASELINE.json configs[1]: B=32, 3x448x448 images, 21 classes, 2 foreground classes per image):
+
+    cam_validation -> cam2mask(refine_model=PAR(num_iter=10, dilations=[1,2,4,8,12,24]))
+                   -> get_energy_loss(DenseEnergyLoss(1e-7, 15, 100, 0.5)) forward -> backward (d loss/d logit)
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          (N > 1: launched under torchrun by the driver)
+    python bench.py --impl reference ...                          (the CPU path on the host cores)
+
+Rank 0 prints ONE JSON line.  `value` is whole-job images/s with inputs resident in HBM; `e2e` is the same
+path called with HOST (pinned) buffers, host<->device copies inside the timed region; `roofline` is the
+dominant kernel against the measured HBM peak; `cpu_baseline` is the CPU path timed on this host.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "refined pseudo-label images/sec (PAR+label+CRF loss, 448^2, 21-cls)"
+DILATIONS = [1, 2, 4, 8, 12, 24]
+NUM_ITER = 10
+THR_HIGH, THR_LOW = 0.7, 0.25
+WORKLOADS = {
+    "voc": dict(C=21, n_fg=2, H=448, W=448, name="VOC-shape B=%d/GPU, 3x448x448, 21 classes, 2 fg/img (BASELINE.json configs[1])"),
+    "coco": dict(C=81, n_fg=3, H=448, W=448, name="COCO-shape B=%d/GPU, 3x448x448, 81 classes, 3 fg/img (BASELINE.json configs[2])"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cosa", choices=["cosa", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak scaling)")
+    ap.add_argument("--workload", default="voc", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.file = None
+
+    def __enter__(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.file is None:
+            return out
+        try:
+            self.file.flush()
+            rows = [r.strip().split(", ") for r in open(self.file.name) if r.strip()]
+            os.unlink(self.file.name)
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                busy = [v for v in sm if v >= 0.5 * max(sm)] or sm
+                out["sm_mhz"] = statistics.median(busy)
+                out["sm_max_mhz"] = float(rows[0][2])
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                out["reasons"] = [n for i, n in enumerate(names) if any(r[5 + i].strip() == "Active" for r in rows)]
+                out["samples"] = len(sm)
+        except Exception as e:   # never let monitoring kill the benchmark
+            out["error"] = str(e)
+        return out
+
+
+def make_inputs(args, rank):
+    from cosa_b200 import synthetic
+    wl = WORKLOADS[args.workload]
+    seed = 1000 * (1 if args.workload == "voc" else 2) + rank
+    return synthetic.synthetic_batch(B=args.batch, C=wl["C"], H=wl["H"], W=wl["W"], n_fg=wl["n_fg"], seed=seed), wl
+
+
+# ----------------------------------------------------------------------------------------------------
+# the CPU path (oracle port + the reference C++ lattice when it was built): cpu_baseline and --impl reference
+# ----------------------------------------------------------------------------------------------------
+def cpu_path_step(d, n_images):
+    """PAR + labelling + CRF loss forward/backward on the first n_images images, on the host cores."""
+    from oracle import reference_port as port
+    # the reference C++ calls omp_set_num_threads(min(max_threads, N)) (bilateralfilter.cpp:45-47), which also
+    # throttles torch's OpenMP pool for everything that follows; give the CPU path all cores again every step
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = slice(0, n_images)
+    cams = port.cam_validation(d["cams"][s], d["cls_label"][s])
+    label = port.cam2mask(images=d["img_denorm"][s], img_boxes=d["img_box"][s], cams=cams, cls_labels=d["cls_label"][s],
+                          threshold_high=THR_HIGH, threshold_low=THR_LOW,
+                          refine_model=port.ParOracle(DILATIONS, NUM_ITER))
+    logit = d["logits"][s].clone().requires_grad_(True)
+    loss = port.get_energy_loss(d["simg"][s], logit, label, d["img_box"][s], weight=1e-7, sigma_rgb=15.0,
+                                sigma_xy=100.0, scale_factor=0.5)
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_kind():
+    from oracle import lattice
+    return ("port (torch-CPU PAR/labelling port + reference C++ lattice built into oracle/_ref)" if lattice.have_ref()
+            else "port (torch-CPU PAR/labelling port + C lattice port)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    d, wl = make_inputs(args, 0)
+    n_img = min(4, args.batch)
+    t0 = time.perf_counter()
+    cpu_path_step(d, 1)                                     # import / first-touch warm-up, also sizes the sample
+    per_image = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_img = max(1, min(n_img, int(budget / max(per_image, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_path_step(d, n_img)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_path_step(d, n_img)
+    dt = time.perf_counter() - t0
+    value = n_img * args.steps / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"] % args.batch, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
+                   "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "sample_images_per_step": n_img},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d images per step of the same seeded batch; %s; torch threads=%d, OpenMP default"
+                                   % (n_img, cpu_kind(), cores)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ----------------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernels, B, C, H, W, nc, M):
+    """Per-launch algorithmic bytes of every kernel (fp32).  h, w = half resolution."""
+    h, w = H // 2, W // 2
+    n, K, T, ND = h * w, C, NUM_ITER, 8 * len(DILATIONS)
+    Kp = (K + 3) // 4 * 4
+    ncm = 2 * nc                                    # high + low stacks share the affinity
+    per = {
+        "cam_validation_kernel": 2 * 4 * B * (C - 1) * H * W,
+        "cam2mask_keys_kernel": 4 * B * (C - 1) + 4 * B * C,
+        "cam2mask_prepare_kernel": 4 * B * (H * W * (3 + (nc - 1)) + n * (3 + ncm)),
+        "par_affinity_kernel": 4 * B * n * (3 + ND),
+        "par_iterate_kernel": 4 * B * n * (ND + 2 * ncm),      # one step: affinity read + masks read + written
+        "cam2mask_finalize_kernel": 4 * B * (n * ncm + H * W),
+        "energy_prepare_kernel": 4 * B * (H * W * (K + 2) + n * (3 + K + 2)),
+        "lattice_clear_kernel": None,                            # sized by the table, not by the problem
+        "lattice_build_kernel": B * n * (12 + 48) + M * 10,
+        "lattice_resolve_kernel": B * n * 48,
+        "lattice_neighbours_kernel": M * (8 + 48),
+        "lattice_zero_values_kernel": 4 * Kp * M,
+        "lattice_splat_kernel": B * n * (48 + 4 * K) + 4 * K * M,
+        "lattice_blur_kernel": M * (8 + 8 * K),                  # one axis
+        "lattice_slice_kernel": B * n * (48 + 4 * K) + 4 * K * M + 4 * B * n * (K + 1),
+        "energy_loss_finalize_kernel": 12,
+        "energy_logit_grad_kernel": 4 * B * (2 * H * W * K + n * (K + 1)),
+    }
+    return {k: per.get(k) for k in kernels}
+
+
+def run_cosa_arm(args):
+    import torch.distributed as dist
+    import cosa_b200
+    from cosa_b200 import _lib, seg_helper, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the cosa_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    host, wl = make_inputs(args, rank)
+    B, C, H, W = args.batch, wl["C"], wl["H"], wl["W"]
+    pinned = {k: v.pin_memory() for k, v in host.items() if k != "img_box"}
+    boxes = host["img_box"]
+    d = {k: v.to(dev) for k, v in pinned.items()}
+    par = cosa_b200.PAR(num_iter=NUM_ITER, dilations=DILATIONS).to(dev)
+    layer = cosa_b200.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+
+    def step(t):
+        cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
+        label = cosa_b200.cam2mask(images=t["img_denorm"], img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
+                                   threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+        logit = t["logits"].detach().requires_grad_(True)
+        loss = cosa_b200.get_energy_loss(img=t["simg"], logit=logit, label=label, img_box=boxes, loss_layer=layer)
+        loss.backward()
+        return label, loss, logit.grad
+
+    def sync_all():
+        torch.cuda.synchronize()
+        sharding.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        label, loss, grad = step(d)
+    sync_all()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            label, loss, grad = step(d)
+        ev1.record()
+        sync_all()
+    ms_total = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+    launches = _lib.launch_count() - launches0
+    total_images = sharding.all_reduce_sum(B * args.steps)
+    value = total_images / (ms_total / 1e3)
+    mean_loss = sharding.mean_loss_over_ranks(float(loss), B)
+
+    # ---- per-kernel event timing for the roofline (same inputs, same stream) ---------------------------
+    prof_steps = min(args.steps, 5)
+    _lib.profile_begin()
+    for _ in range(prof_steps):
+        step(d)
+    prof = _lib.profile_end()
+    M_vertices = seg_helper.last_energy_lattice_stats(B, C, H, W, dev)[0]
+    nc = 1 + wl["n_fg"]
+    peak, peak_src = measured_peak_gbs()
+    alg = algorithmic_bytes(prof.keys(), B, C, H, W, nc, M_vertices)
+    kernels = []
+    for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+        avg_ms = ms / count
+        ab = alg.get(name)
+        gbs = (ab / 1e9) / (avg_ms / 1e3) if ab else None
+        kernels.append({"kernel": name, "launches_per_step": count / prof_steps, "avg_ms": round(avg_ms, 5),
+                        "ms_per_step": round(ms / prof_steps, 5), "alg_bytes": ab,
+                        "achieved_gbs": round(gbs, 1) if gbs else None,
+                        "frac": round(gbs / peak, 4) if gbs else None})
+    top = kernels[0]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            traffic = json.load(f).get(top["kernel"])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_ms": top["avg_ms"], "alg_bytes_per_launch": top["alg_bytes"],
+                "share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 4)}
+
+    # ---- end to end: host (pinned) buffers in, labels + loss out, copies inside the timed region ---------
+    e2e = None
+    if not args.no_e2e:
+        out_label = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+        out_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+        names = ["img_denorm", "simg", "cams", "cls_label", "logits"]
+        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in names) + boxes.numel() * 4
+        d2h = out_label.numel() * 4 + 4
+
+        def e2e_step():
+            t = {k: pinned[k].to(dev, non_blocking=True) for k in names}
+            label, loss, _ = step(t)
+            out_label.copy_(label, non_blocking=True)
+            out_loss.copy_(loss.detach(), non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        sync_all()
+        e2e_steps = max(3, min(args.steps, 10))
+        ev0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        ev1.record()
+        sync_all()
+        e2e_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+        e2e = {"value": sharding.all_reduce_sum(B * e2e_steps) / (e2e_ms / 1e3), "unit": "images/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "ms_per_step": e2e_ms / e2e_steps}
+
+    # ---- CPU baseline on this host (rank 0, N = 1 only), bounded sample ----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_img = min(4, B)
+        cpu_path_step(host, 1)
+        t0 = time.perf_counter()
+        cpu_loss = cpu_path_step(host, n_img)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "first %d images of the same batch, 1 warm-up image + 1 timed pass (%.1f s); %s"
+                         % (n_img, dt, cpu_kind())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"] % B, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
+                       "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "thresholds": [THR_HIGH, THR_LOW],
+                       "parallelism": "batch-sharded, %d image(s)/GPU x %d GPU, no data-path collective" % (B, world),
+                       "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
+                                % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),
+                       "lattice_vertices": M_vertices, "lattice_M_over_n": round(M_vertices / (B * (H // 2) * (W // 2)), 4)},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels, "loss": mean_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_cosa_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,20 @@
+"""cosa_b200 - B200-native CAM -> pseudo-label refinement path of CoSA.
+
+Drop-in replacements (same names, arguments and return conventions as the reference) whose work is done
+by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/cosa_b200.h``:
+
+  ``PAR``                                           models/PAR.py:26-91
+  ``cam_validation, cam_to_label, cam2mask, _refine_cams``   utils/seg_helper.py:515-551, 721-797
+  ``cam_normalize``                                 utils/seg_helper.py:264-270
+  ``get_energy_loss, DenseEnergyLoss, DenseEnergyLossFunction``   utils/seg_helper.py:191-230, 864-903
+  ``bilateralfilter.bilateralfilter_batch``         utils/bilateralfilter (SWIG module)
+
+Everything requires CUDA tensors; there is no CPU fallback and no second backend.
+"""
+from . import _lib  # noqa: F401
+from .par import PAR, get_kernel
+from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
+                         cam_to_label, cam_validation, get_energy_loss)
+
+__all__ = ["PAR", "get_kernel", "cam_validation", "cam_to_label", "cam2mask", "_refine_cams", "cam_normalize",
+           "get_energy_loss", "DenseEnergyLoss", "DenseEnergyLossFunction"]

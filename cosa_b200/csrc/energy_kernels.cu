@@ -1,0 +1,303 @@
+// Dense-CRF energy loss on the GPU lattice.
+//
+// Reference: utils/seg_helper.py:864-903 DenseEnergyLossFunction (dup utils/rrm_utils.py:352-391),
+//            utils/seg_helper.py:191-208 DenseEnergyLoss.forward, :210-230 get_energy_loss.
+//
+//   energy_gate_kernel      Gate = clamp_min(ROI - max_k S, 0), Gate[unlabel] = 1; S <- S * ROI        :870-880
+//   (lattice)               AS = BilateralFilter(S * ROI); AS <- AS * Gate; loss = -<S, AS>/N            :887-893
+//   energy_grad_kernel      grad_S = -2 * g * AS / N * ROI                                               :898-903
+//   energy_prepare_kernel   get_energy_loss + DenseEnergyLoss.forward fused for the exact 2:1 case:
+//                           de-normalise + nearest image, ROI from the boxes, unlabel from the label map,
+//                           bilinear(softmax(logit)), gate                                               :199-229
+//   energy_logit_grad_kernel  the matching backward: d loss / d logit through the bilinear 2:1 reduction
+//                           and the softmax, without materialising the probabilities.
+#include <math.h>
+
+#include "common.cuh"
+#include "lattice.cuh"
+
+namespace cosa {
+
+__global__ void __launch_bounds__(256) energy_gate_kernel(const float *__restrict__ segs,
+                                                          const float *__restrict__ rois,
+                                                          const unsigned char *__restrict__ unlabel,
+                                                          float *__restrict__ s_roi, float *__restrict__ gate, int K,
+                                                          int n, long long P) {
+  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < P;
+       gp += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gp / n), p = (int)(gp % n);
+    const float roi = __ldg(rois + gp);
+    const float *src = segs + (size_t)b * K * n + p;
+    float *dst = s_roi + (size_t)b * K * n + p;
+    float mx = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const float s = __ldg(src + (size_t)k * n);
+      mx = fmaxf(mx, s);
+      dst[(size_t)k * n] = __fmul_rn(s, roi);
+    }
+    float g = __fsub_rn(roi, mx);
+    if (unlabel[gp]) g = 1.0f;
+    if (g < 0.0f) g = 0.0f;
+    gate[gp] = g;
+  }
+}
+
+__global__ void energy_loss_finalize_kernel(const double *__restrict__ acc, float *__restrict__ loss_out, int N,
+                                            float weight, int apply_weight) {
+  // np.dot in float32, negated, divided by N (seg_helper.py:890-893); the layer multiplies by its weight (:207)
+  float l = __fdiv_rn(-(float)(*acc), (float)N);
+  if (apply_weight) l = __fmul_rn(weight, l);
+  loss_out[0] = l;
+}
+
+__global__ void __launch_bounds__(256) energy_grad_kernel(const float *__restrict__ as_saved,
+                                                          const float *__restrict__ rois,
+                                                          const float *__restrict__ grad_out,
+                                                          float *__restrict__ grad_seg, int K, int n, long long P,
+                                                          int N) {
+  const float c = __fmul_rn(-2.0f, __ldg(grad_out));
+  const float fn = (float)N;
+  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < P;
+       gp += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gp / n), p = (int)(gp % n);
+    const float roi = __ldg(rois + gp);
+    const size_t base = (size_t)b * K * n + p;
+    for (int k = 0; k < K; ++k) {
+      const size_t i = base + (size_t)k * n;
+      grad_seg[i] = __fmul_rn(__fdiv_rn(__fmul_rn(c, __ldg(as_saved + i)), fn), roi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused get_energy_loss front end, exact 2:1 reduction (H, W even; scale_factor 0.5).
+// One thread per half-resolution pixel.  The four source pixels of the bilinear reduction are softmax-ed on
+// the fly (online max/sum), so the [B,C,H,W] probability tensor is never written.
+// ------------------------------------------------------------------------------------------------
+struct Affine3 {
+  float mean[3], std[3];
+};
+
+__device__ __forceinline__ void online_softmax_stats(const float *__restrict__ logit, size_t HW, int C, float &mx,
+                                                     float &den) {
+  mx = -INFINITY;
+  den = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(logit + (size_t)c * HW);
+    if (v > mx) {
+      den = den * expf(mx - v) + 1.0f;
+      mx = v;
+    } else {
+      den += expf(v - mx);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) energy_prepare_kernel(const float *__restrict__ simg,
+                                                             const float *__restrict__ logit,
+                                                             const float *__restrict__ label,
+                                                             const int *__restrict__ boxes, Affine3 aff,
+                                                             float *__restrict__ img_half, float *__restrict__ s_roi,
+                                                             float *__restrict__ gate, float *__restrict__ roi_out,
+                                                             int C, int H, int W) {
+  const int h = H / 2, w = W / 2;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (x >= w || y >= h) return;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const size_t pix = (size_t)y * w + x;
+  const size_t src = (size_t)(2 * y) * W + 2 * x;   // nearest: source index 2i (seg_helper.py:201,203,204)
+
+#pragma unroll
+  for (int c = 0; c < 3; ++c)   // img * std + mean, two roundings like the two tensor ops (:225-227)
+    img_half[((size_t)b * 3 + c) * hw + pix] =
+        __fadd_rn(__fmul_rn(__ldg(simg + ((size_t)b * 3 + c) * HW + src), aff.std[c]), aff.mean[c]);
+
+  const int *box = boxes + 4 * b;
+  const float roi = (2 * y >= box[0] && 2 * y < box[1] && 2 * x >= box[2] && 2 * x < box[3]) ? 1.0f : 0.0f;
+  // label.type(uint8) then == 255 (:229, :205)
+  const bool unl = ((int)__ldg(label + (size_t)b * HW + src) & 255) == 255;
+
+  const float *lg = logit + (size_t)b * C * HW + src;
+  float mx[4], rden[4];
+  const size_t tap[4] = {0, 1, (size_t)W, (size_t)W + 1};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float den;
+    online_softmax_stats(lg + tap[t], HW, C, mx[t], den);
+    rden[t] = den;
+  }
+  float smax = -INFINITY;
+  float *dst = s_roi + (size_t)b * C * hw + pix;
+  for (int c = 0; c < C; ++c) {
+    const float *lc = lg + (size_t)c * HW;
+    const float p00 = __fdiv_rn(expf(__ldg(lc + tap[0]) - mx[0]), rden[0]);
+    const float p01 = __fdiv_rn(expf(__ldg(lc + tap[1]) - mx[1]), rden[1]);
+    const float p10 = __fdiv_rn(expf(__ldg(lc + tap[2]) - mx[2]), rden[2]);
+    const float p11 = __fdiv_rn(expf(__ldg(lc + tap[3]) - mx[3]), rden[3]);
+    // exact 2:1 bilinear, align_corners=False: 0.25 * (((p00 + p01) + p10) + p11)
+    const float s = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(p00, p01), p10), p11));
+    smax = fmaxf(smax, s);
+    dst[(size_t)c * hw] = __fmul_rn(s, roi);
+  }
+  float g = __fsub_rn(roi, smax);
+  if (unl) g = 1.0f;
+  if (g < 0.0f) g = 0.0f;
+  gate[(size_t)b * hw + pix] = g;
+  roi_out[(size_t)b * hw + pix] = roi;
+}
+
+// d loss / d logit.  grad wrt the half-resolution S is gS = coef * AS * ROI with coef = -2 * g * weight / N;
+// each of the four source pixels receives 0.25 * gS through the bilinear reduction, then the softmax
+// backward p * (u - <p, u>) is applied per source pixel.
+__global__ void __launch_bounds__(256) energy_logit_grad_kernel(const float *__restrict__ logit,
+                                                                const float *__restrict__ as_saved,
+                                                                const float *__restrict__ roi_half,
+                                                                const float *__restrict__ grad_out, float weight,
+                                                                float *__restrict__ grad_logit, int C, int H, int W,
+                                                                int N) {
+  const int h = H / 2, w = W / 2;
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (X >= W || Y >= H) return;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const size_t pix = (size_t)(Y >> 1) * w + (X >> 1);
+  const float roi = __ldg(roi_half + (size_t)b * hw + pix);
+  const float coef = __fdiv_rn(__fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight)), (float)N) * roi * 0.25f;
+  const float *lg = logit + (size_t)b * C * HW + (size_t)Y * W + X;
+  const float *as = as_saved + (size_t)b * C * hw + pix;
+  float *out = grad_logit + (size_t)b * C * HW + (size_t)Y * W + X;
+  float mx, den;
+  online_softmax_stats(lg, HW, C, mx, den);
+  const float rden = 1.0f / den;
+  float dot = 0.0f;
+  for (int c = 0; c < C; ++c) {
+    const float p = expf(__ldg(lg + (size_t)c * HW) - mx) * rden;
+    dot = fmaf(p, coef * __ldg(as + (size_t)c * hw), dot);
+  }
+  for (int c = 0; c < C; ++c) {
+    const float p = expf(__ldg(lg + (size_t)c * HW) - mx) * rden;
+    out[(size_t)c * HW] = p * (coef * __ldg(as + (size_t)c * hw) - dot);
+  }
+}
+
+static int grid1d(long long items) { return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(items, 256))); }
+
+}  // namespace cosa
+
+using namespace cosa;
+
+// Workspace of the autograd Function: S*ROI [N,K,H,W], gate [N,H,W], then the lattice (one chunk).
+extern "C" size_t cosa_dense_energy_ws_bytes(int N, int K, int H, int W) {
+  if (N < 1 || K < 1 || H < 1 || W < 1) return 0;
+  const size_t n = (size_t)H * W;
+  return align_up((size_t)N * K * n * sizeof(float), 256) + align_up((size_t)N * n * sizeof(float), 256) + 256 +
+         lattice_ws_bytes(min(N, kMaxImagesPerLattice), K, H, W);
+}
+
+static int energy_core(const float *images, const float *s_roi, const float *gate, float *as_out, float *loss_out,
+                       double *acc, int N, int K, int H, int W, float sigmargb, float sigmaxy, float weight,
+                       int apply_weight, void *lattice_ws, cudaStream_t s) {
+  const size_t n = (size_t)H * W;
+  COSA_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
+  for (int n0 = 0; n0 < N; n0 += kMaxImagesPerLattice) {   // chunks reuse the lattice workspace, stream-ordered
+    const int nb = min(kMaxImagesPerLattice, N - n0);
+    LatticeBufs L;
+    lattice_carve(lattice_ws, nb, K, H, W, &L);
+    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, s));
+    COSA_CHECK(lattice_splat_blur(L, s_roi + (size_t)n0 * K * n, nb, K, H, W, s));
+    COSA_CHECK(lattice_slice(L, s_roi + (size_t)n0 * K * n, gate + (size_t)n0 * n, acc, as_out + (size_t)n0 * K * n,
+                             nb, K, H, W, s));
+  }
+  COSA_LAUNCH(energy_loss_finalize_kernel, 1, 1, 0, s, acc, loss_out, N, weight, apply_weight);
+  return 0;
+}
+
+extern "C" int cosa_dense_energy_forward(const float *images, const float *segs, const float *rois,
+                                         const unsigned char *unlabel, float sigmargb, float sigmaxy, float *as_out,
+                                         float *loss_out, int N, int K, int H, int W, void *ws, size_t ws_bytes,
+                                         void *stream) {
+  if (!images || !segs || !rois || !unlabel || !as_out || !loss_out || !ws || N < 1 || K < 1 || H < 1 || W < 1)
+    return COSA_E_ARG;
+  if (ws_bytes < cosa_dense_energy_ws_bytes(N, K, H, W)) return COSA_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = H * W;
+  const long long P = (long long)N * n;
+  Arena a(ws);
+  float *s_roi = a.take<float>((size_t)N * K * n);
+  float *gate = a.take<float>((size_t)P);
+  double *acc = a.take<double>(1);
+  void *lws = a.base + a.off;
+  COSA_LAUNCH(energy_gate_kernel, grid1d(P), 256, 0, s, segs, rois, unlabel, s_roi, gate, K, n, P);
+  return energy_core(images, s_roi, gate, as_out, loss_out, acc, N, K, H, W, sigmargb, sigmaxy, 1.0f, 0, lws, s);
+}
+
+extern "C" int cosa_dense_energy_backward(const float *as_saved, const float *rois, const float *grad_out,
+                                          float *grad_seg, int N, int K, int H, int W, void *stream) {
+  if (!as_saved || !rois || !grad_out || !grad_seg || N < 1 || K < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  const int n = H * W;
+  const long long P = (long long)N * n;
+  COSA_LAUNCH(energy_grad_kernel, grid1d(P), 256, 0, (cudaStream_t)stream, as_saved, rois, grad_out, grad_seg, K, n, P,
+              N);
+  return 0;
+}
+
+// ---- fused get_energy_loss ---------------------------------------------------------------------------
+// saved = [ AS gated [B,C,h,w] | ROI [B,h,w] ];  ws = [ img_half [B,3,h,w] | S*ROI [B,C,h,w] | gate [B,h,w] | lattice ]
+extern "C" size_t cosa_energy_loss_saved_bytes(int B, int C, int H, int W) {
+  const size_t hw = (size_t)(H / 2) * (W / 2);
+  return align_up((size_t)B * C * hw * sizeof(float), 256) + align_up((size_t)B * hw * sizeof(float), 256);
+}
+
+extern "C" size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W) {
+  if (B < 1 || C < 1 || H < 2 || W < 2) return 0;
+  const size_t hw = (size_t)(H / 2) * (W / 2);
+  return align_up((size_t)B * 3 * hw * sizeof(float), 256) + align_up((size_t)B * C * hw * sizeof(float), 256) +
+         align_up((size_t)B * hw * sizeof(float), 256) + 256 +
+         lattice_ws_bytes(min(B, kMaxImagesPerLattice), C, H / 2, W / 2);
+}
+
+extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, const float *label, const int *boxes,
+                                        const float *mean, const float *std, float weight, float sigmargb,
+                                        float sigmaxy_scaled, float *loss_out, void *saved, int B, int C, int H, int W,
+                                        void *ws, size_t ws_bytes, void *stream) {
+  if (!simg || !logit || !label || !boxes || !mean || !std || !loss_out || !saved || !ws || B < 1 || C < 1)
+    return COSA_E_ARG;
+  if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
+  if (ws_bytes < cosa_energy_loss_ws_bytes(B, C, H, W)) return COSA_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int h = H / 2, w = W / 2;
+  const size_t hw = (size_t)h * w;
+  Arena sv(saved);
+  float *as_out = sv.take<float>((size_t)B * C * hw);
+  float *roi_half = sv.take<float>((size_t)B * hw);
+  Arena a(ws);
+  float *img_half = a.take<float>((size_t)B * 3 * hw);
+  float *s_roi = a.take<float>((size_t)B * C * hw);
+  float *gate = a.take<float>((size_t)B * hw);
+  double *acc = a.take<double>(1);
+  void *lws = a.base + a.off;
+  Affine3 aff;
+  for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
+  dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B);
+  COSA_LAUNCH(energy_prepare_kernel, grid, 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi, gate, roi_half,
+              C, H, W);
+  return energy_core(img_half, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1, lws,
+                     s);
+}
+
+extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,
+                                         float *grad_logit, int B, int C, int H, int W, void *stream) {
+  if (!logit || !saved || !grad_out || !grad_logit || B < 1 || C < 1 || H < 2 || W < 2 || (H & 1) || (W & 1))
+    return COSA_E_ARG;
+  const size_t hw = (size_t)(H / 2) * (W / 2);
+  Arena sv(const_cast<void *>(saved));
+  const float *as_saved = sv.take<float>((size_t)B * C * hw);
+  const float *roi_half = sv.take<float>((size_t)B * hw);
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
+  COSA_LAUNCH(energy_logit_grad_kernel, grid, 256, 0, (cudaStream_t)stream, logit, as_saved, roi_half, grad_out, weight,
+              grad_logit, C, H, W, B);
+  return 0;
+}

@@ -1,0 +1,511 @@
+// CAM normalise / validation / labelling kernels (reference: utils/seg_helper.py:264-270, 515-551, 721-797).
+//
+// All of these are streaming, HBM-bound passes: 128-bit loads where the layout allows, warp shuffles for the
+// per-pixel channel reduction, grids sized from the SM count (persistent grid-stride) or one tile per CTA.
+#include <math.h>
+
+#include "common.cuh"
+#include "par.cuh"
+
+namespace cosa {
+
+// ------------------------------------------------------------------------------------------------
+// cam_validation (seg_helper.py:547-551): out = cls_label[b,c] * cam.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cam_validation_kernel(const float *__restrict__ cam,
+                                                             const float *__restrict__ cls_label,
+                                                             float *__restrict__ out, long long HW4, long long HW,
+                                                             int planes) {
+  // grid.y strides over planes, grid.x over float4 chunks of the plane (HW % 4 == 0 path)
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float l = __ldg(cls_label + p);
+    const float *src = cam + (size_t)p * HW;
+    float *dst = out + (size_t)p * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 v = ldg_stream4(src + 4 * i);
+      v.x = __fmul_rn(l, v.x); v.y = __fmul_rn(l, v.y); v.z = __fmul_rn(l, v.z); v.w = __fmul_rn(l, v.w);
+      stg_stream4(dst + 4 * i, v);
+    }
+  }
+}
+__global__ void cam_validation_scalar_kernel(const float *__restrict__ cam, const float *__restrict__ cls_label,
+                                             float *__restrict__ out, long long HW, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fmul_rn(__ldg(cls_label + i / HW), cam[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CAM normalise (seg_helper.py:264-270).  Pass 1: per-plane min/max of the scale sum (several CTAs per
+// plane, float atomics through the order-preserving int mapping).  Pass 2: (sum + (-min)) / (max' + 1e-5),
+// max' = rn(max + (-min)) (rounding is monotonic, so this is the max of the shifted plane).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxScales = 8;
+struct ScalePtrs {
+  const float *p[kMaxScales];
+};
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int *mm, int planes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < planes) {
+    mm[2 * i] = float_to_ordered(INFINITY);
+    mm[2 * i + 1] = float_to_ordered(-INFINITY);
+  }
+}
+
+__device__ __forceinline__ float scale_sum(const ScalePtrs &sp, int n_scales, size_t idx) {
+  float s = __ldg(sp.p[0] + idx);
+  for (int k = 1; k < n_scales; ++k) s = __fadd_rn(s, __ldg(sp.p[k] + idx));
+  return s;
+}
+
+__global__ void __launch_bounds__(256) cam_minmax_kernel(ScalePtrs sp, int n_scales, int *__restrict__ mm,
+                                                         long long HW, int planes) {
+  __shared__ float s_min[8], s_max[8];
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW;
+         i += (long long)gridDim.x * blockDim.x) {
+      const float s = scale_sum(sp, n_scales, (size_t)p * HW + i);
+      lo = fminf(lo, s);
+      hi = fmaxf(hi, s);
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      lo = threadIdx.x < 8 ? s_min[threadIdx.x] : INFINITY;
+      hi = threadIdx.x < 8 ? s_max[threadIdx.x] : -INFINITY;
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      if (threadIdx.x == 0) {
+        atomicMin(mm + 2 * p, float_to_ordered(lo));
+        atomicMax(mm + 2 * p + 1, float_to_ordered(hi));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) cam_normalize_apply_kernel(ScalePtrs sp, int n_scales,
+                                                                  const int *__restrict__ mm, float *__restrict__ out,
+                                                                  long long HW, int planes) {
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float neg_min = -ordered_to_float(mm[2 * p]);                 // max(-cam)
+    const float top = __fadd_rn(ordered_to_float(mm[2 * p + 1]), neg_min);   // max(cam - min)
+    const float den = __fadd_rn(top, 1e-5f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW;
+         i += (long long)gridDim.x * blockDim.x) {
+      const size_t idx = (size_t)p * HW + i;
+      out[idx] = __fdiv_rn(__fadd_rn(scale_sum(sp, n_scales, idx), neg_min), den);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cam_to_label (seg_helper.py:515-545).  A warp covers 32 consecutive pixels as 8 float4 columns x 4 channel
+// groups; each lane scans channels cg, cg+4, ... of its 4 pixels with 128-bit loads, then the 4 groups are
+// merged with two xor-shuffles (larger value wins, lower channel on ties = torch.max's first index).
+// ------------------------------------------------------------------------------------------------
+struct LabelArgs {
+  float bkg_thre, high_thre, low_thre;
+  int ignore_mid;
+  long long ignore_index;
+};
+
+__device__ __forceinline__ void argmax_merge(float &v, int &idx, float ov, int oidx) {
+  // NaN handling follows "first maximal"; CAMs on this path are finite.
+  if (ov > v || (ov == v && oidx < idx)) { v = ov; idx = oidx; }
+}
+
+__device__ __forceinline__ long long decide_label(float v, int idx, int y, int x, const int *box,
+                                                  const LabelArgs &a) {
+  long long lab = (long long)idx + 1;
+  if (v <= a.bkg_thre) lab = 0;
+  if (box) {
+    if (a.ignore_mid) {
+      if (v <= a.high_thre) lab = a.ignore_index;
+      if (v <= a.low_thre) lab = 0;
+    }
+    if (!(y >= box[0] && y < box[1] && x >= box[2] && x < box[3])) lab = a.ignore_index;
+  }
+  return lab;
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) cam_to_label_kernel(const float *__restrict__ cam,
+                                                           const float *__restrict__ cls_label,
+                                                           const int *__restrict__ boxes,
+                                                           float *__restrict__ valid_out,
+                                                           long long *__restrict__ label_out, int B, int C1, int H, int W,
+                                                           LabelArgs args) {
+  const long long HW = (long long)H * W;
+  const int lane = threadIdx.x & 31, cg = lane >> 3, pq = lane & 7;
+  const long long warps_per_img = ceil_div_ll(HW, 32);
+  const long long total_warps = warps_per_img * B;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long warp_stride = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long wi = warp0; wi < total_warps; wi += warp_stride) {
+    const int b = (int)(wi / warps_per_img);
+    const long long p0 = (wi % warps_per_img) * 32 + pq * 4;   // first of this lane's 4 pixels
+    const float *base = cam + (size_t)b * C1 * HW;
+    float *vbase = valid_out ? valid_out + (size_t)b * C1 * HW : nullptr;
+    float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int c = cg; c < C1; c += 4) {
+      const float l = cls_label ? __ldg(cls_label + (size_t)b * C1 + c) : 1.0f;
+      float v[4];
+      if (VEC4) {
+        if (p0 < HW) {
+          const float4 t = ldg_stream4(base + (size_t)c * HW + p0);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+          v[0] = v[1] = v[2] = v[3] = 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (p0 + k < HW) ? __ldg(base + (size_t)c * HW + p0 + k) : 0.0f;
+      }
+      if (cls_label) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __fmul_rn(l, v[k]);
+      }
+      if (vbase) {
+        if (VEC4) {
+          if (p0 < HW) stg_stream4(vbase + (size_t)c * HW + p0, make_float4(v[0], v[1], v[2], v[3]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (p0 + k < HW) vbase[(size_t)c * HW + p0 + k] = v[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (v[k] > bv[k]) { bv[k] = v[k]; bi[k] = c; }   // strictly greater: the first maximum is kept
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv[k], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi[k], o);
+        argmax_merge(bv[k], bi[k], ov, oi);
+      }
+    }
+    if (cg == 0) {
+      const int *box = boxes ? boxes + 4 * b : nullptr;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long p = p0 + k;
+        if (p < HW) {
+          const int y = (int)(p / W), x = (int)(p % W);
+          label_out[(size_t)b * HW + p] = decide_label(bv[k], bi[k], y, x, box, args);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cam2mask (seg_helper.py:721-785), batched over images and over the two threshold stacks.
+//
+//  keys     : per image the list [0] + [c+1 : cls_label[b,c] != 0]  (torch.nonzero order)         :762-767
+//  prepare  : half-resolution image (bilinear, align_corners=False) and, per image, the softmax over the
+//             live channels of [threshold, down(cams)] for the high and the low threshold          :737-769
+//  (PAR)    : par_kernels.cu, both stacks of every image in one ragged batch                         :790
+//  finalize : bilinear up-sampling of the refined stacks, argmax (first max), key lookup, box crop
+//             and the high/low merge rule                                                        :793-795, :777-783
+// Mask buffers are [B, 2*C, h, w]: channels [0,nc) hold the high stack, [nc,2nc) the low stack.
+// ------------------------------------------------------------------------------------------------
+__global__ void cam2mask_keys_kernel(const float *__restrict__ cls_labels, int *__restrict__ keys,
+                                     int *__restrict__ nc_out, int *__restrict__ nch_out, int B, int C1) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int *k = keys + (size_t)b * (C1 + 1);
+  int n = 0;
+  k[n++] = 0;
+  for (int c = 0; c < C1; ++c)
+    if (cls_labels[(size_t)b * C1 + c] != 0.0f) k[n++] = c + 1;
+  nc_out[b] = n;
+  nch_out[b] = 2 * n;
+}
+
+struct ResizeGeom {
+  int H, W, h, w;       // full and reduced size
+  float sy, sx;         // source-index scale for the reduction (H/h, W/w); 1 when downscale == 0
+  int identity;         // no reduction (downscale == 0)
+};
+
+__device__ __forceinline__ float sample_down(const float *plane, const ResizeGeom &g, const Tap &ty, const Tap &tx) {
+  if (g.identity) return __ldg(plane + (size_t)ty.i0 * g.W + tx.i0);
+  return bilerp_down(ty, tx, __ldg(plane + (size_t)ty.i0 * g.W + tx.i0), __ldg(plane + (size_t)ty.i0 * g.W + tx.i1),
+                     __ldg(plane + (size_t)ty.i1 * g.W + tx.i0), __ldg(plane + (size_t)ty.i1 * g.W + tx.i1));
+}
+
+constexpr int kCacheC = 8;   // live channels cached in registers by the prepare kernel
+
+__global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__restrict__ images,
+                                                               const float *__restrict__ cams,
+                                                               const int *__restrict__ keys,
+                                                               const int *__restrict__ nc_dev,
+                                                               float *__restrict__ img_small,
+                                                               float *__restrict__ masks, ResizeGeom g, int C1,
+                                                               float thr_high, float thr_low) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (x >= g.w || y >= g.h) return;
+  const size_t HW = (size_t)g.H * g.W, hw = (size_t)g.h * g.w;
+  const size_t pix = (size_t)y * g.w + x;
+  Tap ty, tx;
+  if (g.identity) {
+    ty.i0 = ty.i1 = y; tx.i0 = tx.i1 = x; ty.w0 = tx.w0 = 1.0f; ty.w1 = tx.w1 = 0.0f;
+  } else {
+    ty = tap_half_pixel(y, g.sy, g.H);
+    tx = tap_half_pixel(x, g.sx, g.W);
+  }
+  if (img_small) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      img_small[((size_t)b * 3 + c) * hw + pix] = sample_down(images + ((size_t)b * 3 + c) * HW, g, ty, tx);
+  }
+  const int nc = nc_dev[b];
+  const int *key = keys + (size_t)b * (C1 + 1);
+  const float *cam_b = cams + (size_t)b * C1 * HW;
+  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * hw + pix;
+  float *m_lo = m_hi + (size_t)nc * hw;
+
+  // live foreground channels: values, their max; the two stacks differ only in channel 0 (the threshold)
+  float v[kCacheC];
+  float mx = -INFINITY;
+  for (int j = 1; j < nc; ++j) {
+    const float t = sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    if (j < kCacheC) v[j] = t;
+    mx = fmaxf(mx, t);
+  }
+  const float mx_hi = fmaxf(mx, thr_high), mx_lo = fmaxf(mx, thr_low);
+  float e0_hi = expf(thr_high - mx_hi), e0_lo = expf(thr_low - mx_lo);
+  float den_hi = e0_hi, den_lo = e0_lo;
+  for (int j = 1; j < nc; ++j) {
+    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    den_hi += expf(t - mx_hi);
+    den_lo += expf(t - mx_lo);
+  }
+  m_hi[0] = e0_hi / den_hi;
+  m_lo[0] = e0_lo / den_lo;
+  for (int j = 1; j < nc; ++j) {
+    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    m_hi[(size_t)j * hw] = expf(t - mx_hi) / den_hi;
+    m_lo[(size_t)j * hw] = expf(t - mx_lo) / den_lo;
+  }
+}
+
+// argmax over nc channels of the bilinearly up-sampled stack at full-resolution pixel (Y, X)
+__device__ __forceinline__ int upsampled_argmax(const float *stack, int nc, size_t hw, int w, const Tap &ty,
+                                                const Tap &tx) {
+  const size_t o00 = (size_t)ty.i0 * w + tx.i0, o01 = (size_t)ty.i0 * w + tx.i1;
+  const size_t o10 = (size_t)ty.i1 * w + tx.i0, o11 = (size_t)ty.i1 * w + tx.i1;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int j = 0; j < nc; ++j) {
+    const float *p = stack + (size_t)j * hw;
+    const float val = bilerp_up(ty, tx, __ldg(p + o00), __ldg(p + o01), __ldg(p + o10), __ldg(p + o11));
+    if (val > best || j == 0) { best = val; arg = j; }
+  }
+  return arg;
+}
+
+__global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__restrict__ refined,
+                                                                const int *__restrict__ keys,
+                                                                const int *__restrict__ nc_dev,
+                                                                const int *__restrict__ boxes,
+                                                                float *__restrict__ label_out,
+                                                                float *__restrict__ label_hi_out,
+                                                                float *__restrict__ label_lo_out, ResizeGeom g, int C1,
+                                                                float ignore_index) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (X >= g.W || Y >= g.H) return;
+  const size_t HW = (size_t)g.H * g.W, hw = (size_t)g.h * g.w;
+  const size_t out_idx = (size_t)b * HW + (size_t)Y * g.W + X;
+  const int *box = boxes + 4 * b;
+  float hi = ignore_index, lo = ignore_index;
+  if (Y >= box[0] && Y < box[1] && X >= box[2] && X < box[3]) {
+    const int nc = nc_dev[b];
+    const int *key = keys + (size_t)b * (C1 + 1);
+    // up-sampling scale = reduced / full (area_pixel_compute_scale with the output size given)
+    const Tap ty = tap_half_pixel(Y, g.identity ? 1.0f : (float)g.h / (float)g.H, g.h);
+    const Tap tx = tap_half_pixel(X, g.identity ? 1.0f : (float)g.w / (float)g.W, g.w);
+    const float *st = refined + (size_t)b * 2 * (C1 + 1) * hw;
+    hi = (float)key[upsampled_argmax(st, nc, hw, g.w, ty, tx)];
+    lo = (float)key[upsampled_argmax(st + (size_t)nc * hw, nc, hw, g.w, ty, tx)];
+  }
+  // merge (seg_helper.py:781-783): high fg stays; high bg becomes ignore unless low also says bg
+  float out = hi;
+  if (hi == 0.0f) out = ignore_index;
+  if (hi + lo == 0.0f) out = 0.0f;
+  label_out[out_idx] = out;
+  if (label_hi_out) label_hi_out[out_idx] = hi;
+  if (label_lo_out) label_lo_out[out_idx] = lo;
+}
+
+// _refine_cams tail for callers that bring their own refined stack (seg_helper.py:793-795)
+__global__ void __launch_bounds__(256) upsample_argmax_kernel(const float *__restrict__ refined,
+                                                              const long long *__restrict__ valid_key,
+                                                              long long *__restrict__ label_out, int nc, int h, int w,
+                                                              int H, int W) {
+  const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (X >= W || Y >= H) return;
+  const size_t hw = (size_t)h * w;
+  const Tap ty = tap_half_pixel(Y, (float)h / (float)H, h);
+  const Tap tx = tap_half_pixel(X, (float)w / (float)W, w);
+  const int arg = upsampled_argmax(refined + (size_t)b * nc * hw, nc, hw, w, ty, tx);
+  label_out[(size_t)b * H * W + (size_t)Y * W + X] = valid_key[arg];
+}
+
+}  // namespace cosa
+
+using namespace cosa;
+
+extern "C" int cosa_cam_validation(const float *cam, const float *cls_label, float *out, int B, int C1, long long HW,
+                                   void *stream) {
+  if (!cam || !cls_label || !out || B < 1 || C1 < 1 || HW < 1) return COSA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int planes = B * C1;
+  const bool vec = (HW % 4 == 0) && (((uintptr_t)cam | (uintptr_t)out) % 16 == 0);
+  if (vec) {
+    const long long HW4 = HW / 4;
+    const int bx = (int)min(ceil_div_ll(HW4, 256), 64LL);
+    const int by = min(planes, max(1, sm_count() * 16 / bx));
+    COSA_LAUNCH(cam_validation_kernel, dim3(bx, by), 256, 0, s, cam, cls_label, out, HW4, HW, planes);
+  } else {
+    const long long total = (long long)planes * HW;
+    const int blocks = (int)min((long long)sm_count() * 8, ceil_div_ll(total, 256));
+    COSA_LAUNCH(cam_validation_scalar_kernel, blocks, 256, 0, s, cam, cls_label, out, HW, total);
+  }
+  return 0;
+}
+
+extern "C" int cosa_cam_normalize(const float *const *scale_maps, int n_scales, float *out, int planes, long long HW,
+                                  float *minmax_ws, void *stream) {
+  if (!scale_maps || n_scales < 1 || n_scales > kMaxScales || !out || !minmax_ws || planes < 1 || HW < 1)
+    return COSA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  ScalePtrs sp;
+  for (int k = 0; k < kMaxScales; ++k) sp.p[k] = k < n_scales ? scale_maps[k] : nullptr;
+  int *mm = (int *)minmax_ws;
+  COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
+  const int bx = (int)min(ceil_div_ll(HW, 256 * 8), 32LL);
+  const int by = min(planes, max(1, sm_count() * 8 / bx));
+  COSA_LAUNCH(cam_minmax_kernel, dim3(bx, by), 256, 0, s, sp, n_scales, mm, HW, planes);
+  COSA_LAUNCH(cam_normalize_apply_kernel, dim3(bx, by), 256, 0, s, sp, n_scales, mm, out, HW, planes);
+  return 0;
+}
+
+extern "C" int cosa_cam_to_label(const float *cam, const float *cls_label, const int *boxes, float *valid_cam_out,
+                                 long long *label_out, int B, int C1, int H, int W, float bkg_thre, float high_thre,
+                                 float low_thre, int ignore_mid, long long ignore_index, void *stream) {
+  if (!cam || !label_out || B < 1 || C1 < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  LabelArgs a{bkg_thre, high_thre, low_thre, ignore_mid, ignore_index};
+  const long long HW = (long long)H * W;
+  const long long warps = ceil_div_ll(HW, 32) * B;
+  const int blocks = (int)min((long long)sm_count() * 8, ceil_div_ll(warps, 8));
+  const bool vec = (HW % 4 == 0) && ((uintptr_t)cam % 16 == 0) && (!valid_cam_out || (uintptr_t)valid_cam_out % 16 == 0);
+  if (vec) {
+    COSA_LAUNCH(cam_to_label_kernel<true>, blocks, 256, 0, s, cam, cls_label, boxes, valid_cam_out, label_out, B, C1,
+                H, W, a);
+  } else {
+    COSA_LAUNCH(cam_to_label_kernel<false>, blocks, 256, 0, s, cam, cls_label, boxes, valid_cam_out, label_out, B, C1,
+                H, W, a);
+  }
+  return 0;
+}
+
+static void cam2mask_geom(int H, int W, int downscale, ResizeGeom *g) {
+  g->H = H; g->W = W;
+  g->identity = downscale == 0;
+  g->h = downscale ? H / downscale : H;
+  g->w = downscale ? W / downscale : W;
+  g->sy = g->identity ? 1.0f : (float)H / (float)g->h;
+  g->sx = g->identity ? 1.0f : (float)W / (float)g->w;
+}
+
+extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downscale, int use_par, int n_dil) {
+  ResizeGeom g;
+  cam2mask_geom(H, W, downscale, &g);
+  const size_t hw = (size_t)g.h * g.w;
+  size_t bytes = align_up((size_t)B * (C1 + 1) * sizeof(int), 256) + 2 * align_up((size_t)B * sizeof(int), 256);
+  const int n_mask_bufs = use_par ? 4 : 1;
+  bytes += n_mask_bufs * align_up((size_t)B * 2 * (C1 + 1) * hw * sizeof(float), 256);
+  if (use_par) {
+    bytes += align_up((size_t)B * 3 * hw * sizeof(float), 256);
+    bytes += align_up((size_t)B * 8 * n_dil * hw * sizeof(float), 256);
+  }
+  return bytes;
+}
+
+extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                             float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
+                             const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
+                             float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes,
+                             void *stream) {
+  if (!images || !boxes || !cams || !cls_labels || !label_out || !ws || B < 1 || C1 < 1 || H < 1 || W < 1 ||
+      downscale < 0)
+    return COSA_E_ARG;
+  ResizeGeom g;
+  cam2mask_geom(H, W, downscale, &g);
+  if (g.h < 1 || g.w < 1) return COSA_E_ARG;
+  if (ws_bytes < cosa_cam2mask_ws_bytes(B, C1, H, W, downscale, use_par, n_dil)) return COSA_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t hw = (size_t)g.h * g.w;
+  const int C = C1 + 1;
+  Arena arena(ws);
+  int *keys = arena.take<int>((size_t)B * C);
+  int *nc = arena.take<int>(B);
+  int *nch = arena.take<int>(B);
+  float *masks = arena.take<float>((size_t)B * 2 * C * hw);
+
+  COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1);
+  float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
+  if (use_par) {
+    sa = arena.take<float>((size_t)B * 2 * C * hw);
+    sb = arena.take<float>((size_t)B * 2 * C * hw);
+    fin = arena.take<float>((size_t)B * 2 * C * hw);
+    img_small = arena.take<float>((size_t)B * 3 * hw);
+    aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
+    COSA_CHECK(par_upload_constants(dilations, n_dil, s));
+  }
+  dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
+  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, img_small, masks, g, C1, threshold_high,
+              threshold_low);
+  const float *refined = masks;
+  if (use_par) {
+    COSA_CHECK(par_launch_affinity(img_small, aff, B, g.h, g.w, n_dil, s));
+    COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, fin, nch, 0, 2 * C, B, g.h, g.w, n_dil, num_iter, s));
+    refined = fin;
+  }
+  dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
+  COSA_LAUNCH(cam2mask_finalize_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
+              label_low_out, g, C1, ignore_index);
+  return 0;
+}
+
+extern "C" int cosa_upsample_argmax(const float *refined, const long long *valid_key, long long *label_out, int B,
+                                    int nc, int h, int w, int H, int W, void *stream) {
+  if (!refined || !valid_key || !label_out || B < 1 || nc < 1 || h < 1 || w < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
+  COSA_LAUNCH(upsample_argmax_kernel, gf, 256, 0, (cudaStream_t)stream, refined, valid_key, label_out, nc, h, w, H, W);
+  return 0;
+}

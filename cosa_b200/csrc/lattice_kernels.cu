@@ -1,0 +1,517 @@
+// Permutohedral-lattice bilateral filter on the GPU (d = 5).
+//
+// Reference: utils/bilateralfilter/bilateralfilter.cpp:4-55 (features, per-image driver, batch loop) and
+// utils/bilateralfilter/permutohedral.cpp:115-297 (Permutohedral::init, SSE branch), :507-571 (compute).
+//
+//   build      one thread per pixel: features -> elevate -> round (half-even) -> rank -> barycentric ->
+//              6 packed vertex keys, inserted into an open-addressing hash table in HBM with 64-bit CAS;
+//              lanes of a warp that hold the same key elect one inserter (warp-aggregated atomics).
+//   resolve    table slot -> dense vertex id for every (pixel, vertex)
+//   neighbours 12 look-ups per vertex -> blur neighbour table                      (permutohedral.cpp:272-297)
+//   splat      values[v] += bary * in, all K channels of a vertex in one row, 128-bit vector reductions
+//   blur       6 Jacobi passes  new = old + 0.5 * (old[n1] + old[n2])               (permutohedral.cpp:536-552)
+//   slice      out = sum_r bary_r * alpha * values[v_r]  (+ fused gate / energy dot)  (permutohedral.cpp:554-567)
+//
+// Arithmetic that decides DISCRETE outcomes (rounding, ranks, keys) and the barycentric weights use explicit
+// round-to-nearest intrinsics in the reference's operation order, so the vertex set and the weights are
+// bit-identical to the CPU code; only the summation order of the splat (atomics) differs.
+#include <math.h>
+
+#include "common.cuh"
+#include "lattice.cuh"
+
+namespace cosa {
+
+// ---- packed keys ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_key(const int q[kLatD], int r, int b, int *bad) {
+  unsigned long long k = 0;
+#pragma unroll
+  for (int i = 0; i < kLatD; ++i) {
+    const int v = q[i] + kQBias;
+    if (v < 0 || v >= (1 << kQBits)) *bad = 1;
+    k |= (unsigned long long)(v & ((1 << kQBits) - 1)) << (kQBits * i);
+  }
+  k |= (unsigned long long)r << (kQBits * kLatD);
+  k |= (unsigned long long)b << (kQBits * kLatD + 3);
+  return k;
+}
+
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
+  // splitmix64 finaliser: full avalanche, so linear probing sees no structure from the lattice geometry
+  k ^= k >> 30; k *= 0xbf58476d1ce4e5b9ULL;
+  k ^= k >> 27; k *= 0x94d049bb133111ebULL;
+  k ^= k >> 31;
+  return k;
+}
+
+// Scale factors of the elevation (permutohedral.cpp:156-159): double arithmetic with a float inv_std_dev,
+// stored as float.  Evaluated on the host, passed by value.
+struct EmbedConst {
+  float sf[kLatD];
+};
+
+static EmbedConst make_embed_const() {
+  EmbedConst c;
+  const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (kLatD + 1));
+  for (int i = 0; i < kLatD; ++i) c.sf[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev);
+  return c;
+}
+
+// One point of Permutohedral::init (permutohedral.cpp:176-252).  Outputs q0[i] = rem0[i]/6 (after the wrap),
+// rank[i] and the six barycentric weights.
+__device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedConst &ec, int q0[kLatD + 1],
+                                            int rank[kLatD + 1], float bary[kLatD + 1]) {
+  constexpr int D = kLatD;
+  const float inv6 = 1.0f / 6.0f;
+  float el[D + 1], rem0[D + 1];
+  float sm = 0.0f;
+#pragma unroll
+  for (int j = D; j > 0; --j) {
+    const float cf = __fmul_rn(f[j - 1], ec.sf[j - 1]);
+    el[j] = __fsub_rn(sm, __fmul_rn((float)j, cf));
+    sm = __fadd_rn(sm, cf);
+  }
+  el[0] = sm;
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    const float v = rintf(__fmul_rn(inv6, el[i]));     // _mm_cvtps_epi32: round half to even
+    rem0[i] = __fmul_rn(v, 6.0f);
+    sum = __fadd_rn(sum, v);
+  }
+  float diff[D + 1];
+#pragma unroll
+  for (int i = 0; i <= D; ++i) { diff[i] = __fsub_rn(el[i], rem0[i]); rank[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i + 1; j <= D; ++j) {
+      const int c = diff[i] < diff[j] ? 1 : 0;
+      rank[i] += c;
+      rank[j] += 1 - c;
+    }
+  const int isum = (int)sum;
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    rank[i] += isum;
+    if (rank[i] < 0) { rank[i] += D + 1; rem0[i] = __fadd_rn(rem0[i], 6.0f); }
+    else if (rank[i] > D) { rank[i] -= D + 1; rem0[i] = __fsub_rn(rem0[i], 6.0f); }
+  }
+  // barycentric (permutohedral.cpp:222-241): b[5-rank] += v, b[6-rank] -= v, then b[0] += 1 + b[6].
+  // rank is a permutation, so b[s] = v(rank = 5-s) - v(rank = 6-s) whatever the visiting order.
+  float vr[D + 1];
+#pragma unroll
+  for (int i = 0; i <= D; ++i) {
+    const float v = __fmul_rn(__fsub_rn(el[i], rem0[i]), inv6);
+#pragma unroll
+    for (int k = 0; k <= D; ++k)
+      if (rank[i] == k) vr[k] = v;
+    q0[i] = (int)rintf(__fmul_rn(rem0[i], inv6));   // exact: rem0 is a small multiple of 6
+  }
+#pragma unroll
+  for (int s = 1; s <= D; ++s) bary[s] = __fsub_rn(vr[D - s], vr[D + 1 - s]);
+  bary[0] = __fadd_rn(vr[D], __fadd_rn(1.0f, -vr[0]));
+}
+
+// ---- build ---------------------------------------------------------------------------------------
+__global__ void lattice_clear_kernel(unsigned long long *table_keys, unsigned long long cap, int *counters) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 2;
+  for (unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 2; i < cap; i += stride)
+    *reinterpret_cast<ulonglong2 *>(table_keys + i) = make_ulonglong2(kEmptyKey, kEmptyKey);
+  if (blockIdx.x == 0 && threadIdx.x < 8) {
+    counters[threadIdx.x] = threadIdx.x == 3 ? (int)min(cap, (unsigned long long)0x7fffffff) : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const float *__restrict__ images,
+                                                            EmbedConst ec, int N, int H, int W, int n_pad,
+                                                            float sigmargb, float sigmaxy) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)N * n_pad;
+  const bool in_range = g < total;
+  const unsigned active = __ballot_sync(0xffffffffu, in_range);
+  if (!in_range) return;
+  const int n = H * W;
+  const int b = (int)(g / n_pad), p = (int)(g % n_pad);
+  const bool real = p < n;   // the SSE loop also embeds zero-feature padding pixels (permutohedral.cpp:168-173)
+
+  float f[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (real) {
+    const float *img = images + (size_t)b * 3 * n;
+    f[0] = __fdiv_rn((float)(p % W), sigmaxy);               // bilateralfilter.cpp:9-13
+    f[1] = __fdiv_rn((float)(p / W), sigmaxy);
+    f[2] = __fdiv_rn(__ldg(img + p), sigmargb);
+    f[3] = __fdiv_rn(__ldg(img + n + p), sigmargb);
+    f[4] = __fdiv_rn(__ldg(img + 2 * n + p), sigmargb);
+  }
+  int q0[kLatD + 1], rank[kLatD + 1];
+  float bary[kLatD + 1];
+  embed_point(f, ec, q0, rank, bary);
+
+  const long long gp = (long long)b * n + p;   // compact pixel index
+  const int lane = threadIdx.x & 31;
+  int bad = 0, max_probe = 0;
+#pragma unroll 1
+  for (int r = 0; r <= kLatD; ++r) {
+    int q[kLatD];
+#pragma unroll
+    for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
+    const unsigned long long key = pack_key(q, r, b, &bad);
+    // warp-aggregated insert: one CAS per distinct key per warp
+    const unsigned peers = __match_any_sync(active, key);
+    const int leader = __ffs(peers) - 1;
+    unsigned long long slot = 0;
+    if (lane == leader) {
+      slot = hash_key(key) & L.cap_mask;
+      int probes = 0;
+      for (;;) {
+        const unsigned long long old = atomicCAS(L.table_keys + slot, kEmptyKey, key);
+        if (old == kEmptyKey) {
+          const int id = atomicAdd(L.counters, 1);
+          L.vkeys[id] = key;
+          L.table_ids[slot] = id + 1;
+          break;
+        }
+        if (old == key) break;
+        slot = (slot + 1) & L.cap_mask;
+        ++probes;
+      }
+      max_probe = max(max_probe, probes);
+    }
+    slot = __shfl_sync(peers, slot, leader);
+    if (real) {
+      L.offsets[(size_t)r * L.P + gp] = (int)slot;
+      L.bary[(size_t)r * L.P + gp] = bary[r];
+    }
+  }
+  if (bad) atomicExch(L.counters + 1, 1);
+  if (max_probe > 0) atomicMax(L.counters + 2, max_probe);
+}
+
+__global__ void lattice_resolve_kernel(LatticeBufs L) {
+  const long long total = 6 * L.P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    L.offsets[i] = L.table_ids[L.offsets[i]];
+}
+
+__device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long long key) {
+  unsigned long long slot = hash_key(key) & L.cap_mask;
+  for (;;) {
+    const unsigned long long cur = L.table_keys[slot];
+    if (cur == key) return L.table_ids[slot];
+    if (cur == kEmptyKey) return 0;
+    slot = (slot + 1) & L.cap_mask;
+  }
+}
+
+// Blur neighbours (permutohedral.cpp:282-294): n1 = key - 1 on every stored coordinate and key[j] + 5 on axis j,
+// n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q carries when it wraps.
+__global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) {
+  const long long M = L.counters[0];
+  const long long total = M * (kLatD + 1);
+  const unsigned long long qmask = (1ULL << kQBits) - 1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / (kLatD + 1);
+    const int j = (int)(idx % (kLatD + 1));
+    const unsigned long long key = L.vkeys[i];
+    const int r = (int)((key >> (kQBits * kLatD)) & 7);
+    const unsigned long long bbits = key >> (kQBits * kLatD + 3);
+    int q[kLatD];
+#pragma unroll
+    for (int k = 0; k < kLatD; ++k) q[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias;
+    int res[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      // side 0: n1 (coordinates -1, axis +5);  side 1: n2 (coordinates +1, axis -5)
+      const int r2 = side == 0 ? (r == 0 ? kLatD : r - 1) : (r == kLatD ? 0 : r + 1);
+      const int dq = side == 0 ? (r == 0 ? -1 : 0) : (r == kLatD ? 1 : 0);
+      int qq[kLatD];
+      int bad = 0;
+#pragma unroll
+      for (int k = 0; k < kLatD; ++k) qq[k] = q[k] + dq + (k == j ? (side == 0 ? 1 : -1) : 0);
+      unsigned long long nk = pack_key(qq, r2, 0, &bad) | (bbits << (kQBits * kLatD + 3));
+      res[side] = bad ? 0 : table_find(L, nk);
+    }
+    L.nbr[(size_t)j * L.m_cap + i] = make_int2(res[0], res[1]);
+  }
+}
+
+// ---- compute -------------------------------------------------------------------------------------
+__global__ void lattice_zero_values_kernel(LatticeBufs L) {
+  const long long rows = (long long)L.counters[0] + 1;
+  const long long total4 = rows * (L.Kp / 4);
+  float4 *v0 = reinterpret_cast<float4 *>(L.val0);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * blockDim.x)
+    v0[i] = z;
+  if (blockIdx.x == 0 && threadIdx.x < L.Kp / 4) reinterpret_cast<float4 *>(L.val1)[threadIdx.x] = z;
+}
+
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Splat (permutohedral.cpp:526-534).  One thread per pixel; the channels of a vertex are contiguous so each
+// (pixel, vertex, 4 channels) is one 128-bit vector reduction in L2.
+__global__ void __launch_bounds__(256) lattice_splat_kernel(LatticeBufs L, const float *__restrict__ ins, int K,
+                                                            int n) {
+  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < L.P;
+       gp += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gp / n), p = (int)(gp % n);
+    int off[kLatD + 1];
+    float w[kLatD + 1];
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      off[r] = L.offsets[(size_t)r * L.P + gp];
+      w[r] = L.bary[(size_t)r * L.P + gp];
+    }
+    const float *src = ins + (size_t)b * K * n + p;
+    for (int c0 = 0; c0 < L.Kp; c0 += 4) {
+      float4 x;
+      x.x = c0 + 0 < K ? __ldg(src + (size_t)(c0 + 0) * n) : 0.f;
+      x.y = c0 + 1 < K ? __ldg(src + (size_t)(c0 + 1) * n) : 0.f;
+      x.z = c0 + 2 < K ? __ldg(src + (size_t)(c0 + 2) * n) : 0.f;
+      x.w = c0 + 3 < K ? __ldg(src + (size_t)(c0 + 3) * n) : 0.f;
+#pragma unroll
+      for (int r = 0; r <= kLatD; ++r)
+        red_add_v4(L.val0 + (size_t)off[r] * L.Kp + c0,
+                   make_float4(__fmul_rn(w[r], x.x), __fmul_rn(w[r], x.y), __fmul_rn(w[r], x.z), __fmul_rn(w[r], x.w)));
+    }
+  }
+}
+
+// One blur axis (permutohedral.cpp:538-551): thread per (vertex, 4 channels).
+__global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const float *__restrict__ src,
+                                                           float *__restrict__ dst, int axis) {
+  const int kq = L.Kp / 4;
+  const long long total = (long long)L.counters[0] * kq;
+  const int2 *nb = L.nbr + (size_t)axis * L.m_cap;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / kq;
+    const int c0 = (int)(idx % kq) * 4;
+    const int2 nn = nb[i];
+    const float4 o = *reinterpret_cast<const float4 *>(src + (size_t)(i + 1) * L.Kp + c0);
+    const float4 a = *reinterpret_cast<const float4 *>(src + (size_t)nn.x * L.Kp + c0);
+    const float4 c = *reinterpret_cast<const float4 *>(src + (size_t)nn.y * L.Kp + c0);
+    float4 rr;
+    rr.x = __fadd_rn(o.x, __fmul_rn(0.5f, __fadd_rn(a.x, c.x)));
+    rr.y = __fadd_rn(o.y, __fmul_rn(0.5f, __fadd_rn(a.y, c.y)));
+    rr.z = __fadd_rn(o.z, __fmul_rn(0.5f, __fadd_rn(a.z, c.z)));
+    rr.w = __fadd_rn(o.w, __fmul_rn(0.5f, __fadd_rn(a.w, c.w)));
+    *reinterpret_cast<float4 *>(dst + (size_t)(i + 1) * L.Kp + c0) = rr;
+  }
+}
+
+// Slice (permutohedral.cpp:554-567) with the optional dense-CRF epilogue (seg_helper.py:888-890).
+template <bool ENERGY>
+__global__ void __launch_bounds__(256) lattice_slice_kernel(LatticeBufs L, const float *__restrict__ values,
+                                                            const float *__restrict__ ins,
+                                                            const float *__restrict__ gate, double *loss_acc,
+                                                            float *__restrict__ outs, int K, int n) {
+  const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
+  float local = 0.0f;
+  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < L.P;
+       gp += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(gp / n), p = (int)(gp % n);
+    int off[kLatD + 1];
+    float w[kLatD + 1];
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      off[r] = L.offsets[(size_t)r * L.P + gp];
+      w[r] = __fmul_rn(L.bary[(size_t)r * L.P + gp], alpha);
+    }
+    const float gt = ENERGY ? __ldg(gate + gp) : 1.0f;
+    float *dst = outs + (size_t)b * K * n + p;
+    const float *src = ins + (size_t)b * K * n + p;
+    for (int c0 = 0; c0 < L.Kp; c0 += 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r <= kLatD; ++r) {
+        const float4 v = *reinterpret_cast<const float4 *>(values + (size_t)off[r] * L.Kp + c0);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(w[r], v.x));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(w[r], v.y));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(w[r], v.z));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(w[r], v.w));
+      }
+      const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c0 + k < K) {
+          float o = a4[k];
+          if (ENERGY) {
+            o = __fmul_rn(o, gt);
+            local = fmaf(__ldg(src + (size_t)(c0 + k) * n), o, local);
+          }
+          dst[(size_t)(c0 + k) * n] = o;
+        }
+      }
+    }
+  }
+  if (ENERGY) {
+    __shared__ float s_part[8];
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) atomicAdd(loss_acc, (double)t);
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static unsigned long long table_capacity(long long m_cap) {
+  unsigned long long cap = 1024;
+  while (cap < 2ULL * (unsigned long long)m_cap) cap <<= 1;
+  return cap;
+}
+
+size_t lattice_ws_bytes(int N, int K, int H, int W) {
+  const long long n = (long long)H * W, n_pad = (n + 3) & ~3LL;
+  const long long P = (long long)N * n, m_cap = 6LL * N * n_pad;
+  const unsigned long long cap = table_capacity(m_cap);
+  const int Kp = (K + 3) & ~3;
+  size_t b = 0;
+  b += align_up(cap * sizeof(unsigned long long), 256);
+  b += align_up(cap * sizeof(int), 256);
+  b += align_up((size_t)m_cap * sizeof(unsigned long long), 256);
+  b += align_up(8 * sizeof(int), 256);
+  b += 2 * align_up((size_t)6 * P * sizeof(float), 256);
+  b += align_up((size_t)6 * m_cap * sizeof(int2), 256);
+  b += 2 * align_up((size_t)(m_cap + 1) * Kp * sizeof(float), 256);
+  return b;
+}
+
+void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
+  const long long n = (long long)H * W, n_pad = (n + 3) & ~3LL;
+  L->P = (long long)N * n;
+  L->m_cap = 6LL * N * n_pad;
+  const unsigned long long cap = table_capacity(L->m_cap);
+  L->cap_mask = cap - 1;
+  L->Kp = (K + 3) & ~3;
+  Arena a(ws);
+  L->table_keys = a.take<unsigned long long>(cap);
+  L->table_ids = a.take<int>(cap);
+  L->vkeys = a.take<unsigned long long>((size_t)L->m_cap);
+  L->counters = a.take<int>(8);
+  L->offsets = a.take<int>((size_t)6 * L->P);
+  L->bary = a.take<float>((size_t)6 * L->P);
+  L->nbr = a.take<int2>((size_t)6 * L->m_cap);
+  L->val0 = a.take<float>((size_t)(L->m_cap + 1) * L->Kp);
+  L->val1 = a.take<float>((size_t)(L->m_cap + 1) * L->Kp);
+}
+
+static int persistent_blocks(long long work_items, int per_block) {
+  return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(work_items, per_block)));
+}
+
+int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
+                  cudaStream_t stream) {
+  if (N < 1 || N > kMaxImagesPerLattice) return COSA_E_ARG;
+  const long long n = (long long)H * W;
+  const int n_pad = (int)((n + 3) & ~3LL);
+  const unsigned long long cap = L.cap_mask + 1;
+  COSA_LAUNCH(lattice_clear_kernel, persistent_blocks((long long)(cap / 2), 256), 256, 0, stream, L.table_keys, cap,
+              L.counters);
+  const long long total = (long long)N * n_pad;
+  COSA_LAUNCH(lattice_build_kernel, (unsigned)ceil_div_ll(total, 256), 256, 0, stream, L, images, make_embed_const(),
+              N, H, W, n_pad, sigmargb, sigmaxy);
+  COSA_LAUNCH(lattice_resolve_kernel, persistent_blocks(6 * L.P, 256), 256, 0, stream, L);
+  // the vertex count lives on the device: size the grid for the SMs and let the kernel read it
+  COSA_LAUNCH(lattice_neighbours_kernel, sm_count() * 8, 256, 0, stream, L);
+  return 0;
+}
+
+int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
+  const int n = H * W;
+  COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
+  COSA_LAUNCH(lattice_splat_kernel, persistent_blocks(L.P, 256), 256, 0, stream, L, ins, K, n);
+  float *src = L.val0, *dst = L.val1;
+  for (int axis = 0; axis <= kLatD; ++axis) {
+    COSA_LAUNCH(lattice_blur_kernel, sm_count() * 8, 256, 0, stream, L, src, dst, axis);
+    float *t = src; src = dst; dst = t;
+  }
+  return 0;   // six swaps: the result is back in val0
+}
+
+int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, double *loss_acc, float *outs, int N,
+                  int K, int H, int W, cudaStream_t stream) {
+  const int n = H * W;
+  const int blocks = persistent_blocks(L.P, 256);
+  if (gate) {
+    COSA_LAUNCH(lattice_slice_kernel<true>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+  } else {
+    COSA_LAUNCH(lattice_slice_kernel<false>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+  }
+  return 0;
+}
+
+}  // namespace cosa
+
+using namespace cosa;
+
+extern "C" size_t cosa_bilateral_ws_bytes(int N, int K, int H, int W) {
+  if (N < 1 || K < 1 || H < 1 || W < 1) return 0;
+  return lattice_ws_bytes(min(N, kMaxImagesPerLattice), K, H, W);
+}
+
+extern "C" int cosa_bilateralfilter_batch(const float *images, const float *ins, float *outs, int N, int K, int H,
+                                          int W, float sigmargb, float sigmaxy, void *ws, size_t ws_bytes,
+                                          void *stream) {
+  if (!images || !ins || !outs || !ws || N < 1 || K < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  if (ws_bytes < cosa_bilateral_ws_bytes(N, K, H, W)) return COSA_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)H * W;
+  for (int n0 = 0; n0 < N; n0 += kMaxImagesPerLattice) {   // chunks share the workspace, stream-ordered
+    const int nb = min(kMaxImagesPerLattice, N - n0);
+    LatticeBufs L;
+    lattice_carve(ws, nb, K, H, W, &L);
+    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, s));
+    COSA_CHECK(lattice_splat_blur(L, ins + (size_t)n0 * K * n, nb, K, H, W, s));
+    COSA_CHECK(lattice_slice(L, ins + (size_t)n0 * K * n, nullptr, nullptr, outs + (size_t)n0 * K * n, nb, K, H, W, s));
+  }
+  return 0;
+}
+
+extern "C" int cosa_bilateral_stats(const void *ws, int N, int K, int H, int W, long long stats[4], void *stream) {
+  if (!ws || !stats || N < 1 || K < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  LatticeBufs L;
+  lattice_carve(const_cast<void *>(ws), min(N, kMaxImagesPerLattice), K, H, W, &L);
+  int h[4];
+  COSA_CUDA(cudaMemcpyAsync(h, L.counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+  COSA_CUDA(cudaStreamSynchronize(s));
+  stats[0] = h[0]; stats[1] = h[1]; stats[2] = (long long)(L.cap_mask + 1); stats[3] = h[2];
+  return h[1] ? COSA_E_KEYRANGE : 0;
+}
+
+extern "C" int cosa_bilateralfilter_batch_host(const float *images, const float *ins, float *outs, int N, int K,
+                                               int H, int W, float sigmargb, float sigmaxy) {
+  if (!images || !ins || !outs || N < 1 || K < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  const size_t n = (size_t)H * W;
+  const size_t ws_bytes = cosa_bilateral_ws_bytes(N, K, H, W);
+  float *d_img = nullptr, *d_in = nullptr, *d_out = nullptr;
+  void *d_ws = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&d_img, (size_t)N * 3 * n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_in, (size_t)N * K * n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_out, (size_t)N * K * n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_ws, ws_bytes) != cudaSuccess) {
+    rc = (int)cudaGetLastError();
+    if (rc == 0) rc = (int)cudaErrorMemoryAllocation;
+  }
+  if (rc == 0) {
+    cudaMemcpy(d_img, images, (size_t)N * 3 * n * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_in, ins, (size_t)N * K * n * sizeof(float), cudaMemcpyHostToDevice);
+    rc = cosa_bilateralfilter_batch(d_img, d_in, d_out, N, K, H, W, sigmargb, sigmaxy, d_ws, ws_bytes, nullptr);
+    if (rc == 0) rc = (int)cudaMemcpy(outs, d_out, (size_t)N * K * n * sizeof(float), cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_img); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
+  return rc;
+}

@@ -1,0 +1,374 @@
+"""Host-side mirror of the hot-path functions of the reference's ``utils/seg_helper.py``.
+
+Same names, keyword arguments, shapes and dtypes as the reference; the arithmetic runs in the sm_100a
+kernels of ``csrc/`` through the C-ABI (``include/cosa_b200.h``).  Inputs must be CUDA tensors.
+
+  cam_normalize            utils/seg_helper.py:264-270 (the normalise tail of multi_scale_camseg)
+  cam_validation           utils/seg_helper.py:547-551
+  cam_to_label             utils/seg_helper.py:515-545
+  cam2mask / _refine_cams  utils/seg_helper.py:721-797
+  DenseEnergyLossFunction  utils/seg_helper.py:864-903
+  DenseEnergyLoss          utils/seg_helper.py:191-208
+  get_energy_loss          utils/seg_helper.py:210-230
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import _lib
+from .par import PAR
+
+
+# ----------------------------------------------------------------------------------------------------
+# CAM normalise / validation / cam_to_label
+# ----------------------------------------------------------------------------------------------------
+def cam_normalize(cam_scales):
+    """sum over the per-scale CAMs, minus the per-(b,c) min, over the per-(b,c) max + 1e-5 (seg_helper.py:264-270).
+
+    ``cam_scales``: a tensor [B,C,H,W] or a list of them (what ``cam_list`` holds at seg_helper.py:264).
+    """
+    lib = _lib.load()
+    if isinstance(cam_scales, torch.Tensor):
+        cam_scales = [cam_scales]
+    maps = [_lib.dev_f32(c, "cam") for c in cam_scales]
+    B, C, H, W = maps[0].shape
+    for m in maps:
+        assert m.shape == maps[0].shape
+    out = torch.empty_like(maps[0])
+    mm = torch.empty(2 * B * C, dtype=torch.float32, device=out.device)
+    ptrs = (ctypes.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+    with torch.cuda.device(out.device):
+        _lib.check(lib.cosa_cam_normalize(ptrs, len(maps), _lib.ptr(out), B * C, H * W, _lib.ptr(mm),
+                                          _lib.stream_ptr()))
+    return out
+
+
+def cam_validation(cam, cls_label):
+    lib = _lib.load()
+    cam = _lib.dev_f32(cam, "cam")
+    cls_label = _lib.dev_f32(cls_label.to(cam.device), "cls_label")
+    b, c, h, w = cam.shape
+    out = torch.empty_like(cam)
+    with torch.cuda.device(cam.device):
+        _lib.check(lib.cosa_cam_validation(_lib.ptr(cam), _lib.ptr(cls_label), _lib.ptr(out), b, c, h * w,
+                                           _lib.stream_ptr()))
+    return out
+
+
+def cam_to_label(cam,
+                 cls_label,
+                 img_box=None,
+                 bkg_thre=None,
+                 high_thre=None,
+                 low_thre=None,
+                 ignore_mid=False,
+                 ignore_index=None):
+    lib = _lib.load()
+    cam = _lib.dev_f32(cam, "cam")
+    b, c, h, w = cam.shape
+    if bkg_thre is None:
+        raise TypeError("bkg_thre is required (the reference compares against it unconditionally)")
+    if cls_label is not None:
+        cls_label = _lib.dev_f32(cls_label.to(cam.device), "cls_label")
+    label = torch.empty((b, h, w), dtype=torch.int64, device=cam.device)
+    with torch.cuda.device(cam.device):
+        if img_box is None:
+            _lib.check(lib.cosa_cam_to_label(_lib.ptr(cam), _lib.ptr(cls_label), None, None, _lib.ptr(label), b, c, h,
+                                             w, float(bkg_thre), 0.0, 0.0, 0, 0, _lib.stream_ptr()))
+            return label
+        if ignore_mid and (high_thre is None or low_thre is None):
+            raise TypeError("ignore_mid needs high_thre and low_thre")
+        if ignore_index is None:
+            raise TypeError("ignore_index is required when img_box is given")
+        boxes = _lib.resolve_boxes(img_box, b, h, w, cam.device)
+        valid_cam = torch.empty_like(cam) if cls_label is not None else None
+        _lib.check(lib.cosa_cam_to_label(_lib.ptr(cam), _lib.ptr(cls_label), _lib.ptr(boxes), _lib.ptr(valid_cam),
+                                         _lib.ptr(label), b, c, h, w, float(bkg_thre),
+                                         float(high_thre if high_thre is not None else 0.0),
+                                         float(low_thre if low_thre is not None else 0.0), int(bool(ignore_mid)),
+                                         int(ignore_index), _lib.stream_ptr()))
+    return (valid_cam if valid_cam is not None else cam), label
+
+
+# ----------------------------------------------------------------------------------------------------
+# cam2mask
+# ----------------------------------------------------------------------------------------------------
+def cam2mask(
+        images,
+        img_boxes,
+        cams,
+        cls_labels,
+        threshold_high,
+        threshold_low,
+        refine_model=None,
+        ignore_index=255,
+        downscale=2,
+        return_parts=False,
+):
+    """Pseudo-label map [B,H,W] float32 with values {0..C-1, ignore_index} (seg_helper.py:721-785).
+
+    ``refine_model`` may be ``None`` (the shipped default), a :class:`cosa_b200.PAR` (whole batch, both
+    threshold stacks, one fused kernel sequence) or any other callable ``(images, cams) -> cams`` (called
+    per image exactly like the reference; only the resize/argmax tail then runs in this package's kernels).
+    """
+    lib = _lib.load()
+    images = _lib.dev_f32(images, "images")
+    cams = _lib.dev_f32(cams, "cams")
+    cls_labels = _lib.dev_f32(cls_labels.to(cams.device), "cls_labels")
+    b, _, h, w = images.shape
+    c1 = cams.shape[1]
+    if refine_model is not None and refine_model is not False and not isinstance(refine_model, PAR):
+        return _cam2mask_generic(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model,
+                                 ignore_index, downscale)
+    use_par = isinstance(refine_model, PAR)
+    dev = cams.device
+    boxes = _lib.resolve_boxes(img_boxes, b, h, w, dev)
+    out = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    hi = torch.empty_like(out) if return_parts else None
+    lo = torch.empty_like(out) if return_parts else None
+    n_dil = len(refine_model.dilations) if use_par else 0
+    with torch.cuda.device(dev):
+        nbytes = lib.cosa_cam2mask_ws_bytes(b, c1, h, w, int(downscale or 0), int(use_par), n_dil)
+        ws = _lib.workspace(nbytes, dev)
+        _lib.check(lib.cosa_cam2mask(_lib.ptr(images), _lib.ptr(boxes), _lib.ptr(cams), _lib.ptr(cls_labels),
+                                     float(threshold_high), float(threshold_low), float(ignore_index),
+                                     int(downscale or 0), int(use_par), refine_model._dil if use_par else None, n_dil,
+                                     int(refine_model.num_iter) if use_par else 0, _lib.ptr(out), _lib.ptr(hi),
+                                     _lib.ptr(lo), b, c1, h, w, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+    if return_parts:
+        return out, hi, lo
+    return out
+
+
+def _refine_cams(refine_model, images, cams, valid_key, orig_size):
+    """refine (optional) -> bilinear resize to ``orig_size`` -> argmax -> ``valid_key`` lookup (seg_helper.py:787-797)."""
+    lib = _lib.load()
+    refined = refine_model(images, cams) if refine_model else cams
+    refined = _lib.dev_f32(refined, "cams")
+    b, nc, h, w = refined.shape
+    H, W = int(orig_size[0]), int(orig_size[1])
+    key = valid_key.to(device=refined.device, dtype=torch.int64).contiguous()
+    out = torch.empty((b, H, W), dtype=torch.int64, device=refined.device)
+    with torch.cuda.device(refined.device):
+        _lib.check(lib.cosa_upsample_argmax(_lib.ptr(refined), _lib.ptr(key), _lib.ptr(out), b, nc, h, w, H, W,
+                                            _lib.stream_ptr()))
+    return out
+
+
+def _cam2mask_generic(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model, ignore_index,
+                      downscale):
+    """Reference control flow for a user-supplied ``refine_model`` (one call per image and threshold)."""
+    b, _, h, w = images.shape
+    dev = cams.device
+    if downscale:
+        size = [h // downscale, w // downscale]
+        small = F.interpolate(images, size=size, mode="bilinear", align_corners=False)
+    else:
+        small = images
+    ones = torch.ones((b, 1, h, w), device=dev)
+    stacks = []
+    for thr in (threshold_high, threshold_low):
+        s = torch.cat([ones * thr, cams], dim=1)
+        if downscale:
+            s = F.interpolate(s, size=size, mode="bilinear", align_corners=False)
+        stacks.append(s)
+    present = torch.cat([torch.ones((b, 1), device=dev), cls_labels], dim=1)
+    boxes = _lib.resolve_boxes(img_boxes, b, h, w, torch.device("cpu")).tolist()
+    n_boxes = len(img_boxes)
+    lab = [torch.full((b, h, w), float(ignore_index), device=dev) for _ in range(2)]
+    for i in range(min(b, n_boxes)):
+        keys = torch.nonzero(present[i])[:, 0]
+        y0, y1, x0, x1 = boxes[i]
+        for stack, dst in zip(stacks, lab):
+            active = stack[i, keys].unsqueeze(0).softmax(dim=1)
+            got = _refine_cams(refine_model, small[[i]], active, keys, (h, w))
+            dst[i, y0:y1, x0:x1] = got[0, y0:y1, x0:x1].to(dst.dtype)
+    out = lab[0].clone()
+    out[lab[0] == 0] = ignore_index
+    out[(lab[0] + lab[1]) == 0] = 0
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# Dense-CRF energy loss
+# ----------------------------------------------------------------------------------------------------
+class DenseEnergyLossFunction(Function):
+    """forward(images, segmentations, sigma_rgb, sigma_xy, ROIs, unlabel_region) -> loss tensor of shape [1].
+
+    Same maths as the reference (seg_helper.py:864-903): gate, ROI masking, bilateral filter on the
+    permutohedral lattice, gated dot product, ``/N``; backward is ``-2 * g * AS / N * ROI`` from the gated
+    filter response saved in forward.  Differences by design: everything stays on the GPU (the result is a
+    CUDA tensor instead of a CPU tensor that the caller moves back with ``.cuda()``), and the caller's
+    ``ROIs`` tensor is not reshaped in place.
+    """
+
+    @staticmethod
+    def forward(ctx, images, segmentations, sigma_rgb, sigma_xy, ROIs, unlabel_region):
+        lib = _lib.load()
+        segs = _lib.dev_f32(segmentations.detach(), "segmentations")
+        dev = segs.device
+        images = _lib.dev_f32(images.detach().to(dev), "images")
+        rois = _lib.dev_f32(ROIs.detach().to(dev), "ROIs")
+        if rois.dim() == 4:
+            rois = rois[:, 0].contiguous()
+        unlabel = unlabel_region.to(dev).to(torch.uint8).contiguous()
+        N, K, H, W = segs.shape
+        ctx.N, ctx.K, ctx.H, ctx.W = N, K, H, W
+        AS = torch.empty_like(segs)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib.cosa_dense_energy_ws_bytes(N, K, H, W)
+            ws = _lib.workspace(nbytes, dev)
+            _lib.check(lib.cosa_dense_energy_forward(_lib.ptr(images), _lib.ptr(segs), _lib.ptr(rois),
+                                                     _lib.ptr(unlabel), float(sigma_rgb), float(sigma_xy),
+                                                     _lib.ptr(AS), _lib.ptr(loss), N, K, H, W, _lib.ptr(ws), nbytes,
+                                                     _lib.stream_ptr()))
+        ctx.AS = AS
+        ctx.ROIs = rois
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        AS, rois = ctx.AS, ctx.ROIs
+        g = _lib.dev_f32(grad_output.to(AS.device), "grad_output").reshape(-1)[:1].contiguous()
+        grad = torch.empty_like(AS)
+        with torch.cuda.device(AS.device):
+            _lib.check(lib.cosa_dense_energy_backward(_lib.ptr(AS), _lib.ptr(rois), _lib.ptr(g), _lib.ptr(grad), ctx.N,
+                                                      ctx.K, ctx.H, ctx.W, _lib.stream_ptr()))
+        return None, grad, None, None, None, None
+
+
+class DenseEnergyLoss(torch.nn.Module):
+    """Same ctor/forward as the reference layer (seg_helper.py:191-208)."""
+
+    # the seg_helper copy passes recompute_scale_factor=True to F.interpolate, the rrm_utils copy does not
+    recompute_scale_factor = True
+
+    def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor):
+        super(DenseEnergyLoss, self).__init__()
+        self.weight = weight
+        self.sigma_rgb = sigma_rgb
+        self.sigma_xy = sigma_xy
+        self.scale_factor = scale_factor
+
+    def _kw(self):
+        kw = dict(scale_factor=self.scale_factor)
+        if self.recompute_scale_factor:
+            kw["recompute_scale_factor"] = True
+        return kw
+
+    def forward(self, images, segmentations, ROIs, seg_label):
+        """ scale imag by scale_factor """
+        kw = self._kw()
+        scaled_images = F.interpolate(images, **kw)
+        scaled_segs = F.interpolate(segmentations, mode='bilinear', align_corners=False, **kw)
+        scaled_ROIs = F.interpolate(ROIs.unsqueeze(1), **kw).squeeze(1)
+        scaled_seg_label = F.interpolate(seg_label, mode='nearest', **kw)
+        unlabel_region = (scaled_seg_label.long() == 255).squeeze(1)
+
+        return self.weight * DenseEnergyLossFunction.apply(
+            scaled_images, scaled_segs, self.sigma_rgb, self.sigma_xy * self.scale_factor, scaled_ROIs, unlabel_region)
+
+    def extra_repr(self):
+        return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}'.format(
+            self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor)
+
+
+class _FusedEnergyLoss(Function):
+    """logit -> loss in two C-ABI calls (``cosa_energy_loss_forward/backward``): softmax, the 2:1 resamplings,
+    ROI / unlabel / gate, lattice filter and the energy, with d loss / d logit computed directly."""
+
+    @staticmethod
+    def forward(ctx, logit, simg, label, boxes, mean, std, weight, sigma_rgb, sigma_xy_scaled):
+        lib = _lib.load()
+        dev = logit.device
+        B, C, H, W = logit.shape
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        mean_c = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        std_c = (ctypes.c_float * 3)(*[float(v) for v in std])
+        with torch.cuda.device(dev):
+            saved = torch.empty(lib.cosa_energy_loss_saved_bytes(B, C, H, W), dtype=torch.uint8, device=dev)
+            nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+            ws = _lib.workspace(nbytes, dev)
+            _lib.check(lib.cosa_energy_loss_forward(_lib.ptr(simg), _lib.ptr(logit), _lib.ptr(label), _lib.ptr(boxes),
+                                                    mean_c, std_c, float(weight), float(sigma_rgb),
+                                                    float(sigma_xy_scaled), _lib.ptr(loss), _lib.ptr(saved), B, C, H,
+                                                    W, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+        ctx.save_for_backward(logit)
+        ctx.saved_blob = saved
+        ctx.weight = float(weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        (logit,) = ctx.saved_tensors
+        B, C, H, W = logit.shape
+        g = _lib.dev_f32(grad_output.to(logit.device), "grad_output").reshape(-1)[:1].contiguous()
+        grad = torch.empty_like(logit)
+        with torch.cuda.device(logit.device):
+            _lib.check(lib.cosa_energy_loss_backward(_lib.ptr(logit), _lib.ptr(ctx.saved_blob), _lib.ptr(g),
+                                                     ctx.weight, _lib.ptr(grad), B, C, H, W, _lib.stream_ptr()))
+        return grad, None, None, None, None, None, None, None, None
+
+
+def get_energy_loss(img,
+                    logit,
+                    label,
+                    img_box,
+                    loss_layer,
+                    mean=[123.675, 116.28, 103.53],
+                    std=[58.395, 57.12, 57.375]):
+    """Dense-CRF regulariser on the segmentation logits (seg_helper.py:210-230); returns a CUDA tensor [1].
+
+    With this package's :class:`DenseEnergyLoss` at ``scale_factor=0.5`` and even H, W (the training
+    configuration, main.py:77) the whole chain runs in the fused kernels; any other layer or geometry takes
+    the reference's composition (softmax / crop mask / de-normalise in torch, then ``loss_layer``).
+    """
+    if not logit.is_cuda:
+        raise _lib.CosaError("cosa_b200: logit must be a CUDA tensor - this package has no CPU fallback")
+    B, C, H, W = logit.shape
+    fused = (type(loss_layer) in _FUSABLE_LAYERS and float(loss_layer.scale_factor) == 0.5 and H % 2 == 0
+             and W % 2 == 0 and H >= 2 and W >= 2 and logit.dtype == torch.float32)
+    if fused:
+        dev = logit.device
+        boxes = _lib.resolve_boxes(img_box, B, H, W, dev)
+        return _FusedEnergyLoss.apply(logit.contiguous(), _lib.dev_f32(img.to(dev), "img"),
+                                      _lib.dev_f32(label.to(dev), "label"), boxes, mean, std, loss_layer.weight,
+                                      loss_layer.sigma_rgb, loss_layer.sigma_xy * loss_layer.scale_factor)
+    pred_prob = F.softmax(logit, dim=1)
+    crop_mask = torch.zeros_like(pred_prob[:, 0, ...])
+    boxes = _lib.resolve_boxes(img_box, B, H, W, torch.device("cpu")).tolist()
+    for idx in range(min(B, len(img_box))):
+        y0, y1, x0, x1 = boxes[idx]
+        crop_mask[idx, y0:y1, x0:x1] = 1
+    _img = torch.zeros_like(img)
+    _img[:, 0, :, :] = img[:, 0, :, :] * std[0] + mean[0]
+    _img[:, 1, :, :] = img[:, 1, :, :] * std[1] + mean[1]
+    _img[:, 2, :, :] = img[:, 2, :, :] * std[2] + mean[2]
+    loss = loss_layer(_img, pred_prob, crop_mask, label.type(torch.uint8).unsqueeze(1), )
+    return loss.cuda()
+
+
+_FUSABLE_LAYERS = {DenseEnergyLoss}
+
+
+def last_energy_lattice_stats(B, C, H, W, device=None):
+    """(M, key_range_error, table_capacity, max_probe) of the lattice built by the last fused
+    ``get_energy_loss`` call with these logit shapes on the current stream (the lattice is the tail of that
+    call's workspace).  Synchronises the stream."""
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    with torch.cuda.device(device):
+        nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+        ws = _lib.workspace(nbytes, device)
+        front = nbytes - lib.cosa_bilateral_ws_bytes(B, C, H // 2, W // 2)
+        stats = (ctypes.c_longlong * 4)()
+        rc = lib.cosa_bilateral_stats(ctypes.c_void_p(ws.data_ptr() + front), B, C, H // 2, W // 2, stats,
+                                      _lib.stream_ptr())
+    if rc not in (0, -3):
+        _lib.check(rc)
+    return tuple(int(v) for v in stats)

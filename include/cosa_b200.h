@@ -1,0 +1,155 @@
+/*
+ * cosa_b200 — C-ABI of the B200 (sm_100a) CAM -> pseudo-label refinement path of CoSA.
+ *
+ * Plain pointers and sizes only; no torch types.  Unless a name ends in `_host`, every pointer is a
+ * DEVICE pointer, every call is asynchronous on `stream` (a cudaStream_t passed as void*) and the
+ * caller owns all buffers, including the scratch `ws` whose size the matching `*_ws_bytes` returns.
+ * All tensors are contiguous, float32 NCHW unless stated.  Return value: 0 = ok, < 0 = COSA_E_*,
+ * > 0 = a cudaError_t raised by a launch.
+ *
+ * Each entry point cites the reference interface (file:line under the CoSA tree) it replaces; the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef COSA_B200_H_
+#define COSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COSA_B200_ABI_VERSION 1
+
+enum {
+  COSA_OK = 0,
+  COSA_E_ARG = -1,        /* bad shape / null pointer / unsupported parameter            */
+  COSA_E_WORKSPACE = -2,  /* ws_bytes smaller than *_ws_bytes() for the same arguments  */
+  COSA_E_KEYRANGE = -3    /* lattice coordinate outside the packed-key range */
+};
+
+int cosa_abi_version(void);
+/* Human-readable text for a return code (static storage). */
+const char *cosa_strerror(int code);
+/* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
+unsigned long long cosa_launch_count(void);
+/* Instrumentation for bench.py's roofline: between begin and end every kernel launch of the library is
+ * bracketed by CUDA events on its own stream; end synchronises the device and writes one text line per
+ * kernel, "name count total_ms\n", into buf.  Returns the number of distinct kernels. */
+void cosa_profile_begin(void);
+int cosa_profile_end(char *buf, size_t buf_len);
+
+/* ------------------------------------------------------------------------------------------------
+ * PAR — pixel-adaptive refinement.            replaces models/PAR.py:64-91 (PAR.forward)
+ *   imgs   [B,3,h,w]; masks_in [B,C,hm,wm] (bilinearly resized to h,w with align_corners=True when
+ *   hm,wm differ, PAR.py:66); masks_out [B,C,h,w].
+ *   dilations[n_dil] is a HOST array (ctor argument, PAR.py:28); the 8*n_dil neighbours follow
+ *   get_kernel() order (PAR.py:10-24) with replicate borders (PAR.py:44).  w1 = 0.3, w2 = 0.01.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil);
+int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out, int B, int C, int h, int w,
+                     int hm, int wm, const int *dilations, int n_dil, int num_iter, void *ws, size_t ws_bytes,
+                     void *stream);
+/* The affinity alone, [B, 8*n_dil, h, w] (PAR.py:69-85); used by tests and by cam2mask internally. */
+int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const int *dilations, int n_dil,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CAM normalise.                              replaces utils/seg_helper.py:264-270
+ *   out = sum_s scale_maps[s]; out -= min over (H,W); out /= max over (H,W) + 1e-5, per (b,c) plane.
+ *   scale_maps: HOST array of n_scales DEVICE pointers, each [planes, HW]; minmax_ws: 2*planes floats.
+ * ---------------------------------------------------------------------------------------------- */
+int cosa_cam_normalize(const float *const *scale_maps, int n_scales, float *out, int planes, long long HW,
+                       float *minmax_ws, void *stream);
+
+/* cam_validation: out[b,c,:,:] = cls_label[b,c] * cam[b,c,:,:].   utils/seg_helper.py:547-551 */
+int cosa_cam_validation(const float *cam, const float *cls_label, float *out, int B, int C1, long long HW,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cam_to_label.                               replaces utils/seg_helper.py:515-545
+ *   cam [B,C1,H,W]; cls_label [B,C1] or NULL; label_out int64 [B,H,W].
+ *   boxes: int32 [B,4] = (y0,y1,x0,x1) already resolved to 0 <= y0 <= y1 <= H (Python slice rules), or
+ *   NULL for the `img_box is None` branch (label only, no ignore_mid, no box fill).
+ *   valid_cam_out may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int cosa_cam_to_label(const float *cam, const float *cls_label, const int *boxes, float *valid_cam_out,
+                      long long *label_out, int B, int C1, int H, int W, float bkg_thre, float high_thre,
+                      float low_thre, int ignore_mid, long long ignore_index, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cam2mask — swapped-assignment pseudo-labels.     replaces utils/seg_helper.py:721-785 + :787-797
+ *   images [B,3,H,W] in [0,1]; cams [B,C1,H,W]; cls_labels [B,C1]; boxes int32 [B,4] resolved as above;
+ *   label_out float32 [B,H,W] with values {0..C1, ignore_index}.
+ *   downscale: 0 = none, else the half-resolution is (H/downscale, W/downscale) (seg_helper.py:738-739).
+ *   use_par = 0 reproduces `refine_model=None` (the shipped default); use_par = 1 runs PAR with
+ *   dilations[n_dil] (HOST) and num_iter on both threshold stacks of every image in one batch.
+ *   label_high_out / label_low_out (float32 [B,H,W], may be NULL) expose the two per-threshold maps
+ *   before the merge rule (seg_helper.py:781-783).
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downscale, int use_par, int n_dil);
+int cosa_cam2mask(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                  float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
+                  const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
+                  float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, void *stream);
+
+/* _refine_cams tail: bilinear (align_corners=False) resize of refined [B,nc,h,w] to (H,W), argmax over
+ * channels (first max wins), label = valid_key[argmax].      utils/seg_helper.py:793-795 */
+int cosa_upsample_argmax(const float *refined, const long long *valid_key, long long *label_out, int B, int nc,
+                         int h, int w, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bilateral filter on the permutohedral lattice.
+ *   replaces utils/bilateralfilter/bilateralfilter.hpp:12 bilateralfilter_batch (SWIG: bilateralfilter.i)
+ *   images [N,3,H,W] (planar RGB, 0..255), ins/outs [N,K,H,W]; outs is the UN-normalised response.
+ *   `_host` takes HOST pointers, allocates its own device scratch and is synchronous: it is the
+ *   9-argument call of utils/seg_helper.py:887.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_bilateral_ws_bytes(int N, int K, int H, int W);
+int cosa_bilateralfilter_batch(const float *images, const float *ins, float *outs, int N, int K, int H, int W,
+                               float sigmargb, float sigmaxy, void *ws, size_t ws_bytes, void *stream);
+int cosa_bilateralfilter_batch_host(const float *images, const float *ins, float *outs, int N, int K, int H,
+                                    int W, float sigmargb, float sigmaxy);
+/* Lattice statistics of the last build in `ws` (same N,K,H,W as that call; for the dense-energy entry points
+ * the lattice is the tail of their workspace), copied to host after synchronising `stream`:
+ * stats[0] = M (vertices over the whole batch), stats[1] = key-range error flag, stats[2] = table
+ * capacity, stats[3] = max probe length. */
+int cosa_bilateral_stats(const void *ws, int N, int K, int H, int W, long long stats[4], void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DenseEnergyLossFunction.                    replaces utils/seg_helper.py:864-903 (rrm_utils.py:352-391)
+ *   forward : gate = clamp_min(ROI - max_k S, 0) with gate[unlabel] = 1; S <- S*ROI; AS = filter(S);
+ *             AS <- AS*gate; loss = -<S, AS>/N.   Writes as_out [N,K,H,W] (gated, saved for backward)
+ *             and loss_out[0].  unlabel: uint8 [N,H,W].
+ *   backward: grad_seg = -2 * grad_out[0] * AS / N * ROI      (grad_out is a DEVICE scalar)
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_dense_energy_ws_bytes(int N, int K, int H, int W);
+int cosa_dense_energy_forward(const float *images, const float *segs, const float *rois,
+                              const unsigned char *unlabel, float sigmargb, float sigmaxy, float *as_out,
+                              float *loss_out, int N, int K, int H, int W, void *ws, size_t ws_bytes,
+                              void *stream);
+int cosa_dense_energy_backward(const float *as_saved, const float *rois, const float *grad_out, float *grad_seg,
+                               int N, int K, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * get_energy_loss fused.      replaces utils/seg_helper.py:210-230 + DenseEnergyLoss.forward :199-208
+ *   simg [B,3,H,W] ImageNet-normalised; logit [B,C,H,W]; label float32 [B,H,W] ({0..C-1,255});
+ *   boxes int32 [B,4] resolved; mean/std: HOST float[3].  Half resolution is (H/2, W/2) (scale 0.5,
+ *   H and W even): images/ROI/label nearest, softmax(logit) bilinear.  loss_out[0] = weight * energy.
+ *   forward keeps what backward needs in `saved` (cosa_energy_loss_saved_bytes): gated AS and ROI.
+ *   backward writes grad_logit [B,C,H,W] = d(loss_out)/d(logit) * grad_out[0].
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W);
+size_t cosa_energy_loss_saved_bytes(int B, int C, int H, int W);
+int cosa_energy_loss_forward(const float *simg, const float *logit, const float *label, const int *boxes,
+                             const float *mean, const float *std, float weight, float sigmargb, float sigmaxy_scaled,
+                             float *loss_out, void *saved, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+                             void *stream);
+int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,
+                              float *grad_logit, int B, int C, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSA_B200_H_ */

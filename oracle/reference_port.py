@@ -247,46 +247,3 @@ def get_energy_loss(img, logit, label, img_box, mean=IMAGENET_MEAN, std=IMAGENET
     for c in range(3):
         raw[:, c] = img[:, c] * std[c] + mean[c]
     return dense_energy_loss(raw, prob, crop, label.type(torch.uint8).unsqueeze(1), **layer_kw)
-
-
-# ----------------------------------------------------------------------------------------------
-# Synthetic VOC/COCO-shaped inputs; shared by tests and bench.py so that the
-# CUDA path and the CPU path always see the same tensors.
-# ----------------------------------------------------------------------------------------------
-def synthetic_batch(B, C, H, W, n_fg, seed, noise_sigma=10.0, cam_kind="blobs", box="full"):
-    g = torch.Generator().manual_seed(seed)
-    ys = torch.arange(H, dtype=torch.float32).view(1, H, 1)
-    xs = torch.arange(W, dtype=torch.float32).view(1, 1, W)
-    cc = torch.arange(3, dtype=torch.float32).view(3, 1, 1)
-    base = 127 + 100 * torch.sin(0.02 * xs + cc) * torch.cos(0.03 * ys)
-    u8 = (base.unsqueeze(0) + noise_sigma * torch.randn((B, 3, H, W), generator=g)).floor().clamp(0, 255)
-    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
-    simg = (u8 - mean) / std
-    img_denorm = u8 / 255.0
-    cls_label = torch.zeros((B, C - 1))
-    for b in range(B):
-        cls_label[b, torch.randperm(C - 1, generator=g)[:n_fg]] = 1
-    if cam_kind == "blobs":
-        cams = 0.05 * torch.rand((B, C - 1, H, W), generator=g)
-        for b in range(B):
-            for c in torch.nonzero(cls_label[b])[:, 0].tolist():
-                for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
-                    cy, cx = (torch.rand(2, generator=g) * torch.tensor([H, W])).tolist()
-                    s = float(torch.rand(1, generator=g)) * (60.0 * H / 448) + 30.0 * H / 448
-                    cams[b, c] += torch.exp(-((ys[0] - cy) ** 2 + (xs[0] - cx) ** 2) / (2 * s * s))
-        cams = normalize_cam([cams])
-    else:
-        gh, gw = max(H // 16, 2), max(W // 16, 2)
-        cams = F.interpolate(torch.rand((B, C - 1, gh, gw), generator=g), size=(H, W), mode="bilinear",
-                             align_corners=False)
-    cams = cam_validation(cams, cls_label)
-    gh, gw = max(H // 16, 2), max(W // 16, 2)
-    logits = F.interpolate(3 * torch.randn((B, C, gh, gw), generator=g), size=(H, W), mode="bilinear",
-                           align_corners=False)
-    if box == "full":
-        boxes = torch.tensor([[0, H, 0, W]] * B, dtype=torch.int16)
-    else:
-        boxes = torch.tensor([[H // 28, H - H // 28, W // 14, W]] * B, dtype=torch.int16)
-    return dict(simg=simg.contiguous(), img_denorm=img_denorm.contiguous(), cams=cams.contiguous(),
-                cls_label=cls_label, logits=logits.contiguous(), img_box=boxes)

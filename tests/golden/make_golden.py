@@ -27,7 +27,7 @@ REF = "/root/reference"
 sys.path.insert(0, ROOT)
 
 from oracle import lattice as olat  # noqa: E402
-from oracle import reference_port as port  # noqa: E402  (only for the shared synthetic-input generator)
+from cosa_b200 import synthetic as port  # noqa: E402  (the shared synthetic-input generator)
 
 
 def load_reference():

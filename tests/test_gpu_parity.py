@@ -1,0 +1,392 @@
+"""GPU parity: the CUDA product (cosa_b200, through the C-ABI) against the CPU oracle and the golden vectors.
+
+Bars: labels / ignore maps bit-exact; refined CAMs, CRF loss and gradient within 1e-4
+relative (||d||_inf / ||ref||_inf).  Where a label is the argmax of floating-point values that the CPU and
+the GPU cannot produce bit-identically (exp, reductions), a differing pixel is accepted only if the oracle's
+own top-1/top-2 margin at that pixel is a numerical tie (NEAR_TIE); the count is printed.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_inf, t
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # north_star tolerance for floating-point outputs
+NEAR_TIE = 1e-5     # top-1/top-2 margin below which an argmax flip is a numerical tie
+DIL = [1, 2, 4, 8, 12, 24]
+
+
+@pytest.fixture(scope="module")
+def cosa():
+    import cosa_b200
+    cosa_b200._lib.load()
+    return cosa_b200
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import reference_port
+    return reference_port
+
+
+def cu(a):
+    a = t(a) if isinstance(a, np.ndarray) else a
+    return a.cuda()
+
+
+def assert_close(got, want, what, tol=TOL):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = want.detach().cpu().numpy() if isinstance(want, torch.Tensor) else np.asarray(want)
+    assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
+    r = rel_inf(got, want)
+    assert r <= tol, "%s: rel_inf = %.3g > %g" % (what, r, tol)
+    return r
+
+
+def assert_same(got, want, what):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = want.detach().cpu().numpy() if isinstance(want, torch.Tensor) else np.asarray(want)
+    assert got.shape == want.shape and got.dtype == want.dtype, "%s: %s/%s vs %s/%s" % (
+        what, got.shape, got.dtype, want.shape, want.dtype)
+    bad = int((got != want).sum())
+    assert bad == 0, "%s: %d of %d elements differ" % (what, bad, want.size)
+
+
+# ---- PAR ---------------------------------------------------------------------------------------------
+def test_par_golden(cosa):
+    g = load_golden("par")
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    out = par(cu(g["imgs"]), cu(g["masks"]))
+    print("PAR rel_inf vs reference:", assert_close(out, g["out"], "PAR 10 iter"))
+    assert_close(cosa.PAR(num_iter=3, dilations=[1, 2, 4])(cu(g["imgs"]), cu(g["masks"])), g["out_iter3_dil124"],
+                 "PAR 3 iter, dilations 1/2/4 (generic affinity kernel)")
+    assert_close(par(cu(g["imgs"]), cu(g["masks_lr"])), g["out_lr"], "PAR with align_corners=True mask resize")
+
+
+def test_par_affinity_vs_oracle(cosa, port):
+    g = load_golden("par")
+    aff = cosa.PAR(num_iter=1, dilations=DIL).affinity(cu(g["imgs"]))
+    want = port.par_affinity(t(g["imgs"]))[:, 0]
+    assert_close(aff, want, "PAR affinity")
+    s = aff.sum(1)
+    assert float((s - 1.01).abs().max()) < 1e-5      # sum of affinities is 1 + w2 (PAR.py:85)
+
+
+def test_par_module_shape_and_state(cosa):
+    par = cosa.PAR(num_iter=2, dilations=DIL)
+    assert list(par.state_dict().keys()) == ["kernel"] and par.kernel.shape == (8, 1, 3, 3)
+    assert par.pos.shape == (1, 1, 48, 1, 1)
+    out = par.cuda()(torch.rand(1, 3, 32, 32).cuda(), torch.rand(1, 20, 64, 64).cuda())   # PAR.py:93-98 smoke shape
+    assert out.shape == (1, 20, 32, 32)
+    with pytest.raises(cosa._lib.CosaError):
+        par(torch.rand(1, 3, 8, 8), torch.rand(1, 2, 8, 8))        # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 97, 61), (1, 42, 50, 130), (3, 1, 33, 33)])
+def test_par_vs_oracle_ragged_shapes(cosa, port, shape):
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(h * w + c)
+    imgs = torch.randint(0, 256, (b, 3, h, w), generator=gen).float() / 255
+    masks = torch.rand((b, c, h, w), generator=gen)
+    out = cosa.PAR(num_iter=10, dilations=DIL)(imgs.cuda(), masks.cuda())
+    assert_close(out, port.par_forward(imgs, masks), "PAR %s" % (shape,))
+
+
+# ---- normalise / validation / cam_to_label -------------------------------------------------------------
+def test_normalize_and_validation(cosa):
+    g = load_golden("normalize")
+    out = cosa.cam_normalize([cu(g["s0"]), cu(g["s1"]), cu(g["s2"])])
+    assert_same(out, g["out"], "cam_normalize (IEEE add/div only: bit-exact)")
+    g = load_golden("cam_to_label")
+    assert_same(cosa.cam_validation(cu(g["cam"]), cu(g["cls_label"])), g["valid"], "cam_validation")
+
+
+def test_cam_to_label_golden(cosa):
+    g = load_golden("cam_to_label")
+    cam, lab, boxes = cu(g["cam"]), cu(g["cls_label"]), t(g["boxes"])
+    assert_same(cosa.cam_to_label(cam, lab, bkg_thre=0.5), g["lab_plain"], "plain")
+    assert_same(cosa.cam_to_label(cam, None, bkg_thre=0.5), g["lab_nolabel"], "no cls_label")
+    vc, out = cosa.cam_to_label(cam, lab, img_box=boxes, bkg_thre=0.5, high_thre=0.7, low_thre=0.25,
+                                ignore_mid=True, ignore_index=255)
+    assert_same(vc, g["valid_cam"], "valid_cam")
+    assert_same(out, g["lab_box"], "boxed + ignore_mid")
+    _, out = cosa.cam_to_label(cam, lab, img_box=boxes, bkg_thre=0.5, ignore_mid=False, ignore_index=255)
+    assert_same(out, g["lab_box_nomid"], "boxed")
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 448, 448), (1, 80, 37, 53), (3, 3, 1, 7)])
+def test_cam_to_label_vs_oracle(cosa, port, shape):
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(c)
+    cam = torch.rand(shape, generator=gen)
+    cam[:, :, : h // 2] = (cam[:, :, : h // 2] * 4).round() / 4          # many exact ties: first index must win
+    lab = (torch.rand((b, c), generator=gen) < 0.4).float()
+    boxes = [[0, h, 0, w]] * b
+    want_v, want = port.cam_to_label(cam, lab, img_box=boxes, bkg_thre=0.5, high_thre=0.7, low_thre=0.25,
+                                     ignore_mid=True, ignore_index=255)
+    got_v, got = cosa.cam_to_label(cam.cuda(), lab.cuda(), img_box=boxes, bkg_thre=0.5, high_thre=0.7, low_thre=0.25,
+                                   ignore_mid=True, ignore_index=255)
+    assert_same(got, want, "cam_to_label %s" % (shape,))
+    assert_same(got_v, want_v, "valid_cam %s" % (shape,))
+    assert_same(cosa.cam_to_label(cam.cuda(), None, bkg_thre=0.5), port.cam_to_label(cam, None, bkg_thre=0.5), "None")
+
+
+# ---- cam2mask ------------------------------------------------------------------------------------------
+def _oracle_margin(port, d, refine_model, downscale=2):
+    """Oracle label map plus, per pixel, the smaller top-1/top-2 margin of the two up-sampled stacks."""
+    images, cams, cls = d["images"], d["cams"], d["cls_label"]
+    b, _, h, w = images.shape
+    margins = torch.full((b, h, w), float("inf"))
+    small = F.interpolate(images, size=[h // downscale, w // downscale], mode="bilinear", align_corners=False)
+    for thr in (0.7, 0.25):
+        stack = torch.cat([torch.ones((b, 1, h, w)) * thr, cams], dim=1)
+        stack = F.interpolate(stack, size=[h // downscale, w // downscale], mode="bilinear", align_corners=False)
+        for i in range(b):
+            keys = torch.nonzero(torch.cat([torch.ones(1), cls[i]]))[:, 0]
+            active = stack[i, keys].unsqueeze(0).softmax(dim=1)
+            refined = refine_model(small[[i]], active) if refine_model else active
+            up = F.interpolate(refined, size=(h, w), mode="bilinear", align_corners=False)[0]
+            if up.shape[0] > 1:
+                top = up.topk(2, dim=0).values
+                margins[i] = torch.minimum(margins[i], top[0] - top[1])
+    return margins
+
+
+def check_labels_near_tie(got, want, margins, what):
+    got, want = got.detach().cpu(), want.detach().cpu()
+    assert got.shape == want.shape and got.dtype == want.dtype
+    diff = got != want
+    n = int(diff.sum())
+    if n:
+        worst = float(margins[diff].max())
+        print("%s: %d of %d pixels differ, all with oracle margin <= %.3g" % (what, n, want.numel(), worst))
+        assert worst <= NEAR_TIE, "%s: %d label mismatches, worst margin %.3g is not a numerical tie" % (what, n, worst)
+        assert n <= 1e-4 * want.numel(), "%s: too many near-tie flips (%d)" % (what, n)
+    return n
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_cam2mask_golden(cosa, port, tag):
+    g = load_golden("cam2mask_" + tag)
+    d = dict(images=t(g["images"]), cams=t(g["cams"]), cls_label=t(g["cls_label"]))
+    args = dict(images=cu(g["images"]), img_boxes=t(g["boxes"]), cams=cu(g["cams"]), cls_labels=cu(g["cls_label"]),
+                threshold_high=0.7, threshold_low=0.25)
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    out = cosa.cam2mask(**args)
+    assert out.dtype == torch.float32 and out.is_cuda
+    n0 = check_labels_near_tie(out, t(g["out_none"]), _oracle_margin(port, d, None), "cam2mask, no refine model")
+    m_par = _oracle_margin(port, d, port.ParOracle())
+    n1 = check_labels_near_tie(cosa.cam2mask(refine_model=par, **args), t(g["out_par"]), m_par, "cam2mask + PAR")
+    evalbox = dict(args, img_boxes=[[0, -1, 0, -1]] * d["images"].shape[0])
+    n2 = check_labels_near_tie(cosa.cam2mask(refine_model=par, **evalbox), t(g["out_par_evalbox"]), m_par,
+                               "cam2mask + PAR, eval-style boxes")
+    got = cosa.cam2mask(downscale=0, **args)
+    n3 = int((got.cpu() != t(g["out_nodownscale"])).sum())
+    print("cam2mask_%s label mismatches vs reference: none=%d par=%d evalbox=%d nodownscale=%d" % (tag, n0, n1, n2, n3))
+    assert n3 <= 1e-4 * got.numel()
+
+
+def test_cam2mask_generic_refine_model_matches_fused(cosa):
+    g = load_golden("cam2mask_a")
+    args = dict(images=cu(g["images"]), img_boxes=t(g["boxes"]), cams=cu(g["cams"]), cls_labels=cu(g["cls_label"]),
+                threshold_high=0.7, threshold_low=0.25)
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    fused = cosa.cam2mask(refine_model=par, **args)
+    generic = cosa.cam2mask(refine_model=lambda im, cm: par(im, cm), **args)     # any callable: per-image path
+    assert int((fused != generic).sum()) <= 1e-4 * fused.numel()
+
+
+def test_refine_cams_tail_bit_exact(cosa, port):
+    """Labelling stage alone (resize + argmax + key lookup) on identical refined CAMs: bit-exact."""
+    gen = torch.Generator().manual_seed(9)
+    refined = torch.rand((2, 5, 31, 47), generator=gen).softmax(dim=1)
+    refined[0, :, :10] = (refined[0, :, :10] * 8).round() / 8            # exact ties
+    keys = torch.tensor([0, 3, 7, 11, 19])
+    want = port.refine_cams(None, None, refined, keys, (62, 94))
+    got = cosa._refine_cams(None, None, refined.cuda(), keys.cuda(), (62, 94))
+    assert_same(got, want, "_refine_cams tail")
+
+
+# ---- bilateral filter ------------------------------------------------------------------------------------
+def test_bilateral_known_answers(cosa):
+    from cosa_b200 import bilateralfilter as bf
+    g = load_golden("bilateral_kat")
+    H = W = 224
+    out = torch.zeros((1, 1, H, W), device="cuda")
+    bf.bilateralfilter_batch(cu(g["kat_img"]).reshape(-1), torch.ones(H * W, device="cuda"), out, 1, 1, H, W, 15.0, 50.0)
+    M, err, cap, probe = bf.lattice_stats(1, 1, H, W)
+    print("KAT lattice: M=%d table=%d max_probe=%d" % (M, cap, probe))
+    assert M == int(g["kat_M"]) == 3809 and err == 0
+    assert_close(out[0, 0], g["kat_out"], "KAT 224x224", tol=1e-5)
+    assert abs(float(out[0, 0, 0, 0]) - 87.9367) < 1e-2 and abs(float(out[0, 0, H // 2, W // 2]) - 324.287) < 5e-2
+    for tag in ("2x3x5x7", "1x2x9x13", "1x4x24x40"):           # H*W % 4 != 0: the SSE padding pixels
+        n_, k_, h_, w_ = (int(v) for v in tag.split("x"))
+        o = torch.zeros((n_, k_, h_, w_), device="cuda")
+        bf.bilateralfilter_batch(cu(g["img_" + tag]), cu(g["in_" + tag]), o, n_, k_, h_, w_, 15.0, 50.0)
+        assert_close(o, g["out_" + tag], "bilateral " + tag, tol=1e-5)
+
+
+def test_bilateral_host_dropin_signature(cosa):
+    """The SWIG call shape of seg_helper.py:887: numpy in, numpy out in place, TypeError on a bad `outs`."""
+    from cosa_b200 import bilateralfilter as bf
+    g = load_golden("bilateral_kat")
+    img, xin, want = g["img_1x4x24x40"], g["in_1x4x24x40"], g["out_1x4x24x40"]
+    outs = np.zeros(xin.size, dtype=np.float32)
+    bf.bilateralfilter_batch(img.flatten(), xin.flatten(), outs, 1, 4, 24, 40, 15, 50.0)
+    assert rel_inf(outs.reshape(want.shape), want) <= 1e-5
+    with pytest.raises(TypeError):
+        bf.bilateralfilter_batch(img.flatten(), xin.flatten(), np.zeros(xin.size, dtype=np.float64), 1, 4, 24, 40, 15, 50.0)
+
+
+@pytest.mark.parametrize("case", [(3, 21, 56, 72, "noise"), (2, 5, 33, 47, "uniform"), (1, 81, 40, 40, "flat")])
+def test_bilateral_vs_oracle(cosa, case):
+    from cosa_b200 import bilateralfilter as bf
+    from oracle import lattice as olat
+    N, K, H, W, kind = case
+    rng = np.random.default_rng(H * W)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    base = np.stack([127 + 100 * np.sin(0.02 * xx + c) * np.cos(0.03 * yy) for c in range(3)])
+    imgs = {"noise": np.floor(np.clip(base[None] + 10 * rng.standard_normal((N, 3, H, W)), 0, 255)),
+            "uniform": rng.uniform(0, 255, (N, 3, H, W)),
+            "flat": np.full((N, 3, H, W), 93.0)}[kind].astype(np.float32)
+    ins = rng.uniform(0, 1, (N, K, H, W)).astype(np.float32)
+    want = np.zeros(ins.size, np.float32)
+    olat.oracle_bilateralfilter_batch(imgs, ins, want, N, K, H, W, 15.0, 50.0)
+    got = torch.zeros((N, K, H, W), device="cuda")
+    bf.bilateralfilter_batch(cu(imgs), cu(ins), got, N, K, H, W, 15.0, 50.0)
+    M = bf.lattice_stats(N, K, H, W)[0]
+    M_want = sum(len(olat.oracle_lattice_embed(imgs[i], H, W, 15.0, 50.0)[2]) for i in range(N))
+    assert M == M_want, "vertex count %d vs oracle %d" % (M, M_want)
+    assert_close(got, want.reshape(N, K, H, W), "bilateral %s" % (case,), tol=1e-5)
+
+
+# ---- dense-CRF energy ------------------------------------------------------------------------------------
+def test_energy_function_golden(cosa):
+    g = load_golden("energy_function")
+    segs = cu(g["segs"]).requires_grad_(True)
+    rois = cu(g["rois"])
+    loss = cosa.DenseEnergyLossFunction.apply(cu(g["images"]), segs, 15, 50.0, rois, cu(g["unlabel"]))
+    assert loss.shape == (1,) and loss.is_cuda and rois.shape == g["rois"].shape
+    (loss * float(g["grad_scale"])).sum().backward()
+    print("energy fn rel:", assert_close(loss, g["loss"], "energy loss"), assert_close(segs.grad, g["grad_segs"], "grad"))
+
+
+@pytest.mark.parametrize("module", ["seg_helper", "rrm_utils"])
+def test_get_energy_loss_golden(cosa, module):
+    import importlib
+    mod = importlib.import_module("cosa_b200." + module)
+    g = load_golden("energy_loss")
+    layer = mod.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = cu(g["logit"]).requires_grad_(True)
+    loss = cosa.get_energy_loss(img=cu(g["simg"]), logit=logit, label=cu(g["label"]), img_box=t(g["boxes"]),
+                                loss_layer=layer)
+    loss.backward()
+    assert loss.shape == (1,) and loss.is_cuda
+    r1 = assert_close(loss, g["loss"], "get_energy_loss (fused)")
+    r2 = assert_close(logit.grad, g["grad_logit"], "d loss / d logit (fused)")
+    print("fused get_energy_loss rel: loss %.3g grad %.3g" % (r1, r2))
+
+
+def test_get_energy_loss_unfused_composition(cosa):
+    """A layer subclass is not fused: softmax / resize run as torch ops, the Function in our kernels."""
+    g = load_golden("energy_loss")
+
+    class MyLayer(cosa.DenseEnergyLoss):
+        pass
+
+    layer = MyLayer(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = cu(g["logit"]).requires_grad_(True)
+    loss = cosa.get_energy_loss(img=cu(g["simg"]), logit=logit, label=cu(g["label"]), img_box=t(g["boxes"]),
+                                loss_layer=layer)
+    loss.backward()
+    assert_close(loss, g["loss"], "get_energy_loss (composed)")
+    assert_close(logit.grad, g["grad_logit"], "d loss / d logit (composed)")
+
+
+# ---- BASELINE.json sizes: size-independent properties ------------------------------------------------------
+@pytest.fixture(scope="module")
+def voc_batch():
+    from cosa_b200 import synthetic
+    d = synthetic.synthetic_batch(B=32, C=21, H=448, W=448, n_fg=2, seed=1000)
+    return {k: v.cuda() if k != "img_box" else v for k, v in d.items()}
+
+
+def test_full_size_labels_and_par_properties(cosa, voc_batch):
+    d = voc_batch
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    out, hi, lo = cosa.cam2mask(images=d["img_denorm"], img_boxes=d["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
+                                threshold_high=0.7, threshold_low=0.25, refine_model=par, return_parts=True)
+    assert out.shape == (32, 448, 448)
+    present = torch.cat([torch.ones(32, 1, device="cuda"), d["cls_label"]], 1)
+    for b in range(32):
+        allowed = set(torch.nonzero(present[b])[:, 0].tolist()) | {255}
+        assert set(out[b].unique().tolist()) <= allowed
+    # merge rule (seg_helper.py:781-783) as an identity on the two parts
+    want = hi.clone()
+    want[hi == 0] = 255
+    want[(hi + lo) == 0] = 0
+    assert torch.equal(out, want)
+    # PAR on a constant mask returns the constant times (1 + w2)^T: affinities sum to 1.01 (PAR.py:85)
+    small = F.interpolate(d["img_denorm"], size=[224, 224], mode="bilinear", align_corners=False)
+    const = torch.full((32, 2, 224, 224), 0.37, device="cuda")
+    res = par(small, const)
+    assert float((res / 0.37 - 1.01 ** 10).abs().max()) < 1e-4
+    # linearity in the masks
+    a, b_ = torch.rand_like(const), torch.rand_like(const)
+    lin = par(small, 2 * a - 3 * b_) - (2 * par(small, a) - 3 * par(small, b_))
+    assert float(lin.abs().max()) < 1e-4
+
+
+def test_full_size_filter_is_linear_and_symmetric(cosa, voc_batch):
+    from cosa_b200 import bilateralfilter as bf
+    d = voc_batch
+    N, K, H, W = 32, 21, 224, 224
+    img = F.interpolate(d["img_denorm"] * 255, scale_factor=0.5).contiguous()
+    x = torch.rand((N, K, H, W), device="cuda")
+    y = torch.rand((N, K, H, W), device="cuda")
+
+    def filt(v):
+        o = torch.empty_like(v)
+        bf.bilateralfilter_batch(img, v.contiguous(), o, N, K, H, W, 15.0, 50.0)
+        return o
+
+    fx, fy = filt(x), filt(y)
+    M = bf.lattice_stats(N, K, H, W)
+    print("VOC B=32 lattice: M=%d (M/n=%.3f) table=%d max_probe=%d" % (M[0], M[0] / (N * H * W), M[2], M[3]))
+    assert M[1] == 0
+    lin = filt(2 * x - 3 * y) - (2 * fx - 3 * fy)
+    assert float(lin.abs().max() / fx.abs().max()) < 1e-5
+    # splat and slice use the same weights and the blur is symmetric, so <x, F y> = <F x, y>
+    lhs, rhs = (x.double() * fy.double()).sum(), (fx.double() * y.double()).sum()
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+    # images are independent: filtering one image alone gives the same rows
+    o1 = torch.empty((1, K, H, W), device="cuda")
+    bf.bilateralfilter_batch(img[5:6].contiguous(), x[5:6].contiguous(), o1, 1, K, H, W, 15.0, 50.0)
+    assert float((o1[0] - fx[5]).abs().max() / fx[5].abs().max()) < 1e-5
+
+
+def test_full_size_energy_loss_and_grad(cosa, voc_batch):
+    d = voc_batch
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    label = cosa.cam2mask(images=d["img_denorm"], img_boxes=d["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
+                          threshold_high=0.7, threshold_low=0.25, refine_model=par)
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = d["logits"].clone().requires_grad_(True)
+    loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=d["img_box"], loss_layer=layer)
+    loss.backward()
+    assert torch.isfinite(loss).all() and float(loss) < 0
+    assert torch.isfinite(logit.grad).all()
+    # softmax backward: the gradient of every pixel sums to zero over the classes
+    assert float(logit.grad.sum(1).abs().max()) <= 1e-5 * float(logit.grad.abs().max())
+    # fused path == composed path (torch softmax / interpolate + the autograd Function) at full size
+    class Plain(cosa.DenseEnergyLoss):
+        pass
+    logit2 = d["logits"].clone().requires_grad_(True)
+    loss2 = cosa.get_energy_loss(img=d["simg"], logit=logit2, label=label, img_box=d["img_box"],
+                                 loss_layer=Plain(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5))
+    loss2.backward()
+    assert_close(loss, loss2, "fused vs composed loss")
+    assert_close(logit.grad, logit2.grad, "fused vs composed grad")
