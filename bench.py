@@ -196,7 +196,9 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
         "cam2mask_keys_kernel": 4 * B * (C - 1) + 4 * B * C,
         "cam2mask_prepare_kernel": 4 * B * (H * W * (3 + (nc - 1)) + n * (3 + ncm)),
         "par_affinity_kernel": 4 * B * n * (3 + ND),
-        "par_iterate_kernel": 4 * B * n * (ND + 2 * ncm),      # one step: affinity read + masks read + written
+        # one propagation step.  SURVEY 8(d): masks read + written once, affinities on-chip.  This design streams
+        # the affinity planes as well (4*B*n*ND more bytes per step); reported separately as "design_bytes".
+        "par_iterate_kernel": 4 * B * n * (2 * ncm),
         "cam2mask_finalize_kernel": 4 * B * (n * ncm + H * W),
         "energy_prepare_kernel": 4 * B * (H * W * (K + 2) + n * (3 + K + 2)),
         "lattice_clear_kernel": None,                            # sized by the table, not by the problem
@@ -210,7 +212,10 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
         "energy_loss_finalize_kernel": 12,
         "energy_logit_grad_kernel": 4 * B * (2 * H * W * K + n * (K + 1)),
     }
-    return {k: per.get(k) for k in kernels}
+    base = lambda k: k.replace("_vec_kernel", "_kernel").replace("_reg_kernel", "_kernel")
+    out = {k: per.get(base(k)) for k in kernels}
+    design = {k: (4 * B * n * (ND + 2 * ncm) if base(k) == "par_iterate_kernel" else out[k]) for k in kernels}
+    return out, design
 
 
 def run_cosa_arm(args):
@@ -280,14 +285,14 @@ def run_cosa_arm(args):
     M_vertices = seg_helper.last_energy_lattice_stats(B, C, H, W, dev)[0]
     nc = 1 + wl["n_fg"]
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(prof.keys(), B, C, H, W, nc, M_vertices)
+    alg, design = algorithmic_bytes(prof.keys(), B, C, H, W, nc, M_vertices)
     kernels = []
     for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         avg_ms = ms / count
         ab = alg.get(name)
         gbs = (ab / 1e9) / (avg_ms / 1e3) if ab else None
         kernels.append({"kernel": name, "launches_per_step": count / prof_steps, "avg_ms": round(avg_ms, 5),
-                        "ms_per_step": round(ms / prof_steps, 5), "alg_bytes": ab,
+                        "ms_per_step": round(ms / prof_steps, 5), "alg_bytes": ab, "design_bytes": design.get(name),
                         "achieved_gbs": round(gbs, 1) if gbs else None,
                         "frac": round(gbs / peak, 4) if gbs else None})
     top = kernels[0]

@@ -139,6 +139,8 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p) {
                : "l"(p));
   return v;
 }
+// 128-bit load that bypasses L1 but may hit L2 (second pass over data the same thread streamed before)
+__device__ __forceinline__ float4 ldg4c(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ void stg_stream4(float *p, const float4 &v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w));

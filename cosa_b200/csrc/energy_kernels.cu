@@ -183,6 +183,149 @@ __global__ void __launch_bounds__(256) energy_logit_grad_kernel(const float *__r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Vectorised streaming variants (W % 4 == 0): 128-bit loads, two passes over the logits (the second one hits
+// L2), online max/sum in the first pass with ONE exponential per element (exp(-|l - max|) serves both the
+// "new maximum" rescale and the ordinary accumulation).  Within the 1e-4 budget the fast ex2-based __expf is
+// used here (relative error ~1e-6 over the softmax range); nothing on this branch decides a label.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void online_update(float l, float &mx, float &den) {
+  const float d = l - mx;
+  const float e = __expf(-fabsf(d));
+  den = d > 0.0f ? fmaf(den, e, 1.0f) : den + e;
+  mx = fmaxf(mx, l);
+}
+
+// One thread = 4 x 2 full-resolution pixels = 2 half-resolution pixels.
+__global__ void __launch_bounds__(256) energy_prepare_vec_kernel(const float *__restrict__ simg,
+                                                                 const float *__restrict__ logit,
+                                                                 const float *__restrict__ label,
+                                                                 const int *__restrict__ boxes, Affine3 aff,
+                                                                 float *__restrict__ img_half,
+                                                                 float *__restrict__ s_roi, float *__restrict__ gate,
+                                                                 float *__restrict__ roi_out, int B, int C, int H,
+                                                                 int W) {
+  const int h = H / 2, w = W / 2, wq = W / 4;
+  const long long total = (long long)B * h * wq;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(t % wq), yh = (int)((t / wq) % h), b = (int)(t / ((long long)wq * h));
+    const int X = xq * 4, Y = yh * 2;
+    const size_t src = (size_t)Y * W + X;
+    const float *lg = logit + (size_t)b * C * HW + src;
+    float mx[8], den[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mx[i] = -INFINITY; den[i] = 0.0f; }
+#pragma unroll 3
+    for (int c = 0; c < C; ++c) {
+      const float4 a = ldg_stream4(lg + (size_t)c * HW);
+      const float4 d = ldg_stream4(lg + (size_t)c * HW + W);
+      online_update(a.x, mx[0], den[0]); online_update(a.y, mx[1], den[1]);
+      online_update(a.z, mx[2], den[2]); online_update(a.w, mx[3], den[3]);
+      online_update(d.x, mx[4], den[4]); online_update(d.y, mx[5], den[5]);
+      online_update(d.z, mx[6], den[6]); online_update(d.w, mx[7], den[7]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) den[i] = 1.0f / den[i];
+
+    const int *box = boxes + 4 * b;
+    const bool rowin = Y >= box[0] && Y < box[1];
+    const float roi0 = (rowin && X >= box[2] && X < box[3]) ? 1.0f : 0.0f;           // nearest: pixel (2y, 2x)
+    const float roi1 = (rowin && X + 2 >= box[2] && X + 2 < box[3]) ? 1.0f : 0.0f;
+    const size_t pix = (size_t)yh * w + (X >> 1);
+    float smax0 = -INFINITY, smax1 = -INFINITY;
+    float *dst = s_roi + (size_t)b * C * hw + pix;
+#pragma unroll 3
+    for (int c = 0; c < C; ++c) {
+      const float4 a = ldg4c(lg + (size_t)c * HW);
+      const float4 d = ldg4c(lg + (size_t)c * HW + W);
+      const float p00 = __expf(a.x - mx[0]) * den[0], p01 = __expf(a.y - mx[1]) * den[1];
+      const float q00 = __expf(a.z - mx[2]) * den[2], q01 = __expf(a.w - mx[3]) * den[3];
+      const float p10 = __expf(d.x - mx[4]) * den[4], p11 = __expf(d.y - mx[5]) * den[5];
+      const float q10 = __expf(d.z - mx[6]) * den[6], q11 = __expf(d.w - mx[7]) * den[7];
+      // exact 2:1 bilinear, align_corners=False: 0.25 * (((p00 + p01) + p10) + p11)
+      const float s0 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(p00, p01), p10), p11));
+      const float s1 = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(q00, q01), q10), q11));
+      smax0 = fmaxf(smax0, s0);
+      smax1 = fmaxf(smax1, s1);
+      *reinterpret_cast<float2 *>(dst + (size_t)c * hw) = make_float2(__fmul_rn(s0, roi0), __fmul_rn(s1, roi1));
+    }
+    // image (nearest, de-normalised), unlabel flag, gate, ROI for the two half-resolution pixels
+    const float4 lab = ldg_stream4(label + (size_t)b * HW + src);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 v = ldg_stream4(simg + ((size_t)b * 3 + c) * HW + src);
+      *reinterpret_cast<float2 *>(img_half + ((size_t)b * 3 + c) * hw + pix) =
+          make_float2(__fadd_rn(__fmul_rn(v.x, aff.std[c]), aff.mean[c]), __fadd_rn(__fmul_rn(v.z, aff.std[c]), aff.mean[c]));
+    }
+    float g0 = __fsub_rn(roi0, smax0), g1 = __fsub_rn(roi1, smax1);
+    if (((int)lab.x & 255) == 255) g0 = 1.0f;
+    if (((int)lab.z & 255) == 255) g1 = 1.0f;
+    *reinterpret_cast<float2 *>(gate + (size_t)b * hw + pix) = make_float2(fmaxf(g0, 0.0f), fmaxf(g1, 0.0f));
+    *reinterpret_cast<float2 *>(roi_out + (size_t)b * hw + pix) = make_float2(roi0, roi1);
+  }
+}
+
+// One thread = 4 full-resolution pixels of one row (two half-resolution pixels of the saved AS / ROI).
+__global__ void __launch_bounds__(256) energy_logit_grad_vec_kernel(const float *__restrict__ logit,
+                                                                    const float *__restrict__ as_saved,
+                                                                    const float *__restrict__ roi_half,
+                                                                    const float *__restrict__ grad_out, float weight,
+                                                                    float *__restrict__ grad_logit, int B, int C,
+                                                                    int H, int W) {
+  const int h = H / 2, w = W / 2, wq = W / 4;
+  const long long total = (long long)B * H * wq;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const float cbase = __fdiv_rn(__fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight)), (float)B) * 0.25f;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(t % wq), Y = (int)((t / wq) % H), b = (int)(t / ((long long)wq * H));
+    const int X = xq * 4;
+    const size_t pix = (size_t)(Y >> 1) * w + (X >> 1);
+    const float *lg = logit + (size_t)b * C * HW + (size_t)Y * W + X;
+    const float *as = as_saved + (size_t)b * C * hw + pix;
+    float *out = grad_logit + (size_t)b * C * HW + (size_t)Y * W + X;
+    const float2 roi = *reinterpret_cast<const float2 *>(roi_half + (size_t)b * hw + pix);
+    float mx[4], den[4], num[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mx[i] = -INFINITY; den[i] = 0.0f; num[i] = 0.0f; }
+#pragma unroll 3
+    for (int c = 0; c < C; ++c) {
+      const float4 l = ldg_stream4(lg + (size_t)c * HW);
+      const float2 a = __ldg(reinterpret_cast<const float2 *>(as + (size_t)c * hw));
+      const float lv[4] = {l.x, l.y, l.z, l.w};
+      const float av[4] = {a.x, a.x, a.y, a.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = lv[i] - mx[i];
+        const float e = __expf(-fabsf(d));
+        if (d > 0.0f) { den[i] = fmaf(den[i], e, 1.0f); num[i] = fmaf(num[i], e, av[i]); }
+        else          { den[i] += e;                    num[i] = fmaf(e, av[i], num[i]); }
+        mx[i] = fmaxf(mx[i], lv[i]);
+      }
+    }
+    float dot[4], cf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      den[i] = 1.0f / den[i];
+      dot[i] = num[i] * den[i];                   // <p, AS> of this pixel
+      cf[i] = cbase * (i < 2 ? roi.x : roi.y);
+    }
+#pragma unroll 3
+    for (int c = 0; c < C; ++c) {
+      const float4 l = ldg4c(lg + (size_t)c * HW);
+      const float2 a = __ldg(reinterpret_cast<const float2 *>(as + (size_t)c * hw));
+      float4 o;
+      o.x = __expf(l.x - mx[0]) * den[0] * (cf[0] * (a.x - dot[0]));
+      o.y = __expf(l.y - mx[1]) * den[1] * (cf[1] * (a.x - dot[1]));
+      o.z = __expf(l.z - mx[2]) * den[2] * (cf[2] * (a.y - dot[2]));
+      o.w = __expf(l.w - mx[3]) * den[3] * (cf[3] * (a.y - dot[3]));
+      stg_stream4(out + (size_t)c * HW, o);
+    }
+  }
+}
+
 static int grid1d(long long items) { return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(items, 256))); }
 
 }  // namespace cosa
@@ -281,9 +424,15 @@ extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, c
   void *lws = a.base + a.off;
   Affine3 aff;
   for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
-  dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B);
-  COSA_LAUNCH(energy_prepare_kernel, grid, 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi, gate, roi_half,
-              C, H, W);
+  if (W % 4 == 0) {
+    const long long threads = (long long)B * h * (W / 4);
+    COSA_LAUNCH(energy_prepare_vec_kernel, grid1d(threads), 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi,
+                gate, roi_half, B, C, H, W);
+  } else {
+    dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B);
+    COSA_LAUNCH(energy_prepare_kernel, grid, 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi, gate,
+                roi_half, C, H, W);
+  }
   return energy_core(img_half, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1, lws,
                      s);
 }
@@ -297,7 +446,14 @@ extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, 
   const float *as_saved = sv.take<float>((size_t)B * C * hw);
   const float *roi_half = sv.take<float>((size_t)B * hw);
   dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
-  COSA_LAUNCH(energy_logit_grad_kernel, grid, 256, 0, (cudaStream_t)stream, logit, as_saved, roi_half, grad_out, weight,
-              grad_logit, C, H, W, B);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (W % 4 == 0) {
+    const long long threads = (long long)B * H * (W / 4);
+    COSA_LAUNCH(energy_logit_grad_vec_kernel, grid1d(threads), 256, 0, s, logit, as_saved, roi_half, grad_out, weight,
+                grad_logit, B, C, H, W);
+  } else {
+    COSA_LAUNCH(energy_logit_grad_kernel, grid, 256, 0, s, logit, as_saved, roi_half, grad_out, weight, grad_logit, C,
+                H, W, B);
+  }
   return 0;
 }

@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
                                                                const int *__restrict__ keys,
                                                                const int *__restrict__ nc_dev,
                                                                float *__restrict__ img_small,
-                                                               float *__restrict__ masks, ResizeGeom g, int C1,
-                                                               float thr_high, float thr_low) {
+                                                               float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
+                                                               int C1, float thr_high, float thr_low) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -280,8 +280,19 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   const int nc = nc_dev[b];
   const int *key = keys + (size_t)b * (C1 + 1);
   const float *cam_b = cams + (size_t)b * C1 * HW;
-  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * hw + pix;
-  float *m_lo = m_hi + (size_t)nc * hw;
+  // mask rows may be padded (MaskLayout): interior at column ml.off, ml.padn replicated columns either side
+  const size_t mplane = (size_t)g.h * ml.pitch;
+  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * mplane + (size_t)y * ml.pitch + ml.off + x;
+  float *m_lo = m_hi + (size_t)nc * mplane;
+  auto put = [&](float *dst, float val) {
+    *dst = val;
+    if (ml.padn) {
+      if (x == 0)
+        for (int i = 1; i <= ml.padn; ++i) dst[-i] = val;
+      if (x == g.w - 1)
+        for (int i = 1; i <= ml.padn; ++i) dst[i] = val;
+    }
+  };
 
   // live foreground channels: values, their max; the two stacks differ only in channel 0 (the threshold)
   float v[kCacheC];
@@ -299,18 +310,19 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
     den_hi += expf(t - mx_hi);
     den_lo += expf(t - mx_lo);
   }
-  m_hi[0] = e0_hi / den_hi;
-  m_lo[0] = e0_lo / den_lo;
+  put(m_hi, e0_hi / den_hi);
+  put(m_lo, e0_lo / den_lo);
   for (int j = 1; j < nc; ++j) {
     const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
-    m_hi[(size_t)j * hw] = expf(t - mx_hi) / den_hi;
-    m_lo[(size_t)j * hw] = expf(t - mx_lo) / den_lo;
+    put(m_hi + (size_t)j * mplane, expf(t - mx_hi) / den_hi);
+    put(m_lo + (size_t)j * mplane, expf(t - mx_lo) / den_lo);
   }
 }
 
 // argmax over nc channels of the bilinearly up-sampled stack at full-resolution pixel (Y, X)
 __device__ __forceinline__ int upsampled_argmax(const float *stack, int nc, size_t hw, int w, const Tap &ty,
                                                 const Tap &tx) {
+  // hw = plane stride, w = row pitch (the caller has already added the interior offset to `stack`)
   const size_t o00 = (size_t)ty.i0 * w + tx.i0, o01 = (size_t)ty.i0 * w + tx.i1;
   const size_t o10 = (size_t)ty.i1 * w + tx.i0, o11 = (size_t)ty.i1 * w + tx.i1;
   float best = -INFINITY;
@@ -329,13 +341,13 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
                                                                 const int *__restrict__ boxes,
                                                                 float *__restrict__ label_out,
                                                                 float *__restrict__ label_hi_out,
-                                                                float *__restrict__ label_lo_out, ResizeGeom g, int C1,
-                                                                float ignore_index) {
+                                                                float *__restrict__ label_lo_out, MaskLayout ml,
+                                                                ResizeGeom g, int C1, float ignore_index) {
   const int X = blockIdx.x * 32 + (threadIdx.x & 31);
   const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
   if (X >= g.W || Y >= g.H) return;
-  const size_t HW = (size_t)g.H * g.W, hw = (size_t)g.h * g.w;
+  const size_t HW = (size_t)g.H * g.W, mplane = (size_t)g.h * ml.pitch;
   const size_t out_idx = (size_t)b * HW + (size_t)Y * g.W + X;
   const int *box = boxes + 4 * b;
   float hi = ignore_index, lo = ignore_index;
@@ -345,9 +357,9 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
     // up-sampling scale = reduced / full (area_pixel_compute_scale with the output size given)
     const Tap ty = tap_half_pixel(Y, g.identity ? 1.0f : (float)g.h / (float)g.H, g.h);
     const Tap tx = tap_half_pixel(X, g.identity ? 1.0f : (float)g.w / (float)g.W, g.w);
-    const float *st = refined + (size_t)b * 2 * (C1 + 1) * hw;
-    hi = (float)key[upsampled_argmax(st, nc, hw, g.w, ty, tx)];
-    lo = (float)key[upsampled_argmax(st + (size_t)nc * hw, nc, hw, g.w, ty, tx)];
+    const float *st = refined + (size_t)b * 2 * (C1 + 1) * mplane + ml.off;
+    hi = (float)key[upsampled_argmax(st, nc, mplane, ml.pitch, ty, tx)];
+    lo = (float)key[upsampled_argmax(st + (size_t)nc * mplane, nc, mplane, ml.pitch, ty, tx)];
   }
   // merge (seg_helper.py:781-783): high fg stays; high bg becomes ignore unless low also says bg
   float out = hi;
@@ -442,13 +454,22 @@ static void cam2mask_geom(int H, int W, int downscale, ResizeGeom *g) {
   g->sx = g->identity ? 1.0f : (float)W / (float)g->w;
 }
 
+// mask rows of the PAR path are padded for the vectorised kernel; pads wider than 24 columns are not used
+// (cosa_cam2mask then keeps the plain layout), which bounds the scratch without knowing the dilation values
+static MaskLayout cam2mask_layout(int w, int use_par, const int *dilations, int n_dil) {
+  if (!use_par) return plain_layout(w);
+  MaskLayout l = padded_layout(w, dilations, n_dil);
+  return l.padn > 24 ? plain_layout(w) : l;
+}
+
 extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downscale, int use_par, int n_dil) {
   ResizeGeom g;
   cam2mask_geom(H, W, downscale, &g);
   const size_t hw = (size_t)g.h * g.w;
+  const size_t pitch = use_par ? (size_t)((32 + g.w + 24 + 31) & ~31) : (size_t)g.w;
   size_t bytes = align_up((size_t)B * (C1 + 1) * sizeof(int), 256) + 2 * align_up((size_t)B * sizeof(int), 256);
   const int n_mask_bufs = use_par ? 4 : 1;
-  bytes += n_mask_bufs * align_up((size_t)B * 2 * (C1 + 1) * hw * sizeof(float), 256);
+  bytes += n_mask_bufs * align_up((size_t)B * 2 * (C1 + 1) * g.h * pitch * sizeof(float), 256);
   if (use_par) {
     bytes += align_up((size_t)B * 3 * hw * sizeof(float), 256);
     bytes += align_up((size_t)B * 8 * n_dil * hw * sizeof(float), 256);
@@ -464,6 +485,7 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
   if (!images || !boxes || !cams || !cls_labels || !label_out || !ws || B < 1 || C1 < 1 || H < 1 || W < 1 ||
       downscale < 0)
     return COSA_E_ARG;
+  if (use_par && (!dilations || n_dil < 1 || num_iter < 0)) return COSA_E_ARG;
   ResizeGeom g;
   cam2mask_geom(H, W, downscale, &g);
   if (g.h < 1 || g.w < 1) return COSA_E_ARG;
@@ -471,34 +493,40 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
   cudaStream_t s = (cudaStream_t)stream;
   const size_t hw = (size_t)g.h * g.w;
   const int C = C1 + 1;
+  const bool refine = use_par && num_iter > 0;
+  const MaskLayout lay = cam2mask_layout(g.w, refine, dilations, n_dil);
+  const size_t mfloats = layout_floats(lay, B, 2 * C, g.h);
   Arena arena(ws);
   int *keys = arena.take<int>((size_t)B * C);
   int *nc = arena.take<int>(B);
   int *nch = arena.take<int>(B);
-  float *masks = arena.take<float>((size_t)B * 2 * C * hw);
+  float *masks = arena.take<float>(mfloats);
 
   COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
-  if (use_par) {
-    sa = arena.take<float>((size_t)B * 2 * C * hw);
-    sb = arena.take<float>((size_t)B * 2 * C * hw);
-    fin = arena.take<float>((size_t)B * 2 * C * hw);
+  if (refine) {
+    sa = arena.take<float>(mfloats);
+    sb = arena.take<float>(mfloats);
+    fin = arena.take<float>(mfloats);
     img_small = arena.take<float>((size_t)B * 3 * hw);
     aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
     COSA_CHECK(par_upload_constants(dilations, n_dil, s));
   }
   dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
-  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, img_small, masks, g, C1, threshold_high,
-              threshold_low);
+  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, img_small, masks, lay, g, C1,
+              threshold_high, threshold_low);
   const float *refined = masks;
-  if (use_par) {
+  MaskLayout lay_fin = lay;
+  lay_fin.padn = 0;   // the labelling kernel never reads the pads
+  if (refine) {
     COSA_CHECK(par_launch_affinity(img_small, aff, B, g.h, g.w, n_dil, s));
-    COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, fin, nch, 0, 2 * C, B, g.h, g.w, n_dil, num_iter, s));
+    COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
+                                     num_iter, s));
     refined = fin;
   }
   dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
   COSA_LAUNCH(cam2mask_finalize_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
-              label_low_out, g, C1, ignore_index);
+              label_low_out, lay_fin, g, C1, ignore_index);
   return 0;
 }
 

@@ -126,14 +126,15 @@ __global__ void lattice_clear_kernel(unsigned long long *table_keys, unsigned lo
 __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const float *__restrict__ images,
                                                             EmbedConst ec, int N, int H, int W, int n_pad,
                                                             float sigmargb, float sigmaxy) {
+  __shared__ int s_new, s_base;
+  if (threadIdx.x == 0) s_new = 0;
+  __syncthreads();
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)N * n_pad;
-  const bool in_range = g < total;
-  const unsigned active = __ballot_sync(0xffffffffu, in_range);
-  if (!in_range) return;
+  const bool in_range = g < total;        // out-of-range threads stay for the warp/block collectives
   const int n = H * W;
-  const int b = (int)(g / n_pad), p = (int)(g % n_pad);
-  const bool real = p < n;   // the SSE loop also embeds zero-feature padding pixels (permutohedral.cpp:168-173)
+  const int b = in_range ? (int)(g / n_pad) : 0, p = in_range ? (int)(g % n_pad) : 0;
+  const bool real = in_range && p < n;   // the SSE loop also embeds zero-feature padding pixels (permutohedral.cpp:168-173)
 
   float f[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
   if (real) {
@@ -151,37 +152,55 @@ __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const
   const long long gp = (long long)b * n + p;   // compact pixel index
   const int lane = threadIdx.x & 31;
   int bad = 0, max_probe = 0;
-#pragma unroll 1
+  unsigned new_mask = 0;                        // bit r: this lane created the table entry of vertex r
+  unsigned long long new_key[kLatD + 1], new_slot[kLatD + 1];
+#pragma unroll
   for (int r = 0; r <= kLatD; ++r) {
     int q[kLatD];
 #pragma unroll
     for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
-    const unsigned long long key = pack_key(q, r, b, &bad);
+    // out-of-range lanes carry a per-lane dummy (residue field 7: never a real key) and insert nothing
+    const unsigned long long key = in_range ? pack_key(q, r, b, &bad) : kEmptyKey - 1ULL - (unsigned long long)lane;
     // warp-aggregated insert: one CAS per distinct key per warp
-    const unsigned peers = __match_any_sync(active, key);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int leader = __ffs(peers) - 1;
     unsigned long long slot = 0;
-    if (lane == leader) {
+    if (lane == leader && in_range) {
       slot = hash_key(key) & L.cap_mask;
       int probes = 0;
       for (;;) {
         const unsigned long long old = atomicCAS(L.table_keys + slot, kEmptyKey, key);
-        if (old == kEmptyKey) {
-          const int id = atomicAdd(L.counters, 1);
-          L.vkeys[id] = key;
-          L.table_ids[slot] = id + 1;
-          break;
-        }
+        if (old == kEmptyKey) { new_mask |= 1u << r; break; }
         if (old == key) break;
         slot = (slot + 1) & L.cap_mask;
         ++probes;
       }
       max_probe = max(max_probe, probes);
     }
+    new_key[r] = key;
+    new_slot[r] = slot;
     slot = __shfl_sync(peers, slot, leader);
     if (real) {
       L.offsets[(size_t)r * L.P + gp] = (int)slot;
       L.bary[(size_t)r * L.P + gp] = bary[r];
+    }
+  }
+  // dense vertex ids: one global atomic per CTA instead of one per new vertex (a single hot address otherwise)
+  const int mine = __popc(new_mask);
+  int local = 0;
+  if (mine) local = atomicAdd(&s_new, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = s_new ? atomicAdd(L.counters, s_new) : 0;
+  __syncthreads();
+  if (mine) {
+    int id = s_base + local;
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      if (new_mask & (1u << r)) {
+        L.vkeys[id] = new_key[r];
+        L.table_ids[new_slot[r]] = id + 1;
+        ++id;
+      }
     }
   }
   if (bad) atomicExch(L.counters + 1, 1);
@@ -195,13 +214,40 @@ __global__ void lattice_resolve_kernel(LatticeBufs L) {
     L.offsets[i] = L.table_ids[L.offsets[i]];
 }
 
-__device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long long key) {
-  unsigned long long slot = hash_key(key) & L.cap_mask;
+// After the build the vertex count M is known on the device.  The neighbour look-ups (12 per vertex) would be
+// DRAM-latency bound in the worst-case-sized build table, so the M keys are re-inserted into a compact table of
+// 2^k >= 2M slots that reuses the head of the build table's storage and stays L2-resident.
+__device__ __forceinline__ unsigned long long compact_mask(const LatticeBufs &L) {
+  const unsigned m2 = 2u * (unsigned)max(L.counters[0], 512);
+  const unsigned long long cap = 1ULL << (32 - __clz(m2 - 1));
+  return min(cap, L.cap_mask + 1) - 1;
+}
+
+__global__ void lattice_compact_clear_kernel(LatticeBufs L) {
+  const unsigned long long cap = compact_mask(L) + 1;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    L.table_keys[i] = kEmptyKey;
+}
+
+__global__ void lattice_compact_insert_kernel(LatticeBufs L) {
+  const unsigned long long mask = compact_mask(L);
+  const long long M = L.counters[0];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = L.vkeys[i];
+    unsigned long long slot = hash_key(key) & mask;
+    while (atomicCAS(L.table_keys + slot, kEmptyKey, key) != kEmptyKey) slot = (slot + 1) & mask;   // keys are distinct
+    L.table_ids[slot] = (int)i + 1;
+  }
+}
+
+__device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long long mask, unsigned long long key) {
+  unsigned long long slot = hash_key(key) & mask;
   for (;;) {
     const unsigned long long cur = L.table_keys[slot];
     if (cur == key) return L.table_ids[slot];
     if (cur == kEmptyKey) return 0;
-    slot = (slot + 1) & L.cap_mask;
+    slot = (slot + 1) & mask;
   }
 }
 
@@ -211,6 +257,7 @@ __global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) 
   const long long M = L.counters[0];
   const long long total = M * (kLatD + 1);
   const unsigned long long qmask = (1ULL << kQBits) - 1;
+  const unsigned long long tmask = compact_mask(L);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long i = idx / (kLatD + 1);
@@ -232,7 +279,7 @@ __global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) 
 #pragma unroll
       for (int k = 0; k < kLatD; ++k) qq[k] = q[k] + dq + (k == j ? (side == 0 ? 1 : -1) : 0);
       unsigned long long nk = pack_key(qq, r2, 0, &bad) | (bbits << (kQBits * kLatD + 3));
-      res[side] = bad ? 0 : table_find(L, nk);
+      res[side] = bad ? 0 : table_find(L, tmask, nk);
     }
     L.nbr[(size_t)j * L.m_cap + i] = make_int2(res[0], res[1]);
   }
@@ -424,6 +471,8 @@ int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W
               N, H, W, n_pad, sigmargb, sigmaxy);
   COSA_LAUNCH(lattice_resolve_kernel, persistent_blocks(6 * L.P, 256), 256, 0, stream, L);
   // the vertex count lives on the device: size the grid for the SMs and let the kernel read it
+  COSA_LAUNCH(lattice_compact_clear_kernel, sm_count() * 8, 256, 0, stream, L);
+  COSA_LAUNCH(lattice_compact_insert_kernel, sm_count() * 8, 256, 0, stream, L);
   COSA_LAUNCH(lattice_neighbours_kernel, sm_count() * 8, 256, 0, stream, L);
   return 0;
 }

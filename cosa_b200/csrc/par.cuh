@@ -12,10 +12,27 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream);
 // aff [B, 8*n_dil, h, w] from imgs [B,3,h,w].
 int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream);
 
-// num_iter propagation steps src0 -> ... -> final_dst through the two scratch buffers (all distinct,
-// [B, c_stride, h, w]).  Live channels per image: nch_dev[b] when given, else nch_uniform.
-int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, float *final_dst,
-                          const int *nch_dev, int nch_uniform, int c_stride, int B, int h, int w, int n_dil,
-                          int num_iter, cudaStream_t stream);
+// Row layout of a mask buffer [B, c_stride, h, pitch]: the w interior columns start at column `off`; `padn`
+// replicated columns on either side make every neighbour load of the vectorised kernel an unclamped, 16-byte
+// aligned access.  {w, 0, 0} is the plain NCHW layout.
+struct MaskLayout {
+  int pitch, off, padn;
+};
+inline MaskLayout plain_layout(int w) { return MaskLayout{w, 0, 0}; }
+// Padded layout for dilations up to max_dil (interior 128-byte aligned), or the plain one when w % 4 != 0.
+MaskLayout padded_layout(int w, const int *dilations, int n_dil);
+inline size_t layout_floats(const MaskLayout &l, int B, int c_stride, int h) {
+  return (size_t)B * c_stride * h * l.pitch;
+}
+
+// num_iter propagation steps src0 -> ... -> final_dst.  The two scratch buffers use layout `lay`; src0 must use
+// `lay` too (use par_launch_pack for a plain tensor); final_dst has its own layout (plain for user tensors).
+// Live channels per image: nch_dev[b] when given, else nch_uniform.
+int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
+                          float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
+                          int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream);
+
+// plain [planes, h, w] -> layout `lay` (interior + replicated pads)
+int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, int h, int w, cudaStream_t stream);
 
 }  // namespace cosa

@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *
 }
 
 // ------------------------------------------------------------------------------------------------
-// One propagation step.  Thread per pixel, CH mask channels per pass held in registers; the affinity of the
-// pixel is streamed once per pass (coalesced per neighbour plane), mask neighbours come through L1.
+// One propagation step, generic form (any width, plain NCHW layout).  Thread per pixel, CH mask channels per
+// pass in registers; clamped scalar neighbour loads through L1.
 // nch_dev (optional) gives the number of live channels per image for the ragged cam2mask batch.
 // ------------------------------------------------------------------------------------------------
 template <int CH>
@@ -206,21 +206,12 @@ __global__ void __launch_bounds__(256) par_iterate_kernel(const float *__restric
       float a[8];
 #pragma unroll
       for (int m = 0; m < 8; ++m) a[m] = __ldg(A + (size_t)(8 * kd + m) * plane);
-      if (live == CH) {
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
+      for (int k = 0; k < CH; ++k) {
+        if (k < live) {
           const float *ch = s0 + (size_t)k * plane;
 #pragma unroll
           for (int m = 0; m < 8; ++m) acc[k] = fmaf(a[m], __ldg(ch + off[m]), acc[k]);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            const float *ch = s0 + (size_t)k * plane;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) acc[k] = fmaf(a[m], __ldg(ch + off[m]), acc[k]);
-          }
         }
       }
     }
@@ -230,23 +221,181 @@ __global__ void __launch_bounds__(256) par_iterate_kernel(const float *__restric
   }
 }
 
-__global__ void resize_align_corners_kernel(const float *__restrict__ in, float *__restrict__ out, int planes, int hi,
-                                            int wi, int ho, int wo, float sy, float sx) {
-  const long long total = (long long)planes * ho * wo;
+// ------------------------------------------------------------------------------------------------
+// One propagation step, vectorised form (w % 4 == 0, padded rows).  A thread owns 4 horizontally adjacent pixels
+// and CH channels: per dilation it streams the 8 affinity quads (128-bit, no L1 allocation) and, per channel and
+// neighbour row, three aligned 128-bit loads that cover the column offsets -d, 0, +d of all four pixels
+// (d % 4 == 0: the quads at x-d, x, x+d; d < 4: the quads left/centre/right, recombined in registers).
+// The replicated column pads make every load unclamped; rows are clamped by index.  A warp covers 4 rows x
+// 8 quads, i.e. one 128-byte line per row when the interior is 128-byte aligned.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ void fma4(float4 &acc, const float4 &a, const float4 &v) {
+  acc.x = fmaf(a.x, v.x, acc.x);
+  acc.y = fmaf(a.y, v.y, acc.y);
+  acc.z = fmaf(a.z, v.z, acc.z);
+  acc.w = fmaf(a.w, v.w, acc.w);
+}
+
+// the quads starting at column offsets -d and +d of the centre quad C, from the aligned quads L, C, R (d = 1..3)
+__device__ __forceinline__ void shifted_quads(const float4 &L, const float4 &C, const float4 &R, int d, float4 &m,
+                                              float4 &p) {
+  if (d == 1) {
+    m = make_float4(L.w, C.x, C.y, C.z);
+    p = make_float4(C.y, C.z, C.w, R.x);
+  } else if (d == 2) {
+    m = make_float4(L.z, L.w, C.x, C.y);
+    p = make_float4(C.z, C.w, R.x, R.y);
+  } else {
+    m = make_float4(L.y, L.z, L.w, C.x);
+    p = make_float4(C.w, R.x, R.y, R.z);
+  }
+}
+
+constexpr int kTileQuads = 8;    // 32 pixels wide
+constexpr int kTileRows = 32;
+
+template <int CH>
+__global__ void __launch_bounds__(256, 3)
+    par_iterate_vec_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
+                           float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
+                           int c_stride, int h, int w, int n_dil) {
+  const int wq = w >> 2;
+  const int xq = blockIdx.x * kTileQuads + (threadIdx.x & (kTileQuads - 1));
+  const int y = blockIdx.y * kTileRows + (threadIdx.x / kTileQuads);
+  const int b = blockIdx.z;
+  if (xq >= wq || y >= h) return;
+  const int x = xq << 2;
+  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
+  const size_t plane = (size_t)h * w;
+  const size_t iplane = (size_t)h * li.pitch, oplane = (size_t)h * lo.pitch;
+  const float *A = aff + (size_t)b * (8 * n_dil) * plane + (size_t)y * w + x;
+  const float *src = in + (size_t)b * c_stride * iplane + li.off + x;
+  float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
+
+  for (int c0 = 0; c0 < nch; c0 += CH) {
+    float4 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int live = min(CH, nch - c0);
+    const float *chan0 = src + (size_t)c0 * iplane;
+#pragma unroll 1
+    for (int kd = 0; kd < n_dil; ++kd) {
+      const int d = c_dil[kd];
+      const float *Ad = A + (size_t)(8 * kd) * plane;
+      // neighbour rows one at a time: three affinity quads (two for the centre row) stay live instead of eight
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const int yy = rr == 0 ? max(y - d, 0) : (rr == 1 ? y : min(y + d, h - 1));
+        const float *row = chan0 + (size_t)yy * li.pitch;
+        // get_kernel() order: row 0 -> taps 0,1,2; row 1 -> taps 3,4 (no centre); row 2 -> taps 5,6,7
+        const int m0 = rr == 0 ? 0 : (rr == 1 ? 3 : 5);
+        const float4 am = ldg_stream4(Ad + (size_t)m0 * plane);
+        const float4 ac = rr == 1 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_stream4(Ad + (size_t)(m0 + 1) * plane);
+        const float4 ap = ldg_stream4(Ad + (size_t)(rr == 1 ? m0 + 1 : m0 + 2) * plane);
+        if ((d & 3) == 0) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *q = row + (size_t)k * iplane;
+              fma4(acc[k], am, ldg4(q - d));
+              if (rr != 1) fma4(acc[k], ac, ldg4(q));
+              fma4(acc[k], ap, ldg4(q + d));
+            }
+          }
+        } else if (d < 4) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *q = row + (size_t)k * iplane;
+              const float4 C = ldg4(q);
+              float4 m, p;
+              shifted_quads(ldg4(q - 4), C, ldg4(q + 4), d, m, p);
+              fma4(acc[k], am, m);
+              if (rr != 1) fma4(acc[k], ac, C);
+              fma4(acc[k], ap, p);
+            }
+          }
+        } else {   // unaligned large dilation: scalar loads, still unclamped thanks to the pads
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *q = row + (size_t)k * iplane;
+              fma4(acc[k], am, make_float4(__ldg(q - d), __ldg(q - d + 1), __ldg(q - d + 2), __ldg(q - d + 3)));
+              if (rr != 1) fma4(acc[k], ac, ldg4(q));
+              fma4(acc[k], ap, make_float4(__ldg(q + d), __ldg(q + d + 1), __ldg(q + d + 2), __ldg(q + d + 3)));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      if (k < live) {
+        float *o = dst + (size_t)(c0 + k) * oplane;
+        *reinterpret_cast<float4 *>(o) = acc[k];
+        if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+          if (xq == 0) {
+            const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+            for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+          }
+          if (xq == wq - 1) {
+            const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+            for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+          }
+        }
+      }
+    }
+  }
+}
+
+// plain [planes, h, w] -> padded layout (interior + replicated column pads)
+__global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
+                                int h, int w) {
+  const int span = w + 2 * l.padn;
+  const long long total = (long long)planes * h * span;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % wo), y = (int)((i / wo) % ho);
-    const long long p = i / ((long long)wo * ho);
+    const int c = (int)(i % span);
+    const long long row = i / span;
+    const int x = clampi(c - l.padn, 0, w - 1);
+    dst[row * l.pitch + l.off - l.padn + c] = __ldg(src + row * w + x);
+  }
+}
+
+__global__ void resize_align_corners_kernel(const float *__restrict__ in, float *__restrict__ out, MaskLayout l,
+                                            int planes, int hi, int wi, int ho, int wo, float sy, float sx) {
+  const int span = wo + 2 * l.padn;
+  const long long total = (long long)planes * ho * span;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % span);
+    const long long row = i / span;
+    const int x = clampi(c - l.padn, 0, wo - 1), y = (int)(row % ho);
+    const long long p = row / ho;
     const Tap ty = tap_align_corners(y, sy, hi), tx = tap_align_corners(x, sx, wi);
     const float *s = in + p * (long long)hi * wi;
-    out[i] = bilerp_up(ty, tx, s[(size_t)ty.i0 * wi + tx.i0], s[(size_t)ty.i0 * wi + tx.i1],
-                       s[(size_t)ty.i1 * wi + tx.i0], s[(size_t)ty.i1 * wi + tx.i1]);
+    out[row * l.pitch + l.off - l.padn + c] =
+        bilerp_up(ty, tx, s[(size_t)ty.i0 * wi + tx.i0], s[(size_t)ty.i0 * wi + tx.i1],
+                  s[(size_t)ty.i1 * wi + tx.i0], s[(size_t)ty.i1 * wi + tx.i1]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host-side launchers (shared with cam2mask).
 // ------------------------------------------------------------------------------------------------
+MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
+  if (w % 4 != 0 || w < 8) return plain_layout(w);
+  int max_dil = 1;
+  for (int k = 0; k < n_dil; ++k) max_dil = max(max_dil, dilations[k]);
+  MaskLayout l;
+  l.padn = (max_dil + 3) & ~3;
+  l.off = (l.padn + 31) & ~31;
+  l.pitch = (l.off + w + l.padn + 31) & ~31;
+  return l;
+}
+
 int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream) {
   dim3 grid(ceil_div(w, 32), ceil_div(h, 4), B), block(128);
   if (n_dil == 6) {
@@ -257,25 +406,43 @@ int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int 
   return 0;
 }
 
-int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, float *final_dst,
-                          const int *nch_dev, int nch_uniform, int c_stride, int B, int h, int w, int n_dil,
-                          int num_iter, cudaStream_t stream) {
-  if (num_iter == 0) {
-    COSA_CUDA(cudaMemcpyAsync(final_dst, src0, (size_t)B * c_stride * h * w * sizeof(float),
-                              cudaMemcpyDeviceToDevice, stream));
-    return 0;
-  }
-  dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B), block(256);
+int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, int h, int w, cudaStream_t stream) {
+  const long long total = (long long)planes * h * (w + 2 * lay.padn);
+  const int blocks = (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(total, 256)));
+  COSA_LAUNCH(par_pack_kernel, blocks, 256, 0, stream, src, dst, lay, planes, h, w);
+  return 0;
+}
+
+int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
+                          float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
+                          int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream) {
+  if (num_iter <= 0) return COSA_E_ARG;   // callers handle the zero-iteration copy themselves
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
+  const bool vec = lay.padn > 0;
   const float *src = src0;
   for (int it = 0; it < num_iter; ++it) {
-    float *dst = (it == num_iter - 1) ? final_dst : ((it & 1) ? scratch_b : scratch_a);
-    if (wide) {
-      COSA_LAUNCH(par_iterate_kernel<8>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h, w,
-                  n_dil);
+    const bool last = it == num_iter - 1;
+    float *dst = last ? final_dst : ((it & 1) ? scratch_b : scratch_a);
+    const MaskLayout lo = last ? lay_final : lay;
+    if (vec) {
+      dim3 grid(ceil_div(w / 4, kTileQuads), ceil_div(h, kTileRows), B), block(256);
+      if (wide) {
+        COSA_LAUNCH(par_iterate_vec_kernel<8>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
+                    c_stride, h, w, n_dil);
+      } else {
+        COSA_LAUNCH(par_iterate_vec_kernel<4>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
+                    c_stride, h, w, n_dil);
+      }
     } else {
-      COSA_LAUNCH(par_iterate_kernel<4>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h, w,
-                  n_dil);
+      if (lo.pitch != w || lo.off != 0) return COSA_E_ARG;   // the generic kernel writes plain NCHW only
+      dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B), block(256);
+      if (wide) {
+        COSA_LAUNCH(par_iterate_kernel<8>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h,
+                    w, n_dil);
+      } else {
+        COSA_LAUNCH(par_iterate_kernel<4>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h,
+                    w, n_dil);
+      }
     }
     src = dst;
   }
@@ -286,10 +453,13 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
 
 using namespace cosa;
 
+// scratch: affinity [B,8*n_dil,h,w] + two mask buffers in the widest layout cosa_par_forward uses
+// (column pads of at most 24: wider dilations take the plain layout and the generic kernel)
 extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
   const size_t plane = (size_t)h * w;
+  const size_t pitch = (size_t)((32 + w + 24 + 31) & ~31);
   return align_up((size_t)B * 8 * n_dil * plane * sizeof(float), 256) +
-         2 * align_up((size_t)B * C * plane * sizeof(float), 256);
+         2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256);
 }
 
 extern "C" int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const int *dilations, int n_dil,
@@ -309,30 +479,40 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
   cudaStream_t s = (cudaStream_t)stream;
   COSA_CHECK(par_upload_constants(dilations, n_dil, s));
   const size_t plane = (size_t)h * w;
+  MaskLayout lay = padded_layout(w, dilations, n_dil);
+  if (lay.padn > 24) lay = plain_layout(w);   // keeps the scratch within cosa_par_ws_bytes
+  const MaskLayout plain = plain_layout(w);
   Arena arena(ws);
   float *aff = arena.take<float>((size_t)B * 8 * n_dil * plane);
-  float *buf_a = arena.take<float>((size_t)B * C * plane);
-  float *buf_b = arena.take<float>((size_t)B * C * plane);
+  float *buf_a = arena.take<float>(layout_floats(lay, B, C, h));
+  float *buf_b = arena.take<float>(layout_floats(lay, B, C, h));
+  const bool resize = (hm != h || wm != w);
+  const long long total = (long long)B * C * plane;
+  const int blocks = (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(total, 256)));
+  if (num_iter == 0) {   // PAR.py:66 alone
+    if (resize) {
+      const float sy = h > 1 ? (float)(hm - 1) / (float)(h - 1) : 0.0f;
+      const float sx = w > 1 ? (float)(wm - 1) / (float)(w - 1) : 0.0f;
+      COSA_LAUNCH(resize_align_corners_kernel, blocks, 256, 0, s, masks_in, masks_out, plain, B * C, hm, wm, h, w, sy,
+                  sx);
+    } else {
+      COSA_CUDA(cudaMemcpyAsync(masks_out, masks_in, total * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+  }
   COSA_CHECK(par_launch_affinity(imgs, aff, B, h, w, n_dil, s));
+  // stage the input in the iteration layout: buf_b (then steps alternate buf_a / buf_b, the last one writes out)
   const float *src0 = masks_in;
-  int iters = num_iter;
-  if (hm != h || wm != w) {
-    // PAR.py:66 - bilinear, align_corners=True.  With no iteration left to run the resize is the output.
+  if (resize) {
     const float sy = h > 1 ? (float)(hm - 1) / (float)(h - 1) : 0.0f;
     const float sx = w > 1 ? (float)(wm - 1) / (float)(w - 1) : 0.0f;
-    const long long total = (long long)B * C * plane;
-    const int blocks = (int)min((long long)sm_count() * 8, ceil_div_ll(total, 256));
-    float *dst = (iters == 0) ? masks_out : buf_b;
-    COSA_LAUNCH(resize_align_corners_kernel, blocks, 256, 0, s, masks_in, dst, B * C, hm, wm, h, w, sy, sx);
-    if (iters == 0) return 0;
-    // first step reads the resized masks from buf_b and writes buf_a (or masks_out when it is the only one)
-    COSA_CHECK(par_launch_iterations(aff, buf_b, buf_a, buf_a, (iters == 1) ? masks_out : buf_a, nullptr, C, C, B, h,
-                                     w, n_dil, 1, s));
-    if (iters == 1) return 0;
-    src0 = buf_a;
-    iters -= 1;
-    // remaining steps ping-pong buf_b / (a third slice is not needed: buf_a is only read by the next step)
-    return par_launch_iterations(aff, src0, buf_b, buf_a, masks_out, nullptr, C, C, B, h, w, n_dil, iters, s);
+    COSA_LAUNCH(resize_align_corners_kernel, blocks, 256, 0, s, masks_in, buf_b, lay, B * C, hm, wm, h, w, sy, sx);
+    src0 = buf_b;
+  } else if (lay.padn > 0) {
+    COSA_CHECK(par_launch_pack(masks_in, buf_b, lay, B * C, h, w, s));
+    src0 = buf_b;
   }
-  return par_launch_iterations(aff, src0, buf_a, buf_b, masks_out, nullptr, C, C, B, h, w, n_dil, iters, s);
+  // step 0 reads src0 (buf_b or the caller's tensor) and writes buf_a, step 1 writes buf_b, ...
+  return par_launch_iterations(aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, n_dil, num_iter,
+                               s);
 }
