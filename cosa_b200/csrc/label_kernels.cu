@@ -519,9 +519,8 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
   MaskLayout lay_fin = lay;
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
   if (refine) {
-    COSA_CHECK(par_launch_affinity(img_small, aff, B, g.h, g.w, n_dil, s));
-    COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
-                                     num_iter, s));
+    COSA_CHECK(par_refine_batch(img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
+                                num_iter, s));
     refined = fin;
   }
   dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);

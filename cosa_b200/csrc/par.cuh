@@ -32,6 +32,12 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
                           float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
                           int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream);
 
+// Affinity (into aff [B, 8*n_dil, h, w]) + num_iter steps for the whole batch.  Buffer conventions as in
+// par_launch_iterations.
+int par_refine_batch(const float *imgs, float *aff, const float *src0, float *scratch_a, float *scratch_b,
+                     MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
+                     int c_stride, int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream);
+
 // plain [planes, h, w] -> layout `lay` (interior + replicated pads)
 int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, int h, int w, cudaStream_t stream);
 

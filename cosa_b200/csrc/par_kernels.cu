@@ -8,6 +8,7 @@
 // Neighbour n = 8*k + m: dilation k in ctor order, direction m in get_kernel() order (PAR.py:10-24):
 // (-,-) (-,0) (-,+) (0,-) (0,+) (+,-) (+,0) (+,+), borders replicated (PAR.py:44).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "par.cuh"
@@ -253,17 +254,25 @@ __device__ __forceinline__ void shifted_quads(const float4 &L, const float4 &C, 
   }
 }
 
-constexpr int kTileQuads = 8;    // 32 pixels wide
-constexpr int kTileRows = 32;
+static int par_tile_log2() {   // width of the CTA tile in quads (log2); COSA_PAR_TILE_LOG2 overrides
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("COSA_PAR_TILE_LOG2");
+    v = e ? atoi(e) : 3;
+    if (v < 0 || v > 8) v = 3;
+  }
+  return v;
+}
 
 template <int CH>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
     par_iterate_vec_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
                            float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
-                           int c_stride, int h, int w, int n_dil) {
+                           int c_stride, int h, int w, int n_dil, int tq_log2) {
+  // CTA tile = 2^tq_log2 quads x (256 >> tq_log2) rows
   const int wq = w >> 2;
-  const int xq = blockIdx.x * kTileQuads + (threadIdx.x & (kTileQuads - 1));
-  const int y = blockIdx.y * kTileRows + (threadIdx.x / kTileQuads);
+  const int xq = (blockIdx.x << tq_log2) + (threadIdx.x & ((1 << tq_log2) - 1));
+  const int y = blockIdx.y * (256 >> tq_log2) + (threadIdx.x >> tq_log2);
   const int b = blockIdx.z;
   if (xq >= wq || y >= h) return;
   const int x = xq << 2;
@@ -279,52 +288,62 @@ __global__ void __launch_bounds__(256, 3)
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int live = min(CH, nch - c0);
-    const float *chan0 = src + (size_t)c0 * iplane;
 #pragma unroll 1
     for (int kd = 0; kd < n_dil; ++kd) {
       const int d = c_dil[kd];
-      const float *Ad = A + (size_t)(8 * kd) * plane;
-      // neighbour rows one at a time: three affinity quads (two for the centre row) stay live instead of eight
+      float4 a[8];
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) {
-        const int yy = rr == 0 ? max(y - d, 0) : (rr == 1 ? y : min(y + d, h - 1));
-        const float *row = chan0 + (size_t)yy * li.pitch;
-        // get_kernel() order: row 0 -> taps 0,1,2; row 1 -> taps 3,4 (no centre); row 2 -> taps 5,6,7
-        const int m0 = rr == 0 ? 0 : (rr == 1 ? 3 : 5);
-        const float4 am = ldg_stream4(Ad + (size_t)m0 * plane);
-        const float4 ac = rr == 1 ? make_float4(0.f, 0.f, 0.f, 0.f) : ldg_stream4(Ad + (size_t)(m0 + 1) * plane);
-        const float4 ap = ldg_stream4(Ad + (size_t)(rr == 1 ? m0 + 1 : m0 + 2) * plane);
-        if ((d & 3) == 0) {
+      for (int m = 0; m < 8; ++m) a[m] = ldg4c(A + (size_t)(8 * kd + m) * plane);   // L2-resident (chunked batch)
+      const size_t rm = (size_t)max(y - d, 0) * li.pitch, r0 = (size_t)y * li.pitch,
+                   rp = (size_t)min(y + d, h - 1) * li.pitch;
+      if ((d & 3) == 0) {
 #pragma unroll
-          for (int k = 0; k < CH; ++k) {
-            if (k < live) {
-              const float *q = row + (size_t)k * iplane;
-              fma4(acc[k], am, ldg4(q - d));
-              if (rr != 1) fma4(acc[k], ac, ldg4(q));
-              fma4(acc[k], ap, ldg4(q + d));
-            }
+        for (int k = 0; k < CH; ++k) {
+          if (k < live) {
+            const float *ch = src + (size_t)(c0 + k) * iplane;
+            fma4(acc[k], a[0], ldg4(ch + rm - d));
+            fma4(acc[k], a[1], ldg4(ch + rm));
+            fma4(acc[k], a[2], ldg4(ch + rm + d));
+            fma4(acc[k], a[3], ldg4(ch + r0 - d));
+            fma4(acc[k], a[4], ldg4(ch + r0 + d));
+            fma4(acc[k], a[5], ldg4(ch + rp - d));
+            fma4(acc[k], a[6], ldg4(ch + rp));
+            fma4(acc[k], a[7], ldg4(ch + rp + d));
           }
-        } else if (d < 4) {
+        }
+      } else if (d < 4) {
 #pragma unroll
-          for (int k = 0; k < CH; ++k) {
-            if (k < live) {
-              const float *q = row + (size_t)k * iplane;
-              const float4 C = ldg4(q);
-              float4 m, p;
-              shifted_quads(ldg4(q - 4), C, ldg4(q + 4), d, m, p);
-              fma4(acc[k], am, m);
-              if (rr != 1) fma4(acc[k], ac, C);
-              fma4(acc[k], ap, p);
-            }
+        for (int k = 0; k < CH; ++k) {
+          if (k < live) {
+            const float *ch = src + (size_t)(c0 + k) * iplane;
+            float4 m, p;
+            float4 C = ldg4(ch + rm);
+            shifted_quads(ldg4(ch + rm - 4), C, ldg4(ch + rm + 4), d, m, p);
+            fma4(acc[k], a[0], m); fma4(acc[k], a[1], C); fma4(acc[k], a[2], p);
+            C = ldg4(ch + r0);
+            shifted_quads(ldg4(ch + r0 - 4), C, ldg4(ch + r0 + 4), d, m, p);
+            fma4(acc[k], a[3], m); fma4(acc[k], a[4], p);
+            C = ldg4(ch + rp);
+            shifted_quads(ldg4(ch + rp - 4), C, ldg4(ch + rp + 4), d, m, p);
+            fma4(acc[k], a[5], m); fma4(acc[k], a[6], C); fma4(acc[k], a[7], p);
           }
-        } else {   // unaligned large dilation: scalar loads, still unclamped thanks to the pads
+        }
+      } else {   // unaligned large dilation: scalar loads, still unclamped thanks to the pads
 #pragma unroll
-          for (int k = 0; k < CH; ++k) {
-            if (k < live) {
-              const float *q = row + (size_t)k * iplane;
-              fma4(acc[k], am, make_float4(__ldg(q - d), __ldg(q - d + 1), __ldg(q - d + 2), __ldg(q - d + 3)));
-              if (rr != 1) fma4(acc[k], ac, ldg4(q));
-              fma4(acc[k], ap, make_float4(__ldg(q + d), __ldg(q + d + 1), __ldg(q + d + 2), __ldg(q + d + 3)));
+        for (int k = 0; k < CH; ++k) {
+          if (k < live) {
+            const float *ch = src + (size_t)(c0 + k) * iplane;
+            const size_t rows[3] = {rm, r0, rp};
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+              const float *q = ch + rows[rr];
+#pragma unroll
+              for (int cc = 0; cc < 3; ++cc) {
+                if (rr == 1 && cc == 1) continue;
+                const int mi = rr * 3 + cc - (rr * 3 + cc > 4 ? 1 : 0);
+                const float *qq = q + (cc - 1) * d;
+                fma4(acc[k], a[mi], make_float4(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3)));
+              }
             }
           }
         }
@@ -425,13 +444,14 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
     float *dst = last ? final_dst : ((it & 1) ? scratch_b : scratch_a);
     const MaskLayout lo = last ? lay_final : lay;
     if (vec) {
-      dim3 grid(ceil_div(w / 4, kTileQuads), ceil_div(h, kTileRows), B), block(256);
+      const int tq = par_tile_log2();
+      dim3 grid(ceil_div(w / 4, 1 << tq), ceil_div(h, 256 >> tq), B), block(256);
       if (wide) {
         COSA_LAUNCH(par_iterate_vec_kernel<8>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
-                    c_stride, h, w, n_dil);
+                    c_stride, h, w, n_dil, tq);
       } else {
         COSA_LAUNCH(par_iterate_vec_kernel<4>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
-                    c_stride, h, w, n_dil);
+                    c_stride, h, w, n_dil, tq);
       }
     } else {
       if (lo.pitch != w || lo.off != 0) return COSA_E_ARG;   // the generic kernel writes plain NCHW only
@@ -447,6 +467,17 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
     src = dst;
   }
   return 0;
+}
+
+// Affinity + num_iter propagation steps for the whole batch.  (Splitting the batch into L2-sized chunks so that
+// the affinity planes are re-read from L2 was measured and is slower: the step is bound by the L1 path of the
+// neighbour loads, not by the affinity stream - see profiles/README.md.)
+int par_refine_batch(const float *imgs, float *aff, const float *src0, float *scratch_a, float *scratch_b,
+                     MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
+                     int c_stride, int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream) {
+  COSA_CHECK(par_launch_affinity(imgs, aff, B, h, w, n_dil, stream));
+  return par_launch_iterations(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
+                               c_stride, B, h, w, n_dil, num_iter, stream);
 }
 
 }  // namespace cosa
@@ -500,7 +531,6 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
     }
     return 0;
   }
-  COSA_CHECK(par_launch_affinity(imgs, aff, B, h, w, n_dil, s));
   // stage the input in the iteration layout: buf_b (then steps alternate buf_a / buf_b, the last one writes out)
   const float *src0 = masks_in;
   if (resize) {
@@ -513,6 +543,7 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
     src0 = buf_b;
   }
   // step 0 reads src0 (buf_b or the caller's tensor) and writes buf_a, step 1 writes buf_b, ...
-  return par_launch_iterations(aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, n_dil, num_iter,
-                               s);
+  // (src0 is the caller's tensor only in the plain layout, whose strides equal the scratch strides)
+  return par_refine_batch(imgs, aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, n_dil, num_iter,
+                          s);
 }

@@ -1,0 +1,174 @@
+"""GPU parity on the edge cases of the path: ragged / odd geometries (generic kernels), COCO-sized class counts,
+empty and missing boxes, images without foreground, batches above the 64-image lattice chunk, exotic dilations,
+and the lattice key-range guard.  Same bars as tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_inf
+from test_gpu_parity import NEAR_TIE, TOL, _oracle_margin, assert_close, assert_same, check_labels_near_tie
+
+pytestmark = pytest.mark.gpu
+DIL = [1, 2, 4, 8, 12, 24]
+
+
+@pytest.fixture(scope="module")
+def cosa():
+    import cosa_b200
+    cosa_b200._lib.load()
+    return cosa_b200
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import reference_port
+    return reference_port
+
+
+def batch(**kw):
+    from cosa_b200 import synthetic
+    return synthetic.synthetic_batch(**kw)
+
+
+def to_cuda(d):
+    return {k: (v.cuda() if k != "img_box" else v) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("kw", [
+    dict(B=2, C=81, H=96, W=96, n_fg=3, seed=101),                   # COCO class count
+    dict(B=2, C=21, H=66, W=90, n_fg=2, seed=102, box="crop"),       # half-res 33x45: generic (non-vector) kernels
+    dict(B=1, C=21, H=50, W=72, n_fg=5, seed=103),                   # 25x36: vector path with nch = 12 (two passes)
+    dict(B=3, C=4, H=32, W=48, n_fg=3, seed=104, cam_kind="grid"),   # all classes present
+])
+def test_cam2mask_and_energy_vs_oracle(cosa, port, kw):
+    host = batch(**kw)
+    d = to_cuda(host)
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    args = dict(img_boxes=host["img_box"], threshold_high=0.7, threshold_low=0.25)
+    got = cosa.cam2mask(images=d["img_denorm"], cams=d["cams"], cls_labels=d["cls_label"], refine_model=par, **args)
+    want = port.cam2mask(images=host["img_denorm"], cams=host["cams"], cls_labels=host["cls_label"],
+                         refine_model=port.ParOracle(), **args)
+    margins = _oracle_margin(port, dict(images=host["img_denorm"], cams=host["cams"], cls_label=host["cls_label"]),
+                             port.ParOracle())
+    n = check_labels_near_tie(got, want, margins, "cam2mask %s" % kw)
+    # energy loss on the ORACLE's labels so that both sides see identical inputs
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = d["logits"].clone().requires_grad_(True)
+    loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=want.cuda(), img_box=host["img_box"], loss_layer=layer)
+    loss.backward()
+    o_logit = host["logits"].clone().requires_grad_(True)
+    o_loss = port.get_energy_loss(host["simg"], o_logit, want, host["img_box"])
+    o_loss.backward()
+    r1 = assert_close(loss, o_loss, "energy loss %s" % kw)
+    r2 = assert_close(logit.grad, o_logit.grad, "energy grad %s" % kw)
+    print("%s: label flips %d, loss rel %.2g, grad rel %.2g" % (kw, n, r1, r2))
+
+
+def test_boxes_empty_missing_and_no_foreground(cosa, port):
+    host = batch(B=4, C=6, H=48, W=64, n_fg=2, seed=7)
+    host["cls_label"][2] = 0                          # image 2: no foreground class -> nc = 1, all background
+    host["cams"][2] = 0
+    d = to_cuda(host)
+    boxes = [[0, 48, 0, 64], [10, 10, 0, 64], [5, 40, -20, -4]]      # full, empty rows, negative ends; image 3: no box
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    got = cosa.cam2mask(images=d["img_denorm"], img_boxes=boxes, cams=d["cams"], cls_labels=d["cls_label"],
+                        threshold_high=0.7, threshold_low=0.25, refine_model=par)
+    want = port.cam2mask(images=host["img_denorm"], img_boxes=boxes, cams=host["cams"], cls_labels=host["cls_label"],
+                         threshold_high=0.7, threshold_low=0.25, refine_model=port.ParOracle())
+    assert int((got.cpu() != want).sum()) <= 1
+    assert bool((got[1] == 255).all()) and bool((got[3] == 255).all())          # empty box / no box: all ignore
+    assert set(got[2].unique().tolist()) <= {0.0, 255.0}
+    # the same boxes through cam_to_label and get_energy_loss
+    _, lab = cosa.cam_to_label(d["cams"], d["cls_label"], img_box=boxes, bkg_thre=0.5, high_thre=0.7, low_thre=0.25,
+                               ignore_mid=True, ignore_index=255)
+    _, olab = port.cam_to_label(host["cams"], host["cls_label"], img_box=boxes, bkg_thre=0.5, high_thre=0.7,
+                                low_thre=0.25, ignore_mid=True, ignore_index=255)
+    assert_same(lab, olab, "cam_to_label with ragged boxes")
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = d["logits"].clone().requires_grad_(True)
+    loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=want.cuda(), img_box=boxes, loss_layer=layer)
+    loss.backward()
+    o_logit = host["logits"].clone().requires_grad_(True)
+    o_loss = port.get_energy_loss(host["simg"], o_logit, want, boxes)
+    o_loss.backward()
+    assert_close(loss, o_loss, "energy loss, ragged boxes")
+    assert_close(logit.grad, o_logit.grad, "energy grad, ragged boxes")
+
+
+def test_energy_function_more_than_one_lattice_chunk(cosa, port):
+    """N = 70 > 64 images: the lattice runs in two chunks that share one loss accumulator."""
+    gen = torch.Generator().manual_seed(5)
+    N, K, H, W = 70, 3, 10, 12
+    images = torch.randint(0, 256, (N, 3, H, W), generator=gen).float()
+    segs = torch.rand((N, K, H, W), generator=gen).softmax(dim=1)
+    rois = (torch.rand((N, H, W), generator=gen) < 0.9).float()
+    unlabel = torch.rand((N, H, W), generator=gen) < 0.2
+    want_loss, want_as, _ = port.dense_energy_function_forward(images, segs, 15.0, 50.0, rois, unlabel)
+    s = segs.cuda().requires_grad_(True)
+    loss = cosa.DenseEnergyLossFunction.apply(images.cuda(), s, 15.0, 50.0, rois.cuda(), unlabel.cuda())
+    loss.backward()
+    assert_close(loss, np.array([want_loss]), "chunked energy loss")
+    want_grad = port.dense_energy_function_backward(torch.ones(1), want_as, rois, N)
+    assert_close(s.grad, want_grad, "chunked energy grad")
+
+
+@pytest.mark.parametrize("dilations", [[3, 6], [1, 5, 9, 32], [2], [1, 2, 4, 8, 12, 24, 30]])
+def test_par_exotic_dilations(cosa, port, dilations):
+    """Unaligned dilations (scalar branch of the vector kernel), pads wider than 24 (plain layout), 1 and 7 dilations."""
+    gen = torch.Generator().manual_seed(sum(dilations))
+    imgs = torch.randint(0, 256, (2, 3, 36, 48), generator=gen).float() / 255
+    masks = torch.rand((2, 5, 36, 48), generator=gen)
+    got = cosa.PAR(num_iter=4, dilations=dilations)(imgs.cuda(), masks.cuda())
+    assert_close(got, port.par_forward(imgs, masks, tuple(dilations), 4), "PAR dilations %s" % dilations)
+
+
+def test_par_zero_iterations_and_resize_only(cosa, port):
+    gen = torch.Generator().manual_seed(1)
+    imgs = torch.rand((1, 3, 24, 32), generator=gen)
+    masks = torch.rand((1, 3, 12, 16), generator=gen)
+    assert_close(cosa.PAR(num_iter=0, dilations=DIL)(imgs.cuda(), masks.cuda()),
+                 port.par_forward(imgs, masks, DIL, 0), "PAR with num_iter=0 (resize only)")
+    same = torch.rand((1, 3, 24, 32), generator=gen)
+    assert torch.equal(cosa.PAR(num_iter=0, dilations=DIL)(imgs.cuda(), same.cuda()).cpu(), same)
+
+
+def test_cam_normalize_large_planes(cosa, port):
+    gen = torch.Generator().manual_seed(3)
+    scales = [torch.rand((2, 20, 448, 448), generator=gen) * s - 0.1 for s in (1.0, 0.5, 1.5)]
+    got = cosa.cam_normalize([s.cuda() for s in scales])
+    assert_same(got, port.normalize_cam(scales), "cam_normalize 448x448 (multi-CTA min/max)")
+    one = cosa.cam_normalize(scales[0].cuda())
+    assert_same(one, port.normalize_cam([scales[0]]), "cam_normalize, single tensor")
+
+
+def test_lattice_key_range_guard(cosa):
+    """Coordinates beyond the packed-key range must raise the flag instead of aliasing silently."""
+    from cosa_b200 import bilateralfilter as bf
+    N, K, H, W = 1, 2, 16, 16
+    img = torch.rand((N, 3, H, W), device="cuda") * 255
+    x = torch.rand((N, K, H, W), device="cuda")
+    out = torch.empty_like(x)
+    bf.bilateralfilter_batch(img, x, out, N, K, H, W, 15.0, 50.0)
+    assert bf.lattice_stats(N, K, H, W)[1] == 0
+    bf.bilateralfilter_batch(img, x, out, N, K, H, W, 0.001, 50.0)       # sigma_rgb = 0.001 -> coordinates ~ 1e6
+    assert bf.lattice_stats(N, K, H, W)[1] == 1
+
+
+def test_high_resolution_energy_matches_oracle(cosa, port):
+    """One image of the 512^2 sweep point (BASELINE.json configs[3]) against the oracle."""
+    host = batch(B=1, C=21, H=512, W=512, n_fg=2, seed=512)
+    d = to_cuda(host)
+    label = port.cam2mask(images=host["img_denorm"], img_boxes=host["img_box"], cams=host["cams"],
+                          cls_labels=host["cls_label"], threshold_high=0.7, threshold_low=0.25)
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    logit = d["logits"].clone().requires_grad_(True)
+    loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=label.cuda(), img_box=host["img_box"], loss_layer=layer)
+    loss.backward()
+    o_logit = host["logits"].clone().requires_grad_(True)
+    o_loss = port.get_energy_loss(host["simg"], o_logit, label, host["img_box"])
+    o_loss.backward()
+    assert_close(loss, o_loss, "512^2 energy loss")
+    assert_close(logit.grad, o_logit.grad, "512^2 energy grad")
+    got = cosa.cam2mask(images=d["img_denorm"], img_boxes=host["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
+                        threshold_high=0.7, threshold_low=0.25)
+    assert int((got.cpu() != label).sum()) <= 1e-5 * label.numel()
