@@ -64,7 +64,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the GPU phases of the benchmark run."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -78,7 +78,7 @@ class ClockSampler:
         try:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -259,17 +259,18 @@ def run_cosa_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()          # sampled from the warm-up to the end of the e2e loop (nvidia-smi period: 50 ms)
     for _ in range(max(3, args.warmup)):
         label, loss, grad = step(d)
     sync_all()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        ev0.record()
-        for _ in range(args.steps):
-            label, loss, grad = step(d)
-        ev1.record()
-        sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        label, loss, grad = step(d)
+    ev1.record()
+    sync_all()
     ms_total = sharding.all_reduce_max(ev0.elapsed_time(ev1))
     launches = _lib.launch_count() - launches0
     total_images = sharding.all_reduce_sum(B * args.steps)
@@ -357,6 +358,8 @@ def run_cosa_arm(args):
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "ms_per_step": e2e_ms / e2e_steps,
                "note": "pinned host buffers; upload of step i+1 overlaps the kernels of step i (copy stream)"}
+
+    clocks.__exit__(None, None, None)
 
     # ---- CPU baseline on this host (rank 0, N = 1 only), bounded sample ----------------------------------
     cpu = None

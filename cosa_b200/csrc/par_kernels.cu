@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256, 2)
     par_iterate_vec_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
                            float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
                            int c_stride, int h, int w, int n_dil, int tq_log2) {
-  // CTA tile = 2^tq_log2 quads x (256 >> tq_log2) rows
+  // CTA tile = 2^tq_log2 quads x (256 >> tq_log2) rows; a warp then covers 4 rows x 8 quads (one 128-byte line per row)
   const int wq = w >> 2;
   const int xq = (blockIdx.x << tq_log2) + (threadIdx.x & ((1 << tq_log2) - 1));
   const int y = blockIdx.y * (256 >> tq_log2) + (threadIdx.x >> tq_log2);
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256, 2)
       const int d = c_dil[kd];
       float4 a[8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) a[m] = ldg4c(A + (size_t)(8 * kd + m) * plane);   // L2-resident (chunked batch)
+      for (int m = 0; m < 8; ++m) a[m] = ldg_stream4(A + (size_t)(8 * kd + m) * plane);
       const size_t rm = (size_t)max(y - d, 0) * li.pitch, r0 = (size_t)y * li.pitch,
                    rp = (size_t)min(y + d, h - 1) * li.pitch;
       if ((d & 3) == 0) {
@@ -417,7 +417,9 @@ MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
 
 int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream) {
   dim3 grid(ceil_div(w, 32), ceil_div(h, 4), B), block(128);
-  if (n_dil == 6) {
+  static int force_generic = -1;
+  if (force_generic < 0) force_generic = getenv("COSA_PAR_AFF_GENERIC") ? 1 : 0;
+  if (n_dil == 6 && !force_generic) {
     COSA_LAUNCH(par_affinity_kernel<6>, grid, block, 0, stream, imgs, aff, h, w);
   } else {
     COSA_LAUNCH(par_affinity_generic_kernel, grid, block, 0, stream, imgs, aff, h, w, n_dil);

@@ -359,9 +359,11 @@ def test_full_size_filter_is_linear_and_symmetric(cosa, voc_batch):
     assert M[1] == 0
     lin = filt(2 * x - 3 * y) - (2 * fx - 3 * fy)
     assert float(lin.abs().max() / fx.abs().max()) < 1e-5
-    # splat and slice use the same weights and the blur is symmetric, so <x, F y> = <F x, y>
+    # splat and slice use the same weights and every blur axis is symmetric, so <x, F y> ~ <F x, y>; only
+    # approximately, because the six axis blurs do not commute where the lattice has missing neighbours (the
+    # reference's backward relies on the same approximation, seg_helper.py:898-903)
     lhs, rhs = (x.double() * fy.double()).sum(), (fx.double() * y.double()).sum()
-    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-5
+    assert abs(float(lhs - rhs)) / abs(float(lhs)) < 1e-3
     # images are independent: filtering one image alone gives the same rows
     o1 = torch.empty((1, K, H, W), device="cuda")
     bf.bilateralfilter_batch(img[5:6].contiguous(), x[5:6].contiguous(), o1, 1, K, H, W, 15.0, 50.0)
@@ -377,7 +379,7 @@ def test_full_size_energy_loss_and_grad(cosa, voc_batch):
     logit = d["logits"].clone().requires_grad_(True)
     loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=d["img_box"], loss_layer=layer)
     loss.backward()
-    assert torch.isfinite(loss).all() and float(loss) < 0
+    assert torch.isfinite(loss).all() and float(loss.detach()) < 0
     assert torch.isfinite(logit.grad).all()
     # softmax backward: the gradient of every pixel sums to zero over the classes
     assert float(logit.grad.sum(1).abs().max()) <= 1e-5 * float(logit.grad.abs().max())
