@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="cosa", choices=["cosa", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak scaling)")
     ap.add_argument("--workload", default="voc", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=0, help="override H = W (BASELINE.json configs[3] sweep: 512..1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -115,7 +116,10 @@ class ClockSampler:
 
 def make_inputs(args, rank):
     from cosa_b200 import synthetic
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.size:
+        wl["H"] = wl["W"] = args.size
+        wl["name"] = wl["name"].replace("448x448", "%dx%d" % (args.size, args.size)) + " [size sweep]"
     seed = 1000 * (1 if args.workload == "voc" else 2) + rank
     return synthetic.synthetic_batch(B=args.batch, C=wl["C"], H=wl["H"], W=wl["W"], n_fg=wl["n_fg"], seed=seed), wl
 
