@@ -551,7 +551,7 @@ extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downsc
   ResizeGeom g;
   cam2mask_geom(H, W, downscale, &g);
   const size_t hw = (size_t)g.h * g.w;
-  const size_t pitch = use_par ? (size_t)((32 + g.w + 24 + 31) & ~31) : (size_t)g.w;
+  const size_t pitch = use_par ? (size_t)max_padded_pitch(g.w) : (size_t)g.w;
   size_t bytes = align_up((size_t)B * (C1 + 1) * sizeof(int), 256) + 2 * align_up((size_t)B * sizeof(int), 256);
   const int n_mask_bufs = use_par ? 4 : 1;
   bytes += n_mask_bufs * align_up((size_t)B * 2 * (C1 + 1) * g.h * pitch * sizeof(float), 256);

@@ -19,6 +19,8 @@ struct MaskLayout {
   int pitch, off, padn;
 };
 inline MaskLayout plain_layout(int w) { return MaskLayout{w, 0, 0}; }
+// Upper bound of the pitch of any padded layout the PAR path uses (pads of at most 24 columns).
+inline int max_padded_pitch(int w) { return (32 + ((w + 31) & ~31) + 24 + 31) & ~31; }
 // Padded layout for dilations up to max_dil (interior 128-byte aligned), or the plain one when w % 4 != 0.
 MaskLayout padded_layout(int w, const int *dilations, int n_dil);
 inline size_t layout_floats(const MaskLayout &l, int B, int c_stride, int h) {

@@ -369,6 +369,202 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One propagation step with the near neighbourhood staged in shared memory by the TMA unit.
+//
+// CTA tile: 32 rows x 32 pixels (256 threads, 4 pixels x CH channels each, as in the vector kernel).  The mask tile
+// of every live channel, with a halo of kHalo = 8 pixels, is brought into shared memory by cp.async.bulk row copies
+// (one 192-byte copy per tile row and channel, completion on an mbarrier): 32 of the 48 neighbours (dilations
+// 1, 2, 4, 8) are then served by conflict-free 128-bit shared-memory loads; only dilations > 8 go to L1/L2.
+// Rows are clamped when the copy is issued (replicate border), columns come from the replicated column pads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHalo = 8;
+constexpr int kTileW = 32, kTileH = 32;
+constexpr int kSmemW = kTileW + 2 * kHalo;   // 48 floats = 192 bytes per staged row
+constexpr int kSmemH = kTileH + 2 * kHalo;   // 48 rows
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                              unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
+    par_iterate_smem_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
+                            float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
+                            int c_stride, int h, int w, int n_dil) {
+  extern __shared__ __align__(128) float s_tile[];   // [CH][kSmemH][kSmemW]
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int wq = w >> 2;
+  const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int xq = (x0 >> 2) + tq, y = y0 + tr, x = x0 + (tq << 2);
+  const int b = blockIdx.z;
+  const bool active = xq < wq && y < h;            // everybody stays for the staging and the barrier
+  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
+  const size_t plane = (size_t)h * w;
+  const size_t iplane = (size_t)h * li.pitch, oplane = (size_t)h * lo.pitch;
+  const float *A = aff + (size_t)b * (8 * n_dil) * plane + (size_t)min(y, h - 1) * w + min(x, w - 4);
+  const float *src = in + (size_t)b * c_stride * iplane + li.off;
+  float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
+
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  unsigned phase = 0;
+  for (int c0 = 0; c0 < nch; c0 += CH) {
+    const int live = min(CH, nch - c0);
+    // ---- stage the halo tile of the live channels: one bulk row copy per (channel, row) ---------------------
+    if (threadIdx.x == 0) mbar_expect_tx(&s_bar, (unsigned)(live * kSmemH * kSmemW * sizeof(float)));
+    for (int i = threadIdx.x; i < live * kSmemH; i += 256) {
+      const int k = i / kSmemH, r = i - k * kSmemH;
+      const int gy = min(max(y0 - kHalo + r, 0), h - 1);
+      bulk_copy_g2s(s_tile + (size_t)i * kSmemW, src + (size_t)(c0 + k) * iplane + (size_t)gy * li.pitch + (x0 - kHalo),
+                    kSmemW * sizeof(float), &s_bar);
+    }
+    float4 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool staged = false;
+    // far dilations first (global loads) while the bulk copies are in flight, then the staged near ones
+#pragma unroll 1
+    for (int it = 0; it < 2 * n_dil; ++it) {
+      const int kd = it < n_dil ? it : it - n_dil;
+      const int d = c_dil[kd];
+      if ((d <= kHalo) != (it >= n_dil)) continue;
+      float4 a[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) a[m] = ldg_stream4(A + (size_t)(8 * kd + m) * plane);
+      if (d <= kHalo) {
+        if (!staged) { mbar_wait(&s_bar, phase); staged = true; }
+        // shared-memory coordinates of this thread's quad: row tr + kHalo, column 4 tq + kHalo
+        const float *t0 = s_tile + (size_t)(tr + kHalo) * kSmemW + (tq << 2) + kHalo;
+        const int rm = -d * kSmemW, rp = d * kSmemW;
+        if ((d & 3) == 0) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *q = t0 + k * (kSmemH * kSmemW);
+              fma4(acc[k], a[0], lds4(q + rm - d)); fma4(acc[k], a[1], lds4(q + rm)); fma4(acc[k], a[2], lds4(q + rm + d));
+              fma4(acc[k], a[3], lds4(q - d));                                          fma4(acc[k], a[4], lds4(q + d));
+              fma4(acc[k], a[5], lds4(q + rp - d)); fma4(acc[k], a[6], lds4(q + rp)); fma4(acc[k], a[7], lds4(q + rp + d));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *q = t0 + k * (kSmemH * kSmemW);
+              float4 m, p, C;
+              if (d < 4) {
+                C = lds4(q + rm); shifted_quads(lds4(q + rm - 4), C, lds4(q + rm + 4), d, m, p);
+                fma4(acc[k], a[0], m); fma4(acc[k], a[1], C); fma4(acc[k], a[2], p);
+                C = lds4(q); shifted_quads(lds4(q - 4), C, lds4(q + 4), d, m, p);
+                fma4(acc[k], a[3], m); fma4(acc[k], a[4], p);
+                C = lds4(q + rp); shifted_quads(lds4(q + rp - 4), C, lds4(q + rp + 4), d, m, p);
+                fma4(acc[k], a[5], m); fma4(acc[k], a[6], C); fma4(acc[k], a[7], p);
+              } else {   // 5, 6, 7: unaligned, scalar shared-memory reads
+                const int rows[3] = {rm, 0, rp};
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                  for (int cc = 0; cc < 3; ++cc) {
+                    if (rr == 1 && cc == 1) continue;
+                    const int mi = rr * 3 + cc - (rr * 3 + cc > 4 ? 1 : 0);
+                    const float *qq = q + rows[rr] + (cc - 1) * d;
+                    fma4(acc[k], a[mi], make_float4(qq[0], qq[1], qq[2], qq[3]));
+                  }
+              }
+            }
+          }
+        }
+      } else if (active) {
+        const float *g0 = src + (size_t)c0 * iplane + x;
+        const size_t rm = (size_t)max(y - d, 0) * li.pitch, r0 = (size_t)y * li.pitch,
+                     rp = (size_t)min(y + d, h - 1) * li.pitch;
+        if ((d & 3) == 0) {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *ch = g0 + (size_t)k * iplane;
+              fma4(acc[k], a[0], ldg4(ch + rm - d)); fma4(acc[k], a[1], ldg4(ch + rm)); fma4(acc[k], a[2], ldg4(ch + rm + d));
+              fma4(acc[k], a[3], ldg4(ch + r0 - d));                                       fma4(acc[k], a[4], ldg4(ch + r0 + d));
+              fma4(acc[k], a[5], ldg4(ch + rp - d)); fma4(acc[k], a[6], ldg4(ch + rp)); fma4(acc[k], a[7], ldg4(ch + rp + d));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < CH; ++k) {
+            if (k < live) {
+              const float *ch = g0 + (size_t)k * iplane;
+              const size_t rows[3] = {rm, r0, rp};
+#pragma unroll
+              for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                  if (rr == 1 && cc == 1) continue;
+                  const int mi = rr * 3 + cc - (rr * 3 + cc > 4 ? 1 : 0);
+                  const float *qq = ch + rows[rr] + (cc - 1) * d;
+                  fma4(acc[k], a[mi], make_float4(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3)));
+                }
+            }
+          }
+        }
+      }
+    }
+    if (!staged) mbar_wait(&s_bar, phase);   // no dilation used the tile: still consume the phase
+    phase ^= 1;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (k < live) {
+          float *o = dst + (size_t)(c0 + k) * oplane;
+          *reinterpret_cast<float4 *>(o) = acc[k];
+          if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+            if (xq == 0) {
+              const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+            }
+            if (xq == wq - 1) {
+              const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();   // the tile is re-staged (async proxy) by the next channel group
+  }
+}
+
 // plain [planes, h, w] -> padded layout (interior + replicated column pads)
 __global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
                                 int h, int w) {
@@ -409,9 +605,9 @@ MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
   int max_dil = 1;
   for (int k = 0; k < n_dil; ++k) max_dil = max(max_dil, dilations[k]);
   MaskLayout l;
-  l.padn = (max_dil + 3) & ~3;
+  l.padn = (max(max_dil, kHalo) + 3) & ~3;              // the staged tile reads kHalo columns beyond the image
   l.off = (l.padn + 31) & ~31;
-  l.pitch = (l.off + w + l.padn + 31) & ~31;
+  l.pitch = (l.off + ((w + 31) & ~31) + l.padn + 31) & ~31;   // whole 32-pixel tiles plus the right pad
   return l;
 }
 
@@ -445,7 +641,29 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
     const bool last = it == num_iter - 1;
     float *dst = last ? final_dst : ((it & 1) ? scratch_b : scratch_a);
     const MaskLayout lo = last ? lay_final : lay;
-    if (vec) {
+    static int step_kind = -1;   // COSA_PAR_STEP=vec selects the L1-only vector kernel (for A/B measurements)
+    if (step_kind < 0) {
+      const char *e = getenv("COSA_PAR_STEP");
+      step_kind = (e && e[0] == 'v') ? 1 : 0;
+    }
+    if (vec && step_kind == 0) {
+      dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileH), B), block(256);
+      static bool attr_set = false;
+      if (!attr_set) {
+        COSA_CUDA(cudaFuncSetAttribute(par_iterate_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       8 * kSmemH * kSmemW * (int)sizeof(float)));
+        COSA_CUDA(cudaFuncSetAttribute(par_iterate_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       4 * kSmemH * kSmemW * (int)sizeof(float)));
+        attr_set = true;
+      }
+      if (wide) {
+        COSA_LAUNCH(par_iterate_smem_kernel<8>, grid, block, 8 * kSmemH * kSmemW * sizeof(float), stream, aff, src, lay,
+                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil);
+      } else {
+        COSA_LAUNCH(par_iterate_smem_kernel<4>, grid, block, 4 * kSmemH * kSmemW * sizeof(float), stream, aff, src, lay,
+                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil);
+      }
+    } else if (vec) {
       const int tq = par_tile_log2();
       dim3 grid(ceil_div(w / 4, 1 << tq), ceil_div(h, 256 >> tq), B), block(256);
       if (wide) {
@@ -490,7 +708,7 @@ using namespace cosa;
 // (column pads of at most 24: wider dilations take the plain layout and the generic kernel)
 extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
   const size_t plane = (size_t)h * w;
-  const size_t pitch = (size_t)((32 + w + 24 + 31) & ~31);
+  const size_t pitch = (size_t)max_padded_pitch(w);
   return align_up((size_t)B * 8 * n_dil * plane * sizeof(float), 256) +
          2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256);
 }
