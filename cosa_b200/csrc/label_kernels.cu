@@ -471,6 +471,118 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const float *__res
   label_out[(size_t)b * H * W + (size_t)Y * W + X] = valid_key[arg];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multi-scale CAM merge (seg_helper.py:245-270, the post-processing of multi_scale_camseg): per scale the raw
+// token-grid CAMs of the image batch and of its horizontally flipped copy ([2B, C1, hs, ws]) are enlarged to
+// (H, W) (bilinear, align_corners=False), max-ed with the un-flipped flipped copy, ReLU-ed, summed over the
+// scales, and the sum is min-max normalised per (b, c) plane.  One thread produces 4 consecutive output pixels;
+// the un-normalised sum is written once together with the per-plane min/max, then normalised in place.
+// ------------------------------------------------------------------------------------------------
+struct RawScales {
+  const float *p[kMaxScales];
+  int hs[kMaxScales], ws[kMaxScales];
+  int n;
+};
+
+__device__ __forceinline__ float merged_value(const RawScales &rs, int B, int C1, int b, int c, int y, int x, int H,
+                                              int W) {
+  float sum = 0.0f;
+  for (int s = 0; s < rs.n; ++s) {
+    const int hs = rs.hs[s], ws = rs.ws[s];
+    const float *a = rs.p[s] + ((size_t)b * C1 + c) * hs * ws;            // original batch
+    const float *f = rs.p[s] + ((size_t)(B + b) * C1 + c) * hs * ws;      // flipped batch
+    const Tap ty = tap_half_pixel(y, (float)hs / (float)H, hs);
+    const Tap tx = tap_half_pixel(x, (float)ws / (float)W, ws);
+    const Tap tf = tap_half_pixel(W - 1 - x, (float)ws / (float)W, ws);   // .flip(-1) after the enlargement
+    const float v0 = bilerp_up(ty, tx, __ldg(a + ty.i0 * ws + tx.i0), __ldg(a + ty.i0 * ws + tx.i1),
+                               __ldg(a + ty.i1 * ws + tx.i0), __ldg(a + ty.i1 * ws + tx.i1));
+    const float v1 = bilerp_up(ty, tf, __ldg(f + ty.i0 * ws + tf.i0), __ldg(f + ty.i0 * ws + tf.i1),
+                               __ldg(f + ty.i1 * ws + tf.i0), __ldg(f + ty.i1 * ws + tf.i1));
+    const float v = fmaxf(fmaxf(v0, v1), 0.0f);                            // torch.max then F.relu
+    sum = s == 0 ? v : __fadd_rn(sum, v);
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(256) cam_merge_sum_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
+                                                            int B, int C1, int H, int W) {
+  __shared__ float s_min[8], s_max[8];
+  const int plane = blockIdx.y;                       // b * C1 + c
+  const int b = plane / C1, c = plane - b * C1;
+  const long long HW = (long long)H * W;
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < HW;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long p = i + k;
+      if (p < HW) {
+        v[k] = merged_value(rs, B, C1, b, c, (int)(p / W), (int)(p % W), H, W);
+        lo = fminf(lo, v[k]);
+        hi = fmaxf(hi, v[k]);
+        out[(size_t)plane * HW + p] = v[k];
+      }
+    }
+  }
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    lo = threadIdx.x < 8 ? s_min[threadIdx.x] : INFINITY;
+    hi = threadIdx.x < 8 ? s_max[threadIdx.x] : -INFINITY;
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if (threadIdx.x == 0) {
+      atomicMin(mm + 2 * plane, float_to_ordered(lo));
+      atomicMax(mm + 2 * plane + 1, float_to_ordered(hi));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cam_normalize_inplace_kernel(float *__restrict__ data,
+                                                                    const int *__restrict__ mm, long long HW,
+                                                                    int planes) {
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float neg_min = -ordered_to_float(mm[2 * p]);
+    const float den = __fadd_rn(__fadd_rn(ordered_to_float(mm[2 * p + 1]), neg_min), 1e-5f);
+    float *d = data + (size_t)p * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW;
+         i += (long long)gridDim.x * blockDim.x)
+      d[i] = __fdiv_rn(__fadd_rn(d[i], neg_min), den);
+  }
+}
+
+// seg = sum_s ( up(seg_s[:B]) + up(seg_s[B:]).flip(-1) )     (seg_helper.py:260-262, :273)
+__global__ void __launch_bounds__(256) seg_merge_kernel(RawScales rs, float *__restrict__ out, int B, int C, int H,
+                                                        int W) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long plane = i / ((long long)W * H);
+    const int b = (int)(plane / C), c = (int)(plane % C);
+    float acc = 0.0f;
+    for (int s = 0; s < rs.n; ++s) {
+      const int hs = rs.hs[s], ws = rs.ws[s];
+      const float *a = rs.p[s] + ((size_t)b * C + c) * hs * ws;
+      const float *f = rs.p[s] + ((size_t)(B + b) * C + c) * hs * ws;
+      const Tap ty = tap_half_pixel(y, (float)hs / (float)H, hs);
+      const Tap tx = tap_half_pixel(x, (float)ws / (float)W, ws);
+      const Tap tf = tap_half_pixel(W - 1 - x, (float)ws / (float)W, ws);
+      const float v0 = bilerp_up(ty, tx, __ldg(a + ty.i0 * ws + tx.i0), __ldg(a + ty.i0 * ws + tx.i1),
+                                 __ldg(a + ty.i1 * ws + tx.i0), __ldg(a + ty.i1 * ws + tx.i1));
+      const float v1 = bilerp_up(ty, tf, __ldg(f + ty.i0 * ws + tf.i0), __ldg(f + ty.i0 * ws + tf.i1),
+                                 __ldg(f + ty.i1 * ws + tf.i0), __ldg(f + ty.i1 * ws + tf.i1));
+      const float v = __fadd_rn(v0, v1);
+      acc = s == 0 ? v : __fadd_rn(acc, v);
+    }
+    out[i] = acc;
+  }
+}
+
 }  // namespace cosa
 
 using namespace cosa;
@@ -625,5 +737,45 @@ extern "C" int cosa_upsample_argmax(const float *refined, const long long *valid
   if (!refined || !valid_key || !label_out || B < 1 || nc < 1 || h < 1 || w < 1 || H < 1 || W < 1) return COSA_E_ARG;
   dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
   COSA_LAUNCH(upsample_argmax_kernel, gf, 256, 0, (cudaStream_t)stream, refined, valid_key, label_out, nc, h, w, H, W);
+  return 0;
+}
+
+static int fill_raw_scales(RawScales *rs, const float *const *raw, const int *hs, const int *ws, int n_scales) {
+  if (!raw || !hs || !ws || n_scales < 1 || n_scales > kMaxScales) return COSA_E_ARG;
+  rs->n = n_scales;
+  for (int k = 0; k < kMaxScales; ++k) {
+    rs->p[k] = k < n_scales ? raw[k] : nullptr;
+    rs->hs[k] = k < n_scales ? hs[k] : 1;
+    rs->ws[k] = k < n_scales ? ws[k] : 1;
+    if (k < n_scales && (!raw[k] || hs[k] < 1 || ws[k] < 1)) return COSA_E_ARG;
+  }
+  return 0;
+}
+
+extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream) {
+  if (!out || !minmax_ws || B < 1 || C1 < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  RawScales rs;
+  COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int planes = B * C1;
+  const long long HW = (long long)H * W;
+  int *mm = (int *)minmax_ws;
+  COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
+  const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
+  COSA_LAUNCH(cam_merge_sum_kernel, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
+  const int by = min(planes, max(1, sm_count() * 8 / bx));
+  COSA_LAUNCH(cam_normalize_inplace_kernel, dim3(bx, by), 256, 0, s, out, mm, HW, planes);
+  return 0;
+}
+
+extern "C" int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                          float *out, int B, int C, int H, int W, void *stream) {
+  if (!out || B < 1 || C < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  RawScales rs;
+  COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
+  const long long total = (long long)B * C * H * W;
+  const int blocks = (int)max(1LL, min((long long)sm_count() * 16, ceil_div_ll(total, 256)));
+  COSA_LAUNCH(seg_merge_kernel, blocks, 256, 0, (cudaStream_t)stream, rs, out, B, C, H, W);
   return 0;
 }

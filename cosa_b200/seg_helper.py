@@ -4,6 +4,7 @@ Same names, keyword arguments, shapes and dtypes as the reference; the arithmeti
 kernels of ``csrc/`` through the C-ABI (``include/cosa_b200.h``).  Inputs must be CUDA tensors.
 
   cam_normalize            utils/seg_helper.py:264-270 (the normalise tail of multi_scale_camseg)
+  multi_scale_camseg       utils/seg_helper.py:232-275 (model calls in torch, the merge fused)
   cam_validation           utils/seg_helper.py:547-551
   cam_to_label             utils/seg_helper.py:515-545
   cam2mask / _refine_cams  utils/seg_helper.py:721-797
@@ -43,6 +44,72 @@ def cam_normalize(cam_scales):
         _lib.check(lib.cosa_cam_normalize(ptrs, len(maps), _lib.ptr(out), B * C, H * W, _lib.ptr(mm),
                                           _lib.stream_ptr()))
     return out
+
+
+def _raw_scale_args(raws, what):
+    raws = [_lib.dev_f32(r, what) for r in raws]
+    n = len(raws)
+    ptrs = (ctypes.c_void_p * n)(*[r.data_ptr() for r in raws])
+    hs = (ctypes.c_int * n)(*[int(r.shape[2]) for r in raws])
+    ws = (ctypes.c_int * n)(*[int(r.shape[3]) for r in raws])
+    for r in raws:
+        assert r.shape[:2] == raws[0].shape[:2] and r.shape[0] % 2 == 0, "raw maps must be [2B, C, hs, ws]"
+    return raws, ptrs, hs, ws
+
+
+def multi_scale_cam_merge(raw_cams, size):
+    """Normalised CAM [B,C1,H,W] from the per-scale raw maps of ``multi_scale_camseg`` (seg_helper.py:253-270).
+
+    ``raw_cams[s]`` is the model output for ``cat([imgs_s, imgs_s.flip(-1)])``: [2B, C1, hs, ws].  Enlargement,
+    un-flip, max, ReLU, sum over scales and the per-plane min-max normalisation run in one kernel sequence.
+    """
+    lib = _lib.load()
+    raws, ptrs, hs, ws = _raw_scale_args(raw_cams, "raw_cam")
+    B, C1 = raws[0].shape[0] // 2, raws[0].shape[1]
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, C1, H, W), dtype=torch.float32, device=raws[0].device)
+    mm = torch.empty(2 * B * C1, dtype=torch.float32, device=out.device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.cosa_multi_scale_cam_merge(ptrs, hs, ws, len(raws), _lib.ptr(out), B, C1, H, W, _lib.ptr(mm),
+                                                  _lib.stream_ptr()))
+    return out
+
+
+def multi_scale_seg_merge(raw_segs, size):
+    """sum over scales of up(seg[:B]) + flip(up(seg[B:])) (seg_helper.py:260-262, :273)."""
+    lib = _lib.load()
+    raws, ptrs, hs, ws = _raw_scale_args(raw_segs, "raw_seg")
+    B, C = raws[0].shape[0] // 2, raws[0].shape[1]
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=raws[0].device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.cosa_multi_scale_seg_merge(ptrs, hs, ws, len(raws), _lib.ptr(out), B, C, H, W,
+                                                  _lib.stream_ptr()))
+    return out
+
+
+def multi_scale_camseg(model, imgs, scales):
+    """Teacher forward over scales and flips, same contract as the reference (seg_helper.py:232-275): returns
+    ``(cam, cam_aux, seg)``.  The model calls stay in torch; everything after them is fused (see above).
+    As in the reference, ``cam_aux`` is built from the LAST scale only (seg_helper.py:258)."""
+    b, c, h, w = imgs.shape
+    assert 1.0 in scales, 'scale 1.0 must be in scales'
+    raw_cam, raw_aux, raw_seg = [], [], []
+    with torch.no_grad():
+        for s in scales:
+            if s != 1.0:
+                imgs_ = F.interpolate(imgs, size=(int(s * h), int(s * w)), mode='bilinear', align_corners=False)
+            else:
+                imgs_ = imgs
+            imgs_cat = torch.cat([imgs_, imgs_.flip(-1)], dim=0)
+            _, _, _, _seg, _cam, _cam_aux = model(imgs_cat, cam_only=False)
+            raw_cam.append(_cam)
+            raw_aux = [_cam_aux]
+            raw_seg.append(_seg)
+        cam = multi_scale_cam_merge(raw_cam, (h, w))
+        cam_aux = multi_scale_cam_merge(raw_aux, (h, w))
+        seg = multi_scale_seg_merge(raw_seg, (h, w))
+    return cam, cam_aux, seg
 
 
 def cam_validation(cam, cls_label):

@@ -63,6 +63,20 @@ int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const 
 int cosa_cam_normalize(const float *const *scale_maps, int n_scales, float *out, int planes, long long HW,
                        float *minmax_ws, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-scale merge of the teacher's raw outputs.   replaces utils/seg_helper.py:253-270 (CAMs) and :260-262,273 (seg)
+ *   raw: HOST array of n_scales DEVICE pointers, raw[s] = [2B, C, hs[s], ws[s]] (the image batch followed by its
+ *   horizontally flipped copy, as multi_scale_camseg feeds the model, :250-251); hs/ws HOST arrays.
+ *   cam merge : out[B,C1,H,W] = normalise( sum_s relu(max(up(raw_s[:B]), flip(up(raw_s[B:])))) ), `up` = bilinear,
+ *               align_corners=False; normalise = per-plane (x - min) / (max - min + 1e-5).  minmax_ws: 2*B*C1 floats.
+ *               (The auxiliary CAM of the reference keeps only the LAST scale, :258 - call with n_scales = 1.)
+ *   seg merge : out[B,C,H,W] = sum_s ( up(raw_s[:B]) + flip(up(raw_s[B:])) ).
+ * ---------------------------------------------------------------------------------------------- */
+int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
+                               int C1, int H, int W, float *minmax_ws, void *stream);
+int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
+                               int C, int H, int W, void *stream);
+
 /* cam_validation: out[b,c,:,:] = cls_label[b,c] * cam[b,c,:,:].   utils/seg_helper.py:547-551 */
 int cosa_cam_validation(const float *cam, const float *cls_label, float *out, int B, int C1, long long HW,
                         void *stream);

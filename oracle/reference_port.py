@@ -12,6 +12,7 @@ where /root/reference is mounted).
 Reference map (paths relative to /root/reference):
   par_forward                  models/PAR.py:39-91 (neighbour order: get_kernel :10-24)
   normalize_cam                utils/seg_helper.py:264-270
+  multi_scale_merge            utils/seg_helper.py:253-273
   cam_validation               utils/seg_helper.py:547-551
   cam_to_label                 utils/seg_helper.py:515-545
   refine_cams                  utils/seg_helper.py:787-797
@@ -109,6 +110,21 @@ def normalize_cam(cam_scales):
     cam = torch.sum(torch.stack(list(cam_scales), dim=0), dim=0)
     cam = cam + (-cam).amax(dim=(2, 3), keepdim=True)
     return cam / (cam.amax(dim=(2, 3), keepdim=True) + 1e-5)
+
+
+def multi_scale_merge(raw_cams, raw_aux_last, raw_segs, size):
+    """Post-processing of multi_scale_camseg (seg_helper.py:253-273) on the per-scale raw model outputs
+    ([2B, C, hs, ws], image batch followed by its flipped copy).  Returns (cam, cam_aux, seg)."""
+    def one(raw, fn):
+        b = raw.shape[0] // 2
+        up = F.interpolate(raw, size=size, mode="bilinear", align_corners=False)
+        return fn(up[:b], up[b:].flip(-1))
+
+    cam = normalize_cam([F.relu(one(r, torch.max)) for r in raw_cams])
+    cam_aux = normalize_cam([F.relu(one(raw_aux_last, torch.max))])
+    seg = torch.sum(torch.stack([one(r, lambda a, f: torch.sum(torch.stack([a, f], dim=0), dim=0)) for r in raw_segs],
+                                dim=0), dim=0)
+    return cam, cam_aux, seg
 
 
 def cam_validation(cam, cls_label):

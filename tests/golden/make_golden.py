@@ -92,6 +92,33 @@ def main():
     cam /= torch.nn.functional.adaptive_max_pool2d(cam, (1, 1)) + 1e-5
     save("normalize", s0=scales[0], s1=scales[1], s2=scales[2], out=cam)
 
+    # ---- multi_scale_camseg with a stub teacher (seg_helper.py:232-275) ----------------------------------
+    class StubTeacher(torch.nn.Module):
+        """Deterministic stand-in for VITNetwork.forward: 16x16 patch means through fixed 1x1 mixes."""
+
+        def __init__(self):
+            super().__init__()
+            gg = torch.Generator().manual_seed(77)
+            self.w_cam = torch.randn((5, 3), generator=gg)
+            self.w_aux = torch.randn((5, 3), generator=gg)
+            self.w_seg = torch.randn((6, 3), generator=gg)
+            self.calls = []
+
+        def forward(self, x, cam_only=False):
+            tok = torch.nn.functional.avg_pool2d(x, 16)
+            mix = lambda wgt: torch.einsum("oc,bchw->bohw", wgt, tok) + 0.1 * torch.sin(7.0 * tok.sum(1, keepdim=True))
+            out = (None, None, None, mix(self.w_seg), mix(self.w_cam), mix(self.w_aux))
+            self.calls.append(out[3:])
+            return out
+
+    teacher = StubTeacher()
+    wimg = torch.randn((2, 3, 64, 96), generator=g)
+    m_cam, m_aux, m_seg = sh.multi_scale_camseg(teacher, wimg, [1.0, 0.5, 1.5])
+    raw = {}
+    for i, (sg, cm, ax) in enumerate(teacher.calls):
+        raw["raw_seg%d" % i], raw["raw_cam%d" % i], raw["raw_aux%d" % i] = sg, cm, ax
+    save("multi_scale", imgs=wimg, cam=m_cam, cam_aux=m_aux, seg=m_seg, **raw)
+
     # ---- cam_validation / cam_to_label ---------------------------------------------------------
     d = port.synthetic_batch(B=3, C=6, H=48, W=64, n_fg=2, seed=5, cam_kind="grid")
     raw_cam = torch.rand((3, 5, 48, 64), generator=g)

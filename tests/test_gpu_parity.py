@@ -104,6 +104,37 @@ def test_normalize_and_validation(cosa):
     assert_same(cosa.cam_validation(cu(g["cam"]), cu(g["cls_label"])), g["valid"], "cam_validation")
 
 
+def test_multi_scale_merge_golden(cosa):
+    """enlargement + un-flip max + ReLU + scale sum + normalise, fused (seg_helper.py:253-273)."""
+    g = load_golden("multi_scale")
+    raw = lambda k: [cu(g["raw_%s%d" % (k, i)]) for i in range(3)]
+    size = g["imgs"].shape[2:]
+    assert_same(cosa.multi_scale_cam_merge(raw("cam"), size), g["cam"], "merged cam")
+    assert_same(cosa.multi_scale_cam_merge([cu(g["raw_aux2"])], size), g["cam_aux"], "merged aux cam")
+    assert_same(cosa.multi_scale_seg_merge(raw("seg"), size), g["seg"], "merged seg")
+
+
+def test_multi_scale_camseg_with_stub_teacher(cosa, port):
+    """Whole multi_scale_camseg contract with a torch stand-in for the teacher, against the oracle merge."""
+    torch.manual_seed(3)
+    w = torch.randn((3, 7, 3), device="cuda")
+    calls = []
+
+    def teacher(x, cam_only=False):
+        tok = F.avg_pool2d(x, 16)
+        outs = [torch.einsum("oc,bchw->bohw", w[i], tok) for i in range(3)]
+        calls.append([o.cpu() for o in outs])
+        return None, None, None, outs[0], outs[1], outs[2]
+
+    imgs = torch.randn((4, 3, 448, 448), device="cuda")
+    cam, aux, seg = cosa.multi_scale_camseg(teacher, imgs, [1.0, 0.5, 1.5])
+    o_cam, o_aux, o_seg = port.multi_scale_merge([c[1] for c in calls], calls[-1][2], [c[0] for c in calls], (448, 448))
+    assert_close(cam, o_cam, "cam", 1e-6)
+    assert_close(aux, o_aux, "cam_aux", 1e-6)
+    assert_close(seg, o_seg, "seg", 1e-6)
+    assert float(cam.amax()) < 1.0 and float(cam.amin()) == 0.0
+
+
 def test_cam_to_label_golden(cosa):
     g = load_golden("cam_to_label")
     cam, lab, boxes = cu(g["cam"]), cu(g["cls_label"]), t(g["boxes"])

@@ -57,6 +57,15 @@ def test_normalize_and_validation():
     check_float(port.cam_validation(t(g["cam"]), t(g["cls_label"])), g["valid"], "cam_validation")
 
 
+def test_multi_scale_merge():
+    g = load_golden("multi_scale")
+    raw = lambda k: [t(g["raw_%s%d" % (k, i)]) for i in range(3)]
+    cam, aux, seg = port.multi_scale_merge(raw("cam"), t(g["raw_aux2"]), raw("seg"), g["imgs"].shape[2:])
+    check_float(cam, g["cam"], "merged cam")
+    check_float(aux, g["cam_aux"], "merged aux cam (last scale only, seg_helper.py:258)")
+    check_float(seg, g["seg"], "merged seg")
+
+
 def test_cam_to_label():
     g = load_golden("cam_to_label")
     cam, lab, boxes = t(g["cam"]), t(g["cls_label"]), t(g["boxes"])
