@@ -217,9 +217,13 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
         "energy_logit_grad_kernel": 4 * B * (2 * H * W * K + n * (K + 1)),
     }
     base = lambda k: (k.replace("_vec_kernel", "_kernel").replace("_smem_kernel", "_kernel")
-                      .replace("_x2_kernel", "_kernel"))
+                      .replace("_tile_kernel", "_kernel").replace("_x2_kernel", "_kernel"))
     out = {k: per.get(base(k)) for k in kernels}
     design = {k: (4 * B * n * (ND + 2 * ncm) if base(k) == "par_iterate_kernel" else out[k]) for k in kernels}
+    if "par_propagate_kernel" in kernels:      # persistent kernel: launches_per_step steps' worth per launch
+        steps_per_launch = T / max(1.0, kernels["par_propagate_kernel"])
+        out["par_propagate_kernel"] = int(per["par_iterate_kernel"] * steps_per_launch)
+        design["par_propagate_kernel"] = int(4 * B * n * (ND + 2 * ncm) * steps_per_launch)
     return out, design
 
 
@@ -291,7 +295,7 @@ def run_cosa_arm(args):
     M_vertices = seg_helper.last_energy_lattice_stats(B, C, H, W, dev)[0]
     nc = 1 + wl["n_fg"]
     peak, peak_src = measured_peak_gbs()
-    alg, design = algorithmic_bytes(prof.keys(), B, C, H, W, nc, M_vertices)
+    alg, design = algorithmic_bytes({k: c / prof_steps for k, (c, _) in prof.items()}, B, C, H, W, nc, M_vertices)
     kernels = []
     for name, (count, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
         avg_ms = ms / count

@@ -7,6 +7,8 @@
 //
 // Neighbour n = 8*k + m: dilation k in ctor order, direction m in get_kernel() order (PAR.py:10-24):
 // (-,-) (-,0) (-,+) (0,-) (0,+) (+,-) (+,0) (+,+), borders replicated (PAR.py:44).
+#include <cooperative_groups.h>
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -17,6 +19,7 @@ namespace cosa {
 
 __constant__ int c_dil[kMaxDil];
 __constant__ float c_pos_term[kMaxDil * 8];   // w2 * softmax(pos_aff), filled by par_upload_constants
+static bool g_std_dilations = false;          // the last uploaded list is the reference's {1,2,4,8,12,24} (PAR.py:94)
 
 // Host: the position term is a constant vector (PAR.py:51-62,77,82); evaluate it in double.
 int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
@@ -47,6 +50,9 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
   for (int n = 0; n < nd; ++n) term[n] = 0.01f * (float)(exp(logit[n] - mx) / sum);
   int dil[kMaxDil] = {0};
   for (int k = 0; k < n_dil; ++k) dil[k] = dilations[k];
+  static const int kStd[6] = {1, 2, 4, 8, 12, 24};
+  g_std_dilations = n_dil == 6;
+  for (int k = 0; k < 6 && g_std_dilations; ++k) g_std_dilations = dil[k] == kStd[k];
   COSA_CUDA(cudaMemcpyToSymbolAsync(c_dil, dil, sizeof(dil), 0, cudaMemcpyHostToDevice, stream));
   COSA_CUDA(cudaMemcpyToSymbolAsync(c_pos_term, term, sizeof(float) * nd, 0, cudaMemcpyHostToDevice, stream));
   return 0;
@@ -565,6 +571,368 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One propagation step for the reference dilation set {1,2,4,8,12,24} with the WHOLE 24-pixel neighbourhood staged in
+// shared memory (the step is bound by the 128 B/clk L1/shared-memory crossbar: every pixel-step consumes
+// 48 x channels neighbour values; from shared memory every 128-bit load costs exactly 4 crossbar cycles, a
+// misaligned global load 5-6 and most far-neighbour loads missed L1).
+//
+// CTA = 32 x 32 pixels (256 threads, one quad x CH channels each).  The (32+48)^2 halo tile of each of the CH staged
+// channels arrives by cp.async.bulk row copies (320 B each, rows clamped = replicate border; columns come from the
+// replicated pads) on two mbarriers: the 48 rows the dilations <= 8 need first, the outer 32 rows second, so the
+// near dilations run while the far rows land.  The dilations are compile-time constants: every shared-memory
+// offset is an immediate and the d = 1, 2 quad recombination is register renaming.  Affinity quads are streamed
+// straight into registers two dilations ahead of their use.
+// blockIdx.z = image * gsplit + g: gsplit CTAs share an image tile and take the channel groups g, g + gsplit, ...
+// ------------------------------------------------------------------------------------------------
+constexpr int kFH = 24;                       // halo of the full-neighbourhood tile
+constexpr int kFS = kTileW + 2 * kFH;         // 80 floats per staged row, 80 rows
+constexpr int kFNear0 = kFH - 8, kFNear1 = kFH + kTileH + 8;   // staged rows [16, 64) serve d <= 8
+
+template <int D, int CH>
+__device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&a)[8], const float *q, int live) {
+  constexpr int R = D * kFS;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < live) {
+      const float *p = q + k * (kFS * kFS);
+      if constexpr ((D & 3) == 0) {
+        fma4(acc[k], a[0], lds4(p - R - D)); fma4(acc[k], a[1], lds4(p - R)); fma4(acc[k], a[2], lds4(p - R + D));
+        fma4(acc[k], a[3], lds4(p - D));                                      fma4(acc[k], a[4], lds4(p + D));
+        fma4(acc[k], a[5], lds4(p + R - D)); fma4(acc[k], a[6], lds4(p + R)); fma4(acc[k], a[7], lds4(p + R + D));
+      } else {
+        float4 m, pl, C;
+        C = lds4(p - R); shifted_quads(lds4(p - R - 4), C, lds4(p - R + 4), D, m, pl);
+        fma4(acc[k], a[0], m); fma4(acc[k], a[1], C); fma4(acc[k], a[2], pl);
+        C = lds4(p); shifted_quads(lds4(p - 4), C, lds4(p + 4), D, m, pl);
+        fma4(acc[k], a[3], m); fma4(acc[k], a[4], pl);
+        C = lds4(p + R); shifted_quads(lds4(p + R - 4), C, lds4(p + R + 4), D, m, pl);
+        fma4(acc[k], a[5], m); fma4(acc[k], a[6], C); fma4(acc[k], a[7], pl);
+      }
+    }
+  }
+}
+
+// the 8 affinity quads of one dilation; A walks through the planes (one live 64-bit address instead of 48)
+__device__ __forceinline__ void load_aff8(float4 (&a)[8], const float *&A, size_t plane) {
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    a[m] = ldg_stream4(A);
+    // opaque increment: keeps ptxas from materialising (and spilling) all 48 plane addresses up front
+    asm volatile("add.u64 %0, %0, %1;" : "+l"(A) : "l"(plane * sizeof(float)));
+  }
+}
+
+// TMA: one 3-D box {80 columns, 16 rows, 1 plane} of the mask tensor [B*c_stride, h, pitch] per request; rows outside
+// the image are zero-filled by the unit and replaced by the replicated border row afterwards.
+__device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *tmap, int x, int y, int z,
+                                             unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+constexpr int kBoxRows = 16;
+
+// rows [0, r_lo) <- row r_lo, rows [r_hi, 80) <- row r_hi - 1 in every staged channel (whole CTA; ends with a barrier)
+__device__ __forceinline__ void replicate_border_rows(float *tile, int live, int r_lo, int r_hi) {
+  constexpr int Q = kFS / 4;
+  const int bad = r_lo + (kFS - r_hi);
+  for (int i = threadIdx.x; i < live * bad * Q; i += 256) {
+    const int k = i / (bad * Q), j = i - k * (bad * Q);
+    const int rr = j / Q, c4 = j - rr * Q;
+    const int r = rr < r_lo ? rr : r_hi + (rr - r_lo);
+    const int from = rr < r_lo ? r_lo : r_hi - 1;
+    float4 *base = reinterpret_cast<float4 *>(tile + (size_t)k * kFS * kFS);
+    base[r * Q + c4] = base[from * Q + c4];
+  }
+  __syncthreads();
+}
+
+// Tile-mode step kernel (default): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
+// passes of its tile.  The hardware CTA scheduler balances the load; 2 CTAs per SM overlap staging and compute.
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
+    par_iterate_tile_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
+                            float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
+                            int c_stride, int h, int w, int gsplit) {
+  extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const int wq = w >> 2;
+  const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int xq = (x0 >> 2) + tq, y = y0 + tr, x = x0 + (tq << 2);
+  const int b = blockIdx.z / gsplit, g = blockIdx.z - b * gsplit;
+  const bool active = xq < wq && y < h;
+  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
+  // the live channels are split evenly over the gsplit CTAs of this tile, at most CH per pass
+  const int n_groups = gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
+  const int chunk = (nch + n_groups - 1) / n_groups;
+  if (g * chunk >= nch) return;
+  const size_t plane = (size_t)h * w;
+  const size_t oplane = (size_t)h * lo.pitch;
+  const float *A = aff + (size_t)b * 48 * plane + (size_t)min(y, h - 1) * w + min(x, w - 4);
+  float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
+  // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
+  const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
+  const bool edge = r_lo > 0 || r_hi < kFS;
+  const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
+
+  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  __syncthreads();
+  unsigned phase = 0;
+  for (int c0 = g * chunk; c0 < nch; c0 += gsplit * chunk) {
+    const int live = min(chunk, nch - c0);
+    constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&s_bar[0], (unsigned)(live * kNear * kFS * sizeof(float)));
+      mbar_expect_tx(&s_bar[1], (unsigned)(live * kFar * kFS * sizeof(float)));
+      const int gx = li.off + x0 - kFH, gz = b * c_stride + c0;
+      for (int r = kFNear0; r < kFNear1; r += kBoxRows)
+        for (int k = 0; k < live; ++k)
+          tma_load_box(s_tile + (k * kFS + r) * kFS, &tmap_in, gx, y0 - kFH + r, gz + k, &s_bar[0]);
+      for (int k = 0; k < live; ++k) {
+        tma_load_box(s_tile + (k * kFS) * kFS, &tmap_in, gx, y0 - kFH, gz + k, &s_bar[1]);
+        tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, &tmap_in, gx, y0 - kFH + kFNear1, gz + k, &s_bar[1]);
+      }
+    }
+    float4 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *Ap = A;
+    float4 a0[8], a1[8], a2[8];   // affinity quads two dilations ahead of their use
+    load_aff8(a0, Ap, plane);
+    load_aff8(a1, Ap, plane);
+    mbar_wait(&s_bar[0], phase);
+    if (edge) {
+      mbar_wait(&s_bar[1], phase);
+      replicate_border_rows(s_tile, live, r_lo, r_hi);
+    }
+    load_aff8(a2, Ap, plane);
+    tile_dilation<1, CH>(acc, a0, q, live);
+    load_aff8(a0, Ap, plane);
+    tile_dilation<2, CH>(acc, a1, q, live);
+    load_aff8(a1, Ap, plane);
+    tile_dilation<4, CH>(acc, a2, q, live);
+    load_aff8(a2, Ap, plane);
+    tile_dilation<8, CH>(acc, a0, q, live);
+    if (!edge) mbar_wait(&s_bar[1], phase);
+    tile_dilation<12, CH>(acc, a1, q, live);
+    tile_dilation<24, CH>(acc, a2, q, live);
+    phase ^= 1;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (k < live) {
+          float *o = dst + (size_t)(c0 + k) * oplane;
+          *reinterpret_cast<float4 *>(o) = acc[k];
+          if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+            if (xq == 0) {
+              const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+            }
+            if (xq == wq - 1) {
+              const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+            }
+          }
+        }
+      }
+    }
+    if (c0 + gsplit * chunk < nch) {   // the tile is re-staged (async proxy) for the next channel group
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+}
+
+// One work unit of the persistent kernel: an image tile and a group of <= CH live channels.
+struct PropUnit {
+  int u;            // linear unit index (>= n_units: none left)
+  int b, x0, y0;    // image, tile origin
+  int c0, live;     // first channel and number of channels of the group
+};
+
+struct PropArgs {
+  const float *aff;              // [B, 48, h, w]
+  float *out_a, *out_b, *out_final;
+  MaskLayout li, lo_final;       // scratch layout (inputs and intermediate outputs), layout of the last output
+  const int *nch_dev;
+  int nch_uniform, c_stride, B, h, w;
+  int tiles_x, tiles_y, gsplit, n_pass;   // n_pass: host upper bound of ceil(nch / (gsplit * CH))
+  int it_begin, it_end, num_iter;         // this launch runs steps [it_begin, it_end) of num_iter
+};
+
+constexpr int kPropMaxCachedB = 256;   // per-image channel counts kept in shared memory up to this batch size
+
+template <int CH>
+__device__ __forceinline__ PropUnit prop_find_unit(const PropArgs &p, const int *s_nch, int n_pass, int u) {
+  const int tiles = p.tiles_x * p.tiles_y;
+  const int per_pass = p.B * tiles * p.gsplit;
+  const int n_units = per_pass * n_pass;
+  PropUnit r;
+  for (; u < n_units; u += gridDim.x) {
+    const int pass = u / per_pass, v = u - pass * per_pass;
+    const int g = v % p.gsplit, bt = v / p.gsplit;
+    const int b = bt / tiles, t = bt - b * tiles;
+    const int nch = !p.nch_dev ? p.nch_uniform : (s_nch && b < kPropMaxCachedB ? s_nch[b] : p.nch_dev[b]);
+    // the live channels are split evenly over the gsplit CTAs of a tile, at most CH per pass
+    const int n_groups = p.gsplit * ((nch + p.gsplit * CH - 1) / (p.gsplit * CH));
+    const int chunk = (nch + n_groups - 1) / n_groups;
+    const int c0 = (pass * p.gsplit + g) * chunk;
+    if (c0 < nch) {
+      r.u = u; r.b = b; r.y0 = (t / p.tiles_x) * kTileH; r.x0 = (t % p.tiles_x) * kTileW;
+      r.c0 = c0; r.live = min(chunk, nch - c0);
+      return r;
+    }
+  }
+  r.u = n_units; r.b = 0; r.x0 = 0; r.y0 = 0; r.c0 = 0; r.live = 0;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent propagation kernel: <= 2 CTAs per SM stride over the work units (image tile x channel group) of a step
+// and - with a cooperative launch - over ALL num_iter steps in ONE launch, separated by grid barriers (the masks
+// ping-pong between two scratch buffers in L2).  Measured slower than the tile-mode kernel above on B200
+// (profiles/README.md: static unit assignment, deeper affinity prefetch runs into the scoreboard limit), so it is
+// selectable (COSA_PAR_STEP=coop | persist, cosa_par_set_step_mode) rather than the default.
+// The affinity quads of the next unit's first two dilations are requested while the far dilations of the current
+// unit are computed, and the next tile is staged by TMA once the last shared-memory read of the current one retired.
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
+    par_propagate_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_src0,
+                         const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+  extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
+  const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
+  const int wq = p.w >> 2;
+  const size_t plane = (size_t)p.h * p.w;
+  const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
+  // live channel counts of the batch: cached in shared memory; their maximum bounds the number of passes, so no
+  // CTA scans the empty units the host's worst-case bound (p.n_pass) would imply
+  __shared__ int s_nch[kPropMaxCachedB];
+  __shared__ int s_max_nch;
+  const int per_pass = p.B * p.tiles_x * p.tiles_y * p.gsplit;
+  const bool persistent = (int)gridDim.x < per_pass;   // else: one CTA per (tile, channel split), passes in sequence
+  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_max_nch = 0; }
+  __syncthreads();
+  int n_pass = p.n_pass;
+  if (p.nch_dev && persistent) {
+    int mx = 0;
+    for (int b = threadIdx.x; b < p.B; b += 256) {
+      const int v = p.nch_dev[b];
+      if (b < kPropMaxCachedB) s_nch[b] = v;
+      mx = max(mx, v);
+    }
+    if (mx > 0) atomicMax(&s_max_nch, mx);
+    __syncthreads();
+    n_pass = min(p.n_pass, (s_max_nch + p.gsplit * CH - 1) / (p.gsplit * CH));
+  }
+  const int *nch_cache = persistent ? s_nch : nullptr;
+  const int n_units = per_pass * n_pass;
+  unsigned phase = 0;
+
+  auto stage = [&](const CUtensorMap *tm, const PropUnit &un) {   // one thread
+    mbar_expect_tx(&s_bar[0], (unsigned)(un.live * kNear * kFS * sizeof(float)));
+    mbar_expect_tx(&s_bar[1], (unsigned)(un.live * kFar * kFS * sizeof(float)));
+    const int gx = p.li.off + un.x0 - kFH, gz = un.b * p.c_stride + un.c0;
+    for (int r = kFNear0; r < kFNear1; r += kBoxRows)
+      for (int k = 0; k < un.live; ++k) tma_load_box(s_tile + (k * kFS + r) * kFS, tm, gx, un.y0 - kFH + r, gz + k, &s_bar[0]);
+    for (int k = 0; k < un.live; ++k) {
+      tma_load_box(s_tile + (k * kFS) * kFS, tm, gx, un.y0 - kFH, gz + k, &s_bar[1]);
+      tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, tm, gx, un.y0 - kFH + kFNear1, gz + k, &s_bar[1]);
+    }
+  };
+  auto aff_ptr = [&](const PropUnit &un) {
+    return p.aff + (size_t)un.b * 48 * plane + (size_t)min(un.y0 + tr, p.h - 1) * p.w + min(un.x0 + (tq << 2), p.w - 4);
+  };
+
+  for (int it = p.it_begin; it < p.it_end; ++it) {
+    const CUtensorMap *tm = it == 0 ? &tm_src0 : (((it - 1) & 1) ? &tm_b : &tm_a);
+    const bool last = it == p.num_iter - 1;
+    float *out = last ? p.out_final : ((it & 1) ? p.out_b : p.out_a);
+    const MaskLayout lo = last ? p.lo_final : p.li;
+    const size_t oplane = (size_t)p.h * lo.pitch;
+
+    PropUnit cur = prop_find_unit<CH>(p, nch_cache, n_pass, blockIdx.x);
+    float4 a0[8], a1[8], a2[8];
+    const float *Ap = aff_ptr(cur);
+    if (cur.u < n_units) {
+      if (threadIdx.x == 0) stage(tm, cur);
+      load_aff8(a0, Ap, plane);
+      load_aff8(a1, Ap, plane);
+    }
+    while (cur.u < n_units) {
+      const int live = cur.live;
+      // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
+      const int r_lo = max(0, kFH - cur.y0), r_hi = min(kFS, p.h - cur.y0 + kFH);
+      const bool edge = r_lo > 0 || r_hi < kFS;
+      float4 acc[CH];
+#pragma unroll
+      for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_wait(&s_bar[0], phase);
+      if (edge) {
+        mbar_wait(&s_bar[1], phase);
+        replicate_border_rows(s_tile, live, r_lo, r_hi);
+      }
+      load_aff8(a2, Ap, plane);
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      tile_dilation<4, CH>(acc, a2, q, live);
+      load_aff8(a2, Ap, plane);
+      tile_dilation<8, CH>(acc, a0, q, live);
+      if (!edge) mbar_wait(&s_bar[1], phase);
+      phase ^= 1;
+      // the next unit's first affinity quads travel while the far dilations of this one are computed
+      const PropUnit nxt = prop_find_unit<CH>(p, nch_cache, n_pass, cur.u + gridDim.x);
+      const bool more = nxt.u < n_units;
+      Ap = aff_ptr(nxt);
+      if (more) load_aff8(a0, Ap, plane);
+      tile_dilation<12, CH>(acc, a1, q, live);
+      if (more) load_aff8(a1, Ap, plane);
+      tile_dilation<24, CH>(acc, a2, q, live);
+      __syncthreads();                       // every shared-memory read of this tile has retired
+      if (more && threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        stage(tm, nxt);
+      }
+      const int xq = (cur.x0 >> 2) + tq, y = cur.y0 + tr;
+      if (xq < wq && y < p.h) {
+        float *dst = out + ((size_t)cur.b * p.c_stride + cur.c0) * oplane + (size_t)y * lo.pitch + lo.off + (xq << 2);
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          if (k < live) {
+            float *o = dst + (size_t)k * oplane;
+            *reinterpret_cast<float4 *>(o) = acc[k];
+            if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+              if (xq == 0) {
+                const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+                for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+              }
+              if (xq == wq - 1) {
+                const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+                for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+              }
+            }
+          }
+        }
+      }
+      cur = nxt;
+    }
+    if (it + 1 < p.it_end) {   // next step reads (through the async proxy) what every CTA wrote in this one
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      cooperative_groups::this_grid().sync();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+  }
+}
+
 // plain [planes, h, w] -> padded layout (interior + replicated column pads)
 __global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
                                 int h, int w) {
@@ -600,6 +968,30 @@ __global__ void resize_align_corners_kernel(const float *__restrict__ in, float 
 // ------------------------------------------------------------------------------------------------
 // Host-side launchers (shared with cam2mask).
 // ------------------------------------------------------------------------------------------------
+// 3-D tensor map over an fp32 buffer [planes, h, pitch] with box {bx, by, bz}, no swizzle, zero fill outside.
+// cuTensorMapEncodeTiled is fetched through the runtime (no link against libcuda).
+static int make_tmap3(CUtensorMap *map, const float *base, long long planes, int h, int pitch, int bx, int by, int bz) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult q;
+    void *fn = nullptr;
+    COSA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return COSA_E_ARG;
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)h, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)h * pitch * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : COSA_E_ARG;
+}
+
 MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
   if (w % 4 != 0 || w < 8) return plain_layout(w);
   int max_dil = 1;
@@ -630,23 +1022,125 @@ int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, in
   return 0;
 }
 
+// Step-kernel selection (COSA_PAR_STEP in the environment, or cosa_par_set_step_mode at run time):
+//   tile (default)  TMA-tile kernel, one CTA per tile and channel split, one launch per step
+//   coop            persistent TMA-tile kernel, every step in ONE cooperative launch (grid barriers)
+//   persist         persistent TMA-tile kernel, one launch per step
+//   smem | vec      the generic per-step kernels (any dilation set): near neighbourhood staged / L1 only
+enum { kStepTile = 0, kStepCoop = 1, kStepPersist = 2, kStepSmem = 3, kStepVec = 4 };
+static int g_step_mode = -1;
+static int parse_step_mode(const char *e) {
+  if (!e) return kStepTile;
+  switch (e[0]) {
+    case 't': return kStepTile;
+    case 'c': return kStepCoop;
+    case 'p': return kStepPersist;
+    case 's': return kStepSmem;
+    case 'v': return kStepVec;
+    default: return -1;
+  }
+}
+static int par_step_mode() {
+  if (g_step_mode < 0) {
+    g_step_mode = parse_step_mode(getenv("COSA_PAR_STEP"));
+    if (g_step_mode < 0) g_step_mode = kStepTile;
+  }
+  return g_step_mode;
+}
+
+template <int CH>
+static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUtensorMap &ta, const CUtensorMap &tb,
+                                  int max_nch, cudaStream_t stream) {
+  const size_t smem = (size_t)CH * kFS * kFS * sizeof(float);
+  static bool attr = false;
+  static int occ = 0, coop_ok = 0;
+  if (!attr) {
+    COSA_CUDA(cudaFuncSetAttribute(par_propagate_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, par_propagate_kernel<CH>, 256, smem));
+    int dev = 0;
+    COSA_CUDA(cudaGetDevice(&dev));
+    COSA_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
+    attr = true;
+  }
+  if (occ < 1) return COSA_E_ARG;
+  a.gsplit = 2;
+  a.n_pass = ceil_div(max_nch, a.gsplit * CH);
+  const long long per_pass = (long long)a.B * a.tiles_x * a.tiles_y * a.gsplit;
+  const int mode = par_step_mode();
+  if (mode == kStepCoop && coop_ok && a.num_iter > 1) {   // every step in one cooperative launch
+    const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
+    a.it_begin = 0;
+    a.it_end = a.num_iter;
+    void *args[] = {(void *)&a, (void *)&t0, (void *)&ta, (void *)&tb};
+    if (g_prof_on) prof_mark("par_propagate_kernel", stream, true);
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)par_propagate_kernel<CH>, dim3(grid), dim3(256), args,
+                                                      smem, stream);
+    ++g_launches;
+    if (g_prof_on) prof_mark("par_propagate_kernel", stream, false);
+    return e == cudaSuccess ? 0 : (int)e;
+  }
+  if (mode == kStepTile) {
+    static bool attr_tile = false;
+    if (!attr_tile) {
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_tile = true;
+    }
+    const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
+    for (int it = 0; it < a.num_iter; ++it) {
+      const bool last = it == a.num_iter - 1;
+      const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
+      float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
+      COSA_LAUNCH(par_iterate_tile_kernel<CH>, grid, 256, smem, stream, a.aff, tm, a.li, dst, last ? a.lo_final : a.li,
+                  a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+    }
+    return 0;
+  }
+  const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
+  for (int it = 0; it < a.num_iter; ++it) {
+    a.it_begin = it;
+    a.it_end = it + 1;
+    COSA_LAUNCH(par_propagate_kernel<CH>, grid, 256, smem, stream, a, t0, ta, tb);
+  }
+  return 0;
+}
+
+static int par_launch_propagate(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
+                                float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
+                                int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
+  PropArgs a;
+  a.aff = aff;
+  a.out_a = scratch_a; a.out_b = scratch_b; a.out_final = final_dst;
+  a.li = lay; a.lo_final = lay_final;
+  a.nch_dev = nch_dev; a.nch_uniform = nch_uniform; a.c_stride = c_stride;
+  a.B = B; a.h = h; a.w = w;
+  a.tiles_x = ceil_div(w, kTileW); a.tiles_y = ceil_div(h, kTileH);
+  a.num_iter = num_iter;
+  const long long planes = (long long)B * c_stride;
+  CUtensorMap t0, ta, tb;
+  COSA_CHECK(make_tmap3(&t0, src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
+  COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
+  COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
+  const int max_nch = nch_dev ? c_stride : nch_uniform;
+  return par_launch_propagate_t<3>(a, t0, ta, tb, max_nch, stream);
+}
+
 int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
                           float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
                           int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream) {
   if (num_iter <= 0) return COSA_E_ARG;   // callers handle the zero-iteration copy themselves
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
   const bool vec = lay.padn > 0;
+  if (vec && g_std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) &&
+      par_step_mode() <= kStepPersist)
+    return par_launch_propagate(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
+                                c_stride, B, h, w, num_iter, stream);
   const float *src = src0;
   for (int it = 0; it < num_iter; ++it) {
     const bool last = it == num_iter - 1;
     float *dst = last ? final_dst : ((it & 1) ? scratch_b : scratch_a);
     const MaskLayout lo = last ? lay_final : lay;
-    static int step_kind = -1;   // COSA_PAR_STEP=vec selects the L1-only vector kernel (for A/B measurements)
-    if (step_kind < 0) {
-      const char *e = getenv("COSA_PAR_STEP");
-      step_kind = (e && e[0] == 'v') ? 1 : 0;
-    }
-    if (vec && step_kind == 0) {
+    const int step_kind = par_step_mode() == kStepVec ? 1 : 0;
+    if (vec && step_kind != 1) {
       dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileH), B), block(256);
       static bool attr_set = false;
       if (!attr_set) {
@@ -711,6 +1205,13 @@ extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
   const size_t pitch = (size_t)max_padded_pitch(w);
   return align_up((size_t)B * 8 * n_dil * plane * sizeof(float), 256) +
          2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256);
+}
+
+extern "C" int cosa_par_set_step_mode(const char *name) {
+  const int m = parse_step_mode(name);
+  if (!name || m < 0) return COSA_E_ARG;
+  g_step_mode = m;
+  return 0;
 }
 
 extern "C" int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const int *dilations, int n_dil,

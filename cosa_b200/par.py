@@ -13,6 +13,11 @@ import torch.nn as nn
 from . import _lib
 
 
+def set_step_mode(name):
+    """Select the propagation kernel ("tile" default, "coop", "persist", "smem", "vec"); see cosa_par_set_step_mode."""
+    _lib.check(_lib.load().cosa_par_set_step_mode(name.encode()))
+
+
 def get_kernel():
     """The 8 one-hot 3x3 taps of the reference (models/PAR.py:10-24); kept as a buffer for state_dict parity."""
     weight = torch.zeros(8, 1, 3, 3)

@@ -95,6 +95,30 @@ def test_par_vs_oracle_ragged_shapes(cosa, port, shape):
     assert_close(out, port.par_forward(imgs, masks), "PAR %s" % (shape,))
 
 
+@pytest.mark.parametrize("mode", ["coop", "persist", "smem", "vec", "tile"])
+def test_par_step_kernels_agree(cosa, port, mode):
+    """Every propagation kernel (single cooperative launch, persistent, generic, default) against the oracle, on a
+    ragged batch shape (partial tiles in both directions) and on the cam2mask path with per-image channel counts."""
+    from cosa_b200 import par as par_mod
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand((3, 3, 72, 104), generator=g)
+    masks = torch.softmax(3 * torch.randn((3, 7, 72, 104), generator=g), dim=1)
+    want = port.par_forward(imgs, masks)
+    d = load_golden("cam2mask_b")
+    args = dict(images=cu(d["images"]), img_boxes=t(d["boxes"]), cams=cu(d["cams"]), cls_labels=cu(d["cls_label"]),
+                threshold_high=0.7, threshold_low=0.25)
+    par_mod.set_step_mode(mode)
+    try:
+        out = cosa.PAR(DIL, 10).cuda()(imgs.cuda(), masks.cuda())
+        lab = cosa.cam2mask(refine_model=cosa.PAR(DIL, 10).cuda(), **args)
+    finally:
+        par_mod.set_step_mode("tile")
+    assert_close(out, want, "PAR, step kernel %s" % mode)
+    assert_same(lab, d["out_par"], "cam2mask + PAR, step kernel %s" % mode)
+    with pytest.raises(cosa._lib.CosaError):
+        par_mod.set_step_mode("nonsense")
+
+
 # ---- normalise / validation / cam_to_label -------------------------------------------------------------
 def test_normalize_and_validation(cosa):
     g = load_golden("normalize")
