@@ -13,6 +13,8 @@
 //                           and the softmax, without materialising the probabilities.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "lattice.cuh"
 
@@ -326,6 +328,139 @@ __global__ void __launch_bounds__(256) energy_logit_grad_vec_kernel(const float 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variants for a compile-time class count (C = 21, the VOC shape): every logit is read from HBM
+// exactly once and stays in registers between the softmax statistics and the output pass, all C loads of a thread are
+// in flight together (no L2 re-read whose hit rate depends on how much of the grid is resident), and each element
+// costs one ex2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ldg_stream2(const float *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+// One thread = one half-resolution pixel = 2 x 2 source pixels.
+template <int C>
+__global__ void __launch_bounds__(128, 4) energy_prepare_reg_kernel(const float *__restrict__ simg,
+                                                                    const float *__restrict__ logit,
+                                                                    const float *__restrict__ label,
+                                                                    const int *__restrict__ boxes, Affine3 aff,
+                                                                    float *__restrict__ img_half,
+                                                                    float *__restrict__ s_roi, float *__restrict__ gate,
+                                                                    float *__restrict__ roi_out, int B, int H, int W) {
+  const int h = H / 2, w = W / 2;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)B * h * w) return;
+  const int x = (int)(t % w), y = (int)((t / w) % h), b = (int)(t / ((long long)w * h));
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const size_t src = (size_t)(2 * y) * W + 2 * x, pix = (size_t)y * w + x;
+  const float *lg = logit + (size_t)b * C * HW + src;
+  float2 top[C], bot[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    top[c] = ldg_stream2(lg + (size_t)c * HW);
+    bot[c] = ldg_stream2(lg + (size_t)c * HW + W);
+  }
+  const float lab = __ldg(label + (size_t)b * HW + src);
+  float im[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) im[c] = __ldg(simg + ((size_t)b * 3 + c) * HW + src);
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    m0 = fmaxf(m0, top[c].x); m1 = fmaxf(m1, top[c].y);
+    m2 = fmaxf(m2, bot[c].x); m3 = fmaxf(m3, bot[c].y);
+  }
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    top[c].x = __expf(top[c].x - m0); d0 += top[c].x;
+    top[c].y = __expf(top[c].y - m1); d1 += top[c].y;
+    bot[c].x = __expf(bot[c].x - m2); d2 += bot[c].x;
+    bot[c].y = __expf(bot[c].y - m3); d3 += bot[c].y;
+  }
+  d0 = 1.0f / d0; d1 = 1.0f / d1; d2 = 1.0f / d2; d3 = 1.0f / d3;
+  const int *box = boxes + 4 * b;
+  const float roi = (2 * y >= box[0] && 2 * y < box[1] && 2 * x >= box[2] && 2 * x < box[3]) ? 1.0f : 0.0f;
+  float smax = -INFINITY;
+  float *dst = s_roi + (size_t)b * C * hw + pix;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    // exact 2:1 bilinear, align_corners=False: 0.25 * (((p00 + p01) + p10) + p11)
+    const float sv = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(top[c].x * d0, top[c].y * d1), bot[c].x * d2),
+                                                bot[c].y * d3));
+    smax = fmaxf(smax, sv);
+    dst[(size_t)c * hw] = __fmul_rn(sv, roi);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+  float g = __fsub_rn(roi, smax);
+  if (((int)lab & 255) == 255) g = 1.0f;
+  gate[(size_t)b * hw + pix] = fmaxf(g, 0.0f);
+  roi_out[(size_t)b * hw + pix] = roi;
+}
+
+// One thread = 4 full-resolution pixels of one row.
+template <int C>
+__global__ void __launch_bounds__(128, 2) energy_logit_grad_reg_kernel(const float *__restrict__ logit,
+                                                                       const float *__restrict__ as_saved,
+                                                                       const float *__restrict__ roi_half,
+                                                                       const float *__restrict__ grad_out, float weight,
+                                                                       float *__restrict__ grad_logit, int B, int H,
+                                                                       int W) {
+  const int h = H / 2, w = W / 2, wq = W / 4;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)B * H * wq) return;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const int xq = (int)(t % wq), Y = (int)((t / wq) % H), b = (int)(t / ((long long)wq * H));
+  const int X = xq * 4;
+  const size_t pix = (size_t)(Y >> 1) * w + (X >> 1);
+  const float *lg = logit + (size_t)b * C * HW + (size_t)Y * W + X;
+  const float *as = as_saved + (size_t)b * C * hw + pix;
+  float *out = grad_logit + (size_t)b * C * HW + (size_t)Y * W + X;
+  float4 l[C];
+  float2 a[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    l[c] = ldg_stream4(lg + (size_t)c * HW);
+    a[c] = __ldg(reinterpret_cast<const float2 *>(as + (size_t)c * hw));
+  }
+  const float2 roi = *reinterpret_cast<const float2 *>(roi_half + (size_t)b * hw + pix);
+  const float cbase = __fdiv_rn(__fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight)), (float)B) * 0.25f;
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    mx.x = fmaxf(mx.x, l[c].x); mx.y = fmaxf(mx.y, l[c].y); mx.z = fmaxf(mx.z, l[c].z); mx.w = fmaxf(mx.w, l[c].w);
+  }
+  float4 den = make_float4(0.f, 0.f, 0.f, 0.f), num = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    l[c].x = __expf(l[c].x - mx.x); den.x += l[c].x; num.x = fmaf(l[c].x, a[c].x, num.x);
+    l[c].y = __expf(l[c].y - mx.y); den.y += l[c].y; num.y = fmaf(l[c].y, a[c].x, num.y);
+    l[c].z = __expf(l[c].z - mx.z); den.z += l[c].z; num.z = fmaf(l[c].z, a[c].y, num.z);
+    l[c].w = __expf(l[c].w - mx.w); den.w += l[c].w; num.w = fmaf(l[c].w, a[c].y, num.w);
+  }
+  den.x = 1.0f / den.x; den.y = 1.0f / den.y; den.z = 1.0f / den.z; den.w = 1.0f / den.w;
+  const float4 dot = make_float4(num.x * den.x, num.y * den.y, num.z * den.z, num.w * den.w);   // <p, AS> per pixel
+  const float c0 = cbase * roi.x, c1 = cbase * roi.y;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float4 o;
+    o.x = l[c].x * den.x * (c0 * (a[c].x - dot.x));
+    o.y = l[c].y * den.y * (c0 * (a[c].x - dot.y));
+    o.z = l[c].z * den.z * (c1 * (a[c].y - dot.z));
+    o.w = l[c].w * den.w * (c1 * (a[c].y - dot.w));
+    stg_stream4(out + (size_t)c * HW, o);
+  }
+}
+
+static bool energy_force_generic() {   // COSA_ENERGY_GENERIC=1: two-pass kernels for every class count (A/B runs)
+  static int v = -1;
+  if (v < 0) v = getenv("COSA_ENERGY_GENERIC") ? 1 : 0;
+  return v == 1;
+}
 static int grid1d(long long items) { return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(items, 256))); }
 
 }  // namespace cosa
@@ -424,7 +559,11 @@ extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, c
   void *lws = a.base + a.off;
   Affine3 aff;
   for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
-  if (W % 4 == 0) {
+  if (C == 21 && !energy_force_generic()) {   // VOC: register-resident single pass
+    const long long threads = (long long)B * h * w;
+    COSA_LAUNCH(energy_prepare_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label, boxes,
+                aff, img_half, s_roi, gate, roi_half, B, H, W);
+  } else if (W % 4 == 0) {
     const long long threads = (long long)B * h * (W / 4);
     COSA_LAUNCH(energy_prepare_vec_kernel, grid1d(threads), 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi,
                 gate, roi_half, B, C, H, W);
@@ -447,7 +586,11 @@ extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, 
   const float *roi_half = sv.take<float>((size_t)B * hw);
   dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (W % 4 == 0) {
+  if (C == 21 && W % 4 == 0 && !energy_force_generic()) {
+    const long long threads = (long long)B * H * (W / 4);
+    COSA_LAUNCH(energy_logit_grad_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
+                roi_half, grad_out, weight, grad_logit, B, H, W);
+  } else if (W % 4 == 0) {
     const long long threads = (long long)B * H * (W / 4);
     COSA_LAUNCH(energy_logit_grad_vec_kernel, grid1d(threads), 256, 0, s, logit, as_saved, roi_half, grad_out, weight,
                 grad_logit, B, C, H, W);
