@@ -650,6 +650,108 @@ __device__ __forceinline__ void replicate_border_rows(float *tile, int live, int
   __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Affinity for the reference dilation set from a TMA-staged image tile: the (32+48)^2 halo tile of the three colour
+// planes sits in shared memory (replicate border repaired in place), so the 48 x 3 neighbour reads are conflict-free
+// shared-memory loads at immediate offsets instead of clamped global loads with per-neighbour index arithmetic.
+// 256 threads; a thread produces the 4 pixels (tx, ty + 8 r) one after the other, arithmetic identical (operation
+// for operation) to par_affinity_kernel<6>.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void replicate_border(float *tile, int planes, int r_lo, int r_hi, int c_lo, int c_hi) {
+  // columns first (valid rows only), then whole rows
+  if (c_lo > 0 || c_hi < kFS) {
+    const int badc = c_lo + (kFS - c_hi), rows = r_hi - r_lo;
+    for (int i = threadIdx.x; i < planes * rows * badc; i += 256) {
+      const int k = i / (rows * badc), j = i - k * (rows * badc);
+      const int r = r_lo + j / badc, cc = j % badc;
+      const int c = cc < c_lo ? cc : c_hi + (cc - c_lo);
+      float *row = tile + ((size_t)k * kFS + r) * kFS;
+      row[c] = row[cc < c_lo ? c_lo : c_hi - 1];
+    }
+    __syncthreads();
+  }
+  if (r_lo > 0 || r_hi < kFS) replicate_border_rows(tile, planes, r_lo, r_hi);
+}
+
+__global__ void __launch_bounds__(256, 2)
+    par_affinity_tile_kernel(const __grid_constant__ CUtensorMap tm_img, float *__restrict__ aff, int h, int w) {
+  extern __shared__ __align__(128) float s_tile[];   // [3][80][80]
+  __shared__ __align__(8) unsigned long long s_bar;
+  constexpr int ND = 48;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH, b = blockIdx.z;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, (unsigned)(3 * kFS * kFS * sizeof(float)));
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < kFS; r += kBoxRows)
+        tma_load_box(s_tile + (c * kFS + r) * kFS, &tm_img, x0 - kFH, y0 - kFH + r, b * 3 + c, &s_bar);
+  }
+  __syncthreads();
+  mbar_wait(&s_bar, 0);
+  const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
+  const int c_lo = max(0, kFH - x0), c_hi = min(kFS, w - x0 + kFH);
+  if (r_lo > 0 || r_hi < kFS || c_lo > 0 || c_hi < kFS) replicate_border(s_tile, 3, r_lo, r_hi, c_lo, c_hi);
+
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const size_t plane = (size_t)h * w;
+  constexpr int kD[6] = {1, 2, 4, 8, 12, 24};
+#pragma unroll 1
+  for (int rr = 0; rr < 4; ++rr) {
+    const int yl = ty + 8 * rr;
+    const int x = x0 + tx, y = y0 + yl;
+    if (x >= w || y >= h) continue;
+    float logit[ND];
+#pragma unroll
+    for (int n = 0; n < ND; ++n) logit[n] = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+      const float *q = s_tile + (c * kFS + kFH + yl) * kFS + kFH + tx;
+      const float ctr = q[0];
+      float v[ND];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int d = kD[k], R = kD[k] * kFS;
+        v[8 * k + 0] = q[-R - d]; v[8 * k + 1] = q[-R]; v[8 * k + 2] = q[-R + d];
+        v[8 * k + 3] = q[-d];                           v[8 * k + 4] = q[d];
+        v[8 * k + 5] = q[R - d];  v[8 * k + 6] = q[R];  v[8 * k + 7] = q[R + d];
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int n = 0; n < ND; ++n) sum += v[n];
+      const float mean = sum / (float)ND;
+      float ss = 0.0f;
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        const float t = v[n] - mean;
+        ss = fmaf(t, t, ss);
+      }
+      const float sd = sqrtf(ss / (float)(ND - 1));
+      const float inv = 1.0f / ((sd + 1e-8f) * 0.3f);
+#pragma unroll
+      for (int n = 0; n < ND; ++n) {
+        const float t = fabsf(v[n] - ctr) * inv;
+        logit[n] = fmaf(t, t, logit[n]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < ND; ++n) {
+      logit[n] = -logit[n] / 3.0f;
+      mx = fmaxf(mx, logit[n]);
+    }
+    float den = 0.0f;
+#pragma unroll
+    for (int n = 0; n < ND; ++n) {
+      logit[n] = expf(logit[n] - mx);
+      den += logit[n];
+    }
+    const float rden = 1.0f / den;
+    float *out = aff + (size_t)b * ND * plane + (size_t)y * w + x;
+#pragma unroll
+    for (int n = 0; n < ND; ++n) out[(size_t)n * plane] = fmaf(logit[n], rden, c_pos_term[n]);
+  }
+}
+
 // Tile-mode step kernel (default): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
 // passes of its tile.  The hardware CTA scheduler balances the load; 2 CTAs per SM overlap staging and compute.
 template <int CH>
@@ -1007,7 +1109,20 @@ int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int 
   dim3 grid(ceil_div(w, 32), ceil_div(h, 4), B), block(128);
   static int force_generic = -1;
   if (force_generic < 0) force_generic = getenv("COSA_PAR_AFF_GENERIC") ? 1 : 0;
-  if (n_dil == 6 && !force_generic) {
+  static int use_tile = -1;
+  if (use_tile < 0) use_tile = getenv("COSA_PAR_AFF_L1") ? 0 : 1;
+  if (n_dil == 6 && g_std_dilations && w % 4 == 0 && use_tile && !force_generic) {
+    static bool attr = false;
+    const int smem = 3 * kFS * kFS * (int)sizeof(float);
+    if (!attr) {
+      COSA_CUDA(cudaFuncSetAttribute(par_affinity_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    CUtensorMap tm;
+    COSA_CHECK(make_tmap3(&tm, imgs, (long long)B * 3, h, w, kFS, kBoxRows, 1));
+    COSA_LAUNCH(par_affinity_tile_kernel, dim3(ceil_div(w, kTileW), ceil_div(h, kTileH), B), 256, smem, stream, tm, aff,
+                h, w);
+  } else if (n_dil == 6 && !force_generic) {
     COSA_LAUNCH(par_affinity_kernel<6>, grid, block, 0, stream, imgs, aff, h, w);
   } else {
     COSA_LAUNCH(par_affinity_generic_kernel, grid, block, 0, stream, imgs, aff, h, w, n_dil);
