@@ -284,7 +284,7 @@ def run_cosa_arm(args):
     launches = _lib.launch_count() - launches0
     total_images = sharding.all_reduce_sum(B * args.steps)
     value = total_images / (ms_total / 1e3)
-    mean_loss = sharding.mean_loss_over_ranks(float(loss), B)
+    mean_loss = sharding.mean_loss_over_ranks(float(loss.detach()), B)
 
     # ---- per-kernel event timing for the roofline (same inputs, same stream) ---------------------------
     prof_steps = min(args.steps, 5)
@@ -317,70 +317,33 @@ def run_cosa_arm(args):
                 "avg_launch_ms": top["avg_ms"], "alg_bytes_per_launch": top["alg_bytes"],
                 "share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 4)}
 
-    # ---- end to end: host (pinned) buffers in, labels + loss out, copies inside the timed region ---------
+    # ---- end to end through the host-buffer API (cosa_b200.HostPipeline): pinned host tensors in, labels + loss in
+    # pinned host memory out; every step's uploads and read-backs are inside the timed region ---------------------
     e2e = None
     if not args.no_e2e:
-        out_label = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
-        out_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-        names = ["img_denorm", "simg", "cams", "cls_label", "logits"]
-        h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in names) + boxes.numel() * 4
-        d2h = out_label.numel() * 4 + 4
-
-        # Double-buffered host->device staging on a copy stream: the upload of step i+1 overlaps the kernels of
-        # step i.  Every step's upload (from pinned memory) and read-back still happen inside the timed region.
-        main = torch.cuda.current_stream()
-        copy_stream = torch.cuda.Stream()
-        stage = [{k: torch.empty_like(d[k]) for k in names} for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-
-        # cam_validation zeroes every plane whose class is absent (label 0), and cam2mask only reads the present
-        # ones, so the host->device copy of the CAMs carries just the planes with a non-zero label; the rest of
-        # the device tensor is cleared on the GPU.  (Everything else is uploaded in full.)
-        present = [(b, c) for b, c in torch.nonzero(pinned["cls_label"]).tolist()]
-        plane_bytes = H * W * 4
-        h2d = (sum(pinned[k].numel() * pinned[k].element_size() for k in names if k != "cams")
-               + len(present) * plane_bytes + boxes.numel() * 4)
-
-        def upload(i):
-            slot = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])          # the step that last read this slot has finished
-                for k in names:
-                    if k == "cams":
-                        stage[slot][k].zero_()
-                        for b, c in present:
-                            stage[slot][k][b, c].copy_(pinned[k][b, c], non_blocking=True)
-                    else:
-                        stage[slot][k].copy_(pinned[k], non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        def e2e_run(n_steps):
-            for ev in consumed:
-                ev.record(main)
-            upload(0)
-            for i in range(n_steps):
-                if i + 1 < n_steps:
-                    upload(i + 1)
-                main.wait_event(ready[i % 2])
-                label, loss, _ = step(stage[i % 2])
-                out_label.copy_(label, non_blocking=True)
-                out_loss.copy_(loss.detach(), non_blocking=True)
-                consumed[i % 2].record(main)
-
-        e2e_run(3)
+        pipe = cosa_b200.HostPipeline(par, layer, threshold_high=THR_HIGH, threshold_low=THR_LOW, device=dev)
+        batch = dict(pinned, img_box=boxes)
+        for _ in range(3):
+            pipe.submit(batch)
+        pipe.drain()
         sync_all()
         e2e_steps = max(3, min(args.steps, 10))
+        h2d0, d2h0 = pipe.h2d_bytes, pipe.d2h_bytes
         ev0.record()
-        e2e_run(e2e_steps)
+        for _ in range(e2e_steps):
+            pipe.submit(batch)
+        res = pipe.drain()
         ev1.record()
         sync_all()
         e2e_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+        assert abs(float(res[-1][1]) - float(loss)) <= 1e-6 * abs(float(loss)) + 1e-12, "e2e loss differs from the device path"
         e2e = {"value": sharding.all_reduce_sum(B * e2e_steps) / (e2e_ms / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "h2d_bytes_per_step": (pipe.h2d_bytes - h2d0) // e2e_steps,
+               "d2h_bytes_per_step": (pipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
                "ms_per_step": e2e_ms / e2e_steps,
-               "note": "pinned host buffers; upload of step i+1 overlaps the kernels of step i (copy stream); "
-                       "only the CAM planes of present classes cross PCIe (absent ones are zero after cam_validation)"}
+               "note": "cosa_b200.HostPipeline: pinned host buffers; upload of step i+1 overlaps the kernels of step i "
+                       "(copy stream); CAM planes of absent classes are not uploaded (zero after cam_validation); "
+                       "labels + loss read back every step"}
 
     clocks.__exit__(None, None, None)
 

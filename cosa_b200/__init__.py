@@ -12,6 +12,7 @@ by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/cosa_b200.h``
 Everything requires CUDA tensors; there is no CPU fallback and no second backend.
 """
 from . import _lib  # noqa: F401
+from .host_pipeline import HostPipeline
 from .par import PAR, get_kernel
 from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
                          cam_to_label, cam_validation, get_energy_loss, multi_scale_cam_merge, multi_scale_camseg,
@@ -19,4 +20,4 @@ from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams,
 
 __all__ = ["PAR", "get_kernel", "cam_validation", "cam_to_label", "cam2mask", "_refine_cams", "cam_normalize",
            "get_energy_loss", "DenseEnergyLoss", "DenseEnergyLossFunction", "multi_scale_camseg", "multi_scale_cam_merge",
-           "multi_scale_seg_merge"]
+           "multi_scale_seg_merge", "HostPipeline"]

@@ -1,0 +1,128 @@
+"""Host-buffer front end of the hot path: batches in pinned host memory in, labels and loss in pinned host memory out.
+
+The reference keeps its tensors on the GPU between the network and these functions (main.py:121-212) but crosses
+to the host for the CRF filter every step (seg_helper.py:884-888).  When the producer of the CAMs lives on the
+host side of PCIe (a data-loading or serving process handing over buffers), this class is the entry point:
+
+    pipe = HostPipeline(par, loss_layer, threshold_high=0.7, threshold_low=0.25, device="cuda:0")
+    for batch in batches:                 # dicts of pinned CPU tensors
+        pipe.submit(batch)
+    results = pipe.drain()                # [(label [B,H,W] float32, loss [1]) ...] pinned CPU tensors
+
+``submit`` returns the result of the batch queued ``depth - 1`` calls earlier (None at first) and waits only for
+that batch; the tensors are the pipeline's own pinned buffers and stay valid until the next ``submit``.
+
+The host->device copies of batch i+1 run on a copy stream while the kernels of batch i run on the compute stream
+(``depth`` staging slots), and the labels and the loss of a batch are copied back asynchronously.  Only what the path reads crosses PCIe: ``cam_validation`` multiplies each CAM plane by its class
+label, so planes whose label is 0 are never uploaded (their device copy is cleared instead) - for VOC shapes
+(2 of 20 classes present) that is 90 % of the CAM bytes.
+
+One step is exactly the device path: cam_validation -> cam2mask(refine_model=par) -> get_energy_loss -> backward.
+"""
+import torch
+
+from . import seg_helper
+
+_FULL = ("img_denorm", "simg", "cls_label", "logits")
+
+
+class HostPipeline:
+
+    def __init__(self, par, loss_layer, threshold_high, threshold_low, device=None, depth=2, want_grad=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cosa_b200.HostPipeline needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.par, self.loss_layer = par, loss_layer
+        self.thr = (float(threshold_high), float(threshold_low))
+        self.depth = int(depth)
+        self.want_grad = bool(want_grad)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.slots = []
+        self.n_submitted = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._pending = []
+
+    # -- staging ------------------------------------------------------------------------------------------------
+    def _slot(self, i, batch):
+        while len(self.slots) < self.depth:
+            self.slots.append(None)
+        s = self.slots[i]
+        shapes = {k: tuple(batch[k].shape) for k in _FULL + ("cams",)}
+        if s is None or s["shapes"] != shapes:
+            dev = {k: torch.empty(shapes[k], dtype=torch.float32, device=self.device) for k in shapes}
+            B, _, H, W = shapes["cams"]
+            s = {"shapes": shapes, "dev": dev, "ready": torch.cuda.Event(), "consumed": torch.cuda.Event(),
+                 "label": torch.empty((B, H, W), dtype=torch.float32).pin_memory(),
+                 "loss": torch.empty(1, dtype=torch.float32).pin_memory(),
+                 "grad": (torch.empty(shapes["logits"], dtype=torch.float32).pin_memory() if self.want_grad else None),
+                 "done": torch.cuda.Event()}
+            s["consumed"].record(torch.cuda.current_stream(self.device))
+            self.slots[i] = s
+        return s
+
+    def _upload(self, s, batch):
+        dev = s["dev"]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["consumed"])       # the step that last read this slot has finished
+            for k in _FULL:
+                dev[k].copy_(batch[k], non_blocking=True)
+                self.h2d_bytes += batch[k].numel() * 4
+            # CAM planes of absent classes are zero after cam_validation: clear them on the device, upload the rest
+            cams, lab = batch["cams"], batch["cls_label"]
+            present = torch.nonzero(lab).tolist()
+            if len(present) * 2 >= lab.numel():
+                dev["cams"].copy_(cams, non_blocking=True)
+                self.h2d_bytes += cams.numel() * 4
+            else:
+                dev["cams"].zero_()
+                for b, c in present:
+                    dev["cams"][b, c].copy_(cams[b, c], non_blocking=True)
+                self.h2d_bytes += len(present) * cams.shape[2] * cams.shape[3] * 4
+            s["ready"].record(self.copy_stream)
+
+    # -- public -------------------------------------------------------------------------------------------------
+    def submit(self, batch):
+        """Queue one batch: dict with pinned float32 CPU tensors ``img_denorm`` [B,3,H,W], ``simg`` [B,3,H,W],
+        ``cams`` [B,C-1,H,W], ``cls_label`` [B,C-1], ``logits`` [B,C,H,W] and ``img_box`` (tensor or list, [B,4])."""
+        for k in _FULL + ("cams",):
+            t = batch[k]
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("HostPipeline.submit: %s must be a contiguous float32 CPU tensor" % k)
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            s = self._slot(self.n_submitted % self.depth, batch)
+            self._upload(s, batch)
+            main.wait_event(s["ready"])
+            d, boxes = s["dev"], batch["img_box"]
+            cams = seg_helper.cam_validation(d["cams"], d["cls_label"])
+            label = seg_helper.cam2mask(images=d["img_denorm"], img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
+                                        threshold_high=self.thr[0], threshold_low=self.thr[1], refine_model=self.par)
+            logit = d["logits"].detach().requires_grad_(True)
+            loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,
+                                              loss_layer=self.loss_layer)
+            loss.backward()
+            s["label"].copy_(label, non_blocking=True)
+            s["loss"].copy_(loss.detach(), non_blocking=True)
+            self.d2h_bytes += s["label"].numel() * 4 + 4
+            if self.want_grad:
+                s["grad"].copy_(logit.grad, non_blocking=True)
+                self.d2h_bytes += s["grad"].numel() * 4
+            s["consumed"].record(main)
+            s["done"].record(main)
+        self._pending.append(s)
+        self.n_submitted += 1
+        if len(self._pending) > self.depth - 1:              # keep at most depth-1 unread results behind us
+            return self._collect(self._pending.pop(0))
+        return None
+
+    def _collect(self, s):
+        s["done"].synchronize()
+        out = (s["label"], s["loss"])                        # the slot's pinned buffers: valid until the next submit
+        return out + ((s["grad"],) if self.want_grad else ())
+
+    def drain(self):
+        """Wait for every queued batch; returns the results not yet handed out by ``submit`` (oldest first)."""
+        out = [self._collect(s) for s in self._pending]
+        self._pending = []
+        return out

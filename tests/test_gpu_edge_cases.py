@@ -172,3 +172,38 @@ def test_high_resolution_energy_matches_oracle(cosa, port):
     got = cosa.cam2mask(images=d["img_denorm"], img_boxes=host["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
                         threshold_high=0.7, threshold_low=0.25)
     assert int((got.cpu() != label).sum()) <= 1e-5 * label.numel()
+
+
+def test_host_pipeline_matches_device_path(cosa, port):
+    """cosa_b200.HostPipeline (pinned host buffers in, labels + loss out, sparse CAM upload, two staging slots)
+    returns exactly what the device-resident calls return, batch after batch."""
+    dil = [1, 2, 4, 8, 12, 24]
+    par = cosa.PAR(dil, 10).cuda()
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    pipe = cosa.HostPipeline(par, layer, threshold_high=0.7, threshold_low=0.25, want_grad=True)
+    batches = [batch(B=3, C=21, H=64, W=96, n_fg=2, seed=s) for s in (1, 2, 3)]
+    outs = []
+    for hb in batches:
+        # garbage in the planes of absent classes must not matter (they are never uploaded)
+        hb = dict(hb)
+        hb["cams"] = hb["cams"] + 7.0 * (1 - hb["cls_label"])[:, :, None, None]
+        pinned = {k: (v.pin_memory() if k != "img_box" else v) for k, v in hb.items()}
+        r = pipe.submit(pinned)
+        if r is not None:
+            outs.append(tuple(t.clone() for t in r))
+    outs += [tuple(t.clone() for t in r) for r in pipe.drain()]
+    assert len(outs) == 3
+    for hb, (label, loss, grad) in zip(batches, outs):
+        d = to_cuda(hb)
+        cams = cosa.cam_validation(d["cams"], d["cls_label"])
+        want = cosa.cam2mask(images=d["img_denorm"], img_boxes=hb["img_box"], cams=cams, cls_labels=d["cls_label"],
+                             threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        logit = d["logits"].clone().requires_grad_(True)
+        wl = cosa.get_energy_loss(img=d["simg"], logit=logit, label=want, img_box=hb["img_box"], loss_layer=layer)
+        wl.backward()
+        assert torch.equal(label, want.cpu())
+        assert abs(float(loss) - float(wl.detach())) <= 1e-6 * abs(float(wl.detach()))
+        assert float((grad - logit.grad.cpu()).abs().max()) <= 1e-5 * float(logit.grad.abs().max())
+    assert pipe.h2d_bytes < 3 * sum(v.numel() * 4 for k, v in batches[0].items() if k != "img_box")
+    with pytest.raises(ValueError):
+        pipe.submit({k: (v.cuda() if k != "img_box" else v) for k, v in batches[0].items()})

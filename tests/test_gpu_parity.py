@@ -95,6 +95,20 @@ def test_par_vs_oracle_ragged_shapes(cosa, port, shape):
     assert_close(out, port.par_forward(imgs, masks), "PAR %s" % (shape,))
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 224, 224), (2, 6, 24, 8), (1, 9, 32, 32), (2, 2, 40, 260), (1, 13, 65, 36)])
+def test_par_tile_path_shapes(cosa, port, shape):
+    """w % 4 == 0 shapes that take the TMA-tile kernels: whole tiles, images smaller than one tile (every staged
+    row/column is border), partial tiles in x and y, channel counts that need 1, 2 and 3 passes."""
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    imgs = torch.rand((b, 3, h, w), generator=g)
+    masks = torch.softmax(2 * torch.randn((b, c, h, w), generator=g), dim=1)
+    out = cosa.PAR(DIL, 10).cuda()(imgs.cuda(), masks.cuda())
+    assert_close(out, port.par_forward(imgs, masks), "PAR %s" % (shape,))
+    aff = cosa.PAR(DIL, 10).cuda().affinity(imgs.cuda())
+    assert_close(aff, port.par_affinity(imgs)[:, 0], "affinity %s" % (shape,))
+
+
 @pytest.mark.parametrize("mode", ["coop", "persist", "smem", "vec", "tile"])
 def test_par_step_kernels_agree(cosa, port, mode):
     """Every propagation kernel (single cooperative launch, persistent, generic, default) against the oracle, on a
