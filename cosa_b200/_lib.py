@@ -28,6 +28,12 @@ _SIGNATURES = {
     "cosa_cam_normalize": (_c_int, [_vp, _c_int, _vp, _c_int, _c_ll, _vp, _vp]),
     "cosa_multi_scale_cam_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp, _vp]),
     "cosa_multi_scale_seg_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp]),
+    "cosa_seg_loss_stats_bytes": (_c_size_t, []),
+    "cosa_seg_loss_forward": (_c_int, [_vp, _vp, _c_float, _c_int, _vp, _vp] + [_c_int] * 4 + [_vp]),
+    "cosa_seg_loss_backward": (_c_int, [_vp, _vp, _vp, _vp, _c_float, _c_int, _vp] + [_c_int] * 4 + [_vp]),
+    "cosa_seg_refine_by_label": (_c_int, [_vp, _vp, _c_float, _c_int, _vp] + [_c_int] * 4 + [_vp]),
+    "cosa_cam_loss_forward": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp] + [_c_int] * 6 + [_vp]),
+    "cosa_cam_loss_backward": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp]),
     "cosa_cam_validation": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_ll, _vp]),
     "cosa_cam_to_label": (_c_int, [_vp] * 5 + [_c_int] * 4 + [_c_float] * 3 + [_c_int, _c_ll, _vp]),
     "cosa_cam2mask_ws_bytes": (_c_size_t, [_c_int] * 7),

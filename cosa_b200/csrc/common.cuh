@@ -37,6 +37,17 @@ void prof_mark(const char *name, cudaStream_t stream, bool is_start);
     if (e_ != cudaSuccess) return (int)e_;                                   \
   } while (0)
 
+// Same for template instantiations (commas in the kernel expression): the profile name is given explicitly.
+#define COSA_LAUNCH_T(name, kernel, grid, block, smem, stream, ...)          \
+  do {                                                                       \
+    if (::cosa::g_prof_on) ::cosa::prof_mark(name, (stream), true);          \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+    ++::cosa::g_launches;                                                    \
+    cudaError_t e_ = cudaGetLastError();                                     \
+    if (::cosa::g_prof_on) ::cosa::prof_mark(name, (stream), false);         \
+    if (e_ != cudaSuccess) return (int)e_;                                   \
+  } while (0)
+
 #define COSA_CHECK(expr)                        \
   do {                                          \
     int r_ = (expr);                            \

@@ -505,53 +505,56 @@ __device__ __forceinline__ float merged_value(const RawScales &rs, int B, int C1
   return sum;
 }
 
-__global__ void __launch_bounds__(256) cam_merge_sum_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
-                                                            int B, int C1, int H, int W) {
+// Pass 1 (WRITE == false): per-plane min / max of the merged sum, nothing stored.  Pass 2 (WRITE == true): the merged
+// sum is evaluated again (the raw token-grid maps are a few hundred KB and stay in L1/L2) and stored normalised, so
+// the [B, C1, H, W] result crosses HBM exactly once.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) cam_merge_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
+                                                        int B, int C1, int H, int W) {
   __shared__ float s_min[8], s_max[8];
   const int plane = blockIdx.y;                       // b * C1 + c
   const int b = plane / C1, c = plane - b * C1;
   const long long HW = (long long)H * W;
-  float lo = INFINITY, hi = -INFINITY;
+  float lo = INFINITY, hi = -INFINITY, neg_min = 0.0f, den = 1.0f;
+  if (WRITE) {
+    neg_min = -ordered_to_float(mm[2 * plane]);
+    den = __fadd_rn(__fadd_rn(ordered_to_float(mm[2 * plane + 1]), neg_min), 1e-5f);
+  }
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < HW;
        i += (long long)gridDim.x * blockDim.x * 4) {
     float v[4];
+    const int y = (int)(i / W), x0 = (int)(i % W);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const long long p = i + k;
-      if (p < HW) {
-        v[k] = merged_value(rs, B, C1, b, c, (int)(p / W), (int)(p % W), H, W);
-        lo = fminf(lo, v[k]);
-        hi = fmaxf(hi, v[k]);
-        out[(size_t)plane * HW + p] = v[k];
-      }
+      int yy = y, xx = x0 + k;
+      if (xx >= W) { yy += xx / W; xx %= W; }
+      v[k] = (i + k < HW) ? merged_value(rs, B, C1, b, c, yy, xx, H, W) : 0.0f;
+      if (i + k < HW) { lo = fminf(lo, v[k]); hi = fmaxf(hi, v[k]); }
+    }
+    if (WRITE) {
+      float *o = out + (size_t)plane * HW + i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __fdiv_rn(__fadd_rn(v[k], neg_min), den);
+      if (i + 3 < HW && (HW & 3) == 0) stg_stream4(o, make_float4(v[0], v[1], v[2], v[3]));
+      else
+        for (int k = 0; k < 4 && i + k < HW; ++k) o[k] = v[k];
     }
   }
-  lo = warp_min(lo);
-  hi = warp_max(hi);
-  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    lo = threadIdx.x < 8 ? s_min[threadIdx.x] : INFINITY;
-    hi = threadIdx.x < 8 ? s_max[threadIdx.x] : -INFINITY;
+  if (!WRITE) {
     lo = warp_min(lo);
     hi = warp_max(hi);
-    if (threadIdx.x == 0) {
-      atomicMin(mm + 2 * plane, float_to_ordered(lo));
-      atomicMax(mm + 2 * plane + 1, float_to_ordered(hi));
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      lo = threadIdx.x < 8 ? s_min[threadIdx.x] : INFINITY;
+      hi = threadIdx.x < 8 ? s_max[threadIdx.x] : -INFINITY;
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      if (threadIdx.x == 0) {
+        atomicMin(mm + 2 * plane, float_to_ordered(lo));
+        atomicMax(mm + 2 * plane + 1, float_to_ordered(hi));
+      }
     }
-  }
-}
-
-__global__ void __launch_bounds__(256) cam_normalize_inplace_kernel(float *__restrict__ data,
-                                                                    const int *__restrict__ mm, long long HW,
-                                                                    int planes) {
-  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
-    const float neg_min = -ordered_to_float(mm[2 * p]);
-    const float den = __fadd_rn(__fadd_rn(ordered_to_float(mm[2 * p + 1]), neg_min), 1e-5f);
-    float *d = data + (size_t)p * HW;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW;
-         i += (long long)gridDim.x * blockDim.x)
-      d[i] = __fdiv_rn(__fadd_rn(d[i], neg_min), den);
   }
 }
 
@@ -763,9 +766,8 @@ extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs
   int *mm = (int *)minmax_ws;
   COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
   const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
-  COSA_LAUNCH(cam_merge_sum_kernel, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
-  const int by = min(planes, max(1, sm_count() * 8 / bx));
-  COSA_LAUNCH(cam_normalize_inplace_kernel, dim3(bx, by), 256, 0, s, out, mm, HW, planes);
+  COSA_LAUNCH_T("cam_merge_minmax_kernel", cam_merge_kernel<false>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
+  COSA_LAUNCH_T("cam_merge_write_kernel", cam_merge_kernel<true>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
   return 0;
 }
 

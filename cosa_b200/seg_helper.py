@@ -439,3 +439,105 @@ def last_energy_lattice_stats(B, C, H, W, device=None):
     if rc not in (0, -3):
         _lib.check(rc)
     return tuple(int(v) for v in stats)
+
+
+# ---- the consumers either side of the path ------------------------------------------
+class _SegLossFunction(Function):
+    """seg_helper.py:800-813 in two streaming kernels (forward: CE sums + counts; backward: softmax - onehot)."""
+
+    @staticmethod
+    def forward(ctx, seg_pred, mask_label, fg_alpha, ignore_index):
+        lib = _lib.load()
+        B, C, H, W = seg_pred.shape
+        dev = seg_pred.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stats = torch.empty(lib.cosa_seg_loss_stats_bytes(), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.cosa_seg_loss_forward(_lib.ptr(seg_pred), _lib.ptr(mask_label), float(fg_alpha),
+                                                 int(ignore_index), _lib.ptr(loss), _lib.ptr(stats), B, C, H, W,
+                                                 _lib.stream_ptr()))
+        ctx.save_for_backward(seg_pred, mask_label, stats)
+        ctx.cfg = (float(fg_alpha), int(ignore_index))
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        seg_pred, mask_label, stats = ctx.saved_tensors
+        B, C, H, W = seg_pred.shape
+        g = _lib.dev_f32(grad_output.to(seg_pred.device), "grad_output").reshape(-1)[:1].contiguous()
+        grad = torch.empty_like(seg_pred)
+        with torch.cuda.device(seg_pred.device):
+            _lib.check(lib.cosa_seg_loss_backward(_lib.ptr(seg_pred), _lib.ptr(mask_label), _lib.ptr(stats), _lib.ptr(g),
+                                                  ctx.cfg[0], ctx.cfg[1], _lib.ptr(grad), B, C, H, W,
+                                                  _lib.stream_ptr()))
+        return grad, None, None, None
+
+
+def seg_loss(seg_pred, mask_label, fg_alpha=0.5, ignore_index=255):
+    """Background / foreground balanced cross-entropy on the pseudo-label map (seg_helper.py:800-813).
+
+    ``seg_pred`` [B,C,H,W] logits (differentiable), ``mask_label`` [B,H,W] with values 0..C-1 or ``ignore_index``
+    (the float map ``cam2mask`` returns, or an integer map).  Returns a 0-dim CUDA tensor."""
+    assert fg_alpha >= 0 and fg_alpha <= 1, "fg_alpha should be in [0,1]"
+    seg_pred = _lib.dev_f32(seg_pred, "seg_pred")
+    mask_label = _lib.dev_f32(mask_label, "mask_label")
+    assert mask_label.shape == (seg_pred.shape[0],) + tuple(seg_pred.shape[2:]), "mask_label must be [B,H,W]"
+    return _SegLossFunction.apply(seg_pred, mask_label, fg_alpha, ignore_index)
+
+
+def seg_refine_by_label(seg, cls_label, softmaxtemp, after_softmax=False):
+    """Class-label-masked, temperature-sharpened softmax of the teacher's segmentation (seg_helper.py:553-568).
+
+    ``seg`` [B,C,H,W] logits, ``cls_label`` [B,C-1] (0/1).  No gradient (the reference calls it under no_grad,
+    main.py:226-227)."""
+    lib = _lib.load()
+    seg = _lib.dev_f32(seg.detach(), "seg")
+    lab = _lib.dev_f32(cls_label.to(seg.device), "cls_label")
+    B, C, H, W = seg.shape
+    assert lab.shape == (B, C - 1), "cls_label must be [B, C-1]"
+    out = torch.empty_like(seg)
+    with torch.cuda.device(seg.device):
+        _lib.check(lib.cosa_seg_refine_by_label(_lib.ptr(seg), _lib.ptr(lab), float(softmaxtemp), int(bool(after_softmax)),
+                                                _lib.ptr(out), B, C, H, W, _lib.stream_ptr()))
+    return out
+
+
+class _CamLossFunction(Function):
+
+    @staticmethod
+    def forward(ctx, cam, seg_ps, is_relu):
+        lib = _lib.load()
+        B, C, H, W = cam.shape
+        dev = cam.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        target = torch.empty_like(cam)
+        acc = torch.empty(1, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.cosa_cam_loss_forward(_lib.ptr(cam), _lib.ptr(seg_ps), int(bool(is_relu)), _lib.ptr(loss),
+                                                 _lib.ptr(target), _lib.ptr(acc), B, C, H, W, seg_ps.shape[2],
+                                                 seg_ps.shape[3], _lib.stream_ptr()))
+        ctx.save_for_backward(cam, target)
+        ctx.is_relu = bool(is_relu)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        lib = _lib.load()
+        cam, target = ctx.saved_tensors
+        B, C, H, W = cam.shape
+        g = _lib.dev_f32(grad_output.to(cam.device), "grad_output").reshape(-1)[:1].contiguous()
+        grad = torch.empty_like(cam)
+        with torch.cuda.device(cam.device):
+            _lib.check(lib.cosa_cam_loss_backward(_lib.ptr(cam), _lib.ptr(target), _lib.ptr(g), int(ctx.is_relu),
+                                                  _lib.ptr(grad), B, C, H, W, _lib.stream_ptr()))
+        return grad, None, None
+
+
+def cam_loss(cam, seg_ps, is_relu=True):
+    """Multi-label soft-margin loss between the student CAM [B,C,H,W] (differentiable) and the refined teacher
+    segmentation ``seg_ps`` [B,C+1,Hs,Ws] resized to the CAM grid (seg_helper.py:593-602).  0-dim CUDA tensor."""
+    cam = _lib.dev_f32(cam, "cam")
+    seg_ps = _lib.dev_f32(seg_ps.detach(), "seg_ps")
+    assert seg_ps.shape[0] == cam.shape[0] and seg_ps.shape[1] == cam.shape[1] + 1, "seg_ps must be [B, C+1, Hs, Ws]"
+    return _CamLossFunction.apply(cam, seg_ps, is_relu)

@@ -170,6 +170,33 @@ int cosa_energy_loss_forward(const float *simg, const float *logit, const float 
 int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,
                               float *grad_logit, int B, int C, int H, int W, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The consumers either side of the path.
+ *
+ * seg_loss: fg/bg-balanced cross-entropy of seg_pred [B,C,H,W] against the pseudo-label map mask_label [B,H,W]
+ *   (float, values 0..C-1 or ignore_index).                                  replaces utils/seg_helper.py:800-813
+ *   loss = (1-fg_alpha) * CE_sum(label == 0)/(n_bg + 1e-6) + fg_alpha * CE_sum(label != 0, != ignore)/(n_fg + 1e-6).
+ *   `stats` (cosa_seg_loss_stats_bytes() bytes, device) carries the sums and counts to the backward, which writes
+ *   grad_pred = grad_out * d loss / d seg_pred.  fg_alpha outside [0,1] -> COSA_E_ARG (the reference asserts).
+ * seg_refine_by_label: out = softmax over C of (seg with the channels of absent classes set to -1e5) / softmaxtemp
+ *   (after_softmax = 0), or cls * softmax(seg / softmaxtemp) (after_softmax = 1); channel 0 is always present;
+ *   cls_label [B,C-1] float 0/1.                                             replaces utils/seg_helper.py:553-568
+ * cam_loss: F.multilabel_soft_margin_loss(relu(cam) [B,C,H,W], bilinear(seg_ps[:,1:] [B,C+1,Hs,Ws] -> H,W)).
+ *   target_ws: B*C*H*W floats (kept for the backward), acc_ws: one double.    replaces utils/seg_helper.py:593-602
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_seg_loss_stats_bytes(void);
+int cosa_seg_loss_forward(const float *seg_pred, const float *mask_label, float fg_alpha, int ignore_index,
+                          float *loss_out, void *stats, int B, int C, int H, int W, void *stream);
+int cosa_seg_loss_backward(const float *seg_pred, const float *mask_label, const void *stats, const float *grad_out,
+                           float fg_alpha, int ignore_index, float *grad_pred, int B, int C, int H, int W,
+                           void *stream);
+int cosa_seg_refine_by_label(const float *seg, const float *cls_label, float softmaxtemp, int after_softmax,
+                             float *out, int B, int C, int H, int W, void *stream);
+int cosa_cam_loss_forward(const float *cam, const float *seg_ps, int is_relu, float *loss_out, float *target_ws,
+                          double *acc_ws, int B, int C, int H, int W, int Hs, int Ws, void *stream);
+int cosa_cam_loss_backward(const float *cam, const float *target_ws, const float *grad_out, int is_relu,
+                           float *grad_cam, int B, int C, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,3 +263,40 @@ def get_energy_loss(img, logit, label, img_box, mean=IMAGENET_MEAN, std=IMAGENET
     for c in range(3):
         raw[:, c] = img[:, c] * std[c] + mean[c]
     return dense_energy_loss(raw, prob, crop, label.type(torch.uint8).unsqueeze(1), **layer_kw)
+
+
+# ---- the consumers either side of the path ------------------------------------------
+def seg_loss(seg_pred, mask_label, fg_alpha=0.5, ignore_index=255):
+    """Background/foreground balanced cross-entropy (seg_helper.py:800-813)."""
+    bg_label = mask_label.clone()
+    bg_label[mask_label != 0] = ignore_index
+    bg = F.cross_entropy(seg_pred, bg_label.long(), ignore_index=ignore_index, reduction="sum") / (
+        (bg_label != ignore_index).sum() + 1e-6)
+    fg_label = mask_label.clone()
+    fg_label[mask_label == 0] = ignore_index
+    fg = F.cross_entropy(seg_pred, fg_label.long(), ignore_index=ignore_index, reduction="sum") / (
+        (fg_label != ignore_index).sum() + 1e-6)
+    return (1 - fg_alpha) * bg + fg_alpha * fg
+
+
+def seg_refine_by_label(seg, cls_label, softmaxtemp, after_softmax=False):
+    """Class-label-masked, temperature-sharpened softmax of the teacher's segmentation (seg_helper.py:553-568)."""
+    b, c, h, w = seg.shape
+    lab = torch.cat([torch.ones(b, 1).long(), cls_label.long()], dim=1)
+    if after_softmax:
+        return lab[:, :, None, None].repeat([1, 1, h, w]) * F.softmax(seg / softmaxtemp, dim=1)
+    valid = seg.clone()
+    valid[lab == 0] = -1e5
+    return F.softmax(valid / softmaxtemp, dim=1)
+
+
+def cam_loss(cam, seg_ps, is_relu=True):
+    """Multi-label soft-margin loss between the student CAM and the refined teacher segmentation
+    (seg_helper.py:593-602)."""
+    B, C, H, W = cam.shape
+    fg = F.interpolate(seg_ps[:, 1:], size=[H, W], mode="bilinear", align_corners=False)
+    fg = fg.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
+    if is_relu:
+        cam = F.relu(cam)
+    flat = cam.permute(0, 2, 3, 1).contiguous().reshape(B * H * W, C)
+    return F.multilabel_soft_margin_loss(flat, fg)

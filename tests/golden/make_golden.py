@@ -201,6 +201,32 @@ def main():
     save("bilateral_kat", kat_img=kat_img,
          kat_out=kat_out.reshape(H, W), kat_M=np.int32(3809), **small)
 
+    # ---- seg_loss, seg_refine_by_label, cam_loss -----------------------------------
+    g = torch.Generator().manual_seed(23)
+    d = port.synthetic_batch(B=2, C=21, H=48, W=64, n_fg=2, seed=9)
+    lbl = torch.randint(0, 21, (2, 48, 64), generator=g).float()
+    lbl[torch.rand((2, 48, 64), generator=g) < 0.3] = 255
+    lbl[torch.rand((2, 48, 64), generator=g) < 0.4] = 0
+    sp = d["logits"].clone().requires_grad_(True)
+    sl = sh.seg_loss(sp, lbl, fg_alpha=0.5)
+    sl.backward()
+    sp2 = d["logits"].clone().requires_grad_(True)
+    sl2 = sh.seg_loss(sp2, torch.full_like(lbl, 255), fg_alpha=0.3)     # nothing labelled: both terms 0 / 1e-6
+    sl2.backward()
+    seg_ps = 2.0 * d["logits"]
+    v_a = sh.seg_refine_by_label(seg_ps, d["cls_label"], softmaxtemp=0.01, after_softmax=False)
+    v_b = sh.seg_refine_by_label(seg_ps, d["cls_label"], softmaxtemp=0.5, after_softmax=True)
+    cam_pred = torch.randn((2, 20, 6, 8), generator=g).requires_grad_(True)
+    cl = sh.cam_loss(cam_pred, v_a)
+    cl.backward()
+    cam_pred2 = cam_pred.detach().clone().requires_grad_(True)
+    cl2 = sh.cam_loss(cam_pred2, v_b, is_relu=False)
+    cl2.backward()
+    save("losses", logits=d["logits"], label=lbl, cls_label=d["cls_label"], seg_loss=sl, seg_loss_grad=sp.grad,
+         seg_loss_empty=sl2, seg_loss_empty_grad=sp2.grad, seg_ps=seg_ps, refine_masked=v_a, refine_after=v_b,
+         cam_pred=cam_pred, cam_loss=cl, cam_loss_grad=cam_pred.grad, cam_loss_norelu=cl2,
+         cam_loss_norelu_grad=cam_pred2.grad)
+
     with open(os.path.join(HERE, "META.txt"), "w") as f:
         for k, v in meta.items():
             f.write("%s: %s\n" % (k, v))

@@ -173,6 +173,65 @@ def test_multi_scale_camseg_with_stub_teacher(cosa, port):
     assert float(cam.amax()) < 1.0 and float(cam.amin()) == 0.0
 
 
+def test_losses_next_rows_golden(cosa):
+    """SURVEY 8(f) ranks 2, 3 against the reference's outputs (tests/golden/losses.npz)."""
+    g = load_golden("losses")
+    sp = cu(g["logits"]).requires_grad_(True)
+    loss = cosa.seg_loss(sp, cu(g["label"]), fg_alpha=0.5)
+    loss.backward()
+    assert loss.dim() == 0
+    assert_close(loss, g["seg_loss"], "seg_loss", 1e-5)
+    assert_close(sp.grad, g["seg_loss_grad"], "seg_loss grad", 1e-5)
+    sp2 = cu(g["logits"]).requires_grad_(True)
+    l2 = cosa.seg_loss(sp2, torch.full_like(cu(g["label"]), 255), fg_alpha=0.3)
+    l2.backward()
+    assert float(l2.detach()) == float(g["seg_loss_empty"]) == 0.0 and float(sp2.grad.abs().max()) == 0.0
+    assert_close(cosa.seg_refine_by_label(cu(g["seg_ps"]), cu(g["cls_label"]), 0.01, False), g["refine_masked"],
+                 "seg_refine_by_label", 1e-5)
+    assert_close(cosa.seg_refine_by_label(cu(g["seg_ps"]), cu(g["cls_label"]), 0.5, True), g["refine_after"],
+                 "seg_refine_by_label(after_softmax)", 1e-5)
+    for relu, key, seg in ((True, "cam_loss", "refine_masked"), (False, "cam_loss_norelu", "refine_after")):
+        cp = cu(g["cam_pred"]).requires_grad_(True)
+        cl = cosa.cam_loss(cp, cu(g[seg]), is_relu=relu)
+        cl.backward()
+        assert_close(cl, g[key], key, 1e-5)
+        assert_close(cp.grad, g[key + "_grad"], key + " grad", 1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 21, 448, 448), (2, 81, 40, 36), (1, 5, 7, 9), (3, 21, 30, 30)])
+def test_losses_next_rows_vs_oracle(cosa, port, shape):
+    """Register-resident (C = 21), streamed (other C) and scalar (H*W % 4 != 0) forms against the oracle."""
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(h * w + c)
+    logits = 3 * torch.randn(shape, generator=g)
+    label = torch.randint(0, c, (b, h, w), generator=g).float()
+    label[torch.rand((b, h, w), generator=g) < 0.3] = 255
+    label[torch.rand((b, h, w), generator=g) < 0.5] = 0
+    cls = (torch.rand((b, c - 1), generator=g) < 0.3).float()
+    o = logits.clone().requires_grad_(True)
+    ol = port.seg_loss(o, label, fg_alpha=0.7)
+    ol.backward()
+    d = logits.cuda().requires_grad_(True)
+    dl = cosa.seg_loss(d, label.cuda(), fg_alpha=0.7)
+    (2.0 * dl).backward()
+    assert_close(dl, ol, "seg_loss %s" % (shape,), 1e-5)
+    assert_close(d.grad, 2.0 * o.grad, "seg_loss grad %s" % (shape,), 1e-5)
+    for after in (False, True):
+        assert_close(cosa.seg_refine_by_label(logits.cuda(), cls.cuda(), 0.01, after),
+                     port.seg_refine_by_label(logits, cls, 0.01, after), "seg_refine %s %s" % (shape, after), 1e-5)
+    seg_ps = port.seg_refine_by_label(logits, cls, 0.01, False)
+    for (hc, wc) in ((max(1, h // 16), max(1, w // 16)), (h, w)):
+        cam = torch.randn((b, c - 1, hc, wc), generator=g)
+        oc = cam.clone().requires_grad_(True)
+        ocl = port.cam_loss(oc, seg_ps)
+        ocl.backward()
+        dc = cam.cuda().requires_grad_(True)
+        dcl = cosa.cam_loss(dc, seg_ps.cuda())
+        dcl.backward()
+        assert_close(dcl, ocl, "cam_loss %s" % (shape,), 1e-5)
+        assert_close(dc.grad, oc.grad, "cam_loss grad %s" % (shape,), 1e-5)
+
+
 def test_cam_to_label_golden(cosa):
     g = load_golden("cam_to_label")
     cam, lab, boxes = cu(g["cam"]), cu(g["cls_label"]), t(g["boxes"])

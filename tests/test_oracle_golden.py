@@ -66,6 +66,23 @@ def test_multi_scale_merge():
     check_float(seg, g["seg"], "merged seg")
 
 
+def test_losses_next_rows():
+    """seg_loss, seg_refine_by_label, cam_loss against the reference's outputs."""
+    g = load_golden("losses")
+    sp = t(g["logits"]).requires_grad_(True)
+    loss = port.seg_loss(sp, t(g["label"]), fg_alpha=0.5)
+    loss.backward()
+    check_float(loss, g["seg_loss"], "seg_loss")
+    check_float(sp.grad, g["seg_loss_grad"], "seg_loss grad")
+    check_float(port.seg_refine_by_label(t(g["seg_ps"]), t(g["cls_label"]), 0.01, False), g["refine_masked"], "refine")
+    check_float(port.seg_refine_by_label(t(g["seg_ps"]), t(g["cls_label"]), 0.5, True), g["refine_after"], "refine after")
+    cp = t(g["cam_pred"]).requires_grad_(True)
+    cl = port.cam_loss(cp, t(g["refine_masked"]))
+    cl.backward()
+    check_float(cl, g["cam_loss"], "cam_loss")
+    check_float(cp.grad, g["cam_loss_grad"], "cam_loss grad")
+
+
 def test_cam_to_label():
     g = load_golden("cam_to_label")
     cam, lab, boxes = t(g["cam"]), t(g["cls_label"]), t(g["boxes"])
