@@ -558,6 +558,111 @@ __global__ void __launch_bounds__(256) cam_merge_kernel(RawScales rs, float *__r
   }
 }
 
+// Row-walking form of the merge for W % 4 == 0 and up to 5 scales.  A thread owns 4 adjacent output columns of one
+// plane and walks down a chunk of rows; per scale it keeps the x-interpolated values of its columns on the two
+// source rows that bracket the current output row (plain and flipped copy) and refreshes them only when the source
+// row changes (every H/hs output rows), so an output pixel costs one y-interpolation per scale and copy instead of
+// two full bilinear evaluations.  Arithmetic order per value is torch's (x-lerp, then y-lerp), as in merged_value.
+//   MODE 0: cam, min/max only      MODE 1: cam, normalised store      MODE 2: seg (sum of plain + flipped), store
+template <int NS, int MODE>
+__global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
+                                                         int B, int C, int H, int W, int rows_per_chunk) {
+  const int wq = W >> 2, n_chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)B * C * n_chunks * wq;
+  const bool live = t < total;
+  const int xq = live ? (int)(t % wq) : 0;
+  const int chunk = live ? (int)((t / wq) % n_chunks) : 0;
+  const int plane = live ? (int)(t / ((long long)wq * n_chunks)) : 0;
+  const int b = plane / C, c = plane - b * C;
+  const int x = xq << 2;
+  const int y_begin = chunk * rows_per_chunk, y_end = live ? min(H, y_begin + rows_per_chunk) : y_begin;
+  float neg_min = 0.0f, den = 1.0f;
+  if (MODE == 1) {
+    neg_min = -ordered_to_float(mm[2 * plane]);
+    den = __fadd_rn(__fadd_rn(ordered_to_float(mm[2 * plane + 1]), neg_min), 1e-5f);
+  }
+  float top[NS][4], bot[NS][4], ftop[NS][4], fbot[NS][4], sy[NS];
+  int r0[NS], r1[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) { r0[s] = -1; r1[s] = -1; sy[s] = (float)rs.hs[s] / (float)H; }
+  float lo = INFINITY, hi = -INFINITY;
+  float *o = out + (size_t)plane * H * W + x;
+  for (int y = y_begin; y < y_end; ++y) {
+    float acc[4];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int hs = rs.hs[s], ws = rs.ws[s];
+      const Tap ty = tap_half_pixel(y, sy[s], hs);
+      if (ty.i0 != r0[s] || ty.i1 != r1[s]) {      // new source rows: x-interpolate this thread's columns on them
+        const float *a = rs.p[s] + ((size_t)b * C + c) * hs * ws;
+        const float *f = rs.p[s] + ((size_t)(B + b) * C + c) * hs * ws;
+        const float sx = (float)ws / (float)W;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const Tap tx = tap_half_pixel(x + k, sx, ws), tf = tap_half_pixel(W - 1 - (x + k), sx, ws);
+          top[s][k] = lerp_nested(tx.w0, __ldg(a + ty.i0 * ws + tx.i0), tx.w1, __ldg(a + ty.i0 * ws + tx.i1));
+          bot[s][k] = lerp_nested(tx.w0, __ldg(a + ty.i1 * ws + tx.i0), tx.w1, __ldg(a + ty.i1 * ws + tx.i1));
+          ftop[s][k] = lerp_nested(tf.w0, __ldg(f + ty.i0 * ws + tf.i0), tf.w1, __ldg(f + ty.i0 * ws + tf.i1));
+          fbot[s][k] = lerp_nested(tf.w0, __ldg(f + ty.i1 * ws + tf.i0), tf.w1, __ldg(f + ty.i1 * ws + tf.i1));
+        }
+        r0[s] = ty.i0;
+        r1[s] = ty.i1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v0 = lerp_nested(ty.w0, top[s][k], ty.w1, bot[s][k]);
+        const float v1 = lerp_nested(ty.w0, ftop[s][k], ty.w1, fbot[s][k]);
+        const float v = MODE == 2 ? __fadd_rn(v0, v1) : fmaxf(fmaxf(v0, v1), 0.0f);
+        acc[k] = s == 0 ? v : __fadd_rn(acc[k], v);
+      }
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { lo = fminf(lo, acc[k]); hi = fmaxf(hi, acc[k]); }
+    } else {
+      if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = __fdiv_rn(__fadd_rn(acc[k], neg_min), den);
+      }
+      stg_stream4(o + (size_t)y * W, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+  }
+  if (MODE == 0) {
+    // one pair of atomics per warp when the whole warp works on one plane, else one per thread
+    const int p0 = __shfl_sync(0xffffffffu, plane, 0);
+    const bool uniform = __all_sync(0xffffffffu, plane == p0 && live);
+    if (uniform) {
+      lo = warp_min(lo);
+      hi = warp_max(hi);
+      if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 2 * plane, float_to_ordered(lo));
+        atomicMax(mm + 2 * plane + 1, float_to_ordered(hi));
+      }
+    } else if (live && y_end > y_begin) {
+      atomicMin(mm + 2 * plane, float_to_ordered(lo));
+      atomicMax(mm + 2 * plane + 1, float_to_ordered(hi));
+    }
+  }
+}
+
+template <int MODE>
+static int launch_merge_rows(const RawScales &rs, float *out, int *mm, int B, int C, int H, int W, cudaStream_t s) {
+  const int rows = 56;   // rows per thread: long enough to amortise the source-row refresh, short enough to fill the GPU
+  const long long total = (long long)B * C * ceil_div(H, rows) * (W / 4);
+  const unsigned grid = (unsigned)ceil_div_ll(total, 128);
+  const char *name = MODE == 0 ? "cam_merge_minmax_kernel" : (MODE == 1 ? "cam_merge_write_kernel" : "seg_merge_kernel");
+  switch (rs.n) {
+    case 1: { auto k = merge_rows_kernel<1, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    case 2: { auto k = merge_rows_kernel<2, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    case 3: { auto k = merge_rows_kernel<3, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    case 4: { auto k = merge_rows_kernel<4, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    case 5: { auto k = merge_rows_kernel<5, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    default: return COSA_E_ARG;
+  }
+  return 0;
+}
+
 // seg = sum_s ( up(seg_s[:B]) + up(seg_s[B:]).flip(-1) )     (seg_helper.py:260-262, :273)
 __global__ void __launch_bounds__(256) seg_merge_kernel(RawScales rs, float *__restrict__ out, int B, int C, int H,
                                                         int W) {
@@ -765,6 +870,10 @@ extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs
   const long long HW = (long long)H * W;
   int *mm = (int *)minmax_ws;
   COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
+  if (W % 4 == 0 && n_scales <= 5) {
+    COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, s));
+    return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, s);
+  }
   const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
   COSA_LAUNCH_T("cam_merge_minmax_kernel", cam_merge_kernel<false>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
   COSA_LAUNCH_T("cam_merge_write_kernel", cam_merge_kernel<true>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
@@ -776,6 +885,7 @@ extern "C" int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs
   if (!out || B < 1 || C < 1 || H < 1 || W < 1) return COSA_E_ARG;
   RawScales rs;
   COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
+  if (W % 4 == 0 && n_scales <= 5) return launch_merge_rows<2>(rs, out, nullptr, B, C, H, W, (cudaStream_t)stream);
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)max(1LL, min((long long)sm_count() * 16, ceil_div_ll(total, 256)));
   COSA_LAUNCH(seg_merge_kernel, blocks, 256, 0, (cudaStream_t)stream, rs, out, B, C, H, W);

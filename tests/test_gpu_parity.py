@@ -152,8 +152,10 @@ def test_multi_scale_merge_golden(cosa):
     assert_same(cosa.multi_scale_seg_merge(raw("seg"), size), g["seg"], "merged seg")
 
 
-def test_multi_scale_camseg_with_stub_teacher(cosa, port):
-    """Whole multi_scale_camseg contract with a torch stand-in for the teacher, against the oracle merge."""
+@pytest.mark.parametrize("size", [(448, 448), (80, 50), (64, 32)])
+def test_multi_scale_camseg_with_stub_teacher(cosa, port, size):
+    """Whole multi_scale_camseg contract with a torch stand-in for the teacher, against the oracle merge
+    (row-walking kernels for W % 4 == 0, per-pixel kernels otherwise)."""
     torch.manual_seed(3)
     w = torch.randn((3, 7, 3), device="cuda")
     calls = []
@@ -164,9 +166,9 @@ def test_multi_scale_camseg_with_stub_teacher(cosa, port):
         calls.append([o.cpu() for o in outs])
         return None, None, None, outs[0], outs[1], outs[2]
 
-    imgs = torch.randn((4, 3, 448, 448), device="cuda")
+    imgs = torch.randn((4, 3) + size, device="cuda")
     cam, aux, seg = cosa.multi_scale_camseg(teacher, imgs, [1.0, 0.5, 1.5])
-    o_cam, o_aux, o_seg = port.multi_scale_merge([c[1] for c in calls], calls[-1][2], [c[0] for c in calls], (448, 448))
+    o_cam, o_aux, o_seg = port.multi_scale_merge([c[1] for c in calls], calls[-1][2], [c[0] for c in calls], size)
     assert_close(cam, o_cam, "cam", 1e-6)
     assert_close(aux, o_aux, "cam_aux", 1e-6)
     assert_close(seg, o_seg, "seg", 1e-6)
