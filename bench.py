@@ -194,7 +194,9 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
     h, w = H // 2, W // 2
     n, K, T, ND = h * w, C, NUM_ITER, 8 * len(DILATIONS)
     Kp = (K + 3) // 4 * 4
-    ncm = 2 * nc                                    # high + low stacks share the affinity
+    # high + low stacks share the affinity; the last live channel of each stack is derived from the channel sum
+    # instead of being propagated (label_kernels.cu: cosa_cam2mask) unless COSA_CAM2MASK_ALL_CHANNELS is set
+    ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
     per = {
         "cam_validation_kernel": 2 * 4 * B * (C - 1) * H * W,
         "cam2mask_keys_kernel": 4 * B * (C - 1) + 4 * B * C,

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "cosa_par_ws_bytes": (_c_size_t, [_c_int] * 5),
     "cosa_par_forward": (_c_int, [_vp, _vp, _vp] + [_c_int] * 6 + [_vp, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "cosa_par_set_step_mode": (_c_int, [ctypes.c_char_p]),
+    "cosa_cam2mask_set_all_channels": (_c_int, [_c_int]),
     "cosa_par_affinity": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "cosa_cam_normalize": (_c_int, [_vp, _c_int, _vp, _c_int, _c_ll, _vp, _vp]),
     "cosa_multi_scale_cam_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp, _vp]),

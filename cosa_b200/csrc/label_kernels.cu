@@ -3,6 +3,7 @@
 // All of these are streaming, HBM-bound passes: 128-bit loads where the layout allows, warp shuffles for the
 // per-pixel channel reduction, grids sized from the SM count (persistent grid-stride) or one tile per CTA.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "par.cuh"
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(256) cam_to_label_kernel(const float *__restri
 // Mask buffers are [B, 2*C, h, w]: channels [0,nc) hold the high stack, [nc,2nc) the low stack.
 // ------------------------------------------------------------------------------------------------
 __global__ void cam2mask_keys_kernel(const float *__restrict__ cls_labels, int *__restrict__ keys,
-                                     int *__restrict__ nc_out, int *__restrict__ nch_out, int B, int C1) {
+                                     int *__restrict__ nc_out, int *__restrict__ nch_out, int B, int C1,
+                                     int derive) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int *k = keys + (size_t)b * (C1 + 1);
@@ -235,7 +237,7 @@ __global__ void cam2mask_keys_kernel(const float *__restrict__ cls_labels, int *
   for (int c = 0; c < C1; ++c)
     if (cls_labels[(size_t)b * C1 + c] != 0.0f) k[n++] = c + 1;
   nc_out[b] = n;
-  nch_out[b] = 2 * n;
+  nch_out[b] = 2 * (n - derive);   // stored channels: both stacks, minus the derived one of each
 }
 
 struct ResizeGeom {
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
                                                                const int *__restrict__ nc_dev,
                                                                float *__restrict__ img_small,
                                                                float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
-                                                               int C1, float thr_high, float thr_low) {
+                                                               int C1, float thr_high, float thr_low, int derive) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -283,7 +285,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   // mask rows may be padded (MaskLayout): interior at column ml.off, ml.padn replicated columns either side
   const size_t mplane = (size_t)g.h * ml.pitch;
   float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * mplane + (size_t)y * ml.pitch + ml.off + x;
-  float *m_lo = m_hi + (size_t)nc * mplane;
+  const int ns = nc - derive;   // channels stored per stack (the last live one is derived, see cosa_cam2mask)
+  float *m_lo = m_hi + (size_t)ns * mplane;
   auto put = [&](float *dst, float val) {
     *dst = val;
     if (ml.padn) {
@@ -310,9 +313,11 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
     den_hi += expf(t - mx_hi);
     den_lo += expf(t - mx_lo);
   }
-  put(m_hi, e0_hi / den_hi);
-  put(m_lo, e0_lo / den_lo);
-  for (int j = 1; j < nc; ++j) {
+  if (ns > 0) {
+    put(m_hi, e0_hi / den_hi);
+    put(m_lo, e0_lo / den_lo);
+  }
+  for (int j = 1; j < ns; ++j) {
     const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
     put(m_hi + (size_t)j * mplane, expf(t - mx_hi) / den_hi);
     put(m_lo + (size_t)j * mplane, expf(t - mx_lo) / den_lo);
@@ -320,16 +325,26 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
 }
 
 // argmax over nc channels of the bilinearly up-sampled stack at full-resolution pixel (Y, X)
+// `total` > 0: the stack stores only its first nc - 1 channels and the last one is total - (sum of the others) at
+// every half-resolution tap (see cosa_cam2mask).
 __device__ __forceinline__ int upsampled_argmax(const float *stack, int nc, size_t hw, int w, const Tap &ty,
-                                                const Tap &tx) {
+                                                const Tap &tx, float total = 0.0f) {
   // hw = plane stride, w = row pitch (the caller has already added the interior offset to `stack`)
   const size_t o00 = (size_t)ty.i0 * w + tx.i0, o01 = (size_t)ty.i0 * w + tx.i1;
   const size_t o10 = (size_t)ty.i1 * w + tx.i0, o11 = (size_t)ty.i1 * w + tx.i1;
   float best = -INFINITY;
   int arg = 0;
+  float s00 = 0.0f, s01 = 0.0f, s10 = 0.0f, s11 = 0.0f;
   for (int j = 0; j < nc; ++j) {
-    const float *p = stack + (size_t)j * hw;
-    const float val = bilerp_up(ty, tx, __ldg(p + o00), __ldg(p + o01), __ldg(p + o10), __ldg(p + o11));
+    float a00, a01, a10, a11;
+    if (total > 0.0f && j == nc - 1) {
+      a00 = total - s00; a01 = total - s01; a10 = total - s10; a11 = total - s11;
+    } else {
+      const float *p = stack + (size_t)j * hw;
+      a00 = __ldg(p + o00); a01 = __ldg(p + o01); a10 = __ldg(p + o10); a11 = __ldg(p + o11);
+      s00 += a00; s01 += a01; s10 += a10; s11 += a11;
+    }
+    const float val = bilerp_up(ty, tx, a00, a01, a10, a11);
     if (val > best || j == 0) { best = val; arg = j; }
   }
   return arg;
@@ -342,7 +357,8 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
                                                                 float *__restrict__ label_out,
                                                                 float *__restrict__ label_hi_out,
                                                                 float *__restrict__ label_lo_out, MaskLayout ml,
-                                                                ResizeGeom g, int C1, float ignore_index) {
+                                                                ResizeGeom g, int C1, float ignore_index,
+                                                                float derive_total) {
   const int X = blockIdx.x * 32 + (threadIdx.x & 31);
   const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -358,8 +374,9 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
     const Tap ty = tap_half_pixel(Y, g.identity ? 1.0f : (float)g.h / (float)g.H, g.h);
     const Tap tx = tap_half_pixel(X, g.identity ? 1.0f : (float)g.w / (float)g.W, g.w);
     const float *st = refined + (size_t)b * 2 * (C1 + 1) * mplane + ml.off;
-    hi = (float)key[upsampled_argmax(st, nc, mplane, ml.pitch, ty, tx)];
-    lo = (float)key[upsampled_argmax(st + (size_t)nc * mplane, nc, mplane, ml.pitch, ty, tx)];
+    const int ns = derive_total > 0.0f ? nc - 1 : nc;   // channels stored per stack
+    hi = (float)key[upsampled_argmax(st, nc, mplane, ml.pitch, ty, tx, derive_total)];
+    lo = (float)key[upsampled_argmax(st + (size_t)ns * mplane, nc, mplane, ml.pitch, ty, tx, derive_total)];
   }
   // merge (seg_helper.py:781-783): high fg stays; high bg becomes ignore unless low also says bg
   float out = hi;
@@ -381,7 +398,8 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
                                                                    float *__restrict__ label_out,
                                                                    float *__restrict__ label_hi_out,
                                                                    float *__restrict__ label_lo_out, MaskLayout ml,
-                                                                   ResizeGeom g, int C1, float ignore_index) {
+                                                                   ResizeGeom g, int C1, float ignore_index,
+                                                                   float derive_total) {
   const int xs = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ys = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -413,16 +431,28 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
     const float *st = refined + (size_t)b * 2 * (C1 + 1) * mplane + ml.off;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {                       // high stack, low stack
-      const float *stack = st + (size_t)s * nc * mplane;
+      const bool derive = derive_total > 0.0f;
+      const float *stack = st + (size_t)s * (derive ? nc - 1 : nc) * mplane;
       float best[2][2];
       int arg[2][2] = {{0, 0}, {0, 0}};
+      float sum[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       for (int j = 0; j < nc; ++j) {
         const float *p = stack + (size_t)j * mplane;
         float v[3][3];
+        if (derive && j == nc - 1) {   // the channel that was not propagated: total - (sum of the others)
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
+          for (int a = 0; a < 3; ++a)
 #pragma unroll
-          for (int e = 0; e < 3; ++e) v[a][e] = __ldg(p + r[a] + c[e]);
+            for (int e = 0; e < 3; ++e) v[a][e] = derive_total - sum[a][e];
+        } else {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              v[a][e] = __ldg(p + r[a] + c[e]);
+              sum[a][e] += v[a][e];
+            }
+        }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -782,6 +812,12 @@ extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downsc
   return bytes;
 }
 
+static int g_all_channels = -1;   // -1: not decided yet (environment), 0: derive the last channel, 1: propagate all
+extern "C" int cosa_cam2mask_set_all_channels(int on) {
+  g_all_channels = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float *cams, const float *cls_labels,
                              float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
                              const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
@@ -807,7 +843,17 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
   int *nch = arena.take<int>(B);
   float *masks = arena.take<float>(mfloats);
 
-  COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1);
+  // The stacks PAR refines are softmax outputs: their channels sum to 1 at every pixel, and one propagation step
+  // multiplies that sum by the row sum of the weights (the same 8*n_dil taps at every pixel, replicate padding
+  // included).  So the last live channel of each stack is not propagated: after num_iter steps it is
+  // row_sum^num_iter minus the sum of the others, evaluated by the labelling kernel at every tap (|error| ~ 1e-6,
+  // the same order as the summation-order differences between two fp32 evaluations of the reference).
+  // cosa_cam2mask_set_all_channels(1) / COSA_CAM2MASK_ALL_CHANNELS=1 propagates every channel (A/B runs, tests).
+  if (refine) COSA_CHECK(par_upload_constants(dilations, n_dil, s));
+  if (g_all_channels < 0) g_all_channels = getenv("COSA_CAM2MASK_ALL_CHANNELS") ? 1 : 0;
+  const int derive = (refine && !g_all_channels) ? 1 : 0;
+  const float derive_total = derive ? (float)pow(par_weight_row_sum(), (double)num_iter) : 0.0f;
+  COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
   if (refine) {
     sa = arena.take<float>(mfloats);
@@ -815,11 +861,10 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
     fin = arena.take<float>(mfloats);
     img_small = arena.take<float>((size_t)B * 3 * hw);
     aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
-    COSA_CHECK(par_upload_constants(dilations, n_dil, s));
   }
   dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
   COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, img_small, masks, lay, g, C1,
-              threshold_high, threshold_low);
+              threshold_high, threshold_low, derive);
   const float *refined = masks;
   MaskLayout lay_fin = lay;
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
@@ -831,11 +876,11 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
   if (!g.identity && H == 2 * g.h && W == 2 * g.w) {
     dim3 gf(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH(cam2mask_finalize_x2_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
-                label_low_out, lay_fin, g, C1, ignore_index);
+                label_low_out, lay_fin, g, C1, ignore_index, derive_total);
   } else {
     dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
     COSA_LAUNCH(cam2mask_finalize_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
-                label_low_out, lay_fin, g, C1, ignore_index);
+                label_low_out, lay_fin, g, C1, ignore_index, derive_total);
   }
   return 0;
 }

@@ -16,6 +16,7 @@
 // round-to-nearest intrinsics in the reference's operation order, so the vertex set and the weights are
 // bit-identical to the CPU code; only the summation order of the splat (atomics) differs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "lattice.cuh"
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const
   __syncthreads();
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)N * n_pad;
-  const bool in_range = g < total;        // out-of-range threads stay for the warp/block collectives
+  const bool in_range = g < total;        // out-of-range threads stay for the block collectives
   const int n = H * W;
   const int b = in_range ? (int)(g / n_pad) : 0, p = in_range ? (int)(g % n_pad) : 0;
   const bool real = in_range && p < n;   // the SSE loop also embeds zero-feature padding pixels (permutohedral.cpp:168-173)
@@ -150,39 +151,43 @@ __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const
   embed_point(f, ec, q0, rank, bary);
 
   const long long gp = (long long)b * n + p;   // compact pixel index
-  const int lane = threadIdx.x & 31;
   int bad = 0, max_probe = 0;
-  unsigned new_mask = 0;                        // bit r: this lane created the table entry of vertex r
-  unsigned long long new_key[kLatD + 1], new_slot[kLatD + 1];
+  unsigned new_mask = 0;                        // bit r: this thread created the table entry of vertex r
+  unsigned long long key[kLatD + 1], slot[kLatD + 1], cur[kLatD + 1];
+  // Nine out of ten look-ups find a vertex that an earlier pixel created (M is ~0.5 n for 6 n look-ups), so the
+  // table is probed with plain L2 loads - all six in flight at once - and only an empty slot costs a CAS.  A stale
+  // "empty" is harmless (the CAS decides); an occupied slot never changes again.
 #pragma unroll
   for (int r = 0; r <= kLatD; ++r) {
     int q[kLatD];
 #pragma unroll
     for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
-    // out-of-range lanes carry a per-lane dummy (residue field 7: never a real key) and insert nothing
-    const unsigned long long key = in_range ? pack_key(q, r, b, &bad) : kEmptyKey - 1ULL - (unsigned long long)lane;
-    // warp-aggregated insert: one CAS per distinct key per warp
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    unsigned long long slot = 0;
-    if (lane == leader && in_range) {
-      slot = hash_key(key) & L.cap_mask;
+    key[r] = pack_key(q, r, b, &bad);
+    slot[r] = hash_key(key[r]) & L.cap_mask;
+    cur[r] = in_range ? __ldcg(L.table_keys + slot[r]) : key[r];
+  }
+#pragma unroll
+  for (int r = 0; r <= kLatD; ++r) {
+    if (in_range) {
+      unsigned long long s = slot[r], c = cur[r];
       int probes = 0;
       for (;;) {
-        const unsigned long long old = atomicCAS(L.table_keys + slot, kEmptyKey, key);
-        if (old == kEmptyKey) { new_mask |= 1u << r; break; }
-        if (old == key) break;
-        slot = (slot + 1) & L.cap_mask;
+        if (c == key[r]) break;
+        if (c == kEmptyKey) {
+          c = atomicCAS(L.table_keys + s, kEmptyKey, key[r]);
+          if (c == kEmptyKey) { new_mask |= 1u << r; break; }
+          if (c == key[r]) break;
+        }
+        s = (s + 1) & L.cap_mask;
+        c = __ldcg(L.table_keys + s);
         ++probes;
       }
+      slot[r] = s;
       max_probe = max(max_probe, probes);
-    }
-    new_key[r] = key;
-    new_slot[r] = slot;
-    slot = __shfl_sync(peers, slot, leader);
-    if (real) {
-      L.offsets[(size_t)r * L.P + gp] = (int)slot;
-      L.bary[(size_t)r * L.P + gp] = bary[r];
+      if (real) {
+        L.offsets[(size_t)r * L.P + gp] = (int)s;
+        L.bary[(size_t)r * L.P + gp] = bary[r];
+      }
     }
   }
   // dense vertex ids: one global atomic per CTA instead of one per new vertex (a single hot address otherwise)
@@ -197,8 +202,8 @@ __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const
 #pragma unroll
     for (int r = 0; r <= kLatD; ++r) {
       if (new_mask & (1u << r)) {
-        L.vkeys[id] = new_key[r];
-        L.table_ids[new_slot[r]] = id + 1;
+        L.vkeys[id] = key[r];
+        L.table_ids[slot[r]] = id + 1;
         ++id;
       }
     }
@@ -412,10 +417,291 @@ __global__ void __launch_bounds__(256) lattice_slice_kernel(LatticeBufs L, const
   }
 }
 
+// ---- tile-local vertex sharing ---------------------------------------------------------------------
+// A 32 x 8 pixel tile touches 6 * 256 (pixel, vertex) pairs but only ~22 % as many distinct vertices (the lattice
+// cells are sigma_xy = 50 pixels wide; measured on the synthetic VOC images: 0.22 at 32 x 8, 0.15 at 32 x 32).  The
+// tile kernels below therefore dedup the vertex ids of a tile in a shared-memory hash table first and touch every
+// distinct vertex row in L2 once per tile instead of once per pair:
+//   splat  pairs are bucketed per vertex (count -> scan -> fill), each vertex sums its contributions from a
+//          shared-memory copy of the tile's input channels and issues ONE sector-wide reduction per 8 channels
+//   slice  the distinct vertex rows are staged in shared memory once and the pixels gather from there
+constexpr int kTileW = 32;
+constexpr int kChunk = 24;                       // channels per pass (K = 21 -> one pass)
+
+__device__ __forceinline__ unsigned tile_hash(int id, int bits) { return ((unsigned)id * 2654435761u) >> (32 - bits); }
+
+// Inserts `id` into the open-addressing table hkey[1 << bits] (-1 = empty); returns the slot.  *won is set for the
+// thread whose CAS created the entry.
+__device__ __forceinline__ int tile_insert(int *hkey, int bits, int id, bool *won) {
+  const unsigned mask = (1u << bits) - 1;
+  unsigned h = tile_hash(id, bits);
+  for (;;) {
+    const int old = atomicCAS(hkey + h, -1, id);
+    if (old == -1) { *won = true; return (int)h; }
+    if (old == id) { *won = false; return (int)h; }
+    h = (h + 1) & mask;
+  }
+}
+
+// Splat (permutohedral.cpp:526-534) with tile-local pre-reduction.  CTA = 256 threads = TH/8 pixels per thread of a
+// 32 x TH tile.  Shared memory: hash keys + (start | count) words, the pair list bucketed by vertex, the list of
+// occupied slots and the tile's input channels [kChunk][pixels + 1].
+template <int TH>
+__global__ void __launch_bounds__(256) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins, int K,
+                                                                 int H, int W) {
+  constexpr int PPT = TH / 8, PIX = kTileW * TH, PAIRS = 6 * PIX;
+  constexpr int BITS = PPT == 1 ? 11 : 12, HS = 1 << BITS;   // load factor <= 0.75 when every pair is distinct
+  constexpr int PLANE = PIX + 1;                               // odd plane pitch: channel-strided reads hit distinct banks
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int *hkey = reinterpret_cast<int *>(s_raw);                  // [HS]
+  int *hinfo = hkey + HS;                                      // [HS] count, then (start << 16) | count
+  int2 *plist = reinterpret_cast<int2 *>(hinfo + HS);          // [PAIRS] (pixel, weight bits) bucketed by vertex
+  unsigned short *ulist = reinterpret_cast<unsigned short *>(plist + PAIRS);   // [PAIRS] occupied slots
+  float *in_s = reinterpret_cast<float *>(ulist + PAIRS);      // [kChunk][PLANE]
+  __shared__ int s_scan[8];
+  __shared__ int s_U;
+
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int n = H * W;
+  const int tid = threadIdx.x, lx = tid & 31, ly0 = tid >> 5;
+  for (int i = tid; i < HS; i += 256) { hkey[i] = -1; hinfo[i] = 0; }
+  if (tid == 0) s_U = 0;
+  __syncthreads();
+
+  int hslot[PPT][6], hpos[PPT][6];
+  float wgt[PPT][6];
+  // every vertex id and weight of the thread's pixels is requested before the first shared-memory atomic (the
+  // compiler does not move loads across atomics)
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int x = x0 + lx, y = y0 + ly0 + 8 * j;
+    const bool ok = x < W && y < H;
+    const long long gp = (long long)b * n + (long long)y * W + x;
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      hslot[j][r] = ok ? L.offsets[(size_t)r * L.P + gp] : -1;
+      wgt[j][r] = ok ? L.bary[(size_t)r * L.P + gp] : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      if (hslot[j][r] >= 0) {
+        bool won;
+        const int h = tile_insert(hkey, BITS, hslot[j][r], &won);
+        hslot[j][r] = h;
+        hpos[j][r] = atomicAdd(hinfo + h, 1);
+      }
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the counts (HS / 256 consecutive slots per thread) + list of the occupied slots
+  {
+    constexpr int PER = HS / 256;
+    int cnt[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { cnt[i] = hinfo[tid * PER + i]; sum += cnt[i]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int wv = 0; wv < (tid >> 5); ++wv) base += s_scan[wv];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      if (cnt[i]) {
+        hinfo[tid * PER + i] = (base << 16) | cnt[i];
+        ulist[atomicAdd(&s_U, 1)] = (unsigned short)(tid * PER + i);
+        base += cnt[i];
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PPT; ++j)
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r)
+      if (hslot[j][r] >= 0)
+        plist[(hinfo[hslot[j][r]] >> 16) + hpos[j][r]] = make_int2((ly0 + 8 * j) * kTileW + lx, __float_as_int(wgt[j][r]));
+  const int U = s_U;
+
+  const int sub = (tid & 31) >> 3, cl = tid & 7, wv = tid >> 5;
+  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
+    const int kc = min(kChunk, L.Kp - c0);
+    __syncthreads();   // the pair list is complete / the previous pass has read in_s
+    for (int i0 = tid; i0 < kc * PIX; i0 += 4 * 256) {   // four loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * 256;
+        const int c = i / PIX, pl = i - c * PIX;
+        const int x = x0 + (pl & 31), y = y0 + (pl >> 5);
+        v[k] = 0.0f;
+        if (i < kc * PIX && c0 + c < K && x < W && y < H) v[k] = __ldg(ins + ((size_t)b * K + c0 + c) * n + (size_t)y * W + x);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * 256;
+        const int c = i / PIX, pl = i - c * PIX;
+        if (i < kc * PIX) in_s[c * PLANE + pl] = v[k];
+      }
+    }
+    __syncthreads();
+    // a quarter-warp per vertex: lane cl sums channels cl, cl + 8, cl + 16 over the vertex's pairs
+    for (int u = wv * 4 + sub; u < U; u += 32) {
+      const int slot = ulist[u];
+      const int info = hinfo[slot];
+      const int start = info >> 16, cnt = info & 0xffff;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+      for (int e = 0; e < cnt; ++e) {
+        const int2 pw = plist[start + e];
+        const float wv_ = __int_as_float(pw.y);
+        const float *src = in_s + cl * PLANE + pw.x;
+        a0 = fmaf(wv_, src[0], a0);
+        a1 = fmaf(wv_, src[8 * PLANE], a1);
+        a2 = fmaf(wv_, src[16 * PLANE], a2);
+      }
+      float *dst = L.val0 + (size_t)hkey[slot] * L.Kp + c0 + cl;
+      if (cl < kc) atomicAdd(dst, a0);
+      if (cl + 8 < kc) atomicAdd(dst + 8, a1);
+      if (cl + 16 < kc) atomicAdd(dst + 16, a2);
+    }
+  }
+}
+
+// Slice (permutohedral.cpp:554-567) + optional dense-CRF epilogue with the distinct vertex rows of a 32 x 8 tile staged
+// in shared memory (up to kSliceRows of them; pairs beyond that read L2 directly).
+constexpr int kSliceRows = 512;
+template <bool ENERGY>
+__global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
+                                                                 const float *__restrict__ ins,
+                                                                 const float *__restrict__ gate, double *loss_acc,
+                                                                 float *__restrict__ outs, int K, int H, int W) {
+  constexpr int BITS = 11, HS = 1 << BITS, TH = 8;
+  __shared__ int hkey[HS];
+  __shared__ int hval[HS];                      // local row index of the slot's vertex
+  __shared__ int urow_id[kSliceRows];           // vertex id of local row u
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float *rows = reinterpret_cast<float *>(s_raw);   // [kSliceRows][kChunk]
+  __shared__ int s_U;
+  __shared__ float s_part[8];
+  const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH, b = blockIdx.z;
+  const int n = H * W;
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+  for (int i = tid; i < HS; i += 256) hkey[i] = -1;
+  if (tid == 0) s_U = 0;
+  __syncthreads();
+  const int x = x0 + lx, y = y0 + ly;
+  const bool ok = x < W && y < H;
+  const long long gp = (long long)b * n + (long long)y * W + x;
+  int id[kLatD + 1], hs[kLatD + 1];
+  float w[kLatD + 1];
+#pragma unroll
+  for (int r = 0; r <= kLatD; ++r) {   // all loads first: the compiler does not move loads across the atomics below
+    id[r] = ok ? L.offsets[(size_t)r * L.P + gp] : 0;
+    w[r] = ok ? __fmul_rn(L.bary[(size_t)r * L.P + gp], alpha) : 0.0f;
+    hs[r] = 0;
+  }
+  const float gt = (ENERGY && ok) ? __ldg(gate + gp) : 1.0f;
+  float s_in[kChunk];                   // energy epilogue: the pixel's own inputs of the first channel pass
+  if (ENERGY) {
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c)
+      s_in[c] = (ok && c < K) ? __ldg(ins + ((size_t)b * K + c) * n + (size_t)y * W + x) : 0.0f;
+  }
+#pragma unroll
+  for (int r = 0; r <= kLatD; ++r) {
+    if (ok) {
+      bool won;
+      hs[r] = tile_insert(hkey, BITS, id[r], &won);
+      if (won) {
+        const int u = atomicAdd(&s_U, 1);
+        hval[hs[r]] = u;
+        if (u < kSliceRows) urow_id[u] = id[r];
+      }
+    }
+  }
+  __syncthreads();
+  int u_r[kLatD + 1];
+#pragma unroll
+  for (int r = 0; r <= kLatD; ++r) u_r[r] = ok ? hval[hs[r]] : 0;
+  const int U = min(s_U, kSliceRows);
+  float local = 0.0f;
+  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
+    const int kc = min(kChunk, L.Kp - c0), kq = kc >> 2;
+    __syncthreads();
+    for (int i0 = tid; i0 < U * kq; i0 += 4 * 256) {   // four row quads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * 256;
+        const int u = i / kq, q = i - u * kq;
+        if (i < U * kq) v[k] = *reinterpret_cast<const float4 *>(values + (size_t)urow_id[u] * L.Kp + c0 + 4 * q);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * 256;
+        const int u = i / kq, q = i - u * kq;
+        if (i < U * kq) reinterpret_cast<float4 *>(rows)[u * (kChunk / 4) + q] = v[k];
+      }
+    }
+    __syncthreads();
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < kChunk / 4; ++q) {
+        if (q >= kq) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r <= kLatD; ++r) {
+          const float4 v = u_r[r] < kSliceRows
+                               ? reinterpret_cast<const float4 *>(rows)[u_r[r] * (kChunk / 4) + q]
+                               : *reinterpret_cast<const float4 *>(values + (size_t)id[r] * L.Kp + c0 + 4 * q);
+          acc.x = __fadd_rn(acc.x, __fmul_rn(w[r], v.x));
+          acc.y = __fadd_rn(acc.y, __fmul_rn(w[r], v.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(w[r], v.z));
+          acc.w = __fadd_rn(acc.w, __fmul_rn(w[r], v.w));
+        }
+        const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + 4 * q + k;
+          if (c < K) {
+            float o = a4[k];
+            const size_t at = ((size_t)b * K + c) * n + (size_t)y * W + x;
+            if (ENERGY) {
+              o = __fmul_rn(o, gt);
+              local = fmaf(c0 == 0 ? s_in[4 * q + k] : __ldg(ins + at), o, local);
+            }
+            outs[at] = o;
+          }
+        }
+      }
+    }
+  }
+  if (ENERGY) {
+    local = warp_sum(local);
+    if ((tid & 31) == 0) s_part[tid >> 5] = local;
+    __syncthreads();
+    if (tid < 32) {
+      float t = tid < 8 ? s_part[tid] : 0.0f;
+      t = warp_sum(t);
+      if (tid == 0) atomicAdd(loss_acc, (double)t);
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static unsigned long long table_capacity(long long m_cap) {
   unsigned long long cap = 1024;
-  while (cap < 2ULL * (unsigned long long)m_cap) cap <<= 1;
+  // m_cap is the worst case (six new vertices per pixel; natural images stay below 2.5 n), so the load factor is
+  // at most 0.8 and in practice below 0.1
+  while (cap < (unsigned long long)m_cap + (unsigned long long)m_cap / 4) cap <<= 1;
   return cap;
 }
 
@@ -477,10 +763,43 @@ int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W
   return 0;
 }
 
+// COSA_LATTICE_PIXEL=1 selects the one-thread-per-pixel splat / slice kernels (A/B runs); COSA_SPLAT_TH=16 the
+// 32 x 16 splat tile.
+static int lattice_env(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static bool lattice_per_pixel() {
+  static int v = -1;
+  if (v < 0) v = lattice_env("COSA_LATTICE_PIXEL", 0) ? 1 : 0;
+  return v == 1;
+}
+
+template <int TH>
+static int launch_splat_tile(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
+  constexpr int PIX = kTileW * TH, PAIRS = 6 * PIX, HS = TH == 8 ? 2048 : 4096;
+  const size_t smem = (size_t)HS * 8 + (size_t)PAIRS * 8 + (size_t)PAIRS * 2 + (size_t)kChunk * (PIX + 1) * 4;
+  static bool attr = false;
+  if (!attr) {
+    COSA_CUDA(cudaFuncSetAttribute(lattice_splat_tile_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const dim3 grid(ceil_div(W, kTileW), ceil_div(H, TH), N);
+  COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<TH>, grid, 256, smem, stream, L, ins, K, H, W);
+  return 0;
+}
+
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
   const int n = H * W;
   COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
-  COSA_LAUNCH(lattice_splat_kernel, persistent_blocks(L.P, 256), 256, 0, stream, L, ins, K, n);
+  if (lattice_per_pixel()) {
+    COSA_LAUNCH(lattice_splat_kernel, persistent_blocks(L.P, 256), 256, 0, stream, L, ins, K, n);
+  } else {
+    static int th = 0;
+    if (!th) th = lattice_env("COSA_SPLAT_TH", 8) == 16 ? 16 : 8;
+    if (th == 16) COSA_CHECK(launch_splat_tile<16>(L, ins, N, K, H, W, stream));
+    else COSA_CHECK(launch_splat_tile<8>(L, ins, N, K, H, W, stream));
+  }
   float *src = L.val0, *dst = L.val1;
   for (int axis = 0; axis <= kLatD; ++axis) {
     COSA_LAUNCH(lattice_blur_kernel, sm_count() * 8, 256, 0, stream, L, src, dst, axis);
@@ -492,11 +811,29 @@ int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int
 int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, double *loss_acc, float *outs, int N,
                   int K, int H, int W, cudaStream_t stream) {
   const int n = H * W;
-  const int blocks = persistent_blocks(L.P, 256);
+  if (lattice_per_pixel()) {
+    const int blocks = persistent_blocks(L.P, 256);
+    if (gate) {
+      COSA_LAUNCH(lattice_slice_kernel<true>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+    } else {
+      COSA_LAUNCH(lattice_slice_kernel<false>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+    }
+    return 0;
+  }
+  const size_t smem = (size_t)kSliceRows * kChunk * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const dim3 grid(ceil_div(W, kTileW), ceil_div(H, 8), N);
   if (gate) {
-    COSA_LAUNCH(lattice_slice_kernel<true>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<true>, grid, 256, smem, stream, L, L.val0, ins,
+                  gate, loss_acc, outs, K, H, W);
   } else {
-    COSA_LAUNCH(lattice_slice_kernel<false>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<false>, grid, 256, smem, stream, L, L.val0, ins,
+                  gate, loss_acc, outs, K, H, W);
   }
   return 0;
 }

@@ -9,6 +9,11 @@ constexpr int kMaxDil = 8;   // up to 64 neighbours
 // Uploads the dilation list and the constant position term (PAR.py:51-62,82) for subsequent launches.
 int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream);
 
+// Sum over the neighbours of the weights of one pixel for the last uploaded dilation list: 1 (softmax) + w2 (the
+// position term), evaluated from the float constants the kernels use.  A propagation step multiplies the channel
+// sum of a stack by this factor (PAR.py:85-89; replicate padding keeps all 8*n_dil taps).
+double par_weight_row_sum();
+
 // aff [B, 8*n_dil, h, w] from imgs [B,3,h,w].
 int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream);
 

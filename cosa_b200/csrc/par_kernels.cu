@@ -20,6 +20,8 @@ namespace cosa {
 __constant__ int c_dil[kMaxDil];
 __constant__ float c_pos_term[kMaxDil * 8];   // w2 * softmax(pos_aff), filled by par_upload_constants
 static bool g_std_dilations = false;          // the last uploaded list is the reference's {1,2,4,8,12,24} (PAR.py:94)
+static double g_row_sum = 1.01;               // sum over the neighbours of softmax + w2 * softmax(pos_aff)
+double par_weight_row_sum() { return g_row_sum; }
 
 // Host: the position term is a constant vector (PAR.py:51-62,77,82); evaluate it in double.
 int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
@@ -48,6 +50,8 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
   for (int n = 0; n < nd; ++n) sum += exp(logit[n] - mx);
   float term[kMaxDil * 8];
   for (int n = 0; n < nd; ++n) term[n] = 0.01f * (float)(exp(logit[n] - mx) / sum);
+  g_row_sum = 1.0;
+  for (int n = 0; n < nd; ++n) g_row_sum += (double)term[n];
   int dil[kMaxDil] = {0};
   for (int k = 0; k < n_dil; ++k) dil[k] = dilations[k];
   static const int kStd[6] = {1, 2, 4, 8, 12, 24};
@@ -754,8 +758,8 @@ __global__ void __launch_bounds__(256, 2)
 
 // Tile-mode step kernel (default): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
 // passes of its tile.  The hardware CTA scheduler balances the load; 2 CTAs per SM overlap staging and compute.
-template <int CH>
-__global__ void __launch_bounds__(256, 2)
+template <int CH, int DEPTH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
     par_iterate_tile_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
                             int c_stride, int h, int w, int gsplit) {
@@ -768,8 +772,10 @@ __global__ void __launch_bounds__(256, 2)
   const int b = blockIdx.z / gsplit, g = blockIdx.z - b * gsplit;
   const bool active = xq < wq && y < h;
   const int nch = nch_dev ? nch_dev[b] : nch_uniform;
-  // the live channels are split evenly over the gsplit CTAs of this tile, at most CH per pass
-  const int n_groups = gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
+  if (nch <= 0) return;   // an image without live channels (cam2mask: no foreground class)
+  // up to CH channels: one CTA (the affinity quads are loaded once); more: split evenly over the gsplit CTAs of
+  // this tile, at most CH per pass
+  const int n_groups = nch <= CH ? 1 : gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
   const int chunk = (nch + n_groups - 1) / n_groups;
   if (g * chunk >= nch) return;
   const size_t plane = (size_t)h * w;
@@ -803,7 +809,9 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *Ap = A;
-    float4 a0[8], a1[8], a2[8];   // affinity quads two dilations ahead of their use
+    // affinity quads DEPTH - 1 dilations ahead of their use (DEPTH = 2 leaves 32 more registers to the
+    // shared-memory loads in flight)
+    float4 a0[8], a1[8];
     load_aff8(a0, Ap, plane);
     load_aff8(a1, Ap, plane);
     mbar_wait(&s_bar[0], phase);
@@ -811,17 +819,32 @@ __global__ void __launch_bounds__(256, 2)
       mbar_wait(&s_bar[1], phase);
       replicate_border_rows(s_tile, live, r_lo, r_hi);
     }
-    load_aff8(a2, Ap, plane);
-    tile_dilation<1, CH>(acc, a0, q, live);
-    load_aff8(a0, Ap, plane);
-    tile_dilation<2, CH>(acc, a1, q, live);
-    load_aff8(a1, Ap, plane);
-    tile_dilation<4, CH>(acc, a2, q, live);
-    load_aff8(a2, Ap, plane);
-    tile_dilation<8, CH>(acc, a0, q, live);
-    if (!edge) mbar_wait(&s_bar[1], phase);
-    tile_dilation<12, CH>(acc, a1, q, live);
-    tile_dilation<24, CH>(acc, a2, q, live);
+    if constexpr (DEPTH == 3) {
+      float4 a2[8];
+      load_aff8(a2, Ap, plane);
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      tile_dilation<4, CH>(acc, a2, q, live);
+      load_aff8(a2, Ap, plane);
+      tile_dilation<8, CH>(acc, a0, q, live);
+      if (!edge) mbar_wait(&s_bar[1], phase);
+      tile_dilation<12, CH>(acc, a1, q, live);
+      tile_dilation<24, CH>(acc, a2, q, live);
+    } else {
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      tile_dilation<4, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<8, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      if (!edge) mbar_wait(&s_bar[1], phase);
+      tile_dilation<12, CH>(acc, a0, q, live);
+      tile_dilation<24, CH>(acc, a1, q, live);
+    }
     phase ^= 1;
     if (active) {
 #pragma unroll
@@ -880,7 +903,8 @@ __device__ __forceinline__ PropUnit prop_find_unit(const PropArgs &p, const int 
     const int b = bt / tiles, t = bt - b * tiles;
     const int nch = !p.nch_dev ? p.nch_uniform : (s_nch && b < kPropMaxCachedB ? s_nch[b] : p.nch_dev[b]);
     // the live channels are split evenly over the gsplit CTAs of a tile, at most CH per pass
-    const int n_groups = p.gsplit * ((nch + p.gsplit * CH - 1) / (p.gsplit * CH));
+    if (nch <= 0) continue;   // an image without live channels
+    const int n_groups = nch <= CH ? 1 : p.gsplit * ((nch + p.gsplit * CH - 1) / (p.gsplit * CH));
     const int chunk = (nch + n_groups - 1) / n_groups;
     const int c0 = (pass * p.gsplit + g) * chunk;
     if (c0 < nch) {
@@ -1178,7 +1202,10 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
     attr = true;
   }
   if (occ < 1) return COSA_E_ARG;
+  // two CTAs per tile share the channels of an image with more than CH live ones (the kernel keeps <= CH
+  // channels in one CTA, where the affinity quads are loaded once)
   a.gsplit = 2;
+  if (const char *e = getenv("COSA_PAR_GSPLIT")) a.gsplit = max(1, atoi(e));
   a.n_pass = ceil_div(max_nch, a.gsplit * CH);
   const long long per_pass = (long long)a.B * a.tiles_x * a.tiles_y * a.gsplit;
   const int mode = par_step_mode();
@@ -1196,8 +1223,15 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
   }
   if (mode == kStepTile) {
     static bool attr_tile = false;
+    static int depth = 0, minb = 2;
     if (!attr_tile) {
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const char *e = getenv("COSA_PAR_DEPTH");
+      depth = (e && atoi(e) == 3) ? 3 : 2;
+      e = getenv("COSA_PAR_MINB");
+      minb = (e && atoi(e) == 3) ? 3 : 2;
       attr_tile = true;
     }
     const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
@@ -1205,8 +1239,16 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
       const bool last = it == a.num_iter - 1;
       const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
       float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
-      COSA_LAUNCH(par_iterate_tile_kernel<CH>, grid, 256, smem, stream, a.aff, tm, a.li, dst, last ? a.lo_final : a.li,
-                  a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      if (depth == 2 && minb == 3) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 3>), grid, 256, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 2) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 2>), grid, 256, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 3, 2>), grid, 256, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      }
     }
     return 0;
   }
@@ -1236,7 +1278,14 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
   COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   const int max_nch = nch_dev ? c_stride : nch_uniform;
-  return par_launch_propagate_t<3>(a, t0, ta, tb, max_nch, stream);
+  static int ch = 0;
+  if (!ch) {
+    const char *e = getenv("COSA_PAR_CH");
+    ch = e ? atoi(e) : 3;
+  }
+  if (ch == 2) return par_launch_propagate_t<2>(a, t0, ta, tb, max_nch, stream);
+  if (ch == 3) return par_launch_propagate_t<3>(a, t0, ta, tb, max_nch, stream);
+  return par_launch_propagate_t<4>(a, t0, ta, tb, max_nch, stream);
 }
 
 int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,

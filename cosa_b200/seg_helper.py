@@ -162,6 +162,13 @@ def cam_to_label(cam,
 # ----------------------------------------------------------------------------------------------------
 # cam2mask
 # ----------------------------------------------------------------------------------------------------
+def cam2mask_propagate_all_channels(on):
+    """``True``: PAR propagates every live channel of both threshold stacks, as the reference does.  ``False``
+    (default): the last live channel of each stack is derived from the channel sum (see include/cosa_b200.h,
+    ``cosa_cam2mask_set_all_channels``)."""
+    _lib.check(_lib.load().cosa_cam2mask_set_all_channels(int(bool(on))))
+
+
 def cam2mask(
         images,
         img_boxes,

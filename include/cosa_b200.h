@@ -115,6 +115,13 @@ int cosa_cam2mask(const float *images, const int *boxes, const float *cams, cons
                   const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
                   float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, void *stream);
 
+/* cosa_cam2mask with PAR refines softmax stacks whose channels sum to 1, and a PAR step multiplies that sum by the
+ * constant row sum of its weights (PAR.py:85-89), so by default the last live channel of each stack is not
+ * propagated but evaluated as row_sum^num_iter - (sum of the others) by the labelling kernel (one third of the
+ * propagation work at two foreground classes; labels identical on every fixture).  on != 0 propagates every
+ * channel like the reference does; the environment variable COSA_CAM2MASK_ALL_CHANNELS sets the initial choice. */
+int cosa_cam2mask_set_all_channels(int on);
+
 /* _refine_cams tail: bilinear (align_corners=False) resize of refined [B,nc,h,w] to (H,W), argmax over
  * channels (first max wins), label = valid_key[argmax].      utils/seg_helper.py:793-795 */
 int cosa_upsample_argmax(const float *refined, const long long *valid_key, long long *label_out, int B, int nc,
