@@ -135,7 +135,7 @@ def cpu_path_step(d, n_images):
     torch.set_num_threads(os.cpu_count() or 1)
     s = slice(0, n_images)
     cams = port.cam_validation(d["cams"][s], d["cls_label"][s])
-    label = port.cam2mask(images=d["img_denorm"][s], img_boxes=d["img_box"][s], cams=cams, cls_labels=d["cls_label"][s],
+    label = port.cam2mask(images=port.denormalize_img(d["simg"][s]), img_boxes=d["img_box"][s], cams=cams, cls_labels=d["cls_label"][s],
                           threshold_high=THR_HIGH, threshold_low=THR_LOW,
                           refine_model=port.ParOracle(DILATIONS, NUM_ITER))
     logit = d["logits"][s].clone().requires_grad_(True)
@@ -198,7 +198,9 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
     # instead of being propagated (label_kernels.cu: cosa_cam2mask) unless COSA_CAM2MASK_ALL_CHANNELS is set
     ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
     per = {
-        "cam_validation_kernel": 2 * 4 * B * (C - 1) * H * W,
+        "denormalize_img_kernel": 2 * 4 * B * 3 * H * W,
+        # every plane written, only the planes of present classes read (absent ones are zero-filled)
+        "cam_validation_kernel": 4 * B * ((C - 1) + (nc - 1)) * H * W,
         "cam2mask_keys_kernel": 4 * B * (C - 1) + 4 * B * C,
         "cam2mask_prepare_kernel": 4 * B * (H * W * (3 + (nc - 1)) + n * (3 + ncm)),
         "par_affinity_kernel": 4 * B * n * (3 + ND),
@@ -256,8 +258,9 @@ def run_cosa_arm(args):
     layer = cosa_b200.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
 
     def step(t):
+        img_denorm = cosa_b200.denormalize_img(t["simg"])                       # main.py:117
         cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
-        label = cosa_b200.cam2mask(images=t["img_denorm"], img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
+        label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
                                    threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
         logit = t["logits"].detach().requires_grad_(True)
         loss = cosa_b200.get_energy_loss(img=t["simg"], logit=logit, label=label, img_box=boxes, loss_layer=layer)
@@ -344,7 +347,8 @@ def run_cosa_arm(args):
                "d2h_bytes_per_step": (pipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
                "ms_per_step": e2e_ms / e2e_steps,
                "note": "cosa_b200.HostPipeline: pinned host buffers; upload of step i+1 overlaps the kernels of step i "
-                       "(copy stream); CAM planes of absent classes are not uploaded (zero after cam_validation); "
+                       "(copy stream); CAM planes of absent classes are not uploaded (zero after cam_validation), the [0,1] image "
+                       "is derived on the device from the normalised one as in main.py:117; "
                        "labels + loss read back every step"}
 
     clocks.__exit__(None, None, None)

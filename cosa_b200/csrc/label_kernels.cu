@@ -22,6 +22,16 @@ __global__ void __launch_bounds__(256) cam_validation_kernel(const float *__rest
     const float l = __ldg(cls_label + p);
     const float *src = cam + (size_t)p * HW;
     float *dst = out + (size_t)p * HW;
+    if (l == 0.0f) {
+      // absent class: the plane is written as zeros without being read (19 of 20 planes at VOC).  For finite inputs
+      // this equals the product up to the sign of zero; a NaN/Inf in an absent plane does not propagate as it would
+      // through the reference's multiplication (deliberate differences)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
+           i += (long long)gridDim.x * blockDim.x)
+        stg_stream4(dst + 4 * i, z);
+      continue;
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
          i += (long long)gridDim.x * blockDim.x) {
       float4 v = ldg_stream4(src + 4 * i);
@@ -35,6 +45,45 @@ __global__ void cam_validation_scalar_kernel(const float *__restrict__ cam, cons
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
     out[i] = __fmul_rn(__ldg(cls_label + i / HW), cam[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// denormalize_img (utils/torch_helper.py:354-367, caller main.py:117): the [0,1] image cam2mask and PAR read is
+// derived on the device from the ImageNet-normalised network input: (uint8)(x * std + mean) / 255, the product and
+// the sum rounded separately as torch evaluates them, the cast truncating toward zero.
+// ------------------------------------------------------------------------------------------------
+struct Affine3f {
+  float mean[3], std[3];
+};
+__global__ void __launch_bounds__(256) denormalize_img_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                              Affine3f a, long long HW4, long long HW, int planes) {
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float sd = a.std[p % 3], mu = a.mean[p % 3];
+    const float *src = in + (size_t)p * HW;
+    float *dst = out + (size_t)p * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 v = ldg_stream4(src + 4 * i);
+      float *e = reinterpret_cast<float *>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float t = __fadd_rn(__fmul_rn(e[k], sd), mu);
+        // uint8 cast of an in-range value: truncation (out-of-range inputs are unspecified in the reference itself)
+        const int u = min(max((int)t, 0), 255);
+        e[k] = __fdiv_rn((float)u, 255.0f);
+      }
+      stg_stream4(dst + 4 * i, v);
+    }
+  }
+}
+__global__ void denormalize_img_scalar_kernel(const float *__restrict__ in, float *__restrict__ out, Affine3f a,
+                                              long long HW, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW) % 3);
+    const float t = __fadd_rn(__fmul_rn(in[i], a.std[c]), a.mean[c]);
+    out[i] = __fdiv_rn((float)min(max((int)t, 0), 255), 255.0f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -740,6 +789,26 @@ extern "C" int cosa_cam_validation(const float *cam, const float *cls_label, flo
     const long long total = (long long)planes * HW;
     const int blocks = (int)min((long long)sm_count() * 8, ceil_div_ll(total, 256));
     COSA_LAUNCH(cam_validation_scalar_kernel, blocks, 256, 0, s, cam, cls_label, out, HW, total);
+  }
+  return 0;
+}
+
+extern "C" int cosa_denormalize_img(const float *imgs, float *out, int B, long long HW, const float mean[3],
+                                    const float std[3], void *stream) {
+  if (!imgs || !out || !mean || !std || B < 1 || HW < 1) return COSA_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  Affine3f a;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.std[c] = std[c]; }
+  const int planes = 3 * B;
+  if ((HW % 4 == 0) && (((uintptr_t)imgs | (uintptr_t)out) % 16 == 0)) {
+    const long long HW4 = HW / 4;
+    const int bx = (int)min(ceil_div_ll(HW4, 256), 64LL);
+    const int by = min(planes, max(1, sm_count() * 16 / bx));
+    COSA_LAUNCH(denormalize_img_kernel, dim3(bx, by), 256, 0, s, imgs, out, a, HW4, HW, planes);
+  } else {
+    const long long total = (long long)planes * HW;
+    const int blocks = (int)min((long long)sm_count() * 8, ceil_div_ll(total, 256));
+    COSA_LAUNCH(denormalize_img_scalar_kernel, blocks, 256, 0, s, imgs, out, a, HW, total);
   }
   return 0;
 }

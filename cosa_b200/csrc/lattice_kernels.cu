@@ -811,7 +811,9 @@ int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int
 int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, double *loss_acc, float *outs, int N,
                   int K, int H, int W, cudaStream_t stream) {
   const int n = H * W;
-  if (lattice_per_pixel()) {
+  static int slice_tile = -1;
+  if (slice_tile < 0) slice_tile = lattice_env("COSA_SLICE_TILE", 0) ? 1 : 0;   // measured equal: the simple one is the default
+  if (lattice_per_pixel() || !slice_tile) {
     const int blocks = persistent_blocks(L.P, 256);
     if (gate) {
       COSA_LAUNCH(lattice_slice_kernel<true>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);

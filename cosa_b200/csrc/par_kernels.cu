@@ -643,7 +643,7 @@ constexpr int kBoxRows = 16;
 __device__ __forceinline__ void replicate_border_rows(float *tile, int live, int r_lo, int r_hi) {
   constexpr int Q = kFS / 4;
   const int bad = r_lo + (kFS - r_hi);
-  for (int i = threadIdx.x; i < live * bad * Q; i += 256) {
+  for (int i = threadIdx.x; i < live * bad * Q; i += blockDim.x) {
     const int k = i / (bad * Q), j = i - k * (bad * Q);
     const int rr = j / Q, c4 = j - rr * Q;
     const int r = rr < r_lo ? rr : r_hi + (rr - r_lo);
@@ -860,6 +860,146 @@ __global__ void __launch_bounds__(256, MINB)
             if (xq == wq - 1) {
               const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
               for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+            }
+          }
+        }
+      }
+    }
+    if (c0 + gsplit * chunk < nch) {   // the tile is re-staged (async proxy) for the next channel group
+      __syncthreads();
+      if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scalar tile-mode step kernel: the same TMA-staged (32+48)^2 tiles, but 512 threads per CTA with one pixel COLUMN
+// position and two rows (ty, ty + 16) each instead of 256 threads with a pixel quad.  A warp reads 32 consecutive
+// floats of a staged row (one conflict-free wavefront per LDS.32: the same bytes per wavefront as the quad
+// kernel's LDS.128), every offset is an immediate for every dilation, and a thread needs ~60 registers instead of
+// 128, so 32 warps per SM hide the shared-memory latency the 16-warp quad kernel stalls on (ncu: 63 % of its issue
+// slots wait on the short scoreboard with the LSU data pipe at 48 %).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsPerPass = 16;   // 512 threads = 32 columns x 16 rows; two passes cover the 32-row tile
+
+template <int D, int CH>
+__device__ __forceinline__ void tile_dilation1(float (&acc)[2][CH], const float (&a)[2][8], const float *q, int live) {
+  constexpr int R = D * kFS;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < live) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float *p = q + k * (kFS * kFS) + j * (kRowsPerPass * kFS);
+        float t = acc[j][k];
+        t = fmaf(a[j][0], p[-R - D], t); t = fmaf(a[j][1], p[-R], t); t = fmaf(a[j][2], p[-R + D], t);
+        t = fmaf(a[j][3], p[-D], t);                                   t = fmaf(a[j][4], p[D], t);
+        t = fmaf(a[j][5], p[R - D], t);  t = fmaf(a[j][6], p[R], t);  t = fmaf(a[j][7], p[R + D], t);
+        acc[j][k] = t;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// the 8 affinities of one dilation for the thread's two pixels; A walks through the planes
+__device__ __forceinline__ void load_aff8x2(float (&a)[2][8], const float *&A, size_t plane, size_t row16) {
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    a[0][m] = ldg_stream1(A);
+    a[1][m] = ldg_stream1(A + row16);
+    asm volatile("add.u64 %0, %0, %1;" : "+l"(A) : "l"(plane * sizeof(float)));
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(512, 2)
+    par_iterate_tile1_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
+                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
+                             int c_stride, int h, int w, int gsplit) {
+  extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int x = x0 + tx, y = y0 + ty;
+  const int b = blockIdx.z / gsplit, g = blockIdx.z - b * gsplit;
+  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
+  if (nch <= 0) return;   // an image without live channels (cam2mask: no foreground class)
+  const int n_groups = nch <= CH ? 1 : gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
+  const int chunk = (nch + n_groups - 1) / n_groups;
+  if (g * chunk >= nch) return;
+  const size_t plane = (size_t)h * w;
+  const size_t oplane = (size_t)h * lo.pitch;
+  // second row clamped into the image for the affinity reads of inactive threads
+  const int ya = min(y, h - 1), yb = min(y + kRowsPerPass, h - 1);
+  const float *A = aff + (size_t)b * 48 * plane + (size_t)ya * w + min(x, w - 1);
+  const size_t row16 = (size_t)(yb - ya) * w;
+  const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
+  const bool edge = r_lo > 0 || r_hi < kFS;
+  const float *q = s_tile + (ty + kFH) * kFS + tx + kFH;   // this thread's first pixel in staged channel 0
+
+  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  __syncthreads();
+  unsigned phase = 0;
+  for (int c0 = g * chunk; c0 < nch; c0 += gsplit * chunk) {
+    const int live = min(chunk, nch - c0);
+    constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&s_bar[0], (unsigned)(live * kNear * kFS * sizeof(float)));
+      mbar_expect_tx(&s_bar[1], (unsigned)(live * kFar * kFS * sizeof(float)));
+      const int gx = li.off + x0 - kFH, gz = b * c_stride + c0;
+      for (int r = kFNear0; r < kFNear1; r += kBoxRows)
+        for (int k = 0; k < live; ++k)
+          tma_load_box(s_tile + (k * kFS + r) * kFS, &tmap_in, gx, y0 - kFH + r, gz + k, &s_bar[0]);
+      for (int k = 0; k < live; ++k) {
+        tma_load_box(s_tile + (k * kFS) * kFS, &tmap_in, gx, y0 - kFH, gz + k, &s_bar[1]);
+        tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, &tmap_in, gx, y0 - kFH + kFNear1, gz + k, &s_bar[1]);
+      }
+    }
+    float acc[2][CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[0][k] = acc[1][k] = 0.0f;
+    const float *Ap = A;
+    float a0[2][8], a1[2][8];   // affinities one dilation ahead of their use
+    load_aff8x2(a0, Ap, plane, row16);
+    load_aff8x2(a1, Ap, plane, row16);
+    mbar_wait(&s_bar[0], phase);
+    if (edge) {
+      mbar_wait(&s_bar[1], phase);
+      replicate_border_rows(s_tile, live, r_lo, r_hi);
+    }
+    tile_dilation1<1, CH>(acc, a0, q, live);
+    load_aff8x2(a0, Ap, plane, row16);
+    tile_dilation1<2, CH>(acc, a1, q, live);
+    load_aff8x2(a1, Ap, plane, row16);
+    tile_dilation1<4, CH>(acc, a0, q, live);
+    load_aff8x2(a0, Ap, plane, row16);
+    tile_dilation1<8, CH>(acc, a1, q, live);
+    load_aff8x2(a1, Ap, plane, row16);
+    if (!edge) mbar_wait(&s_bar[1], phase);
+    tile_dilation1<12, CH>(acc, a0, q, live);
+    tile_dilation1<24, CH>(acc, a1, q, live);
+    phase ^= 1;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int yy = y + j * kRowsPerPass;
+      if (x < w && yy < h) {
+        float *dst = out + ((size_t)b * c_stride + c0) * oplane + (size_t)yy * lo.pitch + lo.off + x;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+          if (k < live) {
+            float *o = dst + (size_t)k * oplane;
+            *o = acc[j][k];
+            if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+              if (x == 0)
+                for (int i = 1; i <= lo.padn; ++i) o[-i] = acc[j][k];
+              if (x == w - 1)
+                for (int i = 1; i <= lo.padn; ++i) o[i] = acc[j][k];
             }
           }
         }
@@ -1234,12 +1374,21 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
       minb = (e && atoi(e) == 3) ? 3 : 2;
       attr_tile = true;
     }
+    static int scalar = -1;
+    if (scalar < 0) {
+      const char *e = getenv("COSA_PAR_SCALAR");
+      scalar = e ? atoi(e) : 0;   // measured slower than the quad kernel (1.05 vs 0.95 ms per ten steps at VOC B = 32)
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile1_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
     for (int it = 0; it < a.num_iter; ++it) {
       const bool last = it == a.num_iter - 1;
       const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
       float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
-      if (depth == 2 && minb == 3) {
+      if (scalar) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", par_iterate_tile1_kernel<CH>, grid, 512, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 2 && minb == 3) {
         COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 3>), grid, 256, smem, stream, a.aff, tm, a.li,
                       dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
       } else if (depth == 2) {

@@ -13,17 +13,20 @@ host side of PCIe (a data-loading or serving process handing over buffers), this
 that batch; the tensors are the pipeline's own pinned buffers and stay valid until the next ``submit``.
 
 The host->device copies of batch i+1 run on a copy stream while the kernels of batch i run on the compute stream
-(``depth`` staging slots), and the labels and the loss of a batch are copied back asynchronously.  Only what the path reads crosses PCIe: ``cam_validation`` multiplies each CAM plane by its class
-label, so planes whose label is 0 are never uploaded (their device copy is cleared instead) - for VOC shapes
-(2 of 20 classes present) that is 90 % of the CAM bytes.
+(``depth`` staging slots), and the labels and the loss of a batch are copied back asynchronously.  Only what the
+path reads crosses PCIe: ``cam_validation`` multiplies each CAM plane by its class label, so planes whose label is 0
+are never uploaded (their device copy is cleared instead) - for VOC shapes (2 of 20 classes present) that is 90 % of
+the CAM bytes - and the [0,1] image for cam2mask / PAR is derived on the device from the normalised network input
+exactly as the reference does (main.py:117, ``denormalize_img``), so the image crosses once.
 
-One step is exactly the device path: cam_validation -> cam2mask(refine_model=par) -> get_energy_loss -> backward.
+One step is exactly the device path of main.py:117-212:
+denormalize_img -> cam_validation -> cam2mask(refine_model=par) -> get_energy_loss -> backward.
 """
 import torch
 
 from . import seg_helper
 
-_FULL = ("img_denorm", "simg", "cls_label", "logits")
+_FULL = ("simg", "cls_label", "logits")
 
 
 class HostPipeline:
@@ -83,7 +86,7 @@ class HostPipeline:
 
     # -- public -------------------------------------------------------------------------------------------------
     def submit(self, batch):
-        """Queue one batch: dict with pinned float32 CPU tensors ``img_denorm`` [B,3,H,W], ``simg`` [B,3,H,W],
+        """Queue one batch: dict with pinned float32 CPU tensors ``simg`` [B,3,H,W] (ImageNet-normalised),
         ``cams`` [B,C-1,H,W], ``cls_label`` [B,C-1], ``logits`` [B,C,H,W] and ``img_box`` (tensor or list, [B,4])."""
         for k in _FULL + ("cams",):
             t = batch[k]
@@ -95,8 +98,9 @@ class HostPipeline:
             self._upload(s, batch)
             main.wait_event(s["ready"])
             d, boxes = s["dev"], batch["img_box"]
+            img_denorm = seg_helper.denormalize_img(d["simg"])
             cams = seg_helper.cam_validation(d["cams"], d["cls_label"])
-            label = seg_helper.cam2mask(images=d["img_denorm"], img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
+            label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
                                         threshold_high=self.thr[0], threshold_low=self.thr[1], refine_model=self.par)
             logit = d["logits"].detach().requires_grad_(True)
             loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,

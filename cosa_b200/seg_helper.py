@@ -112,6 +112,23 @@ def multi_scale_camseg(model, imgs, scales):
     return cam, cam_aux, seg
 
 
+def denormalize_img(imgs, mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)):
+    """[0,1] image from the ImageNet-normalised network input, ``(uint8)(imgs * std + mean) / 255``
+    (utils/torch_helper.py:354-367; main.py:117 feeds the result to cam2mask / PAR)."""
+    import ctypes
+    lib = _lib.load()
+    imgs = _lib.dev_f32(imgs, "imgs")
+    b, c, h, w = imgs.shape
+    if c != 3:
+        raise ValueError("denormalize_img expects [B,3,H,W]")
+    out = torch.empty_like(imgs)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    with torch.cuda.device(imgs.device):
+        _lib.check(lib.cosa_denormalize_img(_lib.ptr(imgs), _lib.ptr(out), b, h * w, m, sd, _lib.stream_ptr()))
+    return out
+
+
 def cam_validation(cam, cls_label):
     lib = _lib.load()
     cam = _lib.dev_f32(cam, "cam")

@@ -84,6 +84,13 @@ int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int
 int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
                                int C, int H, int W, void *stream);
 
+/* denormalize_img (utils/torch_helper.py:354-367; main.py:117 derives cam2mask's [0,1] image from the network
+ * input on the device): out = (uint8)(imgs * std[c] + mean[c]) / 255 for imgs [B,3,H,W], HW = H*W.  Product and sum
+ * are rounded separately (torch evaluates two ops), the cast truncates; inputs whose de-normalised value leaves
+ * [0,256) are unspecified in the reference (float -> uint8 overflow) and clamp here. */
+int cosa_denormalize_img(const float *imgs, float *out, int B, long long HW, const float mean[3], const float std[3],
+                         void *stream);
+
 /* cam_validation: out[b,c,:,:] = cls_label[b,c] * cam[b,c,:,:].   utils/seg_helper.py:547-551 */
 int cosa_cam_validation(const float *cam, const float *cls_label, float *out, int B, int C1, long long HW,
                         void *stream);

@@ -127,6 +127,14 @@ def multi_scale_merge(raw_cams, raw_aux_last, raw_segs, size):
     return cam, cam_aux, seg
 
 
+def denormalize_img(imgs, mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)):
+    """utils/torch_helper.py:354-367: per channel x * std + mean (two fp32 ops), cast to uint8, divided by 255."""
+    out = torch.zeros_like(imgs)
+    for c in range(3):
+        out[:, c] = imgs[:, c] * std[c] + mean[c]
+    return out.type(torch.uint8) / 255.0
+
+
 def cam_validation(cam, cls_label):
     return cls_label[:, :, None, None] * cam
 

@@ -48,13 +48,28 @@ def load_reference():
         spec.loader.exec_module(mod)
         return mod
 
+    # utils/torch_helper.py (denormalize_img) imports its sibling ``misc`` and texttable (absent): both unused here
+    pkg = types.ModuleType("utils")
+    pkg.__path__ = []
+    sys.modules.setdefault("utils", pkg)
+    sys.modules.setdefault("utils.misc", types.ModuleType("utils.misc"))
+    tt = types.ModuleType("texttable")
+    tt.Texttable = None
+    sys.modules.setdefault("texttable", tt)
+    global ref_torch_helper
+    ref_torch_helper = by_path("utils.torch_helper", os.path.join(REF, "utils", "torch_helper.py"))
     par = by_path("ref_PAR", os.path.join(REF, "models", "PAR.py"))
     sh = by_path("ref_seg_helper", os.path.join(REF, "utils", "seg_helper.py"))
     rrm = None
     return par, sh, rrm
 
 
+ONLY = set(sys.argv[1:])        # optional: names of the fixtures to (re)write; default all
+
+
 def save(name, **arrays):
+    if ONLY and name not in ONLY:
+        return
     out = {}
     for k, v in arrays.items():
         if isinstance(v, torch.Tensor):
@@ -118,6 +133,15 @@ def main():
     for i, (sg, cm, ax) in enumerate(teacher.calls):
         raw["raw_seg%d" % i], raw["raw_cam%d" % i], raw["raw_aux%d" % i] = sg, cm, ax
     save("multi_scale", imgs=wimg, cam=m_cam, cam_aux=m_aux, seg=m_seg, **raw)
+
+    # ---- denormalize_img (utils/torch_helper.py:354-367, main.py:117) ---------------------------
+    dn = port.synthetic_batch(B=2, C=4, H=24, W=40, n_fg=1, seed=21)
+    x = dn["simg"].clone()
+    x[1, :, :4] += torch.rand((3, 4, 40), generator=g) * 0.01      # values that are not exact (u8 - mean) / std
+    mean_, std_ = torch.tensor(port.IMAGENET_MEAN).view(3, 1), torch.tensor(port.IMAGENET_STD).view(3, 1)
+    ramp = torch.arange(0, 256, dtype=torch.float32).view(1, 256)   # every uint8 level in every channel
+    x[0].view(3, -1)[:, :256] = (ramp - mean_) / std_
+    save("denormalize", simg=x, out=ref_torch_helper.denormalize_img(x))
 
     # ---- cam_validation / cam_to_label ---------------------------------------------------------
     d = port.synthetic_batch(B=3, C=6, H=48, W=64, n_fg=2, seed=5, cam_kind="grid")

@@ -196,8 +196,8 @@ def test_host_pipeline_matches_device_path(cosa, port):
     for hb, (label, loss, grad) in zip(batches, outs):
         d = to_cuda(hb)
         cams = cosa.cam_validation(d["cams"], d["cls_label"])
-        want = cosa.cam2mask(images=d["img_denorm"], img_boxes=hb["img_box"], cams=cams, cls_labels=d["cls_label"],
-                             threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        want = cosa.cam2mask(images=cosa.denormalize_img(d["simg"]), img_boxes=hb["img_box"], cams=cams,
+                             cls_labels=d["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
         logit = d["logits"].clone().requires_grad_(True)
         wl = cosa.get_energy_loss(img=d["simg"], logit=logit, label=want, img_box=hb["img_box"], loss_layer=layer)
         wl.backward()

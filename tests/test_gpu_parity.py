@@ -142,6 +142,20 @@ def test_normalize_and_validation(cosa):
     assert_same(cosa.cam_validation(cu(g["cam"]), cu(g["cls_label"])), g["valid"], "cam_validation")
 
 
+def test_denormalize_img(cosa, port):
+    """utils/torch_helper.py:354-367 (main.py:117): bit-exact against the reference's output, on an odd-sized image
+    (scalar kernel) and at the VOC size against the oracle."""
+    g = load_golden("denormalize")
+    assert_same(cosa.denormalize_img(cu(g["simg"])), g["out"], "denormalize_img (golden)")
+    from cosa_b200 import synthetic
+    for shape in ((2, 21, 37, 45), (4, 21, 448, 448)):
+        d = synthetic.synthetic_batch(shape[0], shape[1], shape[2], shape[3], 2, seed=31)
+        assert_same(cosa.denormalize_img(d["simg"].cuda()), port.denormalize_img(d["simg"]), "denormalize_img %s" % (shape,))
+        # the synthetic generator's own img_denorm is u8 / 255: what the reference derives from simg, up to the
+        # truncation of values that land an ulp below an integer
+        assert float((cosa.denormalize_img(d["simg"].cuda()).cpu() - d["img_denorm"]).abs().max()) <= 1.0 / 255 + 1e-6
+
+
 def test_multi_scale_merge_golden(cosa):
     """enlargement + un-flip max + ReLU + scale sum + normalise, fused (seg_helper.py:253-273)."""
     g = load_golden("multi_scale")

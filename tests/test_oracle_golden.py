@@ -57,6 +57,12 @@ def test_normalize_and_validation():
     check_float(port.cam_validation(t(g["cam"]), t(g["cls_label"])), g["valid"], "cam_validation")
 
 
+def test_denormalize_img():
+    g = load_golden("denormalize")                      # every uint8 level in every channel + inexact inputs
+    out = port.denormalize_img(t(g["simg"]))
+    assert torch.equal(out, t(g["out"]))
+
+
 def test_multi_scale_merge():
     g = load_golden("multi_scale")
     raw = lambda k: [t(g["raw_%s%d" % (k, i)]) for i in range(3)]
