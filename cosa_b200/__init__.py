@@ -7,6 +7,7 @@ by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/cosa_b200.h``
   ``cam_validation, cam_to_label, cam2mask, _refine_cams``   utils/seg_helper.py:515-551, 721-797
   ``cam_normalize``                                 utils/seg_helper.py:264-270
   ``denormalize_img``                               utils/torch_helper.py:354-367 (main.py:117)
+  ``upsample_bilinear``                             main.py:167 (F.interpolate of the logits, with its adjoint)
   ``get_energy_loss, DenseEnergyLoss, DenseEnergyLossFunction``   utils/seg_helper.py:191-230, 864-903
   ``multi_scale_camseg`` (merge fused), ``seg_loss``, ``seg_refine_by_label``, ``cam_loss``   :232-275, 800-813, 553-602
   ``bilateralfilter.bilateralfilter_batch``         utils/bilateralfilter (SWIG module)
@@ -18,9 +19,9 @@ from .host_pipeline import HostPipeline
 from .par import PAR, get_kernel
 from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
                          cam_to_label, cam_validation, denormalize_img, get_energy_loss, multi_scale_cam_merge, multi_scale_camseg,
-                         multi_scale_seg_merge, cam_loss, seg_loss, seg_refine_by_label)
+                         multi_scale_seg_merge, cam_loss, seg_loss, seg_refine_by_label, upsample_bilinear)
 
 __all__ = ["PAR", "get_kernel", "cam_validation", "cam_to_label", "cam2mask", "_refine_cams", "cam_normalize",
            "get_energy_loss", "DenseEnergyLoss", "DenseEnergyLossFunction", "multi_scale_camseg", "multi_scale_cam_merge",
            "multi_scale_seg_merge", "HostPipeline", "seg_loss",
-           "seg_refine_by_label", "cam_loss", "denormalize_img"]
+           "seg_refine_by_label", "cam_loss", "denormalize_img", "upsample_bilinear"]

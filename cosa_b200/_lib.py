@@ -35,6 +35,9 @@ _SIGNATURES = {
     "cosa_seg_refine_by_label": (_c_int, [_vp, _vp, _c_float, _c_int, _vp] + [_c_int] * 4 + [_vp]),
     "cosa_cam_loss_forward": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp] + [_c_int] * 6 + [_vp]),
     "cosa_cam_loss_backward": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp]),
+    "cosa_upsample_bilinear": (_c_int, [_vp, _vp, _c_ll, _c_int, _c_int, _c_int, _c_int, _vp]),
+    "cosa_upsample_bilinear_backward_ws_bytes": (_c_size_t, [_c_ll, _c_int, _c_int]),
+    "cosa_upsample_bilinear_backward": (_c_int, [_vp, _vp, _c_ll, _c_int, _c_int, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "cosa_denormalize_img": (_c_int, [_vp, _vp, _c_int, _c_ll, _vp, _vp, _vp]),
     "cosa_cam_validation": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_ll, _vp]),
     "cosa_cam_to_label": (_c_int, [_vp] * 5 + [_c_int] * 4 + [_c_float] * 3 + [_c_int, _c_ll, _vp]),

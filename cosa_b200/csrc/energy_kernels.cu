@@ -472,7 +472,7 @@ extern "C" size_t cosa_dense_energy_ws_bytes(int N, int K, int H, int W) {
   if (N < 1 || K < 1 || H < 1 || W < 1) return 0;
   const size_t n = (size_t)H * W;
   return align_up((size_t)N * K * n * sizeof(float), 256) + align_up((size_t)N * n * sizeof(float), 256) + 256 +
-         lattice_ws_bytes(min(N, kMaxImagesPerLattice), K, H, W);
+         lattice_ws_bytes(lattice_chunk_images(N, K, H, W), K, H, W);
 }
 
 static int energy_core(const float *images, const float *s_roi, const float *gate, float *as_out, float *loss_out,
@@ -480,11 +480,12 @@ static int energy_core(const float *images, const float *s_roi, const float *gat
                        int apply_weight, void *lattice_ws, cudaStream_t s) {
   const size_t n = (size_t)H * W;
   COSA_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
-  for (int n0 = 0; n0 < N; n0 += kMaxImagesPerLattice) {   // chunks reuse the lattice workspace, stream-ordered
-    const int nb = min(kMaxImagesPerLattice, N - n0);
+  const int chunk = lattice_chunk_images(N, K, H, W);
+  for (int n0 = 0; n0 < N; n0 += chunk) {   // chunks reuse the lattice workspace, stream-ordered
+    const int nb = min(chunk, N - n0);
     LatticeBufs L;
     lattice_carve(lattice_ws, nb, K, H, W, &L);
-    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, s));
+    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, n0 == 0, s));
     COSA_CHECK(lattice_splat_blur(L, s_roi + (size_t)n0 * K * n, nb, K, H, W, s));
     COSA_CHECK(lattice_slice(L, s_roi + (size_t)n0 * K * n, gate + (size_t)n0 * n, acc, as_out + (size_t)n0 * K * n,
                              nb, K, H, W, s));
@@ -534,7 +535,7 @@ extern "C" size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W) {
   const size_t hw = (size_t)(H / 2) * (W / 2);
   return align_up((size_t)B * 3 * hw * sizeof(float), 256) + align_up((size_t)B * C * hw * sizeof(float), 256) +
          align_up((size_t)B * hw * sizeof(float), 256) + 256 +
-         lattice_ws_bytes(min(B, kMaxImagesPerLattice), C, H / 2, W / 2);
+         lattice_ws_bytes(lattice_chunk_images(B, C, H / 2, W / 2), C, H / 2, W / 2);
 }
 
 extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, const float *label, const int *boxes,

@@ -25,7 +25,7 @@ struct LatticeBufs {
   unsigned long long *table_keys;   // [cap]   packed key or kEmptyKey
   int *table_ids;                   // [cap]   vertex id + 1 of an occupied slot
   unsigned long long *vkeys;        // [m_cap] packed key of vertex id
-  int *counters;                    // [8]     0: M   1: key-range error   2: max probe length   3: table capacity
+  int *counters;                    // [8]     0: M   1: key-range error   2: max probe length   3: table capacity   4: M of earlier chunks
   int *offsets;                     // [6][P]  table slot during the build, then vertex id + 1
   float *bary;                      // [6][P]
   int2 *nbr;                        // [6][m_cap]  (n1, n2) as vertex id + 1, 0 = absent
@@ -41,8 +41,11 @@ size_t lattice_ws_bytes(int N, int K, int H, int W);
 void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L);
 
 // Build the lattice of N (<= kMaxImagesPerLattice) planar RGB images [N,3,H,W].
+// first_chunk: this is the first lattice of a call (resets the per-call counters: total vertices, error flag).
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
-                  cudaStream_t stream);
+                  bool first_chunk, cudaStream_t stream);
+// Images per lattice for a batch of N (<= kMaxImagesPerLattice, sized for L2; see lattice_kernels.cu).
+int lattice_chunk_images(int N, int K, int H, int W);
 // values <- splat(ins [N,K,H,W]); six blur passes.  The blurred values end up in L.val0.
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream);
 // outs [N,K,H,W] <- slice.  With gate != nullptr the dense-CRF epilogue is fused: outs <- slice * gate and

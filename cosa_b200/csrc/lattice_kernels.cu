@@ -115,12 +115,18 @@ __device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedCon
 }
 
 // ---- build ---------------------------------------------------------------------------------------
-__global__ void lattice_clear_kernel(unsigned long long *table_keys, unsigned long long cap, int *counters) {
+__global__ void lattice_clear_kernel(unsigned long long *table_keys, unsigned long long cap, int *counters,
+                                     int first_chunk) {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 2;
   for (unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 2; i < cap; i += stride)
     *reinterpret_cast<ulonglong2 *>(table_keys + i) = make_ulonglong2(kEmptyKey, kEmptyKey);
-  if (blockIdx.x == 0 && threadIdx.x < 8) {
-    counters[threadIdx.x] = threadIdx.x == 3 ? (int)min(cap, (unsigned long long)0x7fffffff) : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // 0: M of this chunk   1: key-range error (sticky over the chunks of a call)   2: max probe length (same)
+    // 3: table capacity     4: vertices of the earlier chunks of this call
+    counters[4] = first_chunk ? 0 : counters[4] + counters[0];
+    counters[0] = 0;
+    if (first_chunk) { counters[1] = 0; counters[2] = 0; }
+    counters[3] = (int)min(cap, (unsigned long long)0x7fffffff);
   }
 }
 
@@ -705,6 +711,22 @@ static unsigned long long table_capacity(long long m_cap) {
   return cap;
 }
 
+// Images per lattice: up to kMaxImagesPerLattice (the key's image field).  Smaller chunks whose two value buffers fit
+// in L2 were measured and are slower at every size (VOC B = 32: 2.73 ms per step at 64, 2.80 at 16, 2.95 at 8 - the
+// blur passes are not HBM-bound and the smaller launches fill the GPU worse).  COSA_LATTICE_CHUNK overrides (A/B).
+int lattice_chunk_images(int N, int K, int H, int W) {
+  (void)K; (void)H; (void)W;
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("COSA_LATTICE_CHUNK");
+    forced = e ? atoi(e) : 0;
+  }
+  int c = forced > 0 ? min(forced, kMaxImagesPerLattice) : kMaxImagesPerLattice;
+  c = min(c, N);
+  const int chunks = (N + c - 1) / c;
+  return (N + chunks - 1) / chunks;   // even chunks
+}
+
 size_t lattice_ws_bytes(int N, int K, int H, int W) {
   const long long n = (long long)H * W, n_pad = (n + 3) & ~3LL;
   const long long P = (long long)N * n, m_cap = 6LL * N * n_pad;
@@ -729,10 +751,10 @@ void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
   L->cap_mask = cap - 1;
   L->Kp = (K + 3) & ~3;
   Arena a(ws);
+  L->counters = a.take<int>(8);   // first: the same place for every chunk size (cosa_bilateral_stats)
   L->table_keys = a.take<unsigned long long>(cap);
   L->table_ids = a.take<int>(cap);
   L->vkeys = a.take<unsigned long long>((size_t)L->m_cap);
-  L->counters = a.take<int>(8);
   L->offsets = a.take<int>((size_t)6 * L->P);
   L->bary = a.take<float>((size_t)6 * L->P);
   L->nbr = a.take<int2>((size_t)6 * L->m_cap);
@@ -745,13 +767,13 @@ static int persistent_blocks(long long work_items, int per_block) {
 }
 
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
-                  cudaStream_t stream) {
+                  bool first_chunk, cudaStream_t stream) {
   if (N < 1 || N > kMaxImagesPerLattice) return COSA_E_ARG;
   const long long n = (long long)H * W;
   const int n_pad = (int)((n + 3) & ~3LL);
   const unsigned long long cap = L.cap_mask + 1;
   COSA_LAUNCH(lattice_clear_kernel, persistent_blocks((long long)(cap / 2), 256), 256, 0, stream, L.table_keys, cap,
-              L.counters);
+              L.counters, first_chunk ? 1 : 0);
   const long long total = (long long)N * n_pad;
   COSA_LAUNCH(lattice_build_kernel, (unsigned)ceil_div_ll(total, 256), 256, 0, stream, L, images, make_embed_const(),
               N, H, W, n_pad, sigmargb, sigmaxy);
@@ -846,7 +868,7 @@ using namespace cosa;
 
 extern "C" size_t cosa_bilateral_ws_bytes(int N, int K, int H, int W) {
   if (N < 1 || K < 1 || H < 1 || W < 1) return 0;
-  return lattice_ws_bytes(min(N, kMaxImagesPerLattice), K, H, W);
+  return lattice_ws_bytes(lattice_chunk_images(N, K, H, W), K, H, W);
 }
 
 extern "C" int cosa_bilateralfilter_batch(const float *images, const float *ins, float *outs, int N, int K, int H,
@@ -856,11 +878,12 @@ extern "C" int cosa_bilateralfilter_batch(const float *images, const float *ins,
   if (ws_bytes < cosa_bilateral_ws_bytes(N, K, H, W)) return COSA_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)H * W;
-  for (int n0 = 0; n0 < N; n0 += kMaxImagesPerLattice) {   // chunks share the workspace, stream-ordered
-    const int nb = min(kMaxImagesPerLattice, N - n0);
+  const int chunk = lattice_chunk_images(N, K, H, W);
+  for (int n0 = 0; n0 < N; n0 += chunk) {   // chunks share the workspace, stream-ordered
+    const int nb = min(chunk, N - n0);
     LatticeBufs L;
     lattice_carve(ws, nb, K, H, W, &L);
-    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, s));
+    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, n0 == 0, s));
     COSA_CHECK(lattice_splat_blur(L, ins + (size_t)n0 * K * n, nb, K, H, W, s));
     COSA_CHECK(lattice_slice(L, ins + (size_t)n0 * K * n, nullptr, nullptr, outs + (size_t)n0 * K * n, nb, K, H, W, s));
   }
@@ -871,11 +894,12 @@ extern "C" int cosa_bilateral_stats(const void *ws, int N, int K, int H, int W, 
   if (!ws || !stats || N < 1 || K < 1 || H < 1 || W < 1) return COSA_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   LatticeBufs L;
-  lattice_carve(const_cast<void *>(ws), min(N, kMaxImagesPerLattice), K, H, W, &L);
-  int h[4];
+  lattice_carve(const_cast<void *>(ws), lattice_chunk_images(N, K, H, W), K, H, W, &L);
+  int h[5];
   COSA_CUDA(cudaMemcpyAsync(h, L.counters, sizeof(h), cudaMemcpyDeviceToHost, s));
   COSA_CUDA(cudaStreamSynchronize(s));
-  stats[0] = h[0]; stats[1] = h[1]; stats[2] = (long long)(L.cap_mask + 1); stats[3] = h[2];
+  stats[0] = (long long)h[0] + h[4];   // vertices of all chunks of the last call
+  stats[1] = h[1]; stats[2] = (long long)(L.cap_mask + 1); stats[3] = h[2];
   return h[1] ? COSA_E_KEYRANGE : 0;
 }
 

@@ -1,0 +1,149 @@
+// Bilinear enlargement of the segmentation logits and its adjoint.
+//
+// Reference: main.py:167   seg_pred = F.interpolate(seg_pred, size=label.shape[1:], mode='bilinear',
+//                                                   align_corners=False)
+// The decoder emits the logits on the ViT token grid (28 x 28 for a 448^2 crop); this step brings them to the
+// label resolution before seg_loss (seg_helper.py:800-813) and get_energy_loss (:210-230) read them, and autograd
+// carries the gradient of both losses back through it.
+//
+//   upsample_bilinear_kernel        out[p, Y, X] = sum_{i,j} wy(Y,i) wx(X,j) in[p, i, j]        (forward)
+//   upsample_adjoint_rows_kernel    tmp[p, i, X] = sum_Y wy(Y,i) g[p, Y, X]                     (backward, pass 1)
+//   upsample_adjoint_cols_kernel    gin[p, i, j] = sum_X wx(X,j) tmp[p, i, X]                   (backward, pass 2)
+//
+// Forward arithmetic is torch's (common.cuh: source index scale*(dst+0.5)-0.5 clamped at 0, x-lerp then y-lerp as
+// fma(w0, a, rn(w1*b))): bit-exact against the CPU kernel for integer ratios (the path's 16x; dyadic weights), within
+// an ulp otherwise.  The adjoint is a gather in two separable passes - pass 1
+// streams the full-resolution gradient once with coalesced 128-bit loads, pass 2 works on the h/H-times smaller
+// intermediate - instead of the scatter with 4 atomics per element the definition suggests; only its summation
+// order differs from torch's.
+#include "common.cuh"
+
+namespace cosa {
+
+__global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                long long planes, int h, int w, int H, int W,
+                                                                float sy, float sx, int vec) {
+  const int Wq = vec ? W >> 2 : W;
+  const long long total = planes * H * Wq;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(idx % Wq);
+    const long long t = idx / Wq;
+    const int Y = (int)(t % H);
+    const long long p = t / H;
+    const Tap ty = tap_half_pixel(Y, sy, h);
+    const float *r0 = in + (size_t)p * h * w + (size_t)ty.i0 * w;
+    const float *r1 = in + (size_t)p * h * w + (size_t)ty.i1 * w;
+    float *dst = out + ((size_t)p * H + Y) * W;
+    if (vec) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Tap tx = tap_half_pixel(4 * xq + k, sx, w);
+        v[k] = bilerp_up(ty, tx, __ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1));
+      }
+      stg_stream4(dst + 4 * xq, make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+      const Tap tx = tap_half_pixel(xq, sx, w);
+      dst[xq] = bilerp_up(ty, tx, __ldg(r0 + tx.i0), __ldg(r0 + tx.i1), __ldg(r1 + tx.i0), __ldg(r1 + tx.i1));
+    }
+  }
+}
+
+// Range of destination indices whose taps can touch source index i (a superset; the kernels test every tap).
+__device__ __forceinline__ void adjoint_range(int i, float scale, int dst_size, int *lo, int *hi) {
+  const float inv = 1.0f / scale;
+  *lo = max(0, (int)floorf(((float)i - 1.0f + 0.5f) * inv - 0.5f) - 1);
+  *hi = min(dst_size, (int)ceilf(((float)i + 1.0f + 0.5f) * inv - 0.5f) + 2);
+}
+
+// pass 1: one thread per (plane, source row i, 4 destination columns)
+__global__ void __launch_bounds__(256) upsample_adjoint_rows_kernel(const float *__restrict__ g, float *__restrict__ tmp,
+                                                                    long long planes, int h, int H, int W, float sy,
+                                                                    int vec) {
+  const int Wq = vec ? W >> 2 : W;
+  const long long total = planes * h * Wq;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int xq = (int)(idx % Wq);
+    const long long t = idx / Wq;
+    const int i = (int)(t % h);
+    const long long p = t / h;
+    int lo, hi;
+    adjoint_range(i, sy, H, &lo, &hi);
+    const float *src = g + (size_t)p * H * W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int Y = lo; Y < hi; ++Y) {
+      const Tap ty = tap_half_pixel(Y, sy, h);
+      const float wgt = (ty.i0 == i ? ty.w0 : 0.0f) + (ty.i1 == i ? ty.w1 : 0.0f);
+      if (wgt != 0.0f) {
+        if (vec) {
+          const float4 v = ldg_stream4(src + (size_t)Y * W + 4 * xq);
+          acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
+          acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
+        } else {
+          acc.x = fmaf(wgt, __ldg(src + (size_t)Y * W + xq), acc.x);
+        }
+      }
+    }
+    float *dst = tmp + ((size_t)p * h + i) * W;
+    if (vec) *reinterpret_cast<float4 *>(dst + 4 * xq) = acc;
+    else dst[xq] = acc.x;
+  }
+}
+
+// pass 2: one thread per (plane, source row i, source column j)
+__global__ void __launch_bounds__(256) upsample_adjoint_cols_kernel(const float *__restrict__ tmp, float *__restrict__ gin,
+                                                                    long long rows, int w, int W, float sx) {
+  const long long total = rows * w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % w);
+    const long long r = idx / w;
+    int lo, hi;
+    adjoint_range(j, sx, W, &lo, &hi);
+    const float *src = tmp + (size_t)r * W;
+    float acc = 0.0f;
+    for (int X = lo; X < hi; ++X) {
+      const Tap tx = tap_half_pixel(X, sx, w);
+      const float wgt = (tx.i0 == j ? tx.w0 : 0.0f) + (tx.i1 == j ? tx.w1 : 0.0f);
+      acc = fmaf(wgt, __ldg(src + X), acc);
+    }
+    gin[idx] = acc;
+  }
+}
+
+static int grid_for(long long items) { return (int)max(1LL, min((long long)sm_count() * 16, ceil_div_ll(items, 256))); }
+
+}  // namespace cosa
+
+using namespace cosa;
+
+extern "C" int cosa_upsample_bilinear(const float *in, float *out, long long planes, int h, int w, int H, int W,
+                                      void *stream) {
+  if (!in || !out || planes < 1 || h < 1 || w < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  const int vec = (W % 4 == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+  const long long total = planes * H * (vec ? W / 4 : W);
+  COSA_LAUNCH(upsample_bilinear_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, in, out, planes, h, w, H, W,
+              (float)h / (float)H, (float)w / (float)W, vec);
+  return 0;
+}
+
+extern "C" size_t cosa_upsample_bilinear_backward_ws_bytes(long long planes, int h, int W) {
+  if (planes < 1 || h < 1 || W < 1) return 0;
+  return (size_t)planes * h * W * sizeof(float);
+}
+
+extern "C" int cosa_upsample_bilinear_backward(const float *grad_out, float *grad_in, long long planes, int h, int w,
+                                               int H, int W, void *ws, size_t ws_bytes, void *stream) {
+  if (!grad_out || !grad_in || !ws || planes < 1 || h < 1 || w < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  if (ws_bytes < cosa_upsample_bilinear_backward_ws_bytes(planes, h, W)) return COSA_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float *tmp = (float *)ws;
+  const int vec = (W % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)tmp) % 16) == 0) ? 1 : 0;
+  COSA_LAUNCH(upsample_adjoint_rows_kernel, grid_for(planes * h * (vec ? W / 4 : W)), 256, 0, s, grad_out, tmp, planes,
+              h, H, W, (float)h / (float)H, vec);
+  COSA_LAUNCH(upsample_adjoint_cols_kernel, grid_for(planes * h * w), 256, 0, s, tmp, grad_in, planes * h, w, W,
+              (float)w / (float)W);
+  return 0;
+}

@@ -527,6 +527,41 @@ def seg_refine_by_label(seg, cls_label, softmaxtemp, after_softmax=False):
     return out
 
 
+class _UpsampleBilinearFunction(Function):
+
+    @staticmethod
+    def forward(ctx, x, size):
+        lib = _lib.load()
+        x = _lib.dev_f32(x, "input")
+        B, C, h, w = x.shape
+        H, W = int(size[0]), int(size[1])
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cosa_upsample_bilinear(_lib.ptr(x), _lib.ptr(out), B * C, h, w, H, W, _lib.stream_ptr()))
+        ctx.shape = (B, C, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        B, C, h, w, H, W = ctx.shape
+        g = _lib.dev_f32(grad_out, "grad_output")
+        grad_in = torch.empty((B, C, h, w), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            nbytes = lib.cosa_upsample_bilinear_backward_ws_bytes(B * C, h, W)
+            ws = _lib.workspace(nbytes, g.device)
+            _lib.check(lib.cosa_upsample_bilinear_backward(_lib.ptr(g), _lib.ptr(grad_in), B * C, h, w, H, W,
+                                                           _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+        return grad_in, None
+
+
+def upsample_bilinear(x, size):
+    """``F.interpolate(x, size=size, mode='bilinear', align_corners=False)`` for [B,C,h,w] float32 CUDA tensors, with
+    autograd: the step that brings the decoder's logits to the label size before seg_loss and get_energy_loss
+    (main.py:167).  Forward bit-exact against torch's CPU kernel; backward is the adjoint as a two-pass gather."""
+    return _UpsampleBilinearFunction.apply(x, tuple(size))
+
+
 class _CamLossFunction(Function):
 
     @staticmethod

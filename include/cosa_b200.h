@@ -211,6 +211,18 @@ int cosa_cam_loss_forward(const float *cam, const float *seg_ps, int is_relu, fl
 int cosa_cam_loss_backward(const float *cam, const float *target_ws, const float *grad_out, int is_relu,
                            float *grad_cam, int B, int C, int H, int W, void *stream);
 
+
+/* Bilinear enlargement of the segmentation logits to the label size, main.py:167
+ *   seg_pred = F.interpolate(seg_pred, size=(H, W), mode='bilinear', align_corners=False)
+ * in [planes, h, w] -> out [planes, H, W] (planes = B*C), bit-exact against torch's CPU kernel for integer ratios
+ * (28 -> 448), within an ulp otherwise; and its adjoint
+ * (what autograd runs for the step): grad_out [planes, H, W] -> grad_in [planes, h, w], as a two-pass gather with a
+ * caller-owned scratch of cosa_upsample_bilinear_backward_ws_bytes(planes, h, W) bytes. */
+int cosa_upsample_bilinear(const float *in, float *out, long long planes, int h, int w, int H, int W, void *stream);
+size_t cosa_upsample_bilinear_backward_ws_bytes(long long planes, int h, int W);
+int cosa_upsample_bilinear_backward(const float *grad_out, float *grad_in, long long planes, int h, int w, int H,
+                                    int W, void *ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

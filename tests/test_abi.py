@@ -47,7 +47,7 @@ def test_workspace_sizes_are_monotone(lib):
     b = lib.cosa_bilateral_ws_bytes(32, 21, 224, 224)
     c = lib.cosa_bilateral_ws_bytes(32, 81, 224, 224)
     assert 0 < a < b < c < 16 << 30
-    assert lib.cosa_bilateral_ws_bytes(100, 21, 224, 224) == lib.cosa_bilateral_ws_bytes(64, 21, 224, 224)  # chunked
+    assert lib.cosa_bilateral_ws_bytes(100, 21, 224, 224) <= lib.cosa_bilateral_ws_bytes(64, 21, 224, 224)  # two chunks of 50
     assert lib.cosa_cam2mask_ws_bytes(32, 20, 448, 448, 2, 1, 6) > lib.cosa_cam2mask_ws_bytes(32, 20, 448, 448, 2, 0, 0)
     assert lib.cosa_energy_loss_ws_bytes(32, 21, 448, 448) > lib.cosa_dense_energy_ws_bytes(32, 21, 224, 224)
     assert lib.cosa_par_ws_bytes(1, 20, 224, 224, 6) > 48 * 224 * 224 * 4

@@ -156,6 +156,28 @@ def test_denormalize_img(cosa, port):
         assert float((cosa.denormalize_img(d["simg"].cuda()).cpu() - d["img_denorm"]).abs().max()) <= 1.0 / 255 + 1e-6
 
 
+@pytest.mark.parametrize("shape", [(2, 21, 28, 28, 448, 448), (1, 5, 7, 9, 30, 41), (2, 3, 14, 14, 14, 14),
+                                   (1, 4, 20, 12, 64, 36)])
+def test_upsample_bilinear_matches_torch(cosa, shape):
+    """main.py:167: F.interpolate(seg_pred, size, mode='bilinear', align_corners=False).  The oracle of this step is
+    the torch call the reference makes: forward bit-exact for integer ratios (the path's 28 -> 448), within an ulp for
+    others; the adjoint against autograd through the same call, <= 1e-5."""
+    b, c, h, w, H, W = shape
+    gen = torch.Generator().manual_seed(h * 1000 + W)
+    x = (3 * torch.randn((b, c, h, w), generator=gen)).requires_grad_(True)
+    want = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=False)
+    g = torch.randn((b, c, H, W), generator=gen)
+    want.backward(g)
+    xc = x.detach().cuda().requires_grad_(True)
+    got = cosa.upsample_bilinear(xc, (H, W))
+    if H % h == 0 and W % w == 0:      # the path's case (16x): interpolation weights are dyadic, every product exact
+        assert_same(got, want, "upsample_bilinear %s" % (shape,))
+    else:                              # general ratios: torch's vectorised CPU kernel contracts differently, <= 1 ulp
+        assert_close(got, want, "upsample_bilinear %s" % (shape,), tol=1e-6)
+    got.backward(g.cuda())
+    assert_close(xc.grad, x.grad, "upsample_bilinear adjoint %s" % (shape,), tol=1e-5)
+
+
 def test_multi_scale_merge_golden(cosa):
     """enlargement + un-flip max + ReLU + scale sum + normalise, fused (seg_helper.py:253-273)."""
     g = load_golden("multi_scale")
