@@ -234,7 +234,7 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
 def run_cosa_arm(args):
     import torch.distributed as dist
     import cosa_b200
-    from cosa_b200 import _lib, seg_helper, sharding
+    from cosa_b200 import _lib, seg_helper, sharding, synthetic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -325,6 +325,7 @@ def run_cosa_arm(args):
     # ---- end to end through the host-buffer API (cosa_b200.HostPipeline): pinned host tensors in, labels + loss in
     # pinned host memory out; every step's uploads and read-backs are inside the timed region ---------------------
     e2e = None
+    e2e_native = None
     if not args.no_e2e:
         pipe = cosa_b200.HostPipeline(par, layer, threshold_high=THR_HIGH, threshold_low=THR_LOW, device=dev)
         batch = dict(pinned, img_box=boxes)
@@ -350,6 +351,34 @@ def run_cosa_arm(args):
                        "(copy stream); CAM planes of absent classes are not uploaded (zero after cam_validation), the [0,1] image "
                        "is derived on the device from the normalised one as in main.py:117; "
                        "labels + loss read back every step"}
+
+        # the same step fed one stage further upstream, where the tensors are small: the teacher's raw multi-scale
+        # CAMs and the decoder's logits on the ViT token grids (merge + validation and the enlargement run on the device)
+        raw_cams = [t.pin_memory() for t in synthetic.synthetic_raw_cams(host, seed=7000 + rank)]
+        nbatch = dict(simg=pinned["simg"], raw_cams=raw_cams, seg_lowres=pinned["seg_lowres"],
+                      cls_label=pinned["cls_label"], img_box=boxes)
+        npipe = cosa_b200.HostPipeline(par, layer, threshold_high=THR_HIGH, threshold_low=THR_LOW, device=dev)
+        for _ in range(3):
+            npipe.submit_native(nbatch)
+        npipe.drain()
+        sync_all()
+        h2d0, d2h0, l0 = npipe.h2d_bytes, npipe.d2h_bytes, _lib.launch_count()
+        ev0.record()
+        for _ in range(e2e_steps):
+            npipe.submit_native(nbatch)
+        npipe.drain()
+        ev1.record()
+        sync_all()
+        n_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+        e2e_native = {"value": sharding.all_reduce_sum(B * e2e_steps) / (n_ms / 1e3), "unit": "images/s",
+                      "h2d_bytes_per_step": (npipe.h2d_bytes - h2d0) // e2e_steps,
+                      "d2h_bytes_per_step": (npipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
+                      "ms_per_step": n_ms / e2e_steps,
+                      "gpu_launches_per_step": (_lib.launch_count() - l0) / e2e_steps,
+                      "note": "HostPipeline.submit_native: host buffers at the resolution the networks emit them "
+                              "(raw CAMs on the 28/14/42 token grids for images and flips, logits 28x28); "
+                              "multi_scale_cam_merge + cam_validation and the main.py:167 enlargement (with its "
+                              "adjoint in the backward) run on the device in front of the same step"}
 
     clocks.__exit__(None, None, None)
 
@@ -377,7 +406,7 @@ def run_cosa_arm(args):
                        "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
                                 % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),
                        "lattice_vertices": M_vertices, "lattice_M_over_n": round(M_vertices / (B * (H // 2) * (W // 2)), 4)},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "loss": mean_loss,
         }
         print(json.dumps(line), flush=True)

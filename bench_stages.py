@@ -2,6 +2,8 @@
 """Measurements for the rows next to the hot path, same bar as bench.py:
 
     multi_scale merge (teacher post-processing)   utils/seg_helper.py:253-273
+    denormalize_img                               utils/torch_helper.py:354-367 (main.py:117)
+    upsample_bilinear forward + adjoint           main.py:167 (F.interpolate of the logits)
     seg_loss forward + backward                   utils/seg_helper.py:800-813
     seg_refine_by_label                           utils/seg_helper.py:553-568
     cam_loss forward + backward                   utils/seg_helper.py:593-602
@@ -53,7 +55,10 @@ def main():
     for b in range(B):
         cls[b, torch.randperm(C - 1, generator=g)[:2]] = 1
     cam_pred = torch.randn((B, C - 1, 28, 28), generator=g)
-    d = dict(raw_cam=[t.to(dev) for t in raw_cam], raw_seg=[t.to(dev) for t in raw_seg], logits=logits.to(dev),
+    seg_low = 3 * torch.randn((B, C, 28, 28), generator=g)
+    simg = torch.randn((B, 3, H, W), generator=g)
+    g_full = torch.randn((B, C, H, W), generator=g).to(dev)
+    d = dict(seg_low=seg_low.to(dev), simg=simg.to(dev), raw_cam=[t.to(dev) for t in raw_cam], raw_seg=[t.to(dev) for t in raw_seg], logits=logits.to(dev),
              label=label.to(dev), cls=cls.to(dev), cam_pred=cam_pred.to(dev))
     valid_seg = cosa_b200.seg_refine_by_label(d["logits"], d["cls"], 0.01)
     peak, peak_src = measured_peak_gbs()
@@ -69,8 +74,18 @@ def main():
         mod.cam_loss(x, vs).backward()
         return x.grad
 
+    def upsample_fb(x, gfull, mod):
+        x = x.detach().requires_grad_(True)
+        mod.upsample_bilinear(x, (H, W)).backward(gfull)
+        return x.grad
+
     stages = [
         # name, device fn, cpu fn (on n images), algorithmic bytes per call
+        ("denormalize_img", lambda: cosa_b200.denormalize_img(d["simg"]), lambda n: port.denormalize_img(simg[:n]),
+         f32 * B * 3 * H * W * 2),
+        ("upsample_bilinear fwd+bwd (28^2 -> 448^2)", lambda: upsample_fb(d["seg_low"], g_full, cosa_b200),
+         lambda n: upsample_fb(seg_low[:n], g_full[:n].cpu(), port),
+         f32 * B * C * H * W * 2),                                           # full-size logits written, gradient read
         ("multi_scale_cam_merge", lambda: cosa_b200.multi_scale_cam_merge(d["raw_cam"], (H, W)),
          lambda n: port.multi_scale_merge([t[list(range(n)) + list(range(B, B + n))] for t in raw_cam],
                                           raw_cam[2][list(range(n)) + list(range(B, B + n))],

@@ -645,7 +645,8 @@ __global__ void __launch_bounds__(256) cam_merge_kernel(RawScales rs, float *__r
 //   MODE 0: cam, min/max only      MODE 1: cam, normalised store      MODE 2: seg (sum of plain + flipped), store
 template <int NS, int MODE>
 __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
-                                                         int B, int C, int H, int W, int rows_per_chunk) {
+                                                         int B, int C, int H, int W, int rows_per_chunk,
+                                                         const float *__restrict__ cls) {
   const int wq = W >> 2, n_chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long total = (long long)B * C * n_chunks * wq;
@@ -655,7 +656,18 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
   const int plane = live ? (int)(t / ((long long)wq * n_chunks)) : 0;
   const int b = plane / C, c = plane - b * C;
   const int x = xq << 2;
-  const int y_begin = chunk * rows_per_chunk, y_end = live ? min(H, y_begin + rows_per_chunk) : y_begin;
+  const int y_begin = chunk * rows_per_chunk;
+  int y_end = live ? min(H, y_begin + rows_per_chunk) : y_begin;
+  // fused cam_validation (seg_helper.py:547-551): the plane is multiplied by its class label; a plane whose label
+  // is 0 is neither merged nor scanned for its extrema, only zero-filled
+  const float lab = (cls && live) ? __ldg(cls + plane) : 1.0f;
+  if (lab == 0.0f) {
+    if (MODE == 1) {
+      float *z = out + (size_t)plane * H * W + x;
+      for (int y = y_begin; y < y_end; ++y) stg_stream4(z + (size_t)y * W, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    y_end = y_begin;
+  }
   float neg_min = 0.0f, den = 1.0f;
   if (MODE == 1) {
     neg_min = -ordered_to_float(mm[2 * plane]);
@@ -702,7 +714,7 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
     } else {
       if (MODE == 1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = __fdiv_rn(__fadd_rn(acc[k], neg_min), den);
+        for (int k = 0; k < 4; ++k) acc[k] = __fmul_rn(lab, __fdiv_rn(__fadd_rn(acc[k], neg_min), den));
       }
       stg_stream4(o + (size_t)y * W, make_float4(acc[0], acc[1], acc[2], acc[3]));
     }
@@ -726,17 +738,18 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
 }
 
 template <int MODE>
-static int launch_merge_rows(const RawScales &rs, float *out, int *mm, int B, int C, int H, int W, cudaStream_t s) {
+static int launch_merge_rows(const RawScales &rs, float *out, int *mm, int B, int C, int H, int W, const float *cls,
+                             cudaStream_t s) {
   const int rows = 56;   // rows per thread: long enough to amortise the source-row refresh, short enough to fill the GPU
   const long long total = (long long)B * C * ceil_div(H, rows) * (W / 4);
   const unsigned grid = (unsigned)ceil_div_ll(total, 128);
   const char *name = MODE == 0 ? "cam_merge_minmax_kernel" : (MODE == 1 ? "cam_merge_write_kernel" : "seg_merge_kernel");
   switch (rs.n) {
-    case 1: { auto k = merge_rows_kernel<1, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
-    case 2: { auto k = merge_rows_kernel<2, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
-    case 3: { auto k = merge_rows_kernel<3, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
-    case 4: { auto k = merge_rows_kernel<4, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
-    case 5: { auto k = merge_rows_kernel<5, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows); break; }
+    case 1: { auto k = merge_rows_kernel<1, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
+    case 2: { auto k = merge_rows_kernel<2, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
+    case 3: { auto k = merge_rows_kernel<3, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
+    case 4: { auto k = merge_rows_kernel<4, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
+    case 5: { auto k = merge_rows_kernel<5, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
     default: return COSA_E_ARG;
   }
   return 0;
@@ -974,8 +987,8 @@ static int fill_raw_scales(RawScales *rs, const float *const *raw, const int *hs
   return 0;
 }
 
-extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,
-                                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream) {
+static int cam_merge_impl(const float *const *raw, const int *hs, const int *ws, int n_scales, const float *cls_label,
+                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream) {
   if (!out || !minmax_ws || B < 1 || C1 < 1 || H < 1 || W < 1) return COSA_E_ARG;
   RawScales rs;
   COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
@@ -985,13 +998,26 @@ extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs
   int *mm = (int *)minmax_ws;
   COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
   if (W % 4 == 0 && n_scales <= 5) {
-    COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, s));
-    return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, s);
+    COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, cls_label, s));
+    return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, cls_label, s);
   }
   const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
   COSA_LAUNCH_T("cam_merge_minmax_kernel", cam_merge_kernel<false>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
   COSA_LAUNCH_T("cam_merge_write_kernel", cam_merge_kernel<true>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
+  if (cls_label) return cosa_cam_validation(out, cls_label, out, B, C1, HW, stream);   // generic widths: in place
   return 0;
+}
+
+extern "C" int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream) {
+  return cam_merge_impl(raw, hs, ws, n_scales, nullptr, out, B, C1, H, W, minmax_ws, stream);
+}
+
+extern "C" int cosa_multi_scale_cam_merge_valid(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                                const float *cls_label, float *out, int B, int C1, int H, int W,
+                                                float *minmax_ws, void *stream) {
+  if (!cls_label) return COSA_E_ARG;
+  return cam_merge_impl(raw, hs, ws, n_scales, cls_label, out, B, C1, H, W, minmax_ws, stream);
 }
 
 extern "C" int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,
@@ -999,7 +1025,7 @@ extern "C" int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs
   if (!out || B < 1 || C < 1 || H < 1 || W < 1) return COSA_E_ARG;
   RawScales rs;
   COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
-  if (W % 4 == 0 && n_scales <= 5) return launch_merge_rows<2>(rs, out, nullptr, B, C, H, W, (cudaStream_t)stream);
+  if (W % 4 == 0 && n_scales <= 5) return launch_merge_rows<2>(rs, out, nullptr, B, C, H, W, nullptr, (cudaStream_t)stream);
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)max(1LL, min((long long)sm_count() * 16, ceil_div_ll(total, 256)));
   COSA_LAUNCH(seg_merge_kernel, blocks, 256, 0, (cudaStream_t)stream, rs, out, B, C, H, W);

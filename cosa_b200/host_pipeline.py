@@ -21,6 +21,12 @@ exactly as the reference does (main.py:117, ``denormalize_img``), so the image c
 
 One step is exactly the device path of main.py:117-212:
 denormalize_img -> cam_validation -> cam2mask(refine_model=par) -> get_energy_loss -> backward.
+
+``submit_native`` takes the same step one stage further upstream on both inputs, to where the tensors are small:
+the teacher's raw multi-scale CAM maps on the ViT token grids (what ``multi_scale_camseg`` gets from the model,
+seg_helper.py:246-257) and the decoder's logits on the token grid (main.py:167 enlarges them).  The merge / normalise
+and the enlargement then run on the device (``multi_scale_cam_merge``, ``upsample_bilinear``) and 93 MB instead of
+668 MB cross PCIe per VOC batch of 32.
 """
 import torch
 
@@ -117,6 +123,73 @@ class HostPipeline:
         self._pending.append(s)
         self.n_submitted += 1
         if len(self._pending) > self.depth - 1:              # keep at most depth-1 unread results behind us
+            return self._collect(self._pending.pop(0))
+        return None
+
+    # -- native-resolution inputs ---------------------------------------------------------------------------------
+    def submit_native(self, batch):
+        """Queue one batch given at the resolution the networks produce it: pinned float32 CPU tensors ``simg``
+        [B,3,H,W], ``raw_cams`` (list over scales of [2B,C-1,hs,ws]: the teacher's CAMs for the images and their
+        flips, seg_helper.py:246-250), ``seg_lowres`` [B,C,h,w] (decoder logits, main.py:167), ``cls_label`` [B,C-1]
+        and ``img_box``.  Returns like ``submit``; with ``want_grad`` the gradient is the one of ``seg_lowres``."""
+        names = ("simg", "cls_label", "seg_lowres")
+        for t in [batch[k] for k in names] + list(batch["raw_cams"]):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("HostPipeline.submit_native: inputs must be contiguous float32 CPU tensors")
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            i = self.n_submitted % self.depth
+            while len(self.slots) < self.depth:
+                self.slots.append(None)
+            shapes = {k: tuple(batch[k].shape) for k in names}
+            shapes["raw_cams"] = tuple(tuple(t.shape) for t in batch["raw_cams"])
+            s = self.slots[i]
+            if s is None or s["shapes"] != shapes:
+                B, _, H, W = shapes["simg"]
+                dev = {k: torch.empty(shapes[k], dtype=torch.float32, device=self.device) for k in names}
+                dev["raw_cams"] = [torch.empty(sh, dtype=torch.float32, device=self.device) for sh in shapes["raw_cams"]]
+                s = {"shapes": shapes, "dev": dev, "ready": torch.cuda.Event(), "consumed": torch.cuda.Event(),
+                     "label": torch.empty((B, H, W), dtype=torch.float32).pin_memory(),
+                     "loss": torch.empty(1, dtype=torch.float32).pin_memory(),
+                     "grad": (torch.empty(shapes["seg_lowres"], dtype=torch.float32).pin_memory()
+                              if self.want_grad else None),
+                     "done": torch.cuda.Event()}
+                s["consumed"].record(main)
+                self.slots[i] = s
+            d = s["dev"]
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(s["consumed"])
+                for k in names:
+                    d[k].copy_(batch[k], non_blocking=True)
+                    self.h2d_bytes += batch[k].numel() * 4
+                for dst, src in zip(d["raw_cams"], batch["raw_cams"]):
+                    dst.copy_(src, non_blocking=True)
+                    self.h2d_bytes += src.numel() * 4
+                s["ready"].record(self.copy_stream)
+            main.wait_event(s["ready"])
+            boxes = batch["img_box"]
+            H, W = shapes["simg"][2:]
+            img_denorm = seg_helper.denormalize_img(d["simg"])
+            # seg_helper.py:250-270 + cam_validation (main.py:137), absent classes' planes zero-filled
+            cams = seg_helper.multi_scale_cam_merge(d["raw_cams"], (H, W), cls_label=d["cls_label"])
+            label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
+                                        threshold_high=self.thr[0], threshold_low=self.thr[1], refine_model=self.par)
+            low = d["seg_lowres"].detach().requires_grad_(True)
+            logit = seg_helper.upsample_bilinear(low, (H, W))                           # main.py:167
+            loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,
+                                              loss_layer=self.loss_layer)
+            loss.backward()
+            s["label"].copy_(label, non_blocking=True)
+            s["loss"].copy_(loss.detach(), non_blocking=True)
+            self.d2h_bytes += s["label"].numel() * 4 + 4
+            if self.want_grad:
+                s["grad"].copy_(low.grad, non_blocking=True)
+                self.d2h_bytes += s["grad"].numel() * 4
+            s["consumed"].record(main)
+            s["done"].record(main)
+        self._pending.append(s)
+        self.n_submitted += 1
+        if len(self._pending) > self.depth - 1:
             return self._collect(self._pending.pop(0))
         return None
 

@@ -57,11 +57,13 @@ def _raw_scale_args(raws, what):
     return raws, ptrs, hs, ws
 
 
-def multi_scale_cam_merge(raw_cams, size):
+def multi_scale_cam_merge(raw_cams, size, cls_label=None):
     """Normalised CAM [B,C1,H,W] from the per-scale raw maps of ``multi_scale_camseg`` (seg_helper.py:253-270).
 
     ``raw_cams[s]`` is the model output for ``cat([imgs_s, imgs_s.flip(-1)])``: [2B, C1, hs, ws].  Enlargement,
     un-flip, max, ReLU, sum over scales and the per-plane min-max normalisation run in one kernel sequence.
+    With ``cls_label`` [B,C1] the result is ``cam_validation(merged, cls_label)`` (the next call in main.py:137) and
+    the planes of absent classes are zero-filled without being merged.
     """
     lib = _lib.load()
     raws, ptrs, hs, ws = _raw_scale_args(raw_cams, "raw_cam")
@@ -70,8 +72,14 @@ def multi_scale_cam_merge(raw_cams, size):
     out = torch.empty((B, C1, H, W), dtype=torch.float32, device=raws[0].device)
     mm = torch.empty(2 * B * C1, dtype=torch.float32, device=out.device)
     with torch.cuda.device(out.device):
-        _lib.check(lib.cosa_multi_scale_cam_merge(ptrs, hs, ws, len(raws), _lib.ptr(out), B, C1, H, W, _lib.ptr(mm),
-                                                  _lib.stream_ptr()))
+        if cls_label is None:
+            _lib.check(lib.cosa_multi_scale_cam_merge(ptrs, hs, ws, len(raws), _lib.ptr(out), B, C1, H, W,
+                                                      _lib.ptr(mm), _lib.stream_ptr()))
+        else:
+            lab = _lib.dev_f32(cls_label.to(out.device), "cls_label")
+            assert lab.shape == (B, C1), "cls_label must be [B, C-1]"
+            _lib.check(lib.cosa_multi_scale_cam_merge_valid(ptrs, hs, ws, len(raws), _lib.ptr(lab), _lib.ptr(out), B,
+                                                            C1, H, W, _lib.ptr(mm), _lib.stream_ptr()))
     return out
 
 

@@ -47,11 +47,29 @@ def synthetic_batch(B, C, H, W, n_fg, seed, noise_sigma=10.0, cam_kind="blobs", 
                              align_corners=False)
     cams = cls_label[:, :, None, None] * cams
     gh, gw = max(H // 16, 2), max(W // 16, 2)
-    logits = F.interpolate(3 * torch.randn((B, C, gh, gw), generator=g), size=(H, W), mode="bilinear",
-                           align_corners=False)
+    seg_lowres = 3 * torch.randn((B, C, gh, gw), generator=g)          # decoder logits on the token grid
+    logits = F.interpolate(seg_lowres, size=(H, W), mode="bilinear", align_corners=False)      # main.py:167
     if box == "full":
         boxes = torch.tensor([[0, H, 0, W]] * B, dtype=torch.int16)
     else:
         boxes = torch.tensor([[H // 28, H - H // 28, W // 14, W]] * B, dtype=torch.int16)
     return dict(simg=simg.contiguous(), img_denorm=img_denorm.contiguous(), cams=cams.contiguous(),
-                cls_label=cls_label, logits=logits.contiguous(), img_box=boxes)
+                cls_label=cls_label, logits=logits.contiguous(), img_box=boxes, seg_lowres=seg_lowres.contiguous())
+
+
+def synthetic_raw_cams(d, seed, scales=(1.0, 0.5, 1.5)):
+    """Teacher CAMs as ``multi_scale_camseg`` receives them from the model (seg_helper.py:246-250): per scale a tensor
+    [2B, C-1, hs, ws] on the ViT token grid, the second half for the horizontally flipped images.  Built from the
+    batch's full-resolution CAMs (area-averaged onto the grid, a little noise, absent classes at noise level) so that
+    the merged result resembles them."""
+    g = torch.Generator().manual_seed(seed)
+    cams = d["cams"]
+    B, C1, H, W = cams.shape
+    out = []
+    for s in scales:
+        hs, ws = max(int(s * H) // 16, 2), max(int(s * W) // 16, 2)
+        base = F.adaptive_avg_pool2d(cams, (hs, ws))
+        a = base + 0.05 * torch.rand((B, C1, hs, ws), generator=g)
+        f = base.flip(-1) + 0.05 * torch.rand((B, C1, hs, ws), generator=g)
+        out.append(torch.cat([a, f], dim=0).contiguous())
+    return out

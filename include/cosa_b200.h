@@ -81,6 +81,11 @@ int cosa_cam_normalize(const float *const *scale_maps, int n_scales, float *out,
  * ---------------------------------------------------------------------------------------------- */
 int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
                                int C1, int H, int W, float *minmax_ws, void *stream);
+/* The same followed by cam_validation (seg_helper.py:547-551, main.py:137: the very next call on the merged CAMs):
+ * out = cls_label[b,c] * merged.  Planes whose label is 0 are zero-filled without being merged - 18 of 20 at VOC. */
+int cosa_multi_scale_cam_merge_valid(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                     const float *cls_label, float *out, int B, int C1, int H, int W,
+                                     float *minmax_ws, void *stream);
 int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
                                int C, int H, int W, void *stream);
 

@@ -135,6 +135,11 @@ def denormalize_img(imgs, mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57
     return out.type(torch.uint8) / 255.0
 
 
+def upsample_bilinear(x, size):
+    """main.py:167, the torch call the reference makes."""
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+
+
 def cam_validation(cam, cls_label):
     return cls_label[:, :, None, None] * cam
 

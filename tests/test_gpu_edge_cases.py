@@ -207,3 +207,54 @@ def test_host_pipeline_matches_device_path(cosa, port):
     assert pipe.h2d_bytes < 3 * sum(v.numel() * 4 for k, v in batches[0].items() if k != "img_box")
     with pytest.raises(ValueError):
         pipe.submit({k: (v.cuda() if k != "img_box" else v) for k, v in batches[0].items()})
+
+
+def test_cam_merge_with_labels_equals_merge_then_validation(cosa):
+    """multi_scale_cam_merge(..., cls_label) == cam_validation(multi_scale_cam_merge(...)) (main.py:135-137), bit for
+    bit, for 0/1 labels, for a fractional label, and on a width the row-walking kernel does not take."""
+    gen = torch.Generator().manual_seed(3)
+    for (B, C1, H, W) in ((3, 20, 64, 96), (2, 5, 30, 41)):
+        raw = [torch.randn((2 * B, C1, g_, g_ + 1), generator=gen).cuda() for g_ in (4, 2, 6)]
+        cls = (torch.rand((B, C1), generator=gen) < 0.2).float()
+        cls[0, 0] = 0.5
+        want = cosa.cam_validation(cosa.multi_scale_cam_merge(raw, (H, W)), cls.cuda())
+        got = cosa.multi_scale_cam_merge(raw, (H, W), cls_label=cls.cuda())
+        assert torch.equal(got, want), (B, C1, H, W)
+
+
+def test_host_pipeline_native_inputs_match_device_path(cosa):
+    """HostPipeline.submit_native (raw multi-scale CAMs + token-grid logits in pinned host memory) against the same
+    steps called one by one on device tensors: labels identical, loss and token-grid gradient equal."""
+    from cosa_b200 import synthetic
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    pipe = cosa.HostPipeline(par, layer, threshold_high=0.7, threshold_low=0.25, want_grad=True)
+    batches = []
+    for i in range(3):
+        hb = batch(B=2, C=21, H=96, W=128, n_fg=2, seed=300 + i)
+        hb["raw_cams"] = synthetic.synthetic_raw_cams(hb, seed=400 + i)
+        batches.append(hb)
+    outs = []
+    for hb in batches:
+        nb = dict(simg=hb["simg"].pin_memory(), raw_cams=[t.pin_memory() for t in hb["raw_cams"]],
+                  seg_lowres=hb["seg_lowres"].pin_memory(), cls_label=hb["cls_label"].pin_memory(), img_box=hb["img_box"])
+        r = pipe.submit_native(nb)
+        if r is not None:
+            outs.append(tuple(t.clone() for t in r))
+    outs += [tuple(t.clone() for t in r) for r in pipe.drain()]
+    assert len(outs) == 3
+    for hb, (label, loss, grad) in zip(batches, outs):
+        H, W = hb["simg"].shape[2:]
+        cams = cosa.cam_validation(cosa.multi_scale_cam_merge([t.cuda() for t in hb["raw_cams"]], (H, W)),
+                                   hb["cls_label"].cuda())
+        want = cosa.cam2mask(images=cosa.denormalize_img(hb["simg"].cuda()), img_boxes=hb["img_box"], cams=cams,
+                             cls_labels=hb["cls_label"].cuda(), threshold_high=0.7, threshold_low=0.25,
+                             refine_model=par)
+        low = hb["seg_lowres"].cuda().requires_grad_(True)
+        wl = cosa.get_energy_loss(img=hb["simg"].cuda(), logit=cosa.upsample_bilinear(low, (H, W)), label=want,
+                                  img_box=hb["img_box"], loss_layer=layer)
+        wl.backward()
+        assert torch.equal(label, want.cpu())
+        assert_close(loss, wl, "native pipeline loss", tol=1e-5)
+        assert_close(grad, low.grad, "native pipeline token-grid gradient", tol=1e-5)
+    assert pipe.h2d_bytes < 0.3 * 3 * sum(batches[0][k].numel() * 4 for k in ("simg", "cams", "logits"))
