@@ -7,15 +7,15 @@
 // carries the gradient of both losses back through it.
 //
 //   upsample_bilinear_kernel        out[p, Y, X] = sum_{i,j} wy(Y,i) wx(X,j) in[p, i, j]        (forward)
-//   upsample_adjoint_rows_kernel    tmp[p, i, X] = sum_Y wy(Y,i) g[p, Y, X]                     (backward, pass 1)
-//   upsample_adjoint_cols_kernel    gin[p, i, j] = sum_X wx(X,j) tmp[p, i, X]                   (backward, pass 2)
+//   upsample_adjoint_rows_kernel    tmp[p, k, 0|1, X] = sum over the rows Y with upper tap k of (w0 | w1)(Y) g[p, Y, X]
+//   upsample_adjoint_cols_kernel    gin[p, i, j] = sum_X wx(X,j) (tmp[p,i,0,X] + tmp[p,i-1,1,X])          (backward)
 //
 // Forward arithmetic is torch's (common.cuh: source index scale*(dst+0.5)-0.5 clamped at 0, x-lerp then y-lerp as
 // fma(w0, a, rn(w1*b))): bit-exact against the CPU kernel for integer ratios (the path's 16x; dyadic weights), within
 // an ulp otherwise.  The adjoint is a gather in two separable passes - pass 1
-// streams the full-resolution gradient once with coalesced 128-bit loads, pass 2 works on the h/H-times smaller
-// intermediate - instead of the scatter with 4 atomics per element the definition suggests; only its summation
-// order differs from torch's.
+// streams the full-resolution gradient exactly once with coalesced 128-bit loads, pass 2 works on the H/(2h)-times
+// smaller intermediate - instead of the scatter with 4 atomics per element the definition suggests; only its
+// summation order differs from torch's.
 #include "common.cuh"
 
 namespace cosa {
@@ -50,14 +50,17 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float *__r
   }
 }
 
-// Range of destination indices whose taps can touch source index i (a superset; the kernels test every tap).
-__device__ __forceinline__ void adjoint_range(int i, float scale, int dst_size, int *lo, int *hi) {
-  const float inv = 1.0f / scale;
-  *lo = max(0, (int)floorf(((float)i - 1.0f + 0.5f) * inv - 0.5f) - 1);
-  *hi = min(dst_size, (int)ceilf(((float)i + 1.0f + 0.5f) * inv - 0.5f) + 2);
+// First destination index whose upper-left tap is >= k (tap i0 is non-decreasing in the destination index).
+__device__ __forceinline__ int first_dst_with_i0(int k, float scale, int src_size, int dst_size) {
+  if (k <= 0) return 0;   // negative source coordinates are clamped to 0: the first block starts at the border
+  int d = max(0, (int)floorf(((float)k + 0.5f) / scale - 0.5f) - 2);
+  while (d < dst_size && tap_half_pixel(d, scale, src_size).i0 < k) ++d;
+  return d;
 }
 
-// pass 1: one thread per (plane, source row i, 4 destination columns)
+// pass 1: one thread per (plane, source row k, 4 destination columns).  The destination rows whose upper tap is k
+// form one contiguous block; the thread streams that block ONCE and keeps two sums, the part that belongs to source
+// row k (weights w0) and the part that belongs to the row below (weights w1): tmp[p][k][0 | 1][X].
 __global__ void __launch_bounds__(256) upsample_adjoint_rows_kernel(const float *__restrict__ g, float *__restrict__ tmp,
                                                                     long long planes, int h, int H, int W, float sy,
                                                                     int vec) {
@@ -67,47 +70,61 @@ __global__ void __launch_bounds__(256) upsample_adjoint_rows_kernel(const float 
        idx += (long long)gridDim.x * blockDim.x) {
     const int xq = (int)(idx % Wq);
     const long long t = idx / Wq;
-    const int i = (int)(t % h);
+    const int k = (int)(t % h);
     const long long p = t / h;
-    int lo, hi;
-    adjoint_range(i, sy, H, &lo, &hi);
+    const int y0 = first_dst_with_i0(k, sy, h, H), y1 = k + 1 < h ? first_dst_with_i0(k + 1, sy, h, H) : H;
     const float *src = g + (size_t)p * H * W;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int Y = lo; Y < hi; ++Y) {
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    for (int Y = y0; Y < y1; ++Y) {
       const Tap ty = tap_half_pixel(Y, sy, h);
-      const float wgt = (ty.i0 == i ? ty.w0 : 0.0f) + (ty.i1 == i ? ty.w1 : 0.0f);
-      if (wgt != 0.0f) {
-        if (vec) {
-          const float4 v = ldg_stream4(src + (size_t)Y * W + 4 * xq);
-          acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y);
-          acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w);
-        } else {
-          acc.x = fmaf(wgt, __ldg(src + (size_t)Y * W + xq), acc.x);
-        }
+      if (vec) {
+        const float4 v = ldg_stream4(src + (size_t)Y * W + 4 * xq);
+        lo.x = fmaf(ty.w0, v.x, lo.x); lo.y = fmaf(ty.w0, v.y, lo.y);
+        lo.z = fmaf(ty.w0, v.z, lo.z); lo.w = fmaf(ty.w0, v.w, lo.w);
+        hi.x = fmaf(ty.w1, v.x, hi.x); hi.y = fmaf(ty.w1, v.y, hi.y);
+        hi.z = fmaf(ty.w1, v.z, hi.z); hi.w = fmaf(ty.w1, v.w, hi.w);
+      } else {
+        const float v = __ldg(src + (size_t)Y * W + xq);
+        lo.x = fmaf(ty.w0, v, lo.x);
+        hi.x = fmaf(ty.w1, v, hi.x);
       }
     }
-    float *dst = tmp + ((size_t)p * h + i) * W;
-    if (vec) *reinterpret_cast<float4 *>(dst + 4 * xq) = acc;
-    else dst[xq] = acc.x;
+    float *dst = tmp + (((size_t)p * h + k) * 2) * W;
+    if (vec) {
+      *reinterpret_cast<float4 *>(dst + 4 * xq) = lo;
+      *reinterpret_cast<float4 *>(dst + W + 4 * xq) = hi;
+    } else {
+      dst[xq] = lo.x;
+      dst[W + xq] = hi.x;
+    }
   }
 }
 
-// pass 2: one thread per (plane, source row i, source column j)
+// pass 2: one thread per (plane, source row i, source column j): row i collects its own w0 part, the w1 part of the
+// block above and - in the last row, where the lower tap is clamped onto the row itself - its own w1 part; the
+// columns are reduced the same way (destination columns whose left tap is j - 1 or j).
 __global__ void __launch_bounds__(256) upsample_adjoint_cols_kernel(const float *__restrict__ tmp, float *__restrict__ gin,
-                                                                    long long rows, int w, int W, float sx) {
-  const long long total = rows * w;
+                                                                    long long planes, int h, int w, int W, float sx) {
+  const long long total = planes * h * w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(idx % w);
-    const long long r = idx / w;
-    int lo, hi;
-    adjoint_range(j, sx, W, &lo, &hi);
-    const float *src = tmp + (size_t)r * W;
+    const long long t = idx / w;
+    const int i = (int)(t % h);
+    const long long p = t / h;
+    const float *own = tmp + (((size_t)p * h + i) * 2) * W;          // [0]: w0 part of block i, [1]: its w1 part
+    const float *above = i > 0 ? own - 2 * W + W : nullptr;           // w1 part of block i - 1
+    const bool last = i == h - 1;
+    const int x0 = j > 0 ? first_dst_with_i0(j - 1, sx, w, W) : 0;
+    const int x1 = j + 1 < w ? first_dst_with_i0(j + 1, sx, w, W) : W;
     float acc = 0.0f;
-    for (int X = lo; X < hi; ++X) {
+    for (int X = x0; X < x1; ++X) {
       const Tap tx = tap_half_pixel(X, sx, w);
       const float wgt = (tx.i0 == j ? tx.w0 : 0.0f) + (tx.i1 == j ? tx.w1 : 0.0f);
-      acc = fmaf(wgt, __ldg(src + X), acc);
+      float v = __ldg(own + X);
+      if (above) v += __ldg(above + X);
+      if (last) v += __ldg(own + W + X);
+      acc = fmaf(wgt, v, acc);
     }
     gin[idx] = acc;
   }
@@ -131,7 +148,7 @@ extern "C" int cosa_upsample_bilinear(const float *in, float *out, long long pla
 
 extern "C" size_t cosa_upsample_bilinear_backward_ws_bytes(long long planes, int h, int W) {
   if (planes < 1 || h < 1 || W < 1) return 0;
-  return (size_t)planes * h * W * sizeof(float);
+  return (size_t)planes * h * W * 2 * sizeof(float);
 }
 
 extern "C" int cosa_upsample_bilinear_backward(const float *grad_out, float *grad_in, long long planes, int h, int w,
@@ -143,7 +160,7 @@ extern "C" int cosa_upsample_bilinear_backward(const float *grad_out, float *gra
   const int vec = (W % 4 == 0 && (((uintptr_t)grad_out | (uintptr_t)tmp) % 16) == 0) ? 1 : 0;
   COSA_LAUNCH(upsample_adjoint_rows_kernel, grid_for(planes * h * (vec ? W / 4 : W)), 256, 0, s, grad_out, tmp, planes,
               h, H, W, (float)h / (float)H, vec);
-  COSA_LAUNCH(upsample_adjoint_cols_kernel, grid_for(planes * h * w), 256, 0, s, tmp, grad_in, planes * h, w, W,
+  COSA_LAUNCH(upsample_adjoint_cols_kernel, grid_for(planes * h * w), 256, 0, s, tmp, grad_in, planes, h, w, W,
               (float)w / (float)W);
   return 0;
 }
