@@ -534,6 +534,12 @@ def test_full_size_labels_and_par_properties(cosa, voc_batch):
     const = torch.full((32, 2, 224, 224), 0.37, device="cuda")
     res = par(small, const)
     assert float((res / 0.37 - 1.01 ** 10).abs().max()) < 1e-4
+    # channel sums: a stack that sums to 1 sums to (1 + w2)^T after T steps at every pixel - the identity cam2mask
+    # uses to derive the last channel of each stack instead of propagating it
+    soft = torch.rand((32, 4, 224, 224), device="cuda").mul(4).softmax(dim=1)
+    dev_sum = float((par(small, soft).sum(dim=1) - 1.01 ** 10).abs().max())
+    print("PAR channel-sum deviation from 1.01^10 over 32 x 224 x 224 pixels: %.3g" % dev_sum)
+    assert dev_sum < 5e-6
     # linearity in the masks
     a, b_ = torch.rand_like(const), torch.rand_like(const)
     lin = par(small, 2 * a - 3 * b_) - (2 * par(small, a) - 3 * par(small, b_))
