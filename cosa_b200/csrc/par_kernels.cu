@@ -1199,6 +1199,169 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Double-buffered persistent step kernel (COSA_PAR_STEP=db; measured slower than the default, kept selectable).
+// <= 2 CTAs per SM stride over the work units (image tile x group of <= CH channels) of one step and each CTA owns
+// TWO tile buffers: the TMA boxes of unit i+1 are requested before unit i is computed and land while it runs, and
+// the affinity quads of unit i+1's first two dilations are requested while the last dilation of unit i is computed,
+// so after the first unit of a launch a CTA never waits for a tile.  Units that share an image tile (channel
+// groups) are adjacent in the unit order, so the second reader of the tile's affinity planes finds them in L2.
+// Result (VOC B = 32): 1.34 ms for the ten steps against 0.95 ms.  The ncu source view shows why hiding the tile
+// staging does not help: the long-scoreboard stalls sit on the first FFMA of every dilation, i.e. on the affinity
+// quads, whose prefetch distance (one dilation = 16 LDS + 64 FFMA at two channels) is far shorter than an L2 round
+// trip.  With one set of 8 quads effectively in flight per warp, 16 warps per SM keep 64 KB in flight, which at a
+// ~1.2 us loaded latency is ~8 TB/s over the GPU - about what the step moves.  The step is bound by affinity bytes
+// in flight; more of them need registers the kernel does not have.
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__device__ __forceinline__ PropUnit db_find_unit(const PropArgs &p, const int *s_nch, int n_pass, long long u,
+                                                 long long n_units) {
+  const int tiles = p.tiles_x * p.tiles_y;
+  PropUnit r;
+  for (; u < n_units; u += gridDim.x) {
+    const int pass = (int)(u % n_pass);
+    const long long bt = u / n_pass;
+    const int b = (int)(bt / tiles), t = (int)(bt - (long long)b * tiles);
+    const int nch = !p.nch_dev ? p.nch_uniform : (b < kPropMaxCachedB ? s_nch[b] : p.nch_dev[b]);
+    if (nch <= 0) continue;
+    const int n_groups = (nch + CH - 1) / CH;              // even split, at most CH channels per unit
+    const int chunk = (nch + n_groups - 1) / n_groups;
+    const int c0 = pass * chunk;
+    if (c0 < nch) {
+      r.u = (int)min(u, (long long)0x7fffffff); r.b = b; r.y0 = (t / p.tiles_x) * kTileH; r.x0 = (t % p.tiles_x) * kTileW;
+      r.c0 = c0; r.live = min(chunk, nch - c0);
+      return r;
+    }
+  }
+  r.u = -1; r.b = 0; r.x0 = 0; r.y0 = 0; r.c0 = 0; r.live = 0;
+  return r;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
+    par_iterate_db_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_in, float *__restrict__ out,
+                          MaskLayout lo) {
+  extern __shared__ __align__(128) float s_tile[];   // [2][CH][80][80]
+  __shared__ __align__(8) unsigned long long s_bar[2][2];   // [buffer][near | far]
+  __shared__ int s_nch[kPropMaxCachedB];
+  __shared__ int s_max_nch;
+  constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
+  constexpr int kBuf = CH * kFS * kFS;
+  const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
+  const int wq = p.w >> 2;
+  const size_t plane = (size_t)p.h * p.w;
+  const size_t oplane = (size_t)p.h * lo.pitch;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0][0], 1); mbar_init(&s_bar[0][1], 1);
+    mbar_init(&s_bar[1][0], 1); mbar_init(&s_bar[1][1], 1);
+    s_max_nch = 0;
+  }
+  __syncthreads();
+  int n_pass = p.n_pass;
+  if (p.nch_dev) {
+    int mx = 0;
+    for (int b = threadIdx.x; b < p.B; b += 256) {
+      const int v = p.nch_dev[b];
+      if (b < kPropMaxCachedB) s_nch[b] = v;
+      mx = max(mx, v);
+    }
+    if (mx > 0) atomicMax(&s_max_nch, mx);
+    __syncthreads();
+    n_pass = max(1, min(p.n_pass, (s_max_nch + CH - 1) / CH));
+  }
+  const long long n_units = (long long)p.B * p.tiles_x * p.tiles_y * n_pass;
+
+  auto stage = [&](const PropUnit &un, int buf) {   // one thread
+    float *tile = s_tile + buf * kBuf;
+    mbar_expect_tx(&s_bar[buf][0], (unsigned)(un.live * kNear * kFS * sizeof(float)));
+    mbar_expect_tx(&s_bar[buf][1], (unsigned)(un.live * kFar * kFS * sizeof(float)));
+    const int gx = p.li.off + un.x0 - kFH, gz = un.b * p.c_stride + un.c0;
+    for (int r = kFNear0; r < kFNear1; r += kBoxRows)
+      for (int k = 0; k < un.live; ++k)
+        tma_load_box(tile + (k * kFS + r) * kFS, &tm_in, gx, un.y0 - kFH + r, gz + k, &s_bar[buf][0]);
+    for (int k = 0; k < un.live; ++k) {
+      tma_load_box(tile + (k * kFS) * kFS, &tm_in, gx, un.y0 - kFH, gz + k, &s_bar[buf][1]);
+      tma_load_box(tile + (k * kFS + kFNear1) * kFS, &tm_in, gx, un.y0 - kFH + kFNear1, gz + k, &s_bar[buf][1]);
+    }
+  };
+  auto aff_ptr = [&](const PropUnit &un) {
+    return p.aff + (size_t)un.b * 48 * plane + (size_t)min(un.y0 + tr, p.h - 1) * p.w + min(un.x0 + (tq << 2), p.w - 4);
+  };
+
+  unsigned phase0 = 0, phase1 = 0;   // parity of the next completion of each buffer's barriers
+  int buf = 0;
+  PropUnit cur = db_find_unit<CH>(p, s_nch, n_pass, blockIdx.x, n_units);
+  float4 a0[8], a1[8];
+  const float *Ap = aff_ptr(cur);
+  if (cur.u >= 0) {
+    if (threadIdx.x == 0) stage(cur, 0);
+    load_aff8(a0, Ap, plane);
+    load_aff8(a1, Ap, plane);
+  }
+  while (cur.u >= 0) {
+    const PropUnit nxt = db_find_unit<CH>(p, s_nch, n_pass, (long long)cur.u + gridDim.x, n_units);
+    const bool more = nxt.u >= 0;
+    // the other buffer's last reader retired before the barrier that ended the previous unit: stage the next tile now
+    if (more && threadIdx.x == 0) stage(nxt, buf ^ 1);
+    const int live = cur.live;
+    const float *tile = s_tile + buf * kBuf;
+    const float *q = tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
+    // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
+    const int r_lo = max(0, kFH - cur.y0), r_hi = min(kFS, p.h - cur.y0 + kFH);
+    const bool edge = r_lo > 0 || r_hi < kFS;
+    float4 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned ph = buf ? phase1 : phase0;
+    mbar_wait(&s_bar[buf][0], ph);
+    if (edge) {
+      mbar_wait(&s_bar[buf][1], ph);
+      replicate_border_rows(const_cast<float *>(tile), live, r_lo, r_hi);
+    }
+    tile_dilation<1, CH>(acc, a0, q, live);
+    load_aff8(a0, Ap, plane);
+    tile_dilation<2, CH>(acc, a1, q, live);
+    load_aff8(a1, Ap, plane);
+    tile_dilation<4, CH>(acc, a0, q, live);
+    load_aff8(a0, Ap, plane);
+    tile_dilation<8, CH>(acc, a1, q, live);
+    load_aff8(a1, Ap, plane);
+    if (!edge) mbar_wait(&s_bar[buf][1], ph);
+    tile_dilation<12, CH>(acc, a0, q, live);
+    // the next unit's first affinity quads travel while the last dilation of this one is computed
+    Ap = aff_ptr(nxt);
+    if (more) load_aff8(a0, Ap, plane);
+    tile_dilation<24, CH>(acc, a1, q, live);
+    if (more) load_aff8(a1, Ap, plane);
+    __syncthreads();                       // every shared-memory read of this buffer has retired
+    if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int xq = (cur.x0 >> 2) + tq, y = cur.y0 + tr;
+    if (xq < wq && y < p.h) {
+      float *dst = out + ((size_t)cur.b * p.c_stride + cur.c0) * oplane + (size_t)y * lo.pitch + lo.off + (xq << 2);
+#pragma unroll
+      for (int k = 0; k < CH; ++k) {
+        if (k < live) {
+          float *o = dst + (size_t)k * oplane;
+          *reinterpret_cast<float4 *>(o) = acc[k];
+          if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+            if (xq == 0) {
+              const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+            }
+            if (xq == wq - 1) {
+              const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+            }
+          }
+        }
+      }
+    }
+    if (buf) phase1 ^= 1; else phase0 ^= 1;
+    buf ^= 1;
+    cur = nxt;
+  }
+}
+
 // plain [planes, h, w] -> padded layout (interior + replicated column pads)
 __global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
                                 int h, int w) {
@@ -1306,11 +1469,12 @@ int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, in
 //   coop            persistent TMA-tile kernel, every step in ONE cooperative launch (grid barriers)
 //   persist         persistent TMA-tile kernel, one launch per step
 //   smem | vec      the generic per-step kernels (any dilation set): near neighbourhood staged / L1 only
-enum { kStepTile = 0, kStepCoop = 1, kStepPersist = 2, kStepSmem = 3, kStepVec = 4 };
+enum { kStepTile = 0, kStepCoop = 1, kStepPersist = 2, kStepSmem = 3, kStepVec = 4, kStepDb = 5 };
 static int g_step_mode = -1;
 static int parse_step_mode(const char *e) {
   if (!e) return kStepTile;
   switch (e[0]) {
+    case 'd': return kStepDb;
     case 't': return kStepTile;
     case 'c': return kStepCoop;
     case 'p': return kStepPersist;
@@ -1427,6 +1591,27 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
   COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   const int max_nch = nch_dev ? c_stride : nch_uniform;
+  if (par_step_mode() == kStepDb) {
+    constexpr int CH = 2;
+    const size_t smem = (size_t)2 * CH * kFS * kFS * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    a.gsplit = 1;
+    a.n_pass = ceil_div(max_nch, CH);
+    const long long n_units = (long long)a.B * a.tiles_x * a.tiles_y * a.n_pass;
+    const int grid = (int)max(1LL, min(n_units, 2LL * sm_count()));
+    for (int it = 0; it < a.num_iter; ++it) {
+      const bool last = it == a.num_iter - 1;
+      const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
+      float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
+      COSA_LAUNCH_T("par_iterate_tile_kernel", par_iterate_db_kernel<CH>, grid, 256, smem, stream, a, tm, dst,
+                    last ? a.lo_final : a.li);
+    }
+    return 0;
+  }
   static int ch = 0;
   if (!ch) {
     const char *e = getenv("COSA_PAR_CH");
@@ -1444,7 +1629,7 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
   const bool vec = lay.padn > 0;
   if (vec && g_std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) &&
-      par_step_mode() <= kStepPersist)
+      (par_step_mode() <= kStepPersist || par_step_mode() == kStepDb))
     return par_launch_propagate(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
                                 c_stride, B, h, w, num_iter, stream);
   const float *src = src0;

@@ -55,7 +55,7 @@ int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out,
 /* Selects the propagation kernel used by cosa_par_forward / cosa_cam2mask from now on (process-wide; results are
  * identical, only the launch structure differs): "tile" (default; TMA-staged 32x32 tiles, one launch per step),
  * "coop" (persistent kernel, ALL steps in one cooperative launch with grid barriers), "persist" (persistent kernel,
- * one launch per step), "smem" / "vec" (generic per-step kernels, also used for non-reference dilation sets).
+ * one launch per step), "db" (persistent kernel with two tile buffers per CTA), "smem" / "vec" (generic per-step kernels, also used for non-reference dilation sets).
  * The environment variable COSA_PAR_STEP sets the initial choice.  Returns COSA_E_ARG for an unknown name. */
 int cosa_par_set_step_mode(const char *name);
 

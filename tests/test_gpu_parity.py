@@ -109,9 +109,10 @@ def test_par_tile_path_shapes(cosa, port, shape):
     assert_close(aff, port.par_affinity(imgs)[:, 0], "affinity %s" % (shape,))
 
 
-@pytest.mark.parametrize("mode", ["coop", "persist", "smem", "vec", "tile"])
+@pytest.mark.parametrize("mode", ["coop", "persist", "smem", "vec", "tile", "db"])
 def test_par_step_kernels_agree(cosa, port, mode):
-    """Every propagation kernel (single cooperative launch, persistent, generic, default) against the oracle, on a
+    """Every propagation kernel (single cooperative launch, persistent, double-buffered persistent, generic, and
+    the default one CTA per tile) against the oracle, on a
     ragged batch shape (partial tiles in both directions) and on the cam2mask path with per-image channel counts."""
     from cosa_b200 import par as par_mod
     g = torch.Generator().manual_seed(11)
@@ -126,7 +127,7 @@ def test_par_step_kernels_agree(cosa, port, mode):
         out = cosa.PAR(DIL, 10).cuda()(imgs.cuda(), masks.cuda())
         lab = cosa.cam2mask(refine_model=cosa.PAR(DIL, 10).cuda(), **args)
     finally:
-        par_mod.set_step_mode("tile")
+        par_mod.set_step_mode("tile")        # the default
     assert_close(out, want, "PAR, step kernel %s" % mode)
     assert_same(lab, d["out_par"], "cam2mask + PAR, step kernel %s" % mode)
     with pytest.raises(cosa._lib.CosaError):
