@@ -342,7 +342,8 @@ def run_cosa_arm(args):
         ev1.record()
         sync_all()
         e2e_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
-        assert abs(float(res[-1][1]) - float(loss)) <= 1e-6 * abs(float(loss)) + 1e-12, "e2e loss differs from the device path"
+        ref_loss = float(loss.detach())
+        assert abs(float(res[-1][1]) - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-12, "e2e loss differs from the device path"
         e2e = {"value": sharding.all_reduce_sum(B * e2e_steps) / (e2e_ms / 1e3), "unit": "images/s",
                "h2d_bytes_per_step": (pipe.h2d_bytes - h2d0) // e2e_steps,
                "d2h_bytes_per_step": (pipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
