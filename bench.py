@@ -220,7 +220,7 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
         "energy_loss_finalize_kernel": 12,
         "energy_logit_grad_kernel": 4 * B * (2 * H * W * K + n * (K + 1)),
     }
-    base = lambda k: (k.replace("_vec_kernel", "_kernel").replace("_reg_kernel", "_kernel").replace("_smem_kernel", "_kernel")
+    base = lambda k: (k.replace("_vec_kernel", "_kernel").replace("_reg_kernel", "_kernel").replace("_pair_kernel", "_kernel").replace("_smem_kernel", "_kernel")
                       .replace("_tile_kernel", "_kernel").replace("_x2_kernel", "_kernel"))
     out = {k: per.get(base(k)) for k in kernels}
     design = {k: (4 * B * n * (ND + 2 * ncm) if base(k) == "par_iterate_kernel" else out[k]) for k in kernels}

@@ -456,6 +456,139 @@ __global__ void __launch_bounds__(128, 2) energy_logit_grad_reg_kernel(const flo
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident variants for LARGE compile-time class counts (C = 81, the COCO shape).  A pixel quad per thread
+// would need 4 C registers, so a thread owns TWO adjacent pixels of one row (2 C registers, 64-bit loads, a warp's
+// load is one 256-byte row segment) and, in the forward kernel, exchanges its probabilities with the thread that owns
+// the row below for the 2:1 reduction.  The two-pass kernels they replace are DRAM-bound on reading the logits twice
+// (the logits of all resident threads - 786 MB at COCO B = 32 - do not fit in L2): 0.49 of the HBM peak.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ldg_stream2f(const float *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+// Warp = 32 full-resolution columns x 2 rows = 16 half-resolution pixels; lane = 16 * row + column pair.
+template <int C>
+__global__ void __launch_bounds__(128, 2) energy_prepare_pair_kernel(const float *__restrict__ simg,
+                                                                     const float *__restrict__ logit,
+                                                                     const float *__restrict__ label,
+                                                                     const int *__restrict__ boxes, Affine3 aff,
+                                                                     float *__restrict__ img_half,
+                                                                     float *__restrict__ s_roi, float *__restrict__ gate,
+                                                                     float *__restrict__ roi_out, int B, int H, int W) {
+  const int h = H / 2, w = W / 2, wc = W / 32;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (warp >= (long long)B * h * wc) return;              // whole warps leave together
+  const int lane = threadIdx.x & 31, r = lane >> 4, cp = lane & 15;
+  const int xc = (int)(warp % wc), yh = (int)((warp / wc) % h), b = (int)(warp / ((long long)wc * h));
+  const int X = 32 * xc + 2 * cp, Y = 2 * yh + r;
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const size_t src = (size_t)Y * W + X;
+  const float *lg = logit + (size_t)b * C * HW + src;
+  float2 p[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) p[c] = ldg_stream2f(lg + (size_t)c * HW);
+  const bool writer = r == 0;                              // owns half-resolution pixel (yh, X / 2)
+  float lab = 0.0f, im[3] = {0.f, 0.f, 0.f};
+  if (writer) {
+    lab = __ldg(label + (size_t)b * HW + src);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) im[c] = __ldg(simg + ((size_t)b * 3 + c) * HW + src);
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) { m0 = fmaxf(m0, p[c].x); m1 = fmaxf(m1, p[c].y); }
+  float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    p[c].x = __expf(p[c].x - m0); d0 += p[c].x;
+    p[c].y = __expf(p[c].y - m1); d1 += p[c].y;
+  }
+  d0 = 1.0f / d0; d1 = 1.0f / d1;
+  const int *box = boxes + 4 * b;
+  const float roi = (Y >= box[0] && Y < box[1] && X >= box[2] && X < box[3]) ? 1.0f : 0.0f;   // writers: pixel (2y, 2x)
+  const size_t pix = (size_t)yh * w + (X >> 1);
+  float smax = -INFINITY;
+  float *dst = s_roi + (size_t)b * C * hw + pix;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    // exact 2:1 bilinear, align_corners=False: 0.25 * (((p00 + p01) + p10) + p11); the lower row comes from lane + 16
+    const float v0 = p[c].x * d0, v1 = p[c].y * d1;
+    const float p10 = __shfl_xor_sync(0xffffffffu, v0, 16), p11 = __shfl_xor_sync(0xffffffffu, v1, 16);
+    const float sv = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(v0, v1), p10), p11));
+    if (writer) {
+      smax = fmaxf(smax, sv);
+      dst[(size_t)c * hw] = __fmul_rn(sv, roi);
+    }
+  }
+  if (writer) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+    float g = __fsub_rn(roi, smax);
+    if (((int)lab & 255) == 255) g = 1.0f;
+    gate[(size_t)b * hw + pix] = fmaxf(g, 0.0f);
+    roi_out[(size_t)b * hw + pix] = roi;
+  }
+}
+
+// One thread = two adjacent full-resolution pixels of one row = one half-resolution pixel's AS / ROI.  The C values
+// of AS the thread needs twice (for <p, AS> and for the output) are parked in its own shared-memory column by
+// cp.async, so that they neither occupy registers next to the 2 C logits nor are requested twice.
+template <int C>
+__global__ void __launch_bounds__(128, 2) energy_logit_grad_pair_kernel(const float *__restrict__ logit,
+                                                                        const float *__restrict__ as_saved,
+                                                                        const float *__restrict__ roi_half,
+                                                                        const float *__restrict__ grad_out, float weight,
+                                                                        float *__restrict__ grad_logit, int B, int H,
+                                                                        int W) {
+  __shared__ float s_as[C][128];
+  const int h = H / 2, w = W / 2;
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool live = t < (long long)B * H * w;
+  if (!live) t = (long long)B * H * w - 1;                 // clamp: the thread loads valid data and stores nothing
+  const size_t HW = (size_t)H * W, hw = (size_t)h * w;
+  const int xh = (int)(t % w), Y = (int)((t / w) % H), b = (int)(t / ((long long)w * H));
+  const size_t pix = (size_t)(Y >> 1) * w + xh;
+  const float *lg = logit + (size_t)b * C * HW + (size_t)Y * W + 2 * xh;
+  const float *as = as_saved + (size_t)b * C * hw + pix;
+  float *out = grad_logit + (size_t)b * C * HW + (size_t)Y * W + 2 * xh;
+  const unsigned col = (unsigned)__cvta_generic_to_shared(&s_as[0][threadIdx.x]);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(col + c * 128 * 4), "l"(as + (size_t)c * hw) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  float2 l[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) l[c] = ldg_stream2f(lg + (size_t)c * HW);
+  const float roi = __ldg(roi_half + (size_t)b * hw + pix);
+  const float cf = __fdiv_rn(__fmul_rn(-2.0f, __fmul_rn(__ldg(grad_out), weight)), (float)B) * 0.25f * roi;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) { m0 = fmaxf(m0, l[c].x); m1 = fmaxf(m1, l[c].y); }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");     // each thread reads back only what it copied itself
+  float d0 = 0.0f, d1 = 0.0f, n0 = 0.0f, n1 = 0.0f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float a = s_as[c][threadIdx.x];
+    l[c].x = __expf(l[c].x - m0); d0 += l[c].x; n0 = fmaf(l[c].x, a, n0);
+    l[c].y = __expf(l[c].y - m1); d1 += l[c].y; n1 = fmaf(l[c].y, a, n1);
+  }
+  d0 = 1.0f / d0; d1 = 1.0f / d1;
+  const float dot0 = n0 * d0, dot1 = n1 * d1;              // <p, AS> per pixel
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float a = s_as[c][threadIdx.x];
+    float2 o;
+    o.x = l[c].x * d0 * (cf * (a - dot0));
+    o.y = l[c].y * d1 * (cf * (a - dot1));
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(out + (size_t)c * HW), "f"(o.x), "f"(o.y));
+  }
+}
+
 static bool energy_force_generic() {   // COSA_ENERGY_GENERIC=1: two-pass kernels for every class count (A/B runs)
   static int v = -1;
   if (v < 0) v = getenv("COSA_ENERGY_GENERIC") ? 1 : 0;
@@ -564,6 +697,10 @@ extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, c
     const long long threads = (long long)B * h * w;
     COSA_LAUNCH(energy_prepare_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label, boxes,
                 aff, img_half, s_roi, gate, roi_half, B, H, W);
+  } else if (C == 81 && W % 32 == 0 && !energy_force_generic()) {   // COCO: register-resident, two pixels per thread
+    const long long threads = (long long)B * h * (W / 32) * 32;
+    COSA_LAUNCH(energy_prepare_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label,
+                boxes, aff, img_half, s_roi, gate, roi_half, B, H, W);
   } else if (W % 4 == 0) {
     const long long threads = (long long)B * h * (W / 4);
     COSA_LAUNCH(energy_prepare_vec_kernel, grid1d(threads), 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi,
@@ -590,6 +727,10 @@ extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, 
   if (C == 21 && W % 4 == 0 && !energy_force_generic()) {
     const long long threads = (long long)B * H * (W / 4);
     COSA_LAUNCH(energy_logit_grad_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
+                roi_half, grad_out, weight, grad_logit, B, H, W);
+  } else if (C == 81 && !energy_force_generic()) {
+    const long long threads = (long long)B * H * (W / 2);
+    COSA_LAUNCH(energy_logit_grad_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
                 roi_half, grad_out, weight, grad_logit, B, H, W);
   } else if (W % 4 == 0) {
     const long long threads = (long long)B * H * (W / 4);
