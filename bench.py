@@ -47,9 +47,16 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (weak scaling)")
     ap.add_argument("--workload", default="voc", choices=sorted(WORKLOADS))
     ap.add_argument("--size", type=int, default=0, help="override H = W (BASELINE.json configs[3] sweep: 512..1024)")
+    ap.add_argument("--aux-labelling", action="store_true",
+                    help="also label the auxiliary CAMs of the batch (main.py:171-199, the reference's default); "
+                         "reported as a separate workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.aux_labelling:      # a device-side variant only: the host pipeline and the CPU arm run the headline step
+        args.no_e2e = True
+        args.no_cpu_baseline = True
+    return args
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -254,14 +261,27 @@ def run_cosa_arm(args):
     pinned = {k: v.pin_memory() for k, v in host.items() if k != "img_box"}
     boxes = host["img_box"]
     d = {k: v.to(dev) for k, v in pinned.items()}
+    if args.aux_labelling:    # auxiliary CAMs: the same blobs seen a little differently (mirrored mix of the batch)
+        d["cams_aux"] = (0.8 * d["cams"] + 0.2 * d["cams"].flip(0).flip(-1)).contiguous()
+        wl["name"] += " + auxiliary CAMs labelled too (x2 labelling, main.py:171-199)"
     par = cosa_b200.PAR(num_iter=NUM_ITER, dilations=DILATIONS).to(dev)
     layer = cosa_b200.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
 
     def step(t):
         img_denorm = cosa_b200.denormalize_img(t["simg"])                       # main.py:117
         cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
-        label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
+        if args.aux_labelling:
+            # main.py's default (aux_cam2seg=True, :171-199): the auxiliary CAMs of the batch are labelled as well;
+            # the two cam2mask calls share the images, hence the PAR affinity
+            with par.shared_affinity():
+                label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
+                                           threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+                aux = cosa_b200.cam_validation(t["cams_aux"], t["cls_label"])
+                cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=aux, cls_labels=t["cls_label"],
                                    threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+        else:
+            label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
+                                       threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
         logit = t["logits"].detach().requires_grad_(True)
         loss = cosa_b200.get_energy_loss(img=t["simg"], logit=logit, label=label, img_box=boxes, loss_layer=layer)
         loss.backward()

@@ -45,6 +45,8 @@ _SIGNATURES = {
     "cosa_cam2mask_ws_bytes": (_c_size_t, [_c_int] * 7),
     "cosa_cam2mask": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
                       [_c_int] * 4 + [_vp, _c_size_t, _vp]),
+    "cosa_cam2mask_flags": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
+                            [_c_int] * 4 + [_vp, _c_size_t, _c_int, _vp]),
     "cosa_upsample_argmax": (_c_int, [_vp, _vp, _vp] + [_c_int] * 6 + [_vp]),
     "cosa_bilateral_ws_bytes": (_c_size_t, [_c_int] * 4),
     "cosa_bilateralfilter_batch": (_c_int, [_vp, _vp, _vp] + [_c_int] * 4 + [_c_float] * 2 + [_vp, _c_size_t, _vp]),
@@ -131,6 +133,7 @@ def dev_f32(t, what):
 
 # ---- stream-keyed scratch ---------------------------------------------------------------------------
 _scratch = {}
+_scratch_uses = {}     # per (device, stream): how many times the buffer has been handed out
 
 
 def workspace(nbytes, device):
@@ -147,7 +150,15 @@ def workspace(nbytes, device):
         _scratch.pop(key, None)
         buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
         _scratch[key] = buf
+    _scratch_uses[key] = _scratch_uses.get(key, 0) + 1
     return buf
+
+
+def workspace_uses(device):
+    """Number of times the current stream's scratch buffer has been handed out (every hand-out may overwrite it)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    return _scratch_uses.get(key, 0)
 
 
 def release_workspaces():

@@ -905,6 +905,16 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
                              const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
                              float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes,
                              void *stream) {
+  return cosa_cam2mask_flags(images, boxes, cams, cls_labels, threshold_high, threshold_low, ignore_index, downscale,
+                             use_par, dilations, n_dil, num_iter, label_out, label_high_out, label_low_out, B, C1, H, W,
+                             ws, ws_bytes, 0, stream);
+}
+
+extern "C" int cosa_cam2mask_flags(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                                   float threshold_high, float threshold_low, float ignore_index, int downscale,
+                                   int use_par, const int *dilations, int n_dil, int num_iter, float *label_out,
+                                   float *label_high_out, float *label_low_out, int B, int C1, int H, int W, void *ws,
+                                   size_t ws_bytes, int flags, void *stream) {
   if (!images || !boxes || !cams || !cls_labels || !label_out || !ws || B < 1 || C1 < 1 || H < 1 || W < 1 ||
       downscale < 0)
     return COSA_E_ARG;
@@ -944,15 +954,24 @@ extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float 
     img_small = arena.take<float>((size_t)B * 3 * hw);
     aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
   }
+  // COSA_CAM2MASK_REUSE_AFFINITY: the previous call on this workspace had the same images, geometry and dilations
+  // (main.py:158 and :191 label the CAMs and the auxiliary CAMs of one batch): its affinity planes are still in the
+  // workspace, so neither the reduced image nor the affinity is computed again.
+  const bool reuse_aff = refine && (flags & COSA_CAM2MASK_REUSE_AFFINITY);
   dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
-  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, img_small, masks, lay, g, C1,
-              threshold_high, threshold_low, derive);
+  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, reuse_aff ? nullptr : img_small, masks,
+              lay, g, C1, threshold_high, threshold_low, derive);
   const float *refined = masks;
   MaskLayout lay_fin = lay;
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
   if (refine) {
-    COSA_CHECK(par_refine_batch(img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
-                                num_iter, s));
+    if (reuse_aff) {
+      COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
+                                       num_iter, s));
+    } else {
+      COSA_CHECK(par_refine_batch(img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
+                                  num_iter, s));
+    }
     refined = fin;
   }
   if (!g.identity && H == 2 * g.h && W == 2 * g.w) {

@@ -38,6 +38,25 @@ class PAR(nn.Module):
         self.w1 = 0.3
         self.w2 = 0.01
         self._dil = (ctypes.c_int * len(self.dilations))(*[int(d) for d in self.dilations])
+        self._shared = None          # state of shared_affinity(): None outside the context
+
+    def shared_affinity(self):
+        """Context manager for consecutive ``cam2mask(..., refine_model=self)`` calls on the SAME images (main.py:158
+        and :191 label the CAMs and the auxiliary CAMs of one batch): the affinity of the first call is reused by the
+        following ones instead of being recomputed.  The caller vouches for the images being the same; geometry,
+        dilations and an untouched workspace are checked, and anything else falls back to recomputing."""
+        par = self
+
+        class _Ctx:
+            def __enter__(self):
+                par._shared = {"key": None, "uses": None}
+                return par
+
+            def __exit__(self, *exc):
+                par._shared = None
+                return False
+
+        return _Ctx()
 
     def get_pos(self):
         """[1,1,8*len(dilations),1,1] neighbour distances (models/PAR.py:51-62); the kernels use the same table."""

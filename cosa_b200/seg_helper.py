@@ -230,12 +230,25 @@ def cam2mask(
     n_dil = len(refine_model.dilations) if use_par else 0
     with torch.cuda.device(dev):
         nbytes = lib.cosa_cam2mask_ws_bytes(b, c1, h, w, int(downscale or 0), int(use_par), n_dil)
+        flags = 0
+        share = refine_model._shared if use_par else None
+        uses_before = _lib.workspace_uses(dev)
         ws = _lib.workspace(nbytes, dev)
-        _lib.check(lib.cosa_cam2mask(_lib.ptr(images), _lib.ptr(boxes), _lib.ptr(cams), _lib.ptr(cls_labels),
-                                     float(threshold_high), float(threshold_low), float(ignore_index),
-                                     int(downscale or 0), int(use_par), refine_model._dil if use_par else None, n_dil,
-                                     int(refine_model.num_iter) if use_par else 0, _lib.ptr(out), _lib.ptr(hi),
-                                     _lib.ptr(lo), b, c1, h, w, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+        if share is not None:
+            # PAR.shared_affinity(): same images (vouched for by the caller), same geometry / dilations / scratch
+            # buffer, and nobody else was handed the buffer since the call that left the affinity there
+            key = (tuple(images.shape), c1, int(downscale or 0), tuple(refine_model.dilations),
+                   int(refine_model.num_iter) > 0, ws.data_ptr(), int(nbytes),
+                   torch.cuda.current_stream(dev).cuda_stream)
+            if share["key"] == key and share["uses"] == uses_before:
+                flags = 1                                                   # COSA_CAM2MASK_REUSE_AFFINITY
+            share["key"], share["uses"] = key, uses_before + 1
+        _lib.check(lib.cosa_cam2mask_flags(_lib.ptr(images), _lib.ptr(boxes), _lib.ptr(cams), _lib.ptr(cls_labels),
+                                           float(threshold_high), float(threshold_low), float(ignore_index),
+                                           int(downscale or 0), int(use_par), refine_model._dil if use_par else None,
+                                           n_dil, int(refine_model.num_iter) if use_par else 0, _lib.ptr(out),
+                                           _lib.ptr(hi), _lib.ptr(lo), b, c1, h, w, _lib.ptr(ws), nbytes, flags,
+                                           _lib.stream_ptr()))
     if return_parts:
         return out, hi, lo
     return out

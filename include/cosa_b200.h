@@ -127,6 +127,17 @@ int cosa_cam2mask(const float *images, const int *boxes, const float *cams, cons
                   const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
                   float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, void *stream);
 
+/* cosa_cam2mask with option flags.  COSA_CAM2MASK_REUSE_AFFINITY: the caller guarantees that the previous call on
+ * this workspace (same stream, nothing else written to it since) had the same images, geometry and dilations - e.g.
+ * main.py:158 and :191, which label the CAMs and the auxiliary CAMs of one batch - so the PAR affinity still in the
+ * workspace is used instead of being computed again. */
+#define COSA_CAM2MASK_REUSE_AFFINITY 1
+int cosa_cam2mask_flags(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                        float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
+                        const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
+                        float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, int flags,
+                        void *stream);
+
 /* cosa_cam2mask with PAR refines softmax stacks whose channels sum to 1, and a PAR step multiplies that sum by the
  * constant row sum of its weights (PAR.py:85-89), so by default the last live channel of each stack is not
  * propagated but evaluated as row_sum^num_iter - (sum of the others) by the labelling kernel (one third of the

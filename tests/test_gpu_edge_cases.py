@@ -258,3 +258,36 @@ def test_host_pipeline_native_inputs_match_device_path(cosa):
         assert_close(loss, wl, "native pipeline loss", tol=1e-5)
         assert_close(grad, low.grad, "native pipeline token-grid gradient", tol=1e-5)
     assert pipe.h2d_bytes < 0.3 * 3 * sum(batches[0][k].numel() * 4 for k in ("simg", "cams", "logits"))
+
+
+def test_shared_affinity_between_cam2mask_calls(cosa):
+    """main.py:158 and :191 call cam2mask twice per batch (CAMs, auxiliary CAMs) on the same images: inside
+    PAR.shared_affinity() the second call reuses the first call's affinity.  Labels must equal the ones of two
+    independent calls; a call on other images / another geometry inside the context recomputes."""
+    from cosa_b200 import _lib
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    d = to_cuda(batch(B=3, C=21, H=128, W=160, n_fg=2, seed=51))
+    aux = to_cuda(batch(B=3, C=21, H=128, W=160, n_fg=2, seed=52))
+    aux_cams = aux["cams"].flip(-1) * 0.9 + 0.05 * d["cams"]
+    kw = dict(img_boxes=d["img_box"], cls_labels=d["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
+    want1 = cosa.cam2mask(images=d["img_denorm"], cams=d["cams"], **kw)
+    want2 = cosa.cam2mask(images=d["img_denorm"], cams=aux_cams, **kw)
+    small = to_cuda(batch(B=2, C=21, H=64, W=96, n_fg=2, seed=53))
+    want3 = cosa.cam2mask(images=small["img_denorm"], cams=small["cams"], img_boxes=small["img_box"],
+                          cls_labels=small["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
+    n0 = _lib.launch_count()
+    with par.shared_affinity():
+        got1 = cosa.cam2mask(images=d["img_denorm"], cams=d["cams"], **kw)
+        n1 = _lib.launch_count()
+        got2 = cosa.cam2mask(images=d["img_denorm"], cams=aux_cams, **kw)
+        n2 = _lib.launch_count()
+        got3 = cosa.cam2mask(images=small["img_denorm"], cams=small["cams"], img_boxes=small["img_box"],
+                             cls_labels=small["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        # an unrelated user of the scratch buffer in between invalidates the shared affinity
+        got1b = cosa.cam2mask(images=d["img_denorm"], cams=d["cams"], **kw)
+        cosa.PAR(num_iter=1, dilations=DIL).cuda()(small["img_denorm"], small["cams"][:, :2].contiguous())
+        got2b = cosa.cam2mask(images=d["img_denorm"], cams=aux_cams, **kw)
+    assert torch.equal(got1, want1) and torch.equal(got2, want2) and torch.equal(got3, want3)
+    assert torch.equal(got1b, want1) and torch.equal(got2b, want2)
+    assert (n2 - n1) == (n1 - n0) - 1, "the second call must skip exactly the affinity launch"
+    assert par._shared is None
