@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(256) cam_merge_kernel(RawScales rs, float *__r
 // row changes (every H/hs output rows), so an output pixel costs one y-interpolation per scale and copy instead of
 // two full bilinear evaluations.  Arithmetic order per value is torch's (x-lerp, then y-lerp), as in merged_value.
 //   MODE 0: cam, min/max only      MODE 1: cam, normalised store      MODE 2: seg (sum of plain + flipped), store
+//   MODE 3: cam, min/max AND the un-normalised sum stored (cam_normalize_inplace_kernel finishes the plane)
 template <int NS, int MODE>
 __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__restrict__ out, int *__restrict__ mm,
                                                          int B, int C, int H, int W, int rows_per_chunk,
@@ -708,9 +709,10 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
         acc[k] = s == 0 ? v : __fadd_rn(acc[k], v);
       }
     }
-    if (MODE == 0) {
+    if (MODE == 0 || MODE == 3) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) { lo = fminf(lo, acc[k]); hi = fmaxf(hi, acc[k]); }
+      if (MODE == 3) *reinterpret_cast<float4 *>(o + (size_t)y * W) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     } else {
       if (MODE == 1) {
 #pragma unroll
@@ -719,7 +721,7 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
       stg_stream4(o + (size_t)y * W, make_float4(acc[0], acc[1], acc[2], acc[3]));
     }
   }
-  if (MODE == 0) {
+  if (MODE == 0 || MODE == 3) {
     // one pair of atomics per warp when the whole warp works on one plane, else one per thread
     const int p0 = __shfl_sync(0xffffffffu, plane, 0);
     const bool uniform = __all_sync(0xffffffffu, plane == p0 && live);
@@ -737,13 +739,43 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
   }
 }
 
+// Second pass of the CAM merge: the plane holds the un-normalised scale sum (merge_rows_kernel<.., 3>), the extrema
+// are known; one streaming read-modify-write finishes it (and applies the class label of the fused cam_validation).
+// The bilinear merge is then evaluated once per pixel instead of twice (once for the extrema, once for the store).
+__global__ void __launch_bounds__(256) cam_normalize_inplace_kernel(float *__restrict__ out, const int *__restrict__ mm,
+                                                                    const float *__restrict__ cls, long long HW4,
+                                                                    long long HW, int planes) {
+  for (int p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float lab = cls ? __ldg(cls + p) : 1.0f;
+    float *dst = out + (size_t)p * HW;
+    if (lab == 0.0f) {
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
+           i += (long long)gridDim.x * blockDim.x)
+        stg_stream4(dst + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+    const float neg_min = -ordered_to_float(mm[2 * p]);
+    const float den = __fadd_rn(__fadd_rn(ordered_to_float(mm[2 * p + 1]), neg_min), 1e-5f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 v = *reinterpret_cast<const float4 *>(dst + 4 * i);
+      v.x = __fmul_rn(lab, __fdiv_rn(__fadd_rn(v.x, neg_min), den));
+      v.y = __fmul_rn(lab, __fdiv_rn(__fadd_rn(v.y, neg_min), den));
+      v.z = __fmul_rn(lab, __fdiv_rn(__fadd_rn(v.z, neg_min), den));
+      v.w = __fmul_rn(lab, __fdiv_rn(__fadd_rn(v.w, neg_min), den));
+      stg_stream4(dst + 4 * i, v);
+    }
+  }
+}
+
 template <int MODE>
 static int launch_merge_rows(const RawScales &rs, float *out, int *mm, int B, int C, int H, int W, const float *cls,
                              cudaStream_t s) {
   const int rows = 56;   // rows per thread: long enough to amortise the source-row refresh, short enough to fill the GPU
   const long long total = (long long)B * C * ceil_div(H, rows) * (W / 4);
   const unsigned grid = (unsigned)ceil_div_ll(total, 128);
-  const char *name = MODE == 0 ? "cam_merge_minmax_kernel" : (MODE == 1 ? "cam_merge_write_kernel" : "seg_merge_kernel");
+  const char *name = MODE == 0 ? "cam_merge_minmax_kernel"
+                     : (MODE == 1 ? "cam_merge_write_kernel" : (MODE == 2 ? "seg_merge_kernel" : "cam_merge_sum_kernel"));
   switch (rs.n) {
     case 1: { auto k = merge_rows_kernel<1, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
     case 2: { auto k = merge_rows_kernel<2, MODE>; COSA_LAUNCH_T(name, k, grid, 128, 0, s, rs, out, mm, B, C, H, W, rows, cls); break; }
@@ -1017,8 +1049,17 @@ static int cam_merge_impl(const float *const *raw, const int *hs, const int *ws,
   int *mm = (int *)minmax_ws;
   COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
   if (W % 4 == 0 && n_scales <= 5) {
-    COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, cls_label, s));
-    return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, cls_label, s);
+    static int two_eval = -1;
+    if (two_eval < 0) two_eval = getenv("COSA_MERGE_TWO_EVAL") ? 1 : 0;   // A/B: evaluate the merge twice, store once
+    if (two_eval || ((uintptr_t)out % 16) != 0) {
+      COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, cls_label, s));
+      return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, cls_label, s);
+    }
+    COSA_CHECK(launch_merge_rows<3>(rs, out, mm, B, C1, H, W, cls_label, s));
+    const int bx = (int)min(ceil_div_ll(HW / 4, 256), 64LL);
+    const int by = min(planes, max(1, sm_count() * 16 / bx));
+    COSA_LAUNCH(cam_normalize_inplace_kernel, dim3(bx, by), 256, 0, s, out, mm, cls_label, HW / 4, HW, planes);
+    return 0;
   }
   const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
   COSA_LAUNCH_T("cam_merge_minmax_kernel", cam_merge_kernel<false>, dim3(bx, planes), 256, 0, s, rs, out, mm, B, C1, H, W);
