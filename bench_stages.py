@@ -83,6 +83,8 @@ def main():
         # name, device fn, cpu fn (on n images), algorithmic bytes per call
         ("denormalize_img", lambda: cosa_b200.denormalize_img(d["simg"]), lambda n: port.denormalize_img(simg[:n]),
          f32 * B * 3 * H * W * 2),
+        ("upsample_bilinear fwd (28^2 -> 448^2)", lambda: cosa_b200.upsample_bilinear(d["seg_low"], (H, W)), None,
+         f32 * B * C * H * W),
         ("upsample_bilinear fwd+bwd (28^2 -> 448^2)", lambda: upsample_fb(d["seg_low"], g_full, cosa_b200),
          lambda n: upsample_fb(seg_low[:n], g_full[:n].cpu(), port),
          f32 * B * C * H * W * 2),                                           # full-size logits written, gradient read

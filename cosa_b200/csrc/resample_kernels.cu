@@ -50,6 +50,47 @@ __global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float *__r
   }
 }
 
+// Row-walking form for W % 4 == 0: a thread owns 4 adjacent output columns of one plane and walks down a chunk of
+// rows; it keeps the x-interpolated values of its columns on the two source rows that bracket the current output row
+// and refreshes them only when the source row changes (every H/h output rows), so an output pixel costs one
+// y-interpolation instead of a full bilinear evaluation with its index arithmetic.  Same arithmetic order per value
+// (x-lerp, then y-lerp) as upsample_bilinear_kernel.
+__global__ void __launch_bounds__(128) upsample_rows_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                            long long planes, int h, int w, int H, int W, float sy,
+                                                            float sx, int rows_per_chunk) {
+  const int wq = W >> 2, n_chunks = (H + rows_per_chunk - 1) / rows_per_chunk;
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= planes * n_chunks * wq) return;
+  const int xq = (int)(t % wq);
+  const int chunk = (int)((t / wq) % n_chunks);
+  const long long p = t / ((long long)wq * n_chunks);
+  const int x = xq << 2;
+  const int y_begin = chunk * rows_per_chunk, y_end = min(H, y_begin + rows_per_chunk);
+  const float *a = in + (size_t)p * h * w;
+  float *o = out + (size_t)p * H * W + x;
+  Tap tx[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tx[k] = tap_half_pixel(x + k, sx, w);
+  float top[4], bot[4];
+  int r0 = -1, r1 = -1;
+  for (int y = y_begin; y < y_end; ++y) {
+    const Tap ty = tap_half_pixel(y, sy, h);
+    if (ty.i0 != r0 || ty.i1 != r1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        top[k] = lerp_nested(tx[k].w0, __ldg(a + ty.i0 * w + tx[k].i0), tx[k].w1, __ldg(a + ty.i0 * w + tx[k].i1));
+        bot[k] = lerp_nested(tx[k].w0, __ldg(a + ty.i1 * w + tx[k].i0), tx[k].w1, __ldg(a + ty.i1 * w + tx[k].i1));
+      }
+      r0 = ty.i0;
+      r1 = ty.i1;
+    }
+    stg_stream4(o + (size_t)y * W, make_float4(lerp_nested(ty.w0, top[0], ty.w1, bot[0]),
+                                               lerp_nested(ty.w0, top[1], ty.w1, bot[1]),
+                                               lerp_nested(ty.w0, top[2], ty.w1, bot[2]),
+                                               lerp_nested(ty.w0, top[3], ty.w1, bot[3])));
+  }
+}
+
 // First destination index whose upper-left tap is >= k (tap i0 is non-decreasing in the destination index).
 __device__ __forceinline__ int first_dst_with_i0(int k, float scale, int src_size, int dst_size) {
   if (k <= 0) return 0;   // negative source coordinates are clamped to 0: the first block starts at the border
@@ -140,6 +181,13 @@ extern "C" int cosa_upsample_bilinear(const float *in, float *out, long long pla
                                       void *stream) {
   if (!in || !out || planes < 1 || h < 1 || w < 1 || H < 1 || W < 1) return COSA_E_ARG;
   const int vec = (W % 4 == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+  if (vec && H >= 2 * h) {   // enlargement: walk down the rows
+    const int rows = 56;
+    const long long threads = planes * ceil_div(H, rows) * (W / 4);
+    COSA_LAUNCH(upsample_rows_kernel, (unsigned)ceil_div_ll(threads, 128), 128, 0, (cudaStream_t)stream, in, out, planes,
+                h, w, H, W, (float)h / (float)H, (float)w / (float)W, rows);
+    return 0;
+  }
   const long long total = planes * H * (vec ? W / 4 : W);
   COSA_LAUNCH(upsample_bilinear_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, in, out, planes, h, w, H, W,
               (float)h / (float)H, (float)w / (float)W, vec);
