@@ -819,7 +819,33 @@ __global__ void __launch_bounds__(256, MINB)
       mbar_wait(&s_bar[1], phase);
       replicate_border_rows(s_tile, live, r_lo, r_hi);
     }
-    if constexpr (DEPTH == 3) {
+    if constexpr (DEPTH == 6) {          // every affinity quad of the pixel quad in flight before the first FFMA
+      float4 a2[8], a3[8], a4[8], a5[8];
+      load_aff8(a2, Ap, plane);
+      load_aff8(a3, Ap, plane);
+      load_aff8(a4, Ap, plane);
+      load_aff8(a5, Ap, plane);
+      tile_dilation<1, CH>(acc, a0, q, live);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      tile_dilation<4, CH>(acc, a2, q, live);
+      tile_dilation<8, CH>(acc, a3, q, live);
+      if (!edge) mbar_wait(&s_bar[1], phase);
+      tile_dilation<12, CH>(acc, a4, q, live);
+      tile_dilation<24, CH>(acc, a5, q, live);
+    } else if constexpr (DEPTH == 4) {
+      float4 a2[8], a3[8];
+      load_aff8(a2, Ap, plane);
+      load_aff8(a3, Ap, plane);
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      tile_dilation<4, CH>(acc, a2, q, live);
+      tile_dilation<8, CH>(acc, a3, q, live);
+      if (!edge) mbar_wait(&s_bar[1], phase);
+      tile_dilation<12, CH>(acc, a0, q, live);
+      tile_dilation<24, CH>(acc, a1, q, live);
+    } else if constexpr (DEPTH == 3) {
       float4 a2[8];
       load_aff8(a2, Ap, plane);
       tile_dilation<1, CH>(acc, a0, q, live);
@@ -1237,8 +1263,8 @@ __device__ __forceinline__ PropUnit db_find_unit(const PropArgs &p, const int *s
   return r;
 }
 
-template <int CH>
-__global__ void __launch_bounds__(256, 2)
+template <int CH, int DEEP>
+__global__ void __launch_bounds__(256, DEEP ? 1 : 2)
     par_iterate_db_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_in, float *__restrict__ out,
                           MaskLayout lo) {
   extern __shared__ __align__(128) float s_tile[];   // [2][CH][80][80]
@@ -1292,11 +1318,16 @@ __global__ void __launch_bounds__(256, 2)
   int buf = 0;
   PropUnit cur = db_find_unit<CH>(p, s_nch, n_pass, blockIdx.x, n_units);
   float4 a0[8], a1[8];
+  float4 a2[DEEP ? 8 : 1], a3[DEEP ? 8 : 1];   // DEEP: four dilations of affinity quads in flight (one CTA per SM)
   const float *Ap = aff_ptr(cur);
   if (cur.u >= 0) {
     if (threadIdx.x == 0) stage(cur, 0);
     load_aff8(a0, Ap, plane);
     load_aff8(a1, Ap, plane);
+    if constexpr (DEEP) {
+      load_aff8(a2, Ap, plane);
+      load_aff8(a3, Ap, plane);
+    }
   }
   while (cur.u >= 0) {
     const PropUnit nxt = db_find_unit<CH>(p, s_nch, n_pass, (long long)cur.u + gridDim.x, n_units);
@@ -1318,21 +1349,46 @@ __global__ void __launch_bounds__(256, 2)
       mbar_wait(&s_bar[buf][1], ph);
       replicate_border_rows(const_cast<float *>(tile), live, r_lo, r_hi);
     }
-    tile_dilation<1, CH>(acc, a0, q, live);
-    load_aff8(a0, Ap, plane);
-    tile_dilation<2, CH>(acc, a1, q, live);
-    load_aff8(a1, Ap, plane);
-    tile_dilation<4, CH>(acc, a0, q, live);
-    load_aff8(a0, Ap, plane);
-    tile_dilation<8, CH>(acc, a1, q, live);
-    load_aff8(a1, Ap, plane);
-    if (!edge) mbar_wait(&s_bar[buf][1], ph);
-    tile_dilation<12, CH>(acc, a0, q, live);
-    // the next unit's first affinity quads travel while the last dilation of this one is computed
-    Ap = aff_ptr(nxt);
-    if (more) load_aff8(a0, Ap, plane);
-    tile_dilation<24, CH>(acc, a1, q, live);
-    if (more) load_aff8(a1, Ap, plane);
+    if constexpr (DEEP) {
+      // a0..a3 hold d = 1, 2, 4, 8 on entry; a set is refilled as soon as its dilation is done: first with this
+      // unit's d = 12, 24, then with the next unit's d = 1, 2, 4, 8 (which therefore are four dilations ahead)
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);                       // d = 12
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);                       // d = 24
+      tile_dilation<4, CH>(acc, a2, q, live);
+      Ap = aff_ptr(nxt);
+      if (more) load_aff8(a2, Ap, plane);             // next unit, d = 1
+      tile_dilation<8, CH>(acc, a3, q, live);
+      if (more) load_aff8(a3, Ap, plane);             // next unit, d = 2
+      if (!edge) mbar_wait(&s_bar[buf][1], ph);
+      tile_dilation<12, CH>(acc, a0, q, live);
+      if (more) load_aff8(a0, Ap, plane);             // next unit, d = 4
+      tile_dilation<24, CH>(acc, a1, q, live);
+      if (more) load_aff8(a1, Ap, plane);             // next unit, d = 8
+      // rotate the names so that the next unit finds d = 1, 2, 4, 8 in a0..a3 again
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 t0 = a0[m], t1 = a1[m];
+        a0[m] = a2[m]; a1[m] = a3[m]; a2[m] = t0; a3[m] = t1;
+      }
+    } else {
+      tile_dilation<1, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<2, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      tile_dilation<4, CH>(acc, a0, q, live);
+      load_aff8(a0, Ap, plane);
+      tile_dilation<8, CH>(acc, a1, q, live);
+      load_aff8(a1, Ap, plane);
+      if (!edge) mbar_wait(&s_bar[buf][1], ph);
+      tile_dilation<12, CH>(acc, a0, q, live);
+      // the next unit's first affinity quads travel while the last dilation of this one is computed
+      Ap = aff_ptr(nxt);
+      if (more) load_aff8(a0, Ap, plane);
+      tile_dilation<24, CH>(acc, a1, q, live);
+      if (more) load_aff8(a1, Ap, plane);
+    }
     __syncthreads();                       // every shared-memory read of this buffer has retired
     if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int xq = (cur.x0 >> 2) + tq, y = cur.y0 + tr;
@@ -1530,12 +1586,16 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
     static int depth = 0, minb = 2;
     if (!attr_tile) {
       COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const char *e = getenv("COSA_PAR_DEPTH");
-      depth = (e && atoi(e) == 3) ? 3 : 2;
+      depth = e ? atoi(e) : 2;
+      if (depth != 3 && depth != 4 && depth != 6) depth = 2;
       e = getenv("COSA_PAR_MINB");
-      minb = (e && atoi(e) == 3) ? 3 : 2;
+      minb = (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : 2);
       attr_tile = true;
     }
     static int scalar = -1;
@@ -1551,6 +1611,15 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
       float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
       if (scalar) {
         COSA_LAUNCH_T("par_iterate_tile_kernel", par_iterate_tile1_kernel<CH>, grid, 512, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 6) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 6, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 4) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 4, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
+                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 3 && minb == 1) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 3, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
                       dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
       } else if (depth == 2 && minb == 3) {
         COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 3>), grid, 256, smem, stream, a.aff, tm, a.li,
@@ -1592,23 +1661,36 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
   COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   const int max_nch = nch_dev ? c_stride : nch_uniform;
   if (par_step_mode() == kStepDb) {
-    constexpr int CH = 2;
-    const size_t smem = (size_t)2 * CH * kFS * kFS * sizeof(float);
+    static int deep = -1;
+    if (deep < 0) {
+      const char *e = getenv("COSA_PAR_DB_DEEP");
+      deep = e ? atoi(e) : 1;
+    }
+    const int CHv = deep ? 4 : 2;
+    const size_t smem = (size_t)2 * CHv * kFS * kFS * sizeof(float);
     static bool attr = false;
     if (!attr) {
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)2 * 2 * kFS * kFS * sizeof(float))));
+      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)2 * 4 * kFS * kFS * sizeof(float))));
       attr = true;
     }
     a.gsplit = 1;
-    a.n_pass = ceil_div(max_nch, CH);
+    a.n_pass = ceil_div(max_nch, CHv);
     const long long n_units = (long long)a.B * a.tiles_x * a.tiles_y * a.n_pass;
-    const int grid = (int)max(1LL, min(n_units, 2LL * sm_count()));
+    const int grid = (int)max(1LL, min(n_units, (deep ? 1LL : 2LL) * sm_count()));
     for (int it = 0; it < a.num_iter; ++it) {
       const bool last = it == a.num_iter - 1;
       const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
       float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
-      COSA_LAUNCH_T("par_iterate_tile_kernel", par_iterate_db_kernel<CH>, grid, 256, smem, stream, a, tm, dst,
-                    last ? a.lo_final : a.li);
+      if (deep) {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_db_kernel<4, 1>), grid, 256, smem, stream, a, tm, dst,
+                      last ? a.lo_final : a.li);
+      } else {
+        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_db_kernel<2, 0>), grid, 256, smem, stream, a, tm, dst,
+                      last ? a.lo_final : a.li);
+      }
     }
     return 0;
   }
