@@ -46,6 +46,7 @@ class HostPipeline:
         self.depth = int(depth)
         self.want_grad = bool(want_grad)
         self.copy_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)     # read-backs overlap the kernels of the next batch
         self.slots = []
         self.n_submitted = 0
         self.h2d_bytes = 0
@@ -112,14 +113,8 @@ class HostPipeline:
             loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,
                                               loss_layer=self.loss_layer)
             loss.backward()
-            s["label"].copy_(label, non_blocking=True)
-            s["loss"].copy_(loss.detach(), non_blocking=True)
-            self.d2h_bytes += s["label"].numel() * 4 + 4
-            if self.want_grad:
-                s["grad"].copy_(logit.grad, non_blocking=True)
-                self.d2h_bytes += s["grad"].numel() * 4
             s["consumed"].record(main)
-            s["done"].record(main)
+            self._read_back(s, main, label, loss.detach(), logit.grad if self.want_grad else None)
         self._pending.append(s)
         self.n_submitted += 1
         if len(self._pending) > self.depth - 1:              # keep at most depth-1 unread results behind us
@@ -179,19 +174,30 @@ class HostPipeline:
             loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,
                                               loss_layer=self.loss_layer)
             loss.backward()
-            s["label"].copy_(label, non_blocking=True)
-            s["loss"].copy_(loss.detach(), non_blocking=True)
-            self.d2h_bytes += s["label"].numel() * 4 + 4
-            if self.want_grad:
-                s["grad"].copy_(low.grad, non_blocking=True)
-                self.d2h_bytes += s["grad"].numel() * 4
             s["consumed"].record(main)
-            s["done"].record(main)
+            self._read_back(s, main, label, loss.detach(), low.grad if self.want_grad else None)
         self._pending.append(s)
         self.n_submitted += 1
         if len(self._pending) > self.depth - 1:
             return self._collect(self._pending.pop(0))
         return None
+
+    def _read_back(self, s, main, label, loss, grad):
+        """Device -> pinned host copies of a batch's results on their own stream, behind the batch's kernels."""
+        s["computed"] = torch.cuda.Event()
+        s["computed"].record(main)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(s["computed"])
+            for t in (label, loss, grad):
+                if t is not None:
+                    t.record_stream(self.d2h_stream)          # the allocator must not recycle it before the copy ran
+            s["label"].copy_(label, non_blocking=True)
+            s["loss"].copy_(loss, non_blocking=True)
+            self.d2h_bytes += s["label"].numel() * 4 + 4
+            if grad is not None:
+                s["grad"].copy_(grad, non_blocking=True)
+                self.d2h_bytes += s["grad"].numel() * 4
+            s["done"].record(self.d2h_stream)
 
     def _collect(self, s):
         s["done"].synchronize()
