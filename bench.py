@@ -52,6 +52,7 @@ def parse_args():
                          "reported as a separate workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
     args = ap.parse_args()
     if args.aux_labelling:      # a device-side variant only: the host pipeline and the CPU arm run the headline step
         args.no_e2e = True
@@ -311,6 +312,28 @@ def run_cosa_arm(args):
     value = total_images / (ms_total / 1e3)
     mean_loss = sharding.mean_loss_over_ranks(float(loss.detach()), B)
 
+    # ---- the same step replayed from ONE CUDA graph (cosa_b200.GraphedStep): what the GPU needs when the host's
+    # launch path is out of the way; matters for small batches (configs[0]) ----------------------------------
+    graph_replay = None
+    if not args.aux_labelling and not args.no_graph:
+        gs = cosa_b200.GraphedStep(par, layer, THR_HIGH, THR_LOW, B=B, C=C, H=H, W=W, img_box=boxes, device=dev)
+        gs.simg.copy_(d["simg"]); gs.cams.copy_(d["cams"]); gs.cls_label.copy_(d["cls_label"])
+        with torch.no_grad():
+            gs.logits.copy_(d["logits"])
+        for _ in range(3):
+            gs()
+        sync_all()
+        ev0.record()
+        for _ in range(args.steps):
+            gs()
+        ev1.record()
+        sync_all()
+        g_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+        assert abs(float(gs.loss.detach()) - float(loss.detach())) <= 1e-5 * abs(float(loss.detach())) + 1e-12
+        graph_replay = {"value": total_images / (g_ms / 1e3), "unit": "images/s", "ms_per_step": g_ms / args.steps,
+                        "note": "cosa_b200.GraphedStep: the step captured in one CUDA graph, one launch per step"}
+        del gs
+
     # ---- per-kernel event timing for the roofline (same inputs, same stream) ---------------------------
     prof_steps = min(args.steps, 5)
     _lib.profile_begin()
@@ -427,7 +450,7 @@ def run_cosa_arm(args):
                        "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
                                 % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),
                        "lattice_vertices": M_vertices, "lattice_M_over_n": round(M_vertices / (B * (H // 2) * (W // 2)), 4)},
-            "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "graph_replay": graph_replay, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "loss": mean_loss,
         }
         print(json.dumps(line), flush=True)

@@ -15,7 +15,7 @@ by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/cosa_b200.h``
 Everything requires CUDA tensors; there is no CPU fallback and no second backend.
 """
 from . import _lib  # noqa: F401
-from .host_pipeline import HostPipeline
+from .host_pipeline import GraphedStep, HostPipeline
 from .par import PAR, get_kernel
 from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
                          cam_to_label, cam_validation, denormalize_img, get_energy_loss, multi_scale_cam_merge, multi_scale_camseg,
@@ -23,5 +23,5 @@ from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams,
 
 __all__ = ["PAR", "get_kernel", "cam_validation", "cam_to_label", "cam2mask", "_refine_cams", "cam_normalize",
            "get_energy_loss", "DenseEnergyLoss", "DenseEnergyLossFunction", "multi_scale_camseg", "multi_scale_cam_merge",
-           "multi_scale_seg_merge", "HostPipeline", "seg_loss",
+           "multi_scale_seg_merge", "HostPipeline", "GraphedStep", "seg_loss",
            "seg_refine_by_label", "cam_loss", "denormalize_img", "upsample_bilinear"]

@@ -165,6 +165,14 @@ def release_workspaces():
     _scratch.clear()
 
 
+class ResolvedBoxes:
+    """Boxes already resolved for a given (B, H, W) and resident on the device (see ``resolve_boxes``): passing one
+    as ``img_boxes`` / ``img_box`` skips the per-call host work and the small upload."""
+
+    def __init__(self, tensor, B, H, W):
+        self.tensor, self.B, self.H, self.W = tensor, B, H, W
+
+
 def resolve_boxes(img_boxes, B, H, W, device):
     """[B,4] int32 device tensor of (y0, y1, x0, x1) after Python slice resolution.
 
@@ -172,6 +180,10 @@ def resolve_boxes(img_boxes, B, H, W, device):
     list such as ``[[0, -1, 0, -1]]`` at eval time (negative ends drop the last row/column).  Images without
     a box keep ``ignore_index`` everywhere (``enumerate(img_boxes)`` simply stops).
     """
+    if isinstance(img_boxes, ResolvedBoxes):
+        if (img_boxes.B, img_boxes.H, img_boxes.W) != (B, H, W) or img_boxes.tensor.device != torch.device(device):
+            raise CosaError("ResolvedBoxes were made for another batch geometry or device")
+        return img_boxes.tensor
     if isinstance(img_boxes, torch.Tensor):
         rows = img_boxes.detach().cpu().tolist()
     else:

@@ -26,6 +26,16 @@ double par_weight_row_sum() { return g_row_sum; }
 // Host: the position term is a constant vector (PAR.py:51-62,77,82); evaluate it in double.
 int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
   if (n_dil < 1 || n_dil > kMaxDil) return COSA_E_ARG;
+  // the constants of the last dilation list stay on the device: nothing to do for the same list again (this also
+  // keeps the call free of host-to-device copies, which a stream capture of the step could not record)
+  static int last_n = 0, last_dil[kMaxDil], last_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev == last_dev && n_dil == last_n) {
+    bool same = true;
+    for (int k = 0; k < n_dil; ++k) same = same && dilations[k] == last_dil[k];
+    if (same) return 0;
+  }
   const int nd = 8 * n_dil;
   double pos[kMaxDil * 8], mean = 0.0;
   for (int k = 0; k < n_dil; ++k) {
@@ -59,6 +69,9 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
   for (int k = 0; k < 6 && g_std_dilations; ++k) g_std_dilations = dil[k] == kStd[k];
   COSA_CUDA(cudaMemcpyToSymbolAsync(c_dil, dil, sizeof(dil), 0, cudaMemcpyHostToDevice, stream));
   COSA_CUDA(cudaMemcpyToSymbolAsync(c_pos_term, term, sizeof(float) * nd, 0, cudaMemcpyHostToDevice, stream));
+  last_dev = dev;
+  last_n = n_dil;
+  for (int k = 0; k < n_dil; ++k) last_dil[k] = dilations[k];
   return 0;
 }
 

@@ -30,7 +30,7 @@ and the enlargement then run on the device (``multi_scale_cam_merge``, ``upsampl
 """
 import torch
 
-from . import seg_helper
+from . import _lib, seg_helper
 
 _FULL = ("simg", "cls_label", "logits")
 
@@ -209,3 +209,58 @@ class HostPipeline:
         out = [self._collect(s) for s in self._pending]
         self._pending = []
         return out
+
+
+class GraphedStep:
+    """The device step of main.py:117-212 captured ONCE in a CUDA graph and replayed per batch.
+
+        step = GraphedStep(par, loss_layer, 0.7, 0.25, B=4, C=21, H=448, W=448, img_box=boxes)
+        step.simg.copy_(...); step.cams.copy_(...); step.cls_label.copy_(...); step.logits.copy_(...)
+        step()                      # one cudaGraphLaunch: ~35 kernels, no per-kernel launch cost, no Python in between
+        step.label, step.loss, step.grad      # static output tensors, valid until the next call
+
+    The step is 34 short launches; for small batches (BASELINE.json configs[0], B = 4: 0.55 ms per step) the host's
+    launch path, not the GPU, sets the pace.  Inputs and outputs are static device tensors (a CUDA graph bakes
+    addresses in); the boxes are resolved once (they are part of the captured launch parameters).  Class labels may
+    change between replays: the per-image channel lists are built on the device.
+    """
+
+    def __init__(self, par, loss_layer, threshold_high, threshold_low, B, C, H, W, img_box, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("cosa_b200.GraphedStep needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
+        self.simg = torch.zeros((B, 3, H, W), dtype=torch.float32, device=dev)
+        self.cams = torch.zeros((B, C - 1, H, W), dtype=torch.float32, device=dev)
+        self.cls_label = torch.zeros((B, C - 1), dtype=torch.float32, device=dev)
+        self.logits = torch.zeros((B, C, H, W), dtype=torch.float32, device=dev, requires_grad=True)
+        boxes = _lib.ResolvedBoxes(_lib.resolve_boxes(img_box, B, H, W, dev), B, H, W)
+        self._keep = (boxes, par, loss_layer)      # the graph reads the boxes' device memory on every replay
+        thr = (float(threshold_high), float(threshold_low))
+
+        def body():
+            img_denorm = seg_helper.denormalize_img(self.simg)
+            cams = seg_helper.cam_validation(self.cams, self.cls_label)
+            label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=self.cls_label,
+                                        threshold_high=thr[0], threshold_low=thr[1], refine_model=par)
+            loss = seg_helper.get_energy_loss(img=self.simg, logit=self.logits, label=label, img_box=boxes,
+                                              loss_layer=loss_layer)
+            grad, = torch.autograd.grad(loss, self.logits)
+            return label, loss, grad
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):          # first-call work (function attributes, constants, workspaces) outside the capture
+                    body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.label, self.loss, self.grad = body()
+        self.kernels_per_replay = None
+
+    def __call__(self):
+        self.graph.replay()
+        return self.label, self.loss, self.grad

@@ -291,3 +291,29 @@ def test_shared_affinity_between_cam2mask_calls(cosa):
     assert torch.equal(got1b, want1) and torch.equal(got2b, want2)
     assert (n2 - n1) == (n1 - n0) - 1, "the second call must skip exactly the affinity launch"
     assert par._shared is None
+
+
+def test_graphed_step_replays_the_eager_step(cosa):
+    """cosa_b200.GraphedStep: the device step captured in a CUDA graph reproduces the eager calls (labels identical,
+    loss and gradient equal) for successive batches with different class lists, with one launch per replay."""
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    B, C, H, W = 2, 21, 96, 128
+    first = batch(B=B, C=C, H=H, W=W, n_fg=2, seed=61)
+    step = cosa.GraphedStep(par, layer, 0.7, 0.25, B=B, C=C, H=H, W=W, img_box=first["img_box"])
+    for seed, n_fg in ((61, 2), (62, 3), (63, 1)):
+        hb = batch(B=B, C=C, H=H, W=W, n_fg=n_fg, seed=seed)
+        d = to_cuda(hb)
+        step.simg.copy_(d["simg"]); step.cams.copy_(d["cams"]); step.cls_label.copy_(d["cls_label"])
+        with torch.no_grad():
+            step.logits.copy_(d["logits"])
+        label, loss, grad = step()
+        cams = cosa.cam_validation(d["cams"], d["cls_label"])
+        want = cosa.cam2mask(images=cosa.denormalize_img(d["simg"]), img_boxes=hb["img_box"], cams=cams,
+                             cls_labels=d["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        logit = d["logits"].clone().requires_grad_(True)
+        wl = cosa.get_energy_loss(img=d["simg"], logit=logit, label=want, img_box=hb["img_box"], loss_layer=layer)
+        wl.backward()
+        assert torch.equal(label, want), seed
+        assert_close(loss, wl, "graphed loss", tol=1e-5)
+        assert_close(grad, logit.grad, "graphed gradient", tol=1e-5)
