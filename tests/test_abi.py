@@ -57,6 +57,13 @@ def test_argument_errors_do_not_launch(lib):
     before = lib.cosa_launch_count()
     assert lib.cosa_cam_validation(None, None, None, 1, 1, 1, None) == -1
     assert lib.cosa_bilateralfilter_batch(None, None, None, 1, 1, 8, 8, 15.0, 50.0, None, 0, None) == -1
+    assert lib.cosa_denormalize_img(None, None, 1, 64, None, None, None) == -1
+    assert lib.cosa_upsample_bilinear(None, None, 1, 2, 2, 4, 4, None) == -1
+    assert lib.cosa_upsample_bilinear_backward(None, None, 1, 2, 2, 4, 4, None, 0, None) == -1
+    assert lib.cosa_multi_scale_cam_merge_valid(None, None, None, 1, None, None, 1, 1, 4, 4, None, None) == -1
+    assert lib.cosa_cam2mask_flags(None, None, None, None, 0.7, 0.25, 255.0, 2, 0, None, 0, 0, None, None, None,
+                                   1, 1, 4, 4, None, 0, 0, None) == -1
+    assert lib.cosa_upsample_bilinear_backward_ws_bytes(42, 28, 448) == 42 * 28 * 448 * 2 * 4
     assert lib.cosa_launch_count() == before
 
 
