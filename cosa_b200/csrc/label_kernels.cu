@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) cam_validation_kernel(const float *__rest
     const float *src = cam + (size_t)p * HW;
     float *dst = out + (size_t)p * HW;
     if (l == 0.0f) {
-      // absent class: the plane is written as zeros without being read (19 of 20 planes at VOC).  For finite inputs
+      // absent class: the plane is written as zeros without being read (18 of 20 planes at VOC).  For finite inputs
       // this equals the product up to the sign of zero; a NaN/Inf in an absent plane does not propagate as it would
       // through the reference's multiplication (deliberate differences)
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
