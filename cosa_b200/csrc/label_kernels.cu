@@ -373,6 +373,94 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   }
 }
 
+// Exact 2:1 reduction (H = 2h, W = 2w, W % 4 == 0): a thread produces TWO adjacent half-resolution pixels from
+// 128-bit loads of the two source rows of every plane (8 scalar loads with their index arithmetic per plane and pixel
+// in the general kernel).  Arithmetic identical to cam2mask_prepare_kernel: the taps of the exact ratio are the four
+// source pixels with weight 0.25 each, accumulated in bilerp_down's order.
+__device__ __forceinline__ void down2_pair(const float *plane, size_t row0, int W, float &s0, float &s1) {
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(plane + row0));
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(plane + row0 + W));
+  float t = __fmul_rn(0.25f, a.x);
+  t = __fmaf_rn(0.25f, a.y, t); t = __fmaf_rn(0.25f, b.x, t); t = __fmaf_rn(0.25f, b.y, t);
+  s0 = t;
+  t = __fmul_rn(0.25f, a.z);
+  t = __fmaf_rn(0.25f, a.w, t); t = __fmaf_rn(0.25f, b.z, t); t = __fmaf_rn(0.25f, b.w, t);
+  s1 = t;
+}
+
+__global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *__restrict__ images,
+                                                                  const float *__restrict__ cams,
+                                                                  const int *__restrict__ keys,
+                                                                  const int *__restrict__ nc_dev,
+                                                                  float *__restrict__ img_small,
+                                                                  float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
+                                                                  int C1, float thr_high, float thr_low, int derive) {
+  const int xp = blockIdx.x * 32 + (threadIdx.x & 31);     // pair index: half-resolution columns 2 xp, 2 xp + 1
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  const int x = 2 * xp;
+  if (x >= g.w || y >= g.h) return;
+  const size_t HW = (size_t)g.H * g.W, hw = (size_t)g.h * g.w;
+  const size_t pix = (size_t)y * g.w + x;
+  const size_t row0 = (size_t)(2 * y) * g.W + 2 * x;       // first of the 4 source columns, upper source row
+  if (img_small) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s0, s1;
+      down2_pair(images + ((size_t)b * 3 + c) * HW, row0, g.W, s0, s1);
+      *reinterpret_cast<float2 *>(img_small + ((size_t)b * 3 + c) * hw + pix) = make_float2(s0, s1);
+    }
+  }
+  const int nc = nc_dev[b];
+  const int *key = keys + (size_t)b * (C1 + 1);
+  const float *cam_b = cams + (size_t)b * C1 * HW;
+  const size_t mplane = (size_t)g.h * ml.pitch;
+  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * mplane + (size_t)y * ml.pitch + ml.off + x;
+  const int ns = nc - derive;
+  float *m_lo = m_hi + (size_t)ns * mplane;
+  auto put = [&](float *dst, float v0, float v1) {
+    *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);
+    if (ml.padn) {
+      if (x == 0)
+        for (int i = 1; i <= ml.padn; ++i) dst[-i] = v0;
+      if (x + 2 == g.w)
+        for (int i = 1; i <= ml.padn; ++i) dst[1 + i] = v1;
+    }
+  };
+  float v0[kCacheC], v1[kCacheC];
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  for (int j = 1; j < nc; ++j) {
+    float s0, s1;
+    down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    if (j < kCacheC) { v0[j] = s0; v1[j] = s1; }
+    mx0 = fmaxf(mx0, s0);
+    mx1 = fmaxf(mx1, s1);
+  }
+  const float mh0 = fmaxf(mx0, thr_high), ml0 = fmaxf(mx0, thr_low);
+  const float mh1 = fmaxf(mx1, thr_high), ml1 = fmaxf(mx1, thr_low);
+  const float eh0 = expf(thr_high - mh0), el0 = expf(thr_low - ml0);
+  const float eh1 = expf(thr_high - mh1), el1 = expf(thr_low - ml1);
+  float dh0 = eh0, dl0 = el0, dh1 = eh1, dl1 = el1;
+  for (int j = 1; j < nc; ++j) {
+    float s0, s1;
+    if (j < kCacheC) { s0 = v0[j]; s1 = v1[j]; }
+    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    dh0 += expf(s0 - mh0); dl0 += expf(s0 - ml0);
+    dh1 += expf(s1 - mh1); dl1 += expf(s1 - ml1);
+  }
+  if (ns > 0) {
+    put(m_hi, eh0 / dh0, eh1 / dh1);
+    put(m_lo, el0 / dl0, el1 / dl1);
+  }
+  for (int j = 1; j < ns; ++j) {
+    float s0, s1;
+    if (j < kCacheC) { s0 = v0[j]; s1 = v1[j]; }
+    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    put(m_hi + (size_t)j * mplane, expf(s0 - mh0) / dh0, expf(s1 - mh1) / dh1);
+    put(m_lo + (size_t)j * mplane, expf(s0 - ml0) / dl0, expf(s1 - ml1) / dl1);
+  }
+}
+
 // argmax over nc channels of the bilinearly up-sampled stack at full-resolution pixel (Y, X)
 // `total` > 0: the stack stores only its first nc - 1 channels and the last one is total - (sum of the others) at
 // every half-resolution tap (see cosa_cam2mask).
@@ -990,9 +1078,17 @@ extern "C" int cosa_cam2mask_flags(const float *images, const int *boxes, const 
   // (main.py:158 and :191 label the CAMs and the auxiliary CAMs of one batch): its affinity planes are still in the
   // workspace, so neither the reduced image nor the affinity is computed again.
   const bool reuse_aff = refine && (flags & COSA_CAM2MASK_REUSE_AFFINITY);
-  dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
-  COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, reuse_aff ? nullptr : img_small, masks,
-              lay, g, C1, threshold_high, threshold_low, derive);
+  const bool exact2 = !g.identity && H == 2 * g.h && W == 2 * g.w && W % 4 == 0 && (lay.pitch % 2) == 0 &&
+                      (lay.off % 2) == 0 && (((uintptr_t)images | (uintptr_t)cams) % 16) == 0;
+  if (exact2) {
+    dim3 gs(ceil_div(g.w / 2, 32), ceil_div(g.h, 8), B);
+    COSA_LAUNCH_T("cam2mask_prepare_kernel", cam2mask_prepare_x2_kernel, gs, 256, 0, s, images, cams, keys, nc,
+                  reuse_aff ? nullptr : img_small, masks, lay, g, C1, threshold_high, threshold_low, derive);
+  } else {
+    dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
+    COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, reuse_aff ? nullptr : img_small, masks,
+                lay, g, C1, threshold_high, threshold_low, derive);
+  }
   const float *refined = masks;
   MaskLayout lay_fin = lay;
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
