@@ -249,6 +249,9 @@ __global__ void lattice_compact_insert_kernel(LatticeBufs L) {
     unsigned long long slot = hash_key(key) & mask;
     while (atomicCAS(L.table_keys + slot, kEmptyKey, key) != kEmptyKey) slot = (slot + 1) & mask;   // keys are distinct
     L.table_ids[slot] = (int)i + 1;
+    // every neighbour entry starts as "absent"; lattice_neighbours_kernel fills in the ones that exist
+#pragma unroll
+    for (int j = 0; j <= kLatD; ++j) L.nbr[(size_t)j * L.m_cap + i] = make_int2(0, 0);
   }
 }
 
@@ -264,6 +267,8 @@ __device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long lo
 
 // Blur neighbours (permutohedral.cpp:282-294): n1 = key - 1 on every stored coordinate and key[j] + 5 on axis j,
 // n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q carries when it wraps.
+// The relation is symmetric - u = n1_j(v) exactly when v = n2_j(u) - so a thread looks up only n1 (6 instead of 12
+// table walks per vertex) and, when it finds u, also records itself as u's n2.  Entries start as "absent" (0).
 __global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) {
   const long long M = L.counters[0];
   const long long total = M * (kLatD + 1);
@@ -276,23 +281,21 @@ __global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) 
     const unsigned long long key = L.vkeys[i];
     const int r = (int)((key >> (kQBits * kLatD)) & 7);
     const unsigned long long bbits = key >> (kQBits * kLatD + 3);
-    int q[kLatD];
+    // n1: coordinates -1, axis +5
+    const int r2 = r == 0 ? kLatD : r - 1;
+    const int dq = r == 0 ? -1 : 0;
+    int qq[kLatD];
+    int bad = 0;
 #pragma unroll
-    for (int k = 0; k < kLatD; ++k) q[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias;
-    int res[2];
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      // side 0: n1 (coordinates -1, axis +5);  side 1: n2 (coordinates +1, axis -5)
-      const int r2 = side == 0 ? (r == 0 ? kLatD : r - 1) : (r == kLatD ? 0 : r + 1);
-      const int dq = side == 0 ? (r == 0 ? -1 : 0) : (r == kLatD ? 1 : 0);
-      int qq[kLatD];
-      int bad = 0;
-#pragma unroll
-      for (int k = 0; k < kLatD; ++k) qq[k] = q[k] + dq + (k == j ? (side == 0 ? 1 : -1) : 0);
-      unsigned long long nk = pack_key(qq, r2, 0, &bad) | (bbits << (kQBits * kLatD + 3));
-      res[side] = bad ? 0 : table_find(L, tmask, nk);
+    for (int k = 0; k < kLatD; ++k)
+      qq[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias + dq + (k == j ? 1 : 0);
+    const unsigned long long nk = pack_key(qq, r2, 0, &bad) | (bbits << (kQBits * kLatD + 3));
+    const int u = bad ? 0 : table_find(L, tmask, nk);
+    if (u > 0) {
+      int *base = reinterpret_cast<int *>(L.nbr + (size_t)j * L.m_cap);
+      base[2 * i] = u;                       // n1 of vertex i
+      base[2 * (size_t)(u - 1) + 1] = (int)i + 1;   // vertex i is the n2 of vertex u - 1
     }
-    L.nbr[(size_t)j * L.m_cap + i] = make_int2(res[0], res[1]);
   }
 }
 
