@@ -389,21 +389,26 @@ __global__ void __launch_bounds__(256) lattice_slice_kernel(LatticeBufs L, const
     const float gt = ENERGY ? __ldg(gate + gp) : 1.0f;
     float *dst = outs + (size_t)b * K * n + p;
     const float *src = ins + (size_t)b * K * n + p;
-    for (int c0 = 0; c0 < L.Kp; c0 += 4) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // two adjacent quads (one 32-byte sector of each vertex row; rows are 32-byte aligned, Kp % 4 == 0) per pass, so
+    // that a sector is requested by one pair of back-to-back loads instead of twice, five other rows apart
+    for (int c0 = 0; c0 < L.Kp; c0 += 8) {
+      const bool two = c0 + 4 < L.Kp;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
 #pragma unroll
       for (int r = 0; r <= kLatD; ++r) {
-        const float4 v = *reinterpret_cast<const float4 *>(values + (size_t)off[r] * L.Kp + c0);
-        acc.x = __fadd_rn(acc.x, __fmul_rn(w[r], v.x));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(w[r], v.y));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(w[r], v.z));
-        acc.w = __fadd_rn(acc.w, __fmul_rn(w[r], v.w));
+        const float *row = values + (size_t)off[r] * L.Kp + c0;
+        const float4 v0 = *reinterpret_cast<const float4 *>(row);
+        const float4 v1 = two ? *reinterpret_cast<const float4 *>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc0.x = __fadd_rn(acc0.x, __fmul_rn(w[r], v0.x)); acc0.y = __fadd_rn(acc0.y, __fmul_rn(w[r], v0.y));
+        acc0.z = __fadd_rn(acc0.z, __fmul_rn(w[r], v0.z)); acc0.w = __fadd_rn(acc0.w, __fmul_rn(w[r], v0.w));
+        acc1.x = __fadd_rn(acc1.x, __fmul_rn(w[r], v1.x)); acc1.y = __fadd_rn(acc1.y, __fmul_rn(w[r], v1.y));
+        acc1.z = __fadd_rn(acc1.z, __fmul_rn(w[r], v1.z)); acc1.w = __fadd_rn(acc1.w, __fmul_rn(w[r], v1.w));
       }
-      const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+      const float a8[8] = {acc0.x, acc0.y, acc0.z, acc0.w, acc1.x, acc1.y, acc1.z, acc1.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         if (c0 + k < K) {
-          float o = a4[k];
+          float o = a8[k];
           if (ENERGY) {
             o = __fmul_rn(o, gt);
             local = fmaf(__ldg(src + (size_t)(c0 + k) * n), o, local);
