@@ -800,6 +800,11 @@ __global__ void __launch_bounds__(256, MINB)
   const bool edge = r_lo > 0 || r_hi < kFS;
   const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
 
+  // Programmatic dependent launch: the next step's CTAs may become resident as soon as slots free up in this
+  // step's last wave (their barrier set-up and first affinity loads do not depend on this step); they wait for this
+  // grid's completion (griddepcontrol.wait, below) before they touch the masks.  Without the launch attribute both
+  // instructions are no-ops.
+  asm volatile("griddepcontrol.launch_dependents;");
   if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
   __syncthreads();
   unsigned phase = 0;
@@ -807,6 +812,9 @@ __global__ void __launch_bounds__(256, MINB)
     const int live = min(chunk, nch - c0);
     constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
     if (threadIdx.x == 0) {
+      // the previous step (the producer of the tiles, and the last reader of the buffer this step overwrites) is
+      // complete and its writes are visible; every other thread of the CTA is gated by the mbarriers behind this
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       mbar_expect_tx(&s_bar[0], (unsigned)(live * kNear * kFS * sizeof(float)));
       mbar_expect_tx(&s_bar[1], (unsigned)(live * kFar * kFS * sizeof(float)));
       const int gx = li.off + x0 - kFH, gz = b * c_stride + c0;
@@ -1611,6 +1619,11 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
       minb = (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : 2);
       attr_tile = true;
     }
+    static int pdl = -1;
+    if (pdl < 0) {
+      const char *e = getenv("COSA_PAR_PDL");
+      pdl = e ? atoi(e) : 1;
+    }
     static int scalar = -1;
     if (scalar < 0) {
       const char *e = getenv("COSA_PAR_SCALAR");
@@ -1637,6 +1650,23 @@ static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUten
       } else if (depth == 2 && minb == 3) {
         COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 3>), grid, 256, smem, stream, a.aff, tm, a.li,
                       dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+      } else if (depth == 2 && it > 0 && pdl && !g_prof_on) {
+        // steps 2..T: programmatic dependent launch behind the previous step (see the kernel's prologue)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const MaskLayout lo_it = last ? a.lo_final : a.li;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, par_iterate_tile_kernel<CH, 2, 2>, a.aff, tm, a.li, dst, lo_it,
+                                                 a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+        ++g_launches;
+        if (e != cudaSuccess) return (int)e;
       } else if (depth == 2) {
         COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 2>), grid, 256, smem, stream, a.aff, tm, a.li,
                       dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
