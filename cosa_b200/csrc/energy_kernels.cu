@@ -610,15 +610,17 @@ extern "C" size_t cosa_dense_energy_ws_bytes(int N, int K, int H, int W) {
 
 static int energy_core(const float *images, const float *s_roi, const float *gate, float *as_out, float *loss_out,
                        double *acc, int N, int K, int H, int W, float sigmargb, float sigmaxy, float weight,
-                       int apply_weight, void *lattice_ws, cudaStream_t s) {
+                       int apply_weight, void *lattice_ws, cudaStream_t s, bool prebuilt = false) {
   const size_t n = (size_t)H * W;
   COSA_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
   const int chunk = lattice_chunk_images(N, K, H, W);
+  if (prebuilt && chunk < N) return COSA_E_ARG;   // a prebuilt lattice covers the whole batch or nothing
   for (int n0 = 0; n0 < N; n0 += chunk) {   // chunks reuse the lattice workspace, stream-ordered
     const int nb = min(chunk, N - n0);
     LatticeBufs L;
     lattice_carve(lattice_ws, nb, K, H, W, &L);
-    COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, n0 == 0, s));
+    if (!prebuilt)
+      COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, n0 == 0, s));
     COSA_CHECK(lattice_splat_blur(L, s_roi + (size_t)n0 * K * n, nb, K, H, W, s));
     COSA_CHECK(lattice_slice(L, s_roi + (size_t)n0 * K * n, gate + (size_t)n0 * n, acc, as_out + (size_t)n0 * K * n,
                              nb, K, H, W, s));
@@ -671,10 +673,76 @@ extern "C" size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W) {
          lattice_ws_bytes(lattice_chunk_images(B, C, H / 2, W / 2), C, H / 2, W / 2);
 }
 
+// The image-only half of the forward: de-normalised nearest 2:1 image (the same two roundings as the prepare kernels)
+// and the lattice build.  Runs on any stream: the lattice does not depend on the labels or the logits.
+__global__ void __launch_bounds__(256) energy_img_half_kernel(const float *__restrict__ simg, Affine3 aff,
+                                                              float *__restrict__ img_half, int planes, int H, int W) {
+  const int h = H / 2, w2 = W / 4;                 // one thread = two half-resolution pixels from one float4
+  const long long total = (long long)planes * h * w2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xq = (int)(i % w2);
+    const long long t = i / w2;
+    const int y = (int)(t % h), p = (int)(t / h), c = p % 3;
+    const float4 v = ldg_stream4(simg + ((size_t)p * H + 2 * y) * W + 4 * xq);
+    *reinterpret_cast<float2 *>(img_half + ((size_t)p * h + y) * (W / 2) + 2 * xq) =
+        make_float2(__fadd_rn(__fmul_rn(v.x, aff.std[c]), aff.mean[c]), __fadd_rn(__fmul_rn(v.z, aff.std[c]), aff.mean[c]));
+  }
+}
+
+__global__ void __launch_bounds__(256) energy_img_half_scalar_kernel(const float *__restrict__ simg, Affine3 aff,
+                                                                     float *__restrict__ img_half, int planes, int H,
+                                                                     int W) {
+  const int h = H / 2, w = W / 2;
+  const long long total = (long long)planes * h * w;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % w);
+    const long long t = i / w;
+    const int y = (int)(t % h), p = (int)(t / h), c = p % 3;
+    img_half[i] = __fadd_rn(__fmul_rn(__ldg(simg + ((size_t)p * H + 2 * y) * W + 2 * x), aff.std[c]), aff.mean[c]);
+  }
+}
+
+extern "C" int cosa_energy_loss_prebuild(const float *simg, const float *mean, const float *std, float sigmargb,
+                                         float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+                                         void *stream) {
+  if (!simg || !mean || !std || !ws || B < 1 || C < 1) return COSA_E_ARG;
+  if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
+  if (ws_bytes < cosa_energy_loss_ws_bytes(B, C, H, W)) return COSA_E_WORKSPACE;
+  const int h = H / 2, w = W / 2;
+  if (lattice_chunk_images(B, C, h, w) < B) return COSA_E_ARG;   // more than one lattice chunk: nothing to prebuild
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t hw = (size_t)h * w;
+  Arena a(ws);                                     // the carve of cosa_energy_loss_forward
+  float *img_half = a.take<float>((size_t)B * 3 * hw);
+  a.take<float>((size_t)B * C * hw);
+  a.take<float>((size_t)B * hw);
+  a.take<double>(1);
+  void *lws = a.base + a.off;
+  Affine3 aff;
+  for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
+  if (W % 4 == 0) {
+    COSA_LAUNCH(energy_img_half_kernel, grid1d((long long)B * 3 * h * (W / 4)), 256, 0, s, simg, aff, img_half, B * 3, H, W);
+  } else {
+    COSA_LAUNCH(energy_img_half_scalar_kernel, grid1d((long long)B * 3 * hw), 256, 0, s, simg, aff, img_half, B * 3, H, W);
+  }
+  LatticeBufs L;
+  lattice_carve(lws, B, C, h, w, &L);
+  return lattice_build(L, img_half, B, h, w, sigmargb, sigmaxy_scaled, true, s);
+}
+
 extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, const float *label, const int *boxes,
                                         const float *mean, const float *std, float weight, float sigmargb,
                                         float sigmaxy_scaled, float *loss_out, void *saved, int B, int C, int H, int W,
                                         void *ws, size_t ws_bytes, void *stream) {
+  return cosa_energy_loss_forward_flags(simg, logit, label, boxes, mean, std, weight, sigmargb, sigmaxy_scaled, loss_out,
+                                        saved, B, C, H, W, ws, ws_bytes, 0, stream);
+}
+
+extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *logit, const float *label,
+                                              const int *boxes, const float *mean, const float *std, float weight,
+                                              float sigmargb, float sigmaxy_scaled, float *loss_out, void *saved, int B,
+                                              int C, int H, int W, void *ws, size_t ws_bytes, int flags, void *stream) {
+  if (flags & ~COSA_ENERGY_LATTICE_PREBUILT) return COSA_E_ARG;
   if (!simg || !logit || !label || !boxes || !mean || !std || !loss_out || !saved || !ws || B < 1 || C < 1)
     return COSA_E_ARG;
   if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
@@ -711,7 +779,7 @@ extern "C" int cosa_energy_loss_forward(const float *simg, const float *logit, c
                 roi_half, C, H, W);
   }
   return energy_core(img_half, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1, lws,
-                     s);
+                     s, (flags & COSA_ENERGY_LATTICE_PREBUILT) != 0);
 }
 
 extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,

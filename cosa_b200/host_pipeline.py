@@ -105,6 +105,7 @@ class HostPipeline:
             self._upload(s, batch)
             main.wait_event(s["ready"])
             d, boxes = s["dev"], batch["img_box"]
+            self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # overlaps cam2mask
             img_denorm = seg_helper.denormalize_img(d["simg"])
             cams = seg_helper.cam_validation(d["cams"], d["cls_label"])
             label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
@@ -164,6 +165,7 @@ class HostPipeline:
             main.wait_event(s["ready"])
             boxes = batch["img_box"]
             H, W = shapes["simg"][2:]
+            self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # overlaps cam2mask
             img_denorm = seg_helper.denormalize_img(d["simg"])
             # seg_helper.py:250-270 + cam_validation (main.py:137), absent classes' planes zero-filled
             cams = seg_helper.multi_scale_cam_merge(d["raw_cams"], (H, W), cls_label=d["cls_label"])
@@ -239,6 +241,8 @@ class GraphedStep:
         thr = (float(threshold_high), float(threshold_low))
 
         def body():
+            # the lattice needs only the image: built on a second stream (a forked branch of the graph) under cam2mask
+            loss_layer.prebuild_lattice(self.simg, C)
             img_denorm = seg_helper.denormalize_img(self.simg)
             cams = seg_helper.cam_validation(self.cams, self.cls_label)
             label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=self.cls_label,

@@ -13,6 +13,7 @@ kernels of ``csrc/`` through the C-ABI (``include/cosa_b200.h``).  Inputs must b
   get_energy_loss          utils/seg_helper.py:210-230
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -388,13 +389,73 @@ class DenseEnergyLoss(torch.nn.Module):
         return 'sigma_rgb={}, sigma_xy={}, weight={}, scale_factor={}'.format(
             self.sigma_rgb, self.sigma_xy, self.weight, self.scale_factor)
 
+    def prebuild_lattice(self, img, num_classes, mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)):
+        """Start the image-only half of the next ``get_energy_loss(img=img, ..., loss_layer=self)`` on a second stream.
+
+        The permutohedral lattice depends only on the image (bilateralfilter.cpp:4-19), not on the pseudo-labels or
+        the logits, so a training step can call this as soon as the batch is on the device - before ``cam2mask`` -
+        and the build (de-normalise, nearest 2:1, hash-table build, neighbour table: a chain of latency-bound
+        kernels) overlaps the PAR refinement instead of following it.  ``img`` is the ImageNet-normalised batch
+        ``[B,3,H,W]`` that ``get_energy_loss`` will be given; ``num_classes`` its logits' channel count.  The next
+        ``get_energy_loss`` call with the same image tensor, mean/std and shapes picks the lattice up (and waits for it
+        on the caller's stream); any other call builds its own as usual.  The same kernels run on the same data either way
+        (the vertex set is identical; only the run-to-run order of the splat's atomic sums differs, as between any two calls).
+        Returns True when a build was started, False when the fused path does not apply (then nothing happens).
+        """
+        if os.environ.get("COSA_NO_PREBUILD") == "1":        # A/B switch: everything on the caller's stream
+            return False
+        if (type(self) not in _FUSABLE_LAYERS or float(self.scale_factor) != 0.5 or not isinstance(img, torch.Tensor)
+                or not img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or img.dim() != 4):
+            return False
+        B, _, H, W = img.shape
+        C = int(num_classes)
+        if img.shape[1] != 3 or H % 2 or W % 2 or H < 2 or W < 2 or B > 64 or C < 1:
+            return False
+        lib = _lib.load()
+        dev = img.device
+        mean_t, std_t = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+            st = self.__dict__.setdefault("_pre_state", {})
+            side = st.get(("stream", dev.index))
+            if side is None:
+                side = st[("stream", dev.index)] = torch.cuda.Stream(dev)
+            ws = st.get(("ws", dev.index))
+            if ws is None or ws.numel() < nbytes:
+                if ws is not None:
+                    ws.record_stream(side)
+                ws = st[("ws", dev.index)] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+            side.wait_stream(main)          # img is ready; the previous step's filter no longer reads the workspace
+            with torch.cuda.stream(side):
+                _lib.check(lib.cosa_energy_loss_prebuild(
+                    _lib.ptr(img), (ctypes.c_float * 3)(*mean_t), (ctypes.c_float * 3)(*std_t), float(self.sigma_rgb),
+                    float(self.sigma_xy * self.scale_factor), B, C, H, W, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+                done = torch.cuda.Event()
+                done.record(side)
+        self.__dict__["_prebuilt"] = dict(img_ptr=img.data_ptr(), shape=(B, C, H, W), mean=mean_t, std=std_t,
+                                          sigmas=(float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor)),
+                                          ws=ws, nbytes=nbytes, done=done, device=dev)
+        return True
+
+    def _take_prebuilt(self, img, shape, mean, std):
+        """The pending prebuilt lattice if it was made for exactly this call, else None; one-shot."""
+        pre = self.__dict__.pop("_prebuilt", None)
+        if pre is None:
+            return None
+        if (pre["img_ptr"] != img.data_ptr() or pre["shape"] != tuple(shape) or pre["device"] != img.device
+                or pre["mean"] != tuple(float(v) for v in mean) or pre["std"] != tuple(float(v) for v in std)
+                or pre["sigmas"] != (float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor))):
+            return None
+        return pre
+
 
 class _FusedEnergyLoss(Function):
     """logit -> loss in two C-ABI calls (``cosa_energy_loss_forward/backward``): softmax, the 2:1 resamplings,
     ROI / unlabel / gate, lattice filter and the energy, with d loss / d logit computed directly."""
 
     @staticmethod
-    def forward(ctx, logit, simg, label, boxes, mean, std, weight, sigma_rgb, sigma_xy_scaled):
+    def forward(ctx, logit, simg, label, boxes, mean, std, weight, sigma_rgb, sigma_xy_scaled, pre=None):
         lib = _lib.load()
         dev = logit.device
         B, C, H, W = logit.shape
@@ -404,11 +465,17 @@ class _FusedEnergyLoss(Function):
         with torch.cuda.device(dev):
             saved = torch.empty(lib.cosa_energy_loss_saved_bytes(B, C, H, W), dtype=torch.uint8, device=dev)
             nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
-            ws = _lib.workspace(nbytes, dev)
-            _lib.check(lib.cosa_energy_loss_forward(_lib.ptr(simg), _lib.ptr(logit), _lib.ptr(label), _lib.ptr(boxes),
-                                                    mean_c, std_c, float(weight), float(sigma_rgb),
-                                                    float(sigma_xy_scaled), _lib.ptr(loss), _lib.ptr(saved), B, C, H,
-                                                    W, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+            if pre is not None:       # DenseEnergyLoss.prebuild_lattice: the lattice is in the layer's own workspace
+                torch.cuda.current_stream(dev).wait_event(pre["done"])
+                ws, flags = pre["ws"], 1   # COSA_ENERGY_LATTICE_PREBUILT
+                _LAST_ENERGY_WS[dev.index] = ws
+            else:
+                ws, flags = _lib.workspace(nbytes, dev), 0
+                _LAST_ENERGY_WS.pop(dev.index, None)
+            _lib.check(lib.cosa_energy_loss_forward_flags(
+                _lib.ptr(simg), _lib.ptr(logit), _lib.ptr(label), _lib.ptr(boxes), mean_c, std_c, float(weight),
+                float(sigma_rgb), float(sigma_xy_scaled), _lib.ptr(loss), _lib.ptr(saved), B, C, H, W, _lib.ptr(ws),
+                nbytes, flags, _lib.stream_ptr()))
         ctx.save_for_backward(logit)
         ctx.saved_blob = saved
         ctx.weight = float(weight)
@@ -424,7 +491,10 @@ class _FusedEnergyLoss(Function):
         with torch.cuda.device(logit.device):
             _lib.check(lib.cosa_energy_loss_backward(_lib.ptr(logit), _lib.ptr(ctx.saved_blob), _lib.ptr(g),
                                                      ctx.weight, _lib.ptr(grad), B, C, H, W, _lib.stream_ptr()))
-        return grad, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None
+
+
+_LAST_ENERGY_WS = {}    # device index -> the layer-owned workspace of the last fused call, if it used a prebuilt lattice
 
 
 def get_energy_loss(img,
@@ -448,9 +518,11 @@ def get_energy_loss(img,
     if fused:
         dev = logit.device
         boxes = _lib.resolve_boxes(img_box, B, H, W, dev)
-        return _FusedEnergyLoss.apply(logit.contiguous(), _lib.dev_f32(img.to(dev), "img"),
-                                      _lib.dev_f32(label.to(dev), "label"), boxes, mean, std, loss_layer.weight,
-                                      loss_layer.sigma_rgb, loss_layer.sigma_xy * loss_layer.scale_factor)
+        simg = _lib.dev_f32(img.to(dev), "img")
+        pre = loss_layer._take_prebuilt(simg, (B, C, H, W), mean, std)
+        return _FusedEnergyLoss.apply(logit.contiguous(), simg, _lib.dev_f32(label.to(dev), "label"), boxes, mean, std,
+                                      loss_layer.weight, loss_layer.sigma_rgb,
+                                      loss_layer.sigma_xy * loss_layer.scale_factor, pre)
     pred_prob = F.softmax(logit, dim=1)
     crop_mask = torch.zeros_like(pred_prob[:, 0, ...])
     boxes = _lib.resolve_boxes(img_box, B, H, W, torch.device("cpu")).tolist()
@@ -476,7 +548,9 @@ def last_energy_lattice_stats(B, C, H, W, device=None):
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     with torch.cuda.device(device):
         nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
-        ws = _lib.workspace(nbytes, device)
+        ws = _LAST_ENERGY_WS.get(device.index if device.index is not None else torch.cuda.current_device())
+        if ws is None:
+            ws = _lib.workspace(nbytes, device)
         front = nbytes - lib.cosa_bilateral_ws_bytes(B, C, H // 2, W // 2)
         stats = (ctypes.c_longlong * 4)()
         rc = lib.cosa_bilateral_stats(ctypes.c_void_p(ws.data_ptr() + front), B, C, H // 2, W // 2, stats,

@@ -197,6 +197,21 @@ int cosa_energy_loss_forward(const float *simg, const float *logit, const float 
                              const float *mean, const float *std, float weight, float sigmargb, float sigmaxy_scaled,
                              float *loss_out, void *saved, int B, int C, int H, int W, void *ws, size_t ws_bytes,
                              void *stream);
+/* The lattice of get_energy_loss depends only on the image (utils/bilateralfilter/bilateralfilter.cpp:4-19 builds it
+ * from the image alone), not on the labels or logits.  cosa_energy_loss_prebuild runs that image-only half - the
+ * de-normalised nearest 2:1 image and the lattice build - into `ws` on `stream`, which may be a second stream so that
+ * the build overlaps cam2mask.  A later cosa_energy_loss_forward_flags(..., COSA_ENERGY_LATTICE_PREBUILT, ...) with
+ * the same simg / mean / std / sigmas / B,C,H,W / ws (ordered after the prebuild by the caller: event or same stream)
+ * skips the build; the kernels and their inputs are those of cosa_energy_loss_forward.  Batches that need more than one
+ * lattice chunk (B > 64) return COSA_E_ARG from both. */
+#define COSA_ENERGY_LATTICE_PREBUILT 1
+int cosa_energy_loss_prebuild(const float *simg, const float *mean, const float *std, float sigmargb,
+                              float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+                              void *stream);
+int cosa_energy_loss_forward_flags(const float *simg, const float *logit, const float *label, const int *boxes,
+                                   const float *mean, const float *std, float weight, float sigmargb,
+                                   float sigmaxy_scaled, float *loss_out, void *saved, int B, int C, int H, int W,
+                                   void *ws, size_t ws_bytes, int flags, void *stream);
 int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,
                               float *grad_logit, int B, int C, int H, int W, void *stream);
 

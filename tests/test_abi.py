@@ -63,6 +63,9 @@ def test_argument_errors_do_not_launch(lib):
     assert lib.cosa_multi_scale_cam_merge_valid(None, None, None, 1, None, None, 1, 1, 4, 4, None, None) == -1
     assert lib.cosa_cam2mask_flags(None, None, None, None, 0.7, 0.25, 255.0, 2, 0, None, 0, 0, None, None, None,
                                    1, 1, 4, 4, None, 0, 0, None) == -1
+    assert lib.cosa_energy_loss_prebuild(None, None, None, 15.0, 50.0, 1, 21, 8, 8, None, 0, None) == -1
+    assert lib.cosa_energy_loss_forward_flags(None, None, None, None, None, None, 1e-7, 15.0, 50.0, None, None, 1, 21,
+                                              8, 8, None, 0, 2, None) == -1       # unknown flag bit
     assert lib.cosa_upsample_bilinear_backward_ws_bytes(42, 28, 448) == 42 * 28 * 448 * 2 * 4
     assert lib.cosa_launch_count() == before
 

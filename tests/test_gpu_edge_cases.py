@@ -317,3 +317,47 @@ def test_graphed_step_replays_the_eager_step(cosa):
         assert torch.equal(label, want), seed
         assert_close(loss, wl, "graphed loss", tol=1e-5)
         assert_close(grad, logit.grad, "graphed gradient", tol=1e-5)
+
+
+def test_prebuilt_lattice_matches_the_single_stream_call(cosa):
+    """DenseEnergyLoss.prebuild_lattice: the image-only half of get_energy_loss (de-normalise, nearest 2:1, lattice
+    build) started on a second stream before cam2mask.  Same vertex count, loss and gradient as the plain call; a
+    prebuilt lattice is used once and only by the call it was made for."""
+    from cosa_b200 import _lib, seg_helper
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    B, C, H, W = 3, 21, 96, 128
+    d = to_cuda(batch(B=B, C=C, H=H, W=W, n_fg=2, seed=71))
+    other = to_cuda(batch(B=B, C=C, H=H, W=W, n_fg=2, seed=72))
+
+    def run(prebuild, simg_for_loss):
+        if prebuild is not None:
+            assert layer.prebuild_lattice(prebuild, C)
+        cams = cosa.cam_validation(d["cams"], d["cls_label"])
+        label = cosa.cam2mask(images=cosa.denormalize_img(d["simg"]), img_boxes=d["img_box"], cams=cams,
+                              cls_labels=d["cls_label"], threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        logit = d["logits"].clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        loss = cosa.get_energy_loss(img=simg_for_loss, logit=logit, label=label, img_box=d["img_box"], loss_layer=layer)
+        n1 = _lib.launch_count()
+        loss.backward()
+        M = seg_helper.last_energy_lattice_stats(B, C, H, W)[0]
+        return label, loss.detach().clone(), logit.grad.clone(), M, n1 - n0
+
+    label0, loss0, grad0, M0, launches0 = run(None, d["simg"])
+    label1, loss1, grad1, M1, launches1 = run(d["simg"], d["simg"])
+    assert torch.equal(label0, label1) and M0 == M1 and M0 > 0
+    assert launches1 == launches0 - 6, "the forward must skip exactly the six build launches"
+    assert_close(loss1, loss0, "prebuilt loss", tol=1e-5)
+    assert_close(grad1, grad0, "prebuilt gradient", tol=1e-5)
+    # a lattice prebuilt for another image tensor is not picked up ...
+    _, loss2, grad2, M2, launches2 = run(other["simg"], d["simg"])
+    assert launches2 == launches0 and M2 == M0
+    assert_close(loss2, loss0, "loss after a mismatched prebuild", tol=1e-5)
+    # ... and is dropped: the next plain call builds its own
+    _, loss3, _, _, launches3 = run(None, d["simg"])
+    assert launches3 == launches0
+    assert_close(loss3, loss0, "loss after the dropped prebuild", tol=1e-5)
+    # geometries the fused path does not take are refused quietly
+    assert layer.prebuild_lattice(d["simg"].cpu(), C) is False
+    assert cosa.DenseEnergyLoss(1e-7, 15, 100, 1.0).prebuild_lattice(d["simg"], C) is False
