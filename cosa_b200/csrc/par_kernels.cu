@@ -79,6 +79,16 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
 // Affinity.  One thread per pixel; per colour channel the 8*NDIL neighbour differences live in registers
 // (two-pass unbiased variance: the one-pass form cancels catastrophically in flat regions).
 // ------------------------------------------------------------------------------------------------
+// x / 3 correctly rounded without the division routine (MUFU.RCP + Newton + FCHK + slow-path call, ~12 issue slots and
+// a branch per quotient; the affinity kernels need one per neighbour): q = RN(x * RN(1/3)) is within one ulp of the
+// quotient, r = x - 3q is exact in an FMA, and RN(q + r * RN(1/3)) is the correctly rounded x / 3 - checked against
+// IEEE division for every mantissa of two binades.  (Quotients in the denormal range may differ in the last bit.)
+__device__ __forceinline__ float div3_rn(float x) {
+  const float c = 0.333333343267440796f;   // RN(1/3) = 0x3EAAAAAB
+  const float q = __fmul_rn(x, c);
+  return __fmaf_rn(__fmaf_rn(-3.0f, q, x), c, q);
+}
+
 template <int NDIL>
 __global__ void __launch_bounds__(128) par_affinity_kernel(const float *__restrict__ imgs, float *__restrict__ aff,
                                                            int h, int w) {
@@ -131,7 +141,7 @@ __global__ void __launch_bounds__(128) par_affinity_kernel(const float *__restri
   float mx = -INFINITY;
 #pragma unroll
   for (int n = 0; n < ND; ++n) {
-    logit[n] = -logit[n] / 3.0f;
+    logit[n] = div3_rn(-logit[n]);
     mx = fmaxf(mx, logit[n]);
   }
   float den = 0.0f;
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *
       const float t = fabsf(nbr(img + c * plane, n) - ctr[c]) * inv[c];
       l = fmaf(t, t, l);
     }
-    l = -l / 3.0f;
+    l = div3_rn(-l);
     out[(size_t)n * plane] = l;
     mx = fmaxf(mx, l);
   }
@@ -735,7 +745,7 @@ __global__ void __launch_bounds__(256, 2)
       float sum = 0.0f;
 #pragma unroll
       for (int n = 0; n < ND; ++n) sum += v[n];
-      const float mean = sum / (float)ND;
+      const float mean = div3_rn(sum) * 0.0625f;   // sum / 48, correctly rounded (ND = 48)
       float ss = 0.0f;
 #pragma unroll
       for (int n = 0; n < ND; ++n) {
@@ -753,7 +763,7 @@ __global__ void __launch_bounds__(256, 2)
     float mx = -INFINITY;
 #pragma unroll
     for (int n = 0; n < ND; ++n) {
-      logit[n] = -logit[n] / 3.0f;
+      logit[n] = div3_rn(-logit[n]);
       mx = fmaxf(mx, logit[n]);
     }
     float den = 0.0f;
