@@ -181,8 +181,14 @@ __global__ void __launch_bounds__(128) seg_refine_kernel(const float *__restrict
   float *o = out + (size_t)b * C * HW + p;
   const float *lab = cls_label + (size_t)b * (C - 1);
   auto present = [&](int c) { return c == 0 || (long long)__ldg(lab + c - 1) != 0; };
+  // x / temp as q + (x - temp q) * rcp with q = x * rcp, rcp = RN(1 / temp): the quotient of the division routine
+  // (correctly rounded but for rare last-bit cases and magnitudes beyond 1e30) at three issue slots instead of a
+  // dozen and a branch - the kernel spends C divisions per pixel
+  const float rcp = __frcp_rn(temp);
   auto value = [&](int c, float x) {     // the tensor the softmax sees, already divided by the temperature
-    return __fdiv_rn((!after_softmax && !present(c)) ? -1e5f : x, temp);
+    const float a = (!after_softmax && !present(c)) ? -1e5f : x;
+    const float q = __fmul_rn(a, rcp);
+    return __fmaf_rn(__fmaf_rn(-temp, q, a), rcp, q);
   };
   float mx[V], den[V];
 #pragma unroll
