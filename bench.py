@@ -254,6 +254,9 @@ def run_cosa_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: with NCCL_DEBUG set in the environment NCCL prints its version
+        # banner (and anything else it logs) to stdout unless it is given a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 

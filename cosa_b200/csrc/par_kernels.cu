@@ -775,7 +775,12 @@ __global__ void __launch_bounds__(256, 2)
     const float rden = 1.0f / den;
     float *out = aff + (size_t)b * ND * plane + (size_t)y * w + x;
 #pragma unroll
-    for (int n = 0; n < ND; ++n) out[(size_t)n * plane] = fmaf(logit[n], rden, c_pos_term[n]);
+    for (int n = 0; n < ND; ++n) {
+      *out = fmaf(logit[n], rden, c_pos_term[n]);
+      // walk the planes with one opaque 64-bit add: `out[n * plane]` costs a wide multiply and four more integer
+      // instructions per store in a kernel that is bound by instruction issue
+      asm volatile("add.u64 %0, %0, %1;" : "+l"(out) : "l"(plane * sizeof(float)));
+    }
   }
 }
 
