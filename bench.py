@@ -191,7 +191,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -254,9 +254,6 @@ def run_cosa_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: with NCCL_DEBUG set in the environment NCCL prints its version
-        # banner (and anything else it logs) to stdout unless it is given a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
@@ -463,13 +460,33 @@ def run_cosa_arm(args):
             "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "graph_replay": graph_replay, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "loss": mean_loss,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL
+    prints its version banner there when NCCL_DEBUG=VERSION is in the environment, and ignores NCCL_DEBUG_FILE at
+    that level), so the descriptor is pointed at stderr for the rest of the process and the JSON line goes to a
+    private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
