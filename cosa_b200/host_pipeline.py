@@ -28,6 +28,8 @@ seg_helper.py:246-257) and the decoder's logits on the token grid (main.py:167 e
 and the enlargement then run on the device (``multi_scale_cam_merge``, ``upsample_bilinear``) and 93 MB instead of
 668 MB cross PCIe per VOC batch of 32.
 """
+import copy
+
 import torch
 
 from . import _lib, seg_helper
@@ -237,6 +239,11 @@ class GraphedStep:
         self.cls_label = torch.zeros((B, C - 1), dtype=torch.float32, device=dev)
         self.logits = torch.zeros((B, C, H, W), dtype=torch.float32, device=dev, requires_grad=True)
         boxes = _lib.ResolvedBoxes(_lib.resolve_boxes(img_box, B, H, W, dev), B, H, W)
+        # a private copy of the layer: the graph bakes in the address of the layer-owned lattice workspace
+        # (DenseEnergyLoss.prebuild_lattice), which must not be re-allocated by eager calls on the caller's layer
+        loss_layer = copy.copy(loss_layer)
+        loss_layer.__dict__.pop("_pre_state", None)
+        loss_layer.__dict__.pop("_prebuilt", None)
         self._keep = (boxes, par, loss_layer)      # the graph reads the boxes' device memory on every replay
         thr = (float(threshold_high), float(threshold_low))
 

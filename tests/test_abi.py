@@ -110,6 +110,8 @@ def test_cpu_tensors_are_refused_not_emulated():
     with pytest.raises(CosaError):
         cosa_b200.get_energy_loss(torch.rand(1, 3, 8, 8), torch.rand(1, 4, 8, 8), torch.zeros(1, 8, 8), [[0, 8, 0, 8]],
                                   cosa_b200.DenseEnergyLoss(1e-7, 15, 100, 0.5))
+    # the optional lattice prebuild declines CPU tensors (nothing to overlap with); get_energy_loss then refuses them
+    assert cosa_b200.DenseEnergyLoss(1e-7, 15, 100, 0.5).prebuild_lattice(torch.rand(1, 3, 8, 8), 4) is False
 
 
 def test_product_never_imports_the_oracle():
