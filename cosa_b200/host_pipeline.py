@@ -241,9 +241,7 @@ class GraphedStep:
         boxes = _lib.ResolvedBoxes(_lib.resolve_boxes(img_box, B, H, W, dev), B, H, W)
         # a private copy of the layer: the graph bakes in the address of the layer-owned lattice workspace
         # (DenseEnergyLoss.prebuild_lattice), which must not be re-allocated by eager calls on the caller's layer
-        loss_layer = copy.copy(loss_layer)
-        loss_layer.__dict__.pop("_pre_state", None)
-        loss_layer.__dict__.pop("_prebuilt", None)
+        loss_layer = copy.copy(loss_layer)         # DenseEnergyLoss.__getstate__ leaves the prebuild scratch behind
         self._keep = (boxes, par, loss_layer)      # the graph reads the boxes' device memory on every replay
         thr = (float(threshold_high), float(threshold_low))
 

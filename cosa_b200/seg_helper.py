@@ -438,6 +438,13 @@ class DenseEnergyLoss(torch.nn.Module):
                                           ws=ws, nbytes=nbytes, done=done, device=dev)
         return True
 
+    def __getstate__(self):
+        # the prebuild's stream / workspace / pending event are per-process scratch: not copied, not pickled
+        state = self.__dict__.copy()
+        state.pop("_pre_state", None)
+        state.pop("_prebuilt", None)
+        return state
+
     def _take_prebuilt(self, img, shape, mean, std):
         """The pending prebuilt lattice if it was made for exactly this call, else None; one-shot."""
         pre = self.__dict__.pop("_prebuilt", None)

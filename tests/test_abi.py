@@ -102,6 +102,21 @@ def test_module_surface_matches_reference_names():
     assert list(par.state_dict()) == ["kernel"] and par.pos.shape == (1, 1, 48, 1, 1)
 
 
+def test_loss_layer_copies_leave_the_prebuild_scratch_behind():
+    """DenseEnergyLoss.prebuild_lattice keeps a stream, a workspace and a pending event on the layer; copies and
+    pickles of the layer (cosa_b200.GraphedStep takes a private copy) must not share or serialise them."""
+    import copy
+    import pickle
+    import cosa_b200
+    layer = cosa_b200.DenseEnergyLoss(1e-7, 15, 100, 0.5)
+    layer.__dict__["_pre_state"] = {"stream": object()}
+    layer.__dict__["_prebuilt"] = {"img_ptr": 1}
+    for other in (copy.copy(layer), copy.deepcopy(layer), pickle.loads(pickle.dumps(layer))):
+        assert type(other) is type(layer) and other.extra_repr() == layer.extra_repr()
+        assert "_pre_state" not in other.__dict__ and "_prebuilt" not in other.__dict__
+    assert "_pre_state" in layer.__dict__
+
+
 def test_cpu_tensors_are_refused_not_emulated():
     import cosa_b200
     from cosa_b200._lib import CosaError
