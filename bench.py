@@ -33,8 +33,8 @@ DILATIONS = [1, 2, 4, 8, 12, 24]
 NUM_ITER = 10
 THR_HIGH, THR_LOW = 0.7, 0.25
 WORKLOADS = {
-    "voc": dict(C=21, n_fg=2, H=448, W=448, name="VOC-shape B=%d/GPU, 3x448x448, 21 classes, 2 fg/img (BASELINE.json configs[1])"),
-    "coco": dict(C=81, n_fg=3, H=448, W=448, name="COCO-shape B=%d/GPU, 3x448x448, 81 classes, 3 fg/img (BASELINE.json configs[2])"),
+    "voc": dict(C=21, n_fg=2, H=448, W=448, thr=(0.7, 0.25), name="VOC-shape B=%d/GPU, 3x448x448, 21 classes, 2 fg/img (BASELINE.json configs[1])"),
+    "coco": dict(C=81, n_fg=3, H=448, W=448, thr=(0.65, 0.25), name="COCO-shape B=%d/GPU, 3x448x448, 81 classes, 3 fg/img (BASELINE.json configs[2])"),
 }
 
 
@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
+    ap.add_argument("--no-aux", action="store_true", help="skip the x2-labelling (auxiliary CAMs) side measurement")
+    ap.add_argument("--port-only", action="store_true",
+                    help="--impl reference: time the oracle port even where /root/reference is mounted")
     args = ap.parse_args()
     if args.aux_labelling:      # a device-side variant only: the host pipeline and the CPU arm run the headline step
         args.no_e2e = True
@@ -78,16 +81,19 @@ class ClockSampler:
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
+    def __init__(self, gpu_indices):
+        """One nvidia-smi process (rank 0 only) samples every GPU of the job; `gpu_indices` empty = do nothing."""
+        self.gpu_indices = list(gpu_indices)
         self.proc = None
         self.file = None
 
     def __enter__(self):
+        if not self.gpu_indices:
+            return self
         try:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.gpu_indices),
+                                          "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -129,26 +135,60 @@ def make_inputs(args, rank):
         wl["H"] = wl["W"] = args.size
         wl["name"] = wl["name"].replace("448x448", "%dx%d" % (args.size, args.size)) + " [size sweep]"
     seed = 1000 * (1 if args.workload == "voc" else 2) + rank
-    return synthetic.synthetic_batch(B=args.batch, C=wl["C"], H=wl["H"], W=wl["W"], n_fg=wl["n_fg"], seed=seed), wl
+    d = synthetic.synthetic_batch(B=args.batch, C=wl["C"], H=wl["H"], W=wl["W"], n_fg=wl["n_fg"], seed=seed)
+    d["thr"] = wl["thr"]
+    return d, wl
 
 
 # ----------------------------------------------------------------------------------------------------
 # the CPU path (oracle port + the reference C++ lattice when it was built): cpu_baseline and --impl reference
 # ----------------------------------------------------------------------------------------------------
-def cpu_path_step(d, n_images):
-    """PAR + labelling + CRF loss forward/backward on the first n_images images, on the host cores."""
+def cpu_path_step(d, n_images, full=False):
+    """PAR + labelling + CRF loss forward/backward on the first n_images images, on the host cores (the oracle port:
+    torch-CPU PAR / labelling + the reference C++ lattice when oracle/_ref was built, else its C port).
+    full=True also returns what the parity gate compares: labels, near-tie margins, loss, gradient."""
     from oracle import reference_port as port
     # the reference C++ calls omp_set_num_threads(min(max_threads, N)) (bilateralfilter.cpp:45-47), which also
     # throttles torch's OpenMP pool for everything that follows; give the CPU path all cores again every step
     torch.set_num_threads(os.cpu_count() or 1)
     s = slice(0, n_images)
     cams = port.cam_validation(d["cams"][s], d["cls_label"][s])
-    label = port.cam2mask(images=port.denormalize_img(d["simg"][s]), img_boxes=d["img_box"][s], cams=cams, cls_labels=d["cls_label"][s],
-                          threshold_high=THR_HIGH, threshold_low=THR_LOW,
-                          refine_model=port.ParOracle(DILATIONS, NUM_ITER))
+    res = port.cam2mask(images=port.denormalize_img(d["simg"][s]), img_boxes=d["img_box"][s], cams=cams,
+                        cls_labels=d["cls_label"][s], threshold_high=d["thr"][0], threshold_low=d["thr"][1],
+                        refine_model=port.ParOracle(DILATIONS, NUM_ITER), return_margins=full)
+    label, margins = res if full else (res, None)
     logit = d["logits"][s].clone().requires_grad_(True)
     loss = port.get_energy_loss(d["simg"][s], logit, label, d["img_box"][s], weight=1e-7, sigma_rgb=15.0,
                                 sigma_xy=100.0, scale_factor=0.5)
+    loss.backward()
+    if full:
+        return float(loss.detach()), label, margins, logit.grad
+    return float(loss.detach())
+
+
+_REF_MODS = None
+
+
+def reference_path_step(d, n_images):
+    """The same step through the REFERENCE's own code (models/PAR.py, utils/seg_helper.py, utils/torch_helper.py and
+    the reference C++ lattice), imported unmodified by oracle/reference_import.py.  Only where /root/reference is
+    mounted (the build container)."""
+    global _REF_MODS
+    from oracle import reference_import
+    if _REF_MODS is None:
+        _REF_MODS = reference_import.load_reference()
+    par_mod, sh, th = _REF_MODS
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = slice(0, n_images)
+    with torch.no_grad():
+        img_denorm = th.denormalize_img(d["simg"][s])
+        cams = sh.cam_validation(d["cams"][s], d["cls_label"][s])
+        label = sh.cam2mask(images=img_denorm, img_boxes=d["img_box"][s], cams=cams, cls_labels=d["cls_label"][s],
+                            threshold_high=d["thr"][0], threshold_low=d["thr"][1],
+                            refine_model=par_mod.PAR(num_iter=NUM_ITER, dilations=DILATIONS))
+    logit = d["logits"][s].clone().requires_grad_(True)
+    layer = sh.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    loss = sh.get_energy_loss(img=d["simg"][s], logit=logit, label=label, img_box=d["img_box"][s], loss_layer=layer)
     loss.backward()
     return float(loss.detach())
 
@@ -159,35 +199,42 @@ def cpu_kind():
             else "port (torch-CPU PAR/labelling port + C lattice port)")
 
 
+REF_SAMPLE_IMAGES = 4      # images per step of the CPU arms: the same at every N (one host runs them)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import reference_import
     torch.set_num_threads(os.cpu_count() or 1)
     d, wl = make_inputs(args, 0)
-    n_img = min(4, args.batch)
-    t0 = time.perf_counter()
-    cpu_path_step(d, 1)                                     # import / first-touch warm-up, also sizes the sample
-    per_image = time.perf_counter() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_img = max(1, min(n_img, int(budget / max(per_image, 1e-3))))
+    use_ref = reference_import.available() and not args.port_only
+    step_fn = reference_path_step if use_ref else cpu_path_step
+    n_img = min(REF_SAMPLE_IMAGES, args.batch)
+    step_fn(d, 1)                                           # import / first-touch warm-up
     for _ in range(args.warmup):
-        cpu_path_step(d, n_img)
+        step_fn(d, n_img)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_path_step(d, n_img)
+        step_fn(d, n_img)
     dt = time.perf_counter() - t0
     value = n_img * args.steps / dt
     cores = os.cpu_count() or 1
+    kind = "reference" if use_ref else "port"
+    what = ("the reference's own models/PAR.py + utils/seg_helper.py + utils/torch_helper.py + C++ lattice, imported "
+            "unmodified (oracle/reference_import.py)" if use_ref else cpu_kind())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"] % args.batch, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
-                   "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "sample_images_per_step": n_img},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                   "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "sample_images_per_step": n_img,
+                   "host": "ONE host runs this arm whatever --gpus says (rank 0; the other ranks exit): the value does "
+                           "not scale with N, only the N = 1 ratio compares like with like"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": "%d images per step of the same seeded batch; %s; torch threads=%d, OpenMP default"
-                                   % (n_img, cpu_kind(), cores)},
+                                   % (n_img, what, cores)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,10 +253,12 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
     # instead of being propagated (label_kernels.cu: cosa_cam2mask) unless COSA_CAM2MASK_ALL_CHANNELS is set
     ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
     per = {
+        # (denormalize_img / cam_validation are folded into cam2mask_prepare on the bench path: these two entries only
+        # appear when something else materialises their result)
         "denormalize_img_kernel": 2 * 4 * B * 3 * H * W,
-        # every plane written, only the planes of present classes read (absent ones are zero-filled)
         "cam_validation_kernel": 4 * B * ((C - 1) + (nc - 1)) * H * W,
         "cam2mask_keys_kernel": 4 * B * (C - 1) + 4 * B * C,
+        # reads the normalised image and the planes of the present classes, writes the half-res image and the stacks
         "cam2mask_prepare_kernel": 4 * B * (H * W * (3 + (nc - 1)) + n * (3 + ncm)),
         "par_affinity_kernel": 4 * B * n * (3 + ND),
         # one propagation step.  SURVEY 8(d): masks read + written once, affinities on-chip.  This design streams
@@ -217,11 +266,14 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
         "par_iterate_kernel": 4 * B * n * (2 * ncm),
         "cam2mask_finalize_kernel": 4 * B * (n * ncm + H * W),
         "energy_prepare_kernel": 4 * B * (H * W * (K + 2) + n * (3 + K + 2)),
-        "lattice_clear_kernel": None,                            # sized by the table, not by the problem
-        "lattice_build_kernel": B * n * (12 + 48) + M * 10,
-        "lattice_resolve_kernel": B * n * 48,
-        "lattice_neighbours_kernel": M * (8 + 48),
-        "lattice_zero_values_kernel": 4 * Kp * M,
+        # SURVEY 8(d) "lattice build": n*(12 + 48) + M*(10 + 48), split over the three kernels that do it: per pixel
+        # RGB in, (index, weight) x 6 out | per vertex the key | per vertex the blur-neighbour table
+        "lattice_reset_kernel": None,
+        "lattice_table_clear_kernel": None,                      # sized by the table, not by the problem
+        "lattice_tile_build_kernel": B * n * (12 + 48),
+        "lattice_insert_kernel": M * 10,
+        "lattice_finish_kernel": M * 48,
+        "lattice_zero_values_kernel": None,                      # a no-op on this path (the build leaves the rows zeroed)
         "lattice_splat_kernel": B * n * (48 + 4 * K) + 4 * K * M,
         "lattice_blur_kernel": M * (8 + 8 * K),                  # one axis
         "lattice_slice_kernel": B * n * (48 + 4 * K) + 4 * K * M + 4 * B * n * (K + 1),
@@ -259,34 +311,39 @@ def run_cosa_arm(args):
 
     host, wl = make_inputs(args, rank)
     B, C, H, W = args.batch, wl["C"], wl["H"], wl["W"]
-    pinned = {k: v.pin_memory() for k, v in host.items() if k != "img_box"}
+    pinned = {k: v.pin_memory() for k, v in host.items() if isinstance(v, torch.Tensor) and k != "img_box"}
     boxes = host["img_box"]
+    thr_high, thr_low = wl["thr"]
     d = {k: v.to(dev) for k, v in pinned.items()}
-    if args.aux_labelling:    # auxiliary CAMs: the same blobs seen a little differently (mirrored mix of the batch)
+    # auxiliary CAMs for the x2-labelling variant: the same blobs seen a little differently (mirrored mix of the batch)
+    want_aux = args.aux_labelling or not args.no_aux
+    if want_aux:
         d["cams_aux"] = (0.8 * d["cams"] + 0.2 * d["cams"].flip(0).flip(-1)).contiguous()
+    if args.aux_labelling:
         wl["name"] += " + auxiliary CAMs labelled too (x2 labelling, main.py:171-199)"
     par = cosa_b200.PAR(num_iter=NUM_ITER, dilations=DILATIONS).to(dev)
     layer = cosa_b200.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
 
-    def step(t, overlap=True):
+    def step(t, overlap=True, aux=args.aux_labelling, img_box=None):
+        boxes = host["img_box"] if img_box is None else img_box
         if overlap:
             # the CRF lattice needs only the image: DenseEnergyLoss.prebuild_lattice starts it on a second stream so
             # that the build runs under cam2mask; get_energy_loss below picks it up (same kernels, same results)
             layer.prebuild_lattice(t["simg"], C)
         img_denorm = cosa_b200.denormalize_img(t["simg"])                       # main.py:117
         cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
-        if args.aux_labelling:
+        if aux:
             # main.py's default (aux_cam2seg=True, :171-199): the auxiliary CAMs of the batch are labelled as well;
             # the two cam2mask calls share the images, hence the PAR affinity
             with par.shared_affinity():
                 label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
-                                           threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+                                           threshold_high=thr_high, threshold_low=thr_low, refine_model=par)
                 aux = cosa_b200.cam_validation(t["cams_aux"], t["cls_label"])
                 cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=aux, cls_labels=t["cls_label"],
-                                   threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+                                   threshold_high=thr_high, threshold_low=thr_low, refine_model=par)
         else:
             label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
-                                       threshold_high=THR_HIGH, threshold_low=THR_LOW, refine_model=par)
+                                       threshold_high=thr_high, threshold_low=thr_low, refine_model=par)
         logit = t["logits"].detach().requires_grad_(True)
         loss = cosa_b200.get_energy_loss(img=t["simg"], logit=logit, label=label, img_box=boxes, loss_layer=layer)
         loss.backward()
@@ -297,9 +354,45 @@ def run_cosa_arm(args):
         sharding.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity gate + CPU baseline (rank 0, N = 1 only): the CPU path on the first images of this very batch, its
+    # labels / loss / gradient compared with the GPU's on the same images BEFORE anything is timed --------------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_img = min(REF_SAMPLE_IMAGES, B)
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_path_step(host, 1)
+        t0 = time.perf_counter()
+        cpu_loss, cpu_label, cpu_margin, cpu_grad = cpu_path_step(host, n_img, full=True)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "first %d images of the same batch, 1 warm-up image + 1 timed pass (%.1f s); %s"
+                         % (n_img, dt, cpu_kind())}
+        sub = {k: v[:n_img].contiguous() for k, v in d.items()}
+        g_label, g_loss, g_grad = step(sub, img_box=host["img_box"][:n_img])
+        diff = (g_label.cpu() != cpu_label)
+        flips = int(diff.sum())
+        worst = float(cpu_margin[diff].max()) if flips else 0.0
+        # the GPU's loss / gradient on the CPU's labels (a near-tie flip must not leak into the comparison)
+        logit = sub["logits"].detach().requires_grad_(True)
+        l2 = cosa_b200.get_energy_loss(img=sub["simg"], logit=logit, label=cpu_label.to(dev),
+                                       img_box=host["img_box"][:n_img], loss_layer=layer)
+        l2.backward()
+        loss_rel = abs(float(l2.detach()) - cpu_loss) / abs(cpu_loss)
+        grad_rel = float((logit.grad.cpu() - cpu_grad).abs().max() / cpu_grad.abs().max())
+        parity = {"images": n_img, "label_pixels": int(cpu_label.numel()), "label_flips": flips,
+                  "worst_flip_margin": worst, "near_tie_margin": 1e-5, "loss_rel": loss_rel, "grad_rel": grad_rel,
+                  "tolerance": 1e-4, "against": cpu["kind"]}
+        ok = (flips == 0 or (worst <= 1e-5 and flips <= 1e-5 * cpu_label.numel())) and loss_rel <= 1e-4 and grad_rel <= 1e-4
+        parity["ok"] = bool(ok)
+        if not ok:
+            emit({"metric": METRIC, "error": "parity gate failed - nothing was timed", "parity": parity})
+            raise SystemExit("bench.py: GPU results differ from the CPU path: %s" % json.dumps(parity))
+        del sub, logit, l2, g_label, g_loss, g_grad
+
     # ---- device-resident throughput ------------------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    clocks.__enter__()          # sampled from the warm-up to the end of the e2e loop (nvidia-smi period: 50 ms)
+    clocks = ClockSampler(range(world) if rank == 0 else [])     # one sampler process for all GPUs of the job
+    clocks.__enter__()          # sampled from the warm-up to the end of the e2e loop (nvidia-smi period: 100 ms)
     for _ in range(max(3, args.warmup)):
         label, loss, grad = step(d)
     sync_all()
@@ -320,7 +413,7 @@ def run_cosa_arm(args):
     # launch path is out of the way; matters for small batches (configs[0]) ----------------------------------
     graph_replay = None
     if not args.aux_labelling and not args.no_graph:
-        gs = cosa_b200.GraphedStep(par, layer, THR_HIGH, THR_LOW, B=B, C=C, H=H, W=W, img_box=boxes, device=dev)
+        gs = cosa_b200.GraphedStep(par, layer, thr_high, thr_low, B=B, C=C, H=H, W=W, img_box=boxes, device=dev)
         gs.simg.copy_(d["simg"]); gs.cams.copy_(d["cams"]); gs.cls_label.copy_(d["cls_label"])
         with torch.no_grad():
             gs.logits.copy_(d["logits"])
@@ -337,6 +430,25 @@ def run_cosa_arm(args):
         graph_replay = {"value": total_images / (g_ms / 1e3), "unit": "images/s", "ms_per_step": g_ms / args.steps,
                         "note": "cosa_b200.GraphedStep: the step captured in one CUDA graph, one launch per step"}
         del gs
+
+    # ---- the reference's default step also labels the auxiliary CAMs (main.py:171-203, aux_cam2seg=True): the same
+    # step with that second cam2mask call, as a side measurement ("x2 labelling") -------------------
+    aux_line = None
+    if want_aux and not args.aux_labelling:
+        for _ in range(3):
+            step(d, aux=True)
+        sync_all()
+        a_steps = max(3, min(args.steps, 10))
+        ev0.record()
+        for _ in range(a_steps):
+            step(d, aux=True)
+        ev1.record()
+        sync_all()
+        a_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
+        aux_line = {"value": sharding.all_reduce_sum(B * a_steps) / (a_ms / 1e3), "unit": "images/s",
+                    "ms_per_step": a_ms / a_steps, "steps": a_steps,
+                    "note": "the step + cam_validation / cam2mask of the auxiliary CAMs (main.py:171-203); the two "
+                            "cam2mask calls share the PAR affinity (PAR.shared_affinity)"}
 
     # ---- per-kernel event timing for the roofline (same inputs, same stream) ---------------------------
     prof_steps = min(args.steps, 5)
@@ -358,10 +470,15 @@ def run_cosa_arm(args):
                         "achieved_gbs": round(gbs, 1) if gbs else None,
                         "frac": round(gbs / peak, 4) if gbs else None})
     top = kernels[0]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture - only when
+    # that capture was made on THIS configuration (profiles/dram_traffic.json names it); null otherwise
     traffic = None
+    config_key = "%s_b%d_%dx%d" % (args.workload, B, H, W)
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            traffic = json.load(f).get(top["kernel"])
+            tj = json.load(f)
+        if tj.get("config") == config_key:
+            traffic = tj.get("kernels", {}).get(top["kernel"])
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -374,7 +491,7 @@ def run_cosa_arm(args):
     e2e = None
     e2e_native = None
     if not args.no_e2e:
-        pipe = cosa_b200.HostPipeline(par, layer, threshold_high=THR_HIGH, threshold_low=THR_LOW, device=dev)
+        pipe = cosa_b200.HostPipeline(par, layer, threshold_high=thr_high, threshold_low=thr_low, device=dev)
         batch = dict(pinned, img_box=boxes)
         for _ in range(3):
             pipe.submit(batch)
@@ -405,7 +522,7 @@ def run_cosa_arm(args):
         raw_cams = [t.pin_memory() for t in synthetic.synthetic_raw_cams(host, seed=7000 + rank)]
         nbatch = dict(simg=pinned["simg"], raw_cams=raw_cams, seg_lowres=pinned["seg_lowres"],
                       cls_label=pinned["cls_label"], img_box=boxes)
-        npipe = cosa_b200.HostPipeline(par, layer, threshold_high=THR_HIGH, threshold_low=THR_LOW, device=dev)
+        npipe = cosa_b200.HostPipeline(par, layer, threshold_high=thr_high, threshold_low=thr_low, device=dev)
         for _ in range(3):
             npipe.submit_native(nbatch)
         npipe.drain()
@@ -430,26 +547,17 @@ def run_cosa_arm(args):
 
     clocks.__exit__(None, None, None)
 
-    # ---- CPU baseline on this host (rank 0, N = 1 only), bounded sample ----------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
-        n_img = min(4, B)
-        cpu_path_step(host, 1)
-        t0 = time.perf_counter()
-        cpu_loss = cpu_path_step(host, n_img)
-        dt = time.perf_counter() - t0
-        cpu = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "first %d images of the same batch, 1 warm-up image + 1 timed pass (%.1f s); %s"
-                         % (n_img, dt, cpu_kind())}
-
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"] % B, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
-                       "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "thresholds": [THR_HIGH, THR_LOW],
+                       "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "thresholds": [thr_high, thr_low],
+                       "par_step": "1 affinity launch + 10 step launches (programmatic dependent launches); the "
+                                   "single cooperative launch of north_star exists (COSA_PAR_STEP=coop) and is slower",
+                       "fused_producers": "denormalize_img and cam_validation are folded into cam2mask's first kernel "
+                                          "(cosa_cam2mask_ex); their tensors are never written",
                        "streams": ("CRF lattice build (image-only) on a second stream under cam2mask "
                                    "(DenseEnergyLoss.prebuild_lattice)" if os.environ.get("COSA_NO_PREBUILD") != "1"
                                    else "single stream (COSA_NO_PREBUILD=1)"),
@@ -457,7 +565,8 @@ def run_cosa_arm(args):
                        "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
                                 % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),
                        "lattice_vertices": M_vertices, "lattice_M_over_n": round(M_vertices / (B * (H // 2) * (W // 2)), 4)},
-            "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "graph_replay": graph_replay, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks.summary(), "e2e": e2e, "e2e_native": e2e_native, "graph_replay": graph_replay,
+            "aux_labelling": aux_line, "gpu_launches": launches, "roofline": roofline, "parity": parity,
             "cpu_baseline": cpu, "kernels": kernels, "loss": mean_loss,
         }
         emit(line)

@@ -8,6 +8,8 @@ import os
 
 import torch
 
+from . import _lazy
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcosa_b200.so")
 
@@ -24,7 +26,6 @@ _SIGNATURES = {
     "cosa_par_ws_bytes": (_c_size_t, [_c_int] * 5),
     "cosa_par_forward": (_c_int, [_vp, _vp, _vp] + [_c_int] * 6 + [_vp, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "cosa_par_set_step_mode": (_c_int, [ctypes.c_char_p]),
-    "cosa_cam2mask_set_all_channels": (_c_int, [_c_int]),
     "cosa_par_affinity": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _vp, _c_int, _vp]),
     "cosa_cam_normalize": (_c_int, [_vp, _c_int, _vp, _c_int, _c_ll, _vp, _vp]),
     "cosa_multi_scale_cam_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp, _vp]),
@@ -47,6 +48,8 @@ _SIGNATURES = {
                       [_c_int] * 4 + [_vp, _c_size_t, _vp]),
     "cosa_cam2mask_flags": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
                             [_c_int] * 4 + [_vp, _c_size_t, _c_int, _vp]),
+    "cosa_cam2mask_ex": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
+                         [_c_int] * 4 + [_vp, _c_size_t, _c_int, _vp, _vp, _vp]),
     "cosa_upsample_argmax": (_c_int, [_vp, _vp, _vp] + [_c_int] * 6 + [_vp]),
     "cosa_bilateral_ws_bytes": (_c_size_t, [_c_int] * 4),
     "cosa_bilateralfilter_batch": (_c_int, [_vp, _vp, _vp] + [_c_int] * 4 + [_c_float] * 2 + [_vp, _c_size_t, _vp]),
@@ -66,6 +69,7 @@ _SIGNATURES = {
     "cosa_energy_loss_backward": (_c_int, [_vp] * 3 + [_c_float, _vp] + [_c_int] * 4 + [_vp]),
 }
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -85,7 +89,7 @@ def load():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.cosa_abi_version() != 1:
+        if lib.cosa_abi_version() != ABI_VERSION:
             raise CosaError("cosa_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -127,6 +131,7 @@ def dev_f32(t, what):
     """A contiguous float32 CUDA view of ``t``; refuses CPU tensors (no CPU path in this package)."""
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % what)
+    t = _lazy.plain(t)
     if not t.is_cuda:
         raise CosaError("cosa_b200: %s must be a CUDA tensor - this package has no CPU fallback" % what)
     if t.dtype != torch.float32:

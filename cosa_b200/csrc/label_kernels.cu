@@ -302,10 +302,37 @@ struct ResizeGeom {
   int identity;         // no reduction (downscale == 0)
 };
 
-__device__ __forceinline__ float sample_down(const float *plane, const ResizeGeom &g, const Tap &ty, const Tap &tx) {
-  if (g.identity) return __ldg(plane + (size_t)ty.i0 * g.W + tx.i0);
-  return bilerp_down(ty, tx, __ldg(plane + (size_t)ty.i0 * g.W + tx.i0), __ldg(plane + (size_t)ty.i0 * g.W + tx.i1),
-                     __ldg(plane + (size_t)ty.i1 * g.W + tx.i0), __ldg(plane + (size_t)ty.i1 * g.W + tx.i1));
+// Optional producers folded into the prepare kernels (cosa_cam2mask_ex):
+//  * images given as the ImageNet-normalised network input: each source pixel is de-normalised exactly as
+//    denormalize_img_kernel does it (utils/torch_helper.py:354-367) before the reduction - no [0,1] image in HBM;
+//  * CAMs given before cam_validation: each source value is multiplied by cls_label[b,c] (seg_helper.py:547-551);
+//    only the planes of present classes are ever read, so the zero planes cam_validation would write never exist.
+struct Denorm {
+  float mean[3], std[3];
+  int on;
+};
+__device__ __forceinline__ float denorm_px(float v, const Denorm &d, int c) {
+  if (!d.on) return v;
+  const float t = __fadd_rn(__fmul_rn(v, d.std[c]), d.mean[c]);
+  return div255_u8((float)min(max((int)t, 0), 255));
+}
+
+// `scale` multiplies every source value (1 = identity, bit for bit)
+__device__ __forceinline__ float sample_down(const float *plane, const ResizeGeom &g, const Tap &ty, const Tap &tx,
+                                             float scale = 1.0f) {
+  if (g.identity) return __fmul_rn(__ldg(plane + (size_t)ty.i0 * g.W + tx.i0), scale);
+  return bilerp_down(ty, tx, __fmul_rn(__ldg(plane + (size_t)ty.i0 * g.W + tx.i0), scale),
+                     __fmul_rn(__ldg(plane + (size_t)ty.i0 * g.W + tx.i1), scale),
+                     __fmul_rn(__ldg(plane + (size_t)ty.i1 * g.W + tx.i0), scale),
+                     __fmul_rn(__ldg(plane + (size_t)ty.i1 * g.W + tx.i1), scale));
+}
+__device__ __forceinline__ float sample_down_img(const float *plane, const ResizeGeom &g, const Tap &ty, const Tap &tx,
+                                                 const Denorm &d, int c) {
+  if (g.identity) return denorm_px(__ldg(plane + (size_t)ty.i0 * g.W + tx.i0), d, c);
+  return bilerp_down(ty, tx, denorm_px(__ldg(plane + (size_t)ty.i0 * g.W + tx.i0), d, c),
+                     denorm_px(__ldg(plane + (size_t)ty.i0 * g.W + tx.i1), d, c),
+                     denorm_px(__ldg(plane + (size_t)ty.i1 * g.W + tx.i0), d, c),
+                     denorm_px(__ldg(plane + (size_t)ty.i1 * g.W + tx.i1), d, c));
 }
 
 constexpr int kCacheC = 8;   // live channels cached in registers by the prepare kernel
@@ -316,7 +343,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
                                                                const int *__restrict__ nc_dev,
                                                                float *__restrict__ img_small,
                                                                float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
-                                                               int C1, float thr_high, float thr_low, int derive) {
+                                                               int C1, float thr_high, float thr_low, int derive,
+                                                               Denorm dn, const float *__restrict__ cam_scale) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -333,7 +361,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   if (img_small) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      img_small[((size_t)b * 3 + c) * hw + pix] = sample_down(images + ((size_t)b * 3 + c) * HW, g, ty, tx);
+      img_small[((size_t)b * 3 + c) * hw + pix] = sample_down_img(images + ((size_t)b * 3 + c) * HW, g, ty, tx, dn, c);
   }
   const int nc = nc_dev[b];
   const int *key = keys + (size_t)b * (C1 + 1);
@@ -356,8 +384,10 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   // live foreground channels: values, their max; the two stacks differ only in channel 0 (the threshold)
   float v[kCacheC];
   float mx = -INFINITY;
+  const float *sc_b = cam_scale ? cam_scale + (size_t)b * C1 : nullptr;
+  auto scale_of = [&](int j) { return sc_b ? __ldg(sc_b + key[j] - 1) : 1.0f; };
   for (int j = 1; j < nc; ++j) {
-    const float t = sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    const float t = sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx, scale_of(j));
     if (j < kCacheC) v[j] = t;
     mx = fmaxf(mx, t);
   }
@@ -365,7 +395,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   float e0_hi = expf(thr_high - mx_hi), e0_lo = expf(thr_low - mx_lo);
   float den_hi = e0_hi, den_lo = e0_lo;
   for (int j = 1; j < nc; ++j) {
-    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx, scale_of(j));
     den_hi += expf(t - mx_hi);
     den_lo += expf(t - mx_lo);
   }
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
     put(m_lo, e0_lo / den_lo);
   }
   for (int j = 1; j < ns; ++j) {
-    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx);
+    const float t = (j < kCacheC) ? v[j] : sample_down(cam_b + (size_t)(key[j] - 1) * HW, g, ty, tx, scale_of(j));
     put(m_hi + (size_t)j * mplane, expf(t - mx_hi) / den_hi);
     put(m_lo + (size_t)j * mplane, expf(t - mx_lo) / den_lo);
   }
@@ -384,9 +414,24 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
 // 128-bit loads of the two source rows of every plane (8 scalar loads with their index arithmetic per plane and pixel
 // in the general kernel).  Arithmetic identical to cam2mask_prepare_kernel: the taps of the exact ratio are the four
 // source pixels with weight 0.25 each, accumulated in bilerp_down's order.
-__device__ __forceinline__ void down2_pair(const float *plane, size_t row0, int W, float &s0, float &s1) {
-  const float4 a = __ldg(reinterpret_cast<const float4 *>(plane + row0));
-  const float4 b = __ldg(reinterpret_cast<const float4 *>(plane + row0 + W));
+__device__ __forceinline__ void down2_sum(const float4 &a, const float4 &b, float &s0, float &s1);
+__device__ __forceinline__ void down2_pair(const float *plane, size_t row0, int W, float &s0, float &s1,
+                                           float scale = 1.0f) {
+  float4 a = __ldg(reinterpret_cast<const float4 *>(plane + row0));
+  float4 b = __ldg(reinterpret_cast<const float4 *>(plane + row0 + W));
+  a.x = __fmul_rn(a.x, scale); a.y = __fmul_rn(a.y, scale); a.z = __fmul_rn(a.z, scale); a.w = __fmul_rn(a.w, scale);
+  b.x = __fmul_rn(b.x, scale); b.y = __fmul_rn(b.y, scale); b.z = __fmul_rn(b.z, scale); b.w = __fmul_rn(b.w, scale);
+  down2_sum(a, b, s0, s1);
+}
+__device__ __forceinline__ void down2_pair_img(const float *plane, size_t row0, int W, float &s0, float &s1,
+                                               const Denorm &d, int c) {
+  float4 a = __ldg(reinterpret_cast<const float4 *>(plane + row0));
+  float4 b = __ldg(reinterpret_cast<const float4 *>(plane + row0 + W));
+  a.x = denorm_px(a.x, d, c); a.y = denorm_px(a.y, d, c); a.z = denorm_px(a.z, d, c); a.w = denorm_px(a.w, d, c);
+  b.x = denorm_px(b.x, d, c); b.y = denorm_px(b.y, d, c); b.z = denorm_px(b.z, d, c); b.w = denorm_px(b.w, d, c);
+  down2_sum(a, b, s0, s1);
+}
+__device__ __forceinline__ void down2_sum(const float4 &a, const float4 &b, float &s0, float &s1) {
   float t = __fmul_rn(0.25f, a.x);
   t = __fmaf_rn(0.25f, a.y, t); t = __fmaf_rn(0.25f, b.x, t); t = __fmaf_rn(0.25f, b.y, t);
   s0 = t;
@@ -401,7 +446,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
                                                                   const int *__restrict__ nc_dev,
                                                                   float *__restrict__ img_small,
                                                                   float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
-                                                                  int C1, float thr_high, float thr_low, int derive) {
+                                                                  int C1, float thr_high, float thr_low, int derive,
+                                                                  Denorm dn, const float *__restrict__ cam_scale) {
   const int xp = blockIdx.x * 32 + (threadIdx.x & 31);     // pair index: half-resolution columns 2 xp, 2 xp + 1
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -414,7 +460,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s0, s1;
-      down2_pair(images + ((size_t)b * 3 + c) * HW, row0, g.W, s0, s1);
+      down2_pair_img(images + ((size_t)b * 3 + c) * HW, row0, g.W, s0, s1, dn, c);
       *reinterpret_cast<float2 *>(img_small + ((size_t)b * 3 + c) * hw + pix) = make_float2(s0, s1);
     }
   }
@@ -436,9 +482,11 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
   };
   float v0[kCacheC], v1[kCacheC];
   float mx0 = -INFINITY, mx1 = -INFINITY;
+  const float *sc_b = cam_scale ? cam_scale + (size_t)b * C1 : nullptr;
+  auto scale_of = [&](int j) { return sc_b ? __ldg(sc_b + key[j] - 1) : 1.0f; };
   for (int j = 1; j < nc; ++j) {
     float s0, s1;
-    down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1, scale_of(j));
     if (j < kCacheC) { v0[j] = s0; v1[j] = s1; }
     mx0 = fmaxf(mx0, s0);
     mx1 = fmaxf(mx1, s1);
@@ -451,7 +499,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
   for (int j = 1; j < nc; ++j) {
     float s0, s1;
     if (j < kCacheC) { s0 = v0[j]; s1 = v1[j]; }
-    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1, scale_of(j));
     dh0 += expf(s0 - mh0); dl0 += expf(s0 - ml0);
     dh1 += expf(s1 - mh1); dl1 += expf(s1 - ml1);
   }
@@ -462,7 +510,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
   for (int j = 1; j < ns; ++j) {
     float s0, s1;
     if (j < kCacheC) { s0 = v0[j]; s1 = v1[j]; }
-    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1);
+    else down2_pair(cam_b + (size_t)(key[j] - 1) * HW, row0, g.W, s0, s1, scale_of(j));
     put(m_hi + (size_t)j * mplane, expf(s0 - mh0) / dh0, expf(s1 - mh1) / dh1);
     put(m_lo + (size_t)j * mplane, expf(s0 - ml0) / dl0, expf(s1 - ml1) / dl1);
   }
@@ -1021,12 +1069,6 @@ extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downsc
   return bytes;
 }
 
-static int g_all_channels = -1;   // -1: not decided yet (environment), 0: derive the last channel, 1: propagate all
-extern "C" int cosa_cam2mask_set_all_channels(int on) {
-  g_all_channels = on ? 1 : 0;
-  return 0;
-}
-
 extern "C" int cosa_cam2mask(const float *images, const int *boxes, const float *cams, const float *cls_labels,
                              float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
                              const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
@@ -1042,6 +1084,20 @@ extern "C" int cosa_cam2mask_flags(const float *images, const int *boxes, const 
                                    int use_par, const int *dilations, int n_dil, int num_iter, float *label_out,
                                    float *label_high_out, float *label_low_out, int B, int C1, int H, int W, void *ws,
                                    size_t ws_bytes, int flags, void *stream) {
+  return cosa_cam2mask_ex(images, boxes, cams, cls_labels, threshold_high, threshold_low, ignore_index, downscale,
+                          use_par, dilations, n_dil, num_iter, label_out, label_high_out, label_low_out, B, C1, H, W,
+                          ws, ws_bytes, flags, nullptr, nullptr, stream);
+}
+
+extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                                float threshold_high, float threshold_low, float ignore_index, int downscale,
+                                int use_par, const int *dilations, int n_dil, int num_iter, float *label_out,
+                                float *label_high_out, float *label_low_out, int B, int C1, int H, int W, void *ws,
+                                size_t ws_bytes, int flags, const float *denorm_mean, const float *denorm_std,
+                                void *stream) {
+  if (flags & ~(COSA_CAM2MASK_REUSE_AFFINITY | COSA_CAM2MASK_ALL_CHANNELS | COSA_CAM2MASK_CAMS_UNVALIDATED))
+    return COSA_E_ARG;
+  if ((denorm_mean == nullptr) != (denorm_std == nullptr)) return COSA_E_ARG;
   if (!images || !boxes || !cams || !cls_labels || !label_out || !ws || B < 1 || C1 < 1 || H < 1 || W < 1 ||
       downscale < 0)
     return COSA_E_ARG;
@@ -1067,10 +1123,13 @@ extern "C" int cosa_cam2mask_flags(const float *images, const int *boxes, const 
   // included).  So the last live channel of each stack is not propagated: after num_iter steps it is
   // row_sum^num_iter minus the sum of the others, evaluated by the labelling kernel at every tap (|error| ~ 1e-6,
   // the same order as the summation-order differences between two fp32 evaluations of the reference).
-  // cosa_cam2mask_set_all_channels(1) / COSA_CAM2MASK_ALL_CHANNELS=1 propagates every channel (A/B runs, tests).
+  // COSA_CAM2MASK_ALL_CHANNELS (a per-call flag) propagates every channel instead.
   if (refine) COSA_CHECK(par_upload_constants(dilations, n_dil, s));
-  if (g_all_channels < 0) g_all_channels = getenv("COSA_CAM2MASK_ALL_CHANNELS") ? 1 : 0;
-  const int derive = (refine && !g_all_channels) ? 1 : 0;
+  const int derive = (refine && !(flags & COSA_CAM2MASK_ALL_CHANNELS)) ? 1 : 0;
+  Denorm dn;
+  dn.on = denorm_mean != nullptr;
+  for (int c = 0; c < 3; ++c) { dn.mean[c] = dn.on ? denorm_mean[c] : 0.0f; dn.std[c] = dn.on ? denorm_std[c] : 1.0f; }
+  const float *cam_scale = (flags & COSA_CAM2MASK_CAMS_UNVALIDATED) ? cls_labels : nullptr;
   const float derive_total = derive ? (float)pow(par_weight_row_sum(), (double)num_iter) : 0.0f;
   COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
@@ -1090,11 +1149,11 @@ extern "C" int cosa_cam2mask_flags(const float *images, const int *boxes, const 
   if (exact2) {
     dim3 gs(ceil_div(g.w / 2, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH_T("cam2mask_prepare_kernel", cam2mask_prepare_x2_kernel, gs, 256, 0, s, images, cams, keys, nc,
-                  reuse_aff ? nullptr : img_small, masks, lay, g, C1, threshold_high, threshold_low, derive);
+                  reuse_aff ? nullptr : img_small, masks, lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale);
   } else {
     dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, reuse_aff ? nullptr : img_small, masks,
-                lay, g, C1, threshold_high, threshold_low, derive);
+                lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale);
   }
   const float *refined = masks;
   MaskLayout lay_fin = lay;

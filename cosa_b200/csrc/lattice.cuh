@@ -6,10 +6,21 @@
 //
 // Key packing (64 bit).  A lattice point has coordinates key[i] = 6*q[i] + r with one common residue
 // r in [0,5] (rem0 is a multiple of d+1 = 6 and canonical[r][.] is r or r-6, permutohedral.cpp:148-153,247):
-//     bits  0..54 : q[0..4] + 1024, 11 bits each   (|key[i]| <= 6143; the reference stores `short`)
+//     bits  0..54 : q[0..4] + 1024, 11 bits each   (|key[i]| <= 6143; the reference stores `short`, +-32767)
 //     bits 55..57 : r
 //     bits 58..63 : image index within the chunk (chunks of 64 images; EMPTY is all-ones, i.e. r = 7: never a key)
-// A coordinate outside the range raises the error flag (COSA_E_KEYRANGE) instead of aliasing.
+// A coordinate outside the range raises the sticky error flag (counters[1] bit 0): the slice then writes NaN and the
+// energy loss is NaN, and cosa_bilateral_stats / the host form return COSA_E_KEYRANGE - never an aliased vertex.
+//
+// Tile-local vertex lists.  The image is cut into 32 x 8 pixel tiles.  The 1536 (pixel, vertex) pairs of a tile
+// touch only ~22 % as many distinct vertices (the lattice cells are sigma_xy pixels wide), so the build
+// de-duplicates a tile's keys ONCE in shared memory and writes
+//     tile_info[t]          (first list entry, U = number of distinct vertices of the tile)
+//     tkeys / tvid / tseg   per list entry: packed key, vertex row (id + 1), (first pair << 16 | pairs) in plist
+//     plist[t][1536]        the tile's pairs bucketed by list entry: (pixel in tile << 3 | r)
+//     lidx[r][P], bary[r][P] per pixel: 16-bit index into the tile's list and the barycentric weight
+// Only the distinct keys of a tile go to the global hash table (4-5x fewer probes); the splat reduces a tile's pairs
+// per vertex from shared memory without hashing, and the slice stages the tile's vertex rows once.
 #pragma once
 #include "common.cuh"
 
@@ -21,18 +32,33 @@ constexpr int kQBias = 1 << (kQBits - 1);          // 1024
 constexpr int kMaxImagesPerLattice = 64;
 constexpr unsigned long long kEmptyKey = ~0ULL;
 
+constexpr int kTileW = 32, kTileH = 8;
+constexpr int kTilePix = kTileW * kTileH;           // 256 = threads per tile CTA
+constexpr int kTilePairs = (kLatD + 1) * kTilePix;  // 1536
+constexpr int kTileMaxU = kTilePairs + kLatD + 1;   // + the keys of the SSE padding pixels (first tile of an image)
+
+// counters[]: 0: M   1: error flags (1 = key range, 2 = list / vertex capacity)   2: max probe length
+//             3: table capacity in use   4: M of the earlier chunks of this call   5: T = list entries
+//             6: 1 while val0 is known to be all zero (set by the build, cleared by the splat)
 struct LatticeBufs {
-  unsigned long long *table_keys;   // [cap]   packed key or kEmptyKey
+  unsigned long long *table_keys;   // [cap]   packed key or kEmptyKey (the build uses the first 2^k >= 2T slots)
   int *table_ids;                   // [cap]   vertex id + 1 of an occupied slot
   unsigned long long *vkeys;        // [m_cap] packed key of vertex id
-  int *counters;                    // [8]     0: M   1: key-range error   2: max probe length   3: table capacity   4: M of earlier chunks
-  int *offsets;                     // [6][P]  table slot during the build, then vertex id + 1
+  int *counters;                    // [8]
+  int2 *tile_info;                  // [tiles] (first list entry, U)
+  unsigned long long *tkeys;        // [t_cap] packed key of a list entry
+  int *tvid;                        // [t_cap] table slot during the build, then vertex id + 1 (row of val0 / val1)
+  unsigned *tseg;                   // [t_cap] (first pair << 16) | pairs
+  unsigned short *plist;            // [tiles][kTilePairs]
+  unsigned short *lidx;             // [6][P]  index into the tile's list
   float *bary;                      // [6][P]
   int2 *nbr;                        // [6][m_cap]  (n1, n2) as vertex id + 1, 0 = absent
   float *val0, *val1;               // [m_cap + 1][Kp]   row 0 is the all-zero "absent" row
   long long P;                      // N * H * W
   long long m_cap;                  // upper bound on the number of vertices
-  unsigned long long cap_mask;      // table capacity - 1 (power of two)
+  long long t_cap;                  // upper bound on the number of list entries
+  unsigned long long cap_mask;      // allocated table capacity - 1 (power of two)
+  int tiles_x, tiles_y;             // tiles per image
   int Kp;                           // channels rounded up to a multiple of 4
 };
 
@@ -44,7 +70,7 @@ void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L);
 // first_chunk: this is the first lattice of a call (resets the per-call counters: total vertices, error flag).
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
                   bool first_chunk, cudaStream_t stream);
-// Images per lattice for a batch of N (<= kMaxImagesPerLattice, sized for L2; see lattice_kernels.cu).
+// Images per lattice for a batch of N (<= kMaxImagesPerLattice).
 int lattice_chunk_images(int N, int K, int H, int W);
 // values <- splat(ins [N,K,H,W]); six blur passes.  The blurred values end up in L.val0.
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream);

@@ -3,18 +3,23 @@
 // Reference: utils/bilateralfilter/bilateralfilter.cpp:4-55 (features, per-image driver, batch loop) and
 // utils/bilateralfilter/permutohedral.cpp:115-297 (Permutohedral::init, SSE branch), :507-571 (compute).
 //
-//   build      one thread per pixel: features -> elevate -> round (half-even) -> rank -> barycentric ->
-//              6 packed vertex keys, inserted into an open-addressing hash table in HBM with 64-bit CAS;
-//              lanes of a warp that hold the same key elect one inserter (warp-aggregated atomics).
-//   resolve    table slot -> dense vertex id for every (pixel, vertex)
-//   neighbours 12 look-ups per vertex -> blur neighbour table                      (permutohedral.cpp:272-297)
-//   splat      values[v] += bary * in, all K channels of a vertex in one row, 128-bit vector reductions
+//   tile build one CTA per 32 x 8 pixel tile, one thread per pixel: features -> elevate -> round (half-even) -> rank ->
+//              barycentric -> 6 packed vertex keys; the tile's keys are de-duplicated in a shared-memory hash table and
+//              the pairs bucketed per distinct vertex (count -> scan -> fill).  No global hash traffic at all.
+//   insert     the distinct keys of all tiles (T of them, ~22 % of the 6 n pairs) are found-or-inserted in an
+//              open-addressing table in HBM (load first, 64-bit CAS only on an empty slot) sized 2^k >= 2T on the
+//              device, so it stays L2-resident; new vertices get dense ids, one global atomic per CTA
+//   finish     list entries: table slot -> vertex row; 6 look-ups per vertex -> blur neighbour table
+//              (permutohedral.cpp:272-297); value rows zeroed
+//   splat      per tile: a quarter-warp per distinct vertex sums its pairs from the tile's staged inputs and issues
+//              one reduction per vertex row (permutohedral.cpp:526-534)
 //   blur       6 Jacobi passes  new = old + 0.5 * (old[n1] + old[n2])               (permutohedral.cpp:536-552)
-//   slice      out = sum_r bary_r * alpha * values[v_r]  (+ fused gate / energy dot)  (permutohedral.cpp:554-567)
+//   slice      per tile: the distinct vertex rows are staged in shared memory once, pixels gather from there;
+//              out = sum_r bary_r * alpha * values[v_r]  (+ fused gate / energy dot)  (permutohedral.cpp:554-567)
 //
 // Arithmetic that decides DISCRETE outcomes (rounding, ranks, keys) and the barycentric weights use explicit
 // round-to-nearest intrinsics in the reference's operation order, so the vertex set and the weights are
-// bit-identical to the CPU code; only the summation order of the splat (atomics) differs.
+// bit-identical to the CPU code; only the summation order of the splat differs.
 #include <math.h>
 #include <stdlib.h>
 
@@ -115,39 +120,74 @@ __device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedCon
 }
 
 // ---- build ---------------------------------------------------------------------------------------
-__global__ void lattice_clear_kernel(unsigned long long *table_keys, unsigned long long cap, int *counters,
-                                     int first_chunk) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 2;
-  for (unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 2; i < cap; i += stride)
-    *reinterpret_cast<ulonglong2 *>(table_keys + i) = make_ulonglong2(kEmptyKey, kEmptyKey);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // 0: M of this chunk   1: key-range error (sticky over the chunks of a call)   2: max probe length (same)
-    // 3: table capacity     4: vertices of the earlier chunks of this call
-    counters[4] = first_chunk ? 0 : counters[4] + counters[0];
-    counters[0] = 0;
-    if (first_chunk) { counters[1] = 0; counters[2] = 0; }
-    counters[3] = (int)min(cap, (unsigned long long)0x7fffffff);
+// Table capacity of this build: 2^k >= 2T (T = distinct keys summed over the tiles >= M), at most what was allocated.
+__device__ __forceinline__ unsigned long long live_mask(const LatticeBufs &L) {
+  const unsigned t2 = 2u * (unsigned)max(L.counters[5], 512);
+  const unsigned long long cap = 1ULL << (32 - __clz(t2 - 1));
+  return min(cap, L.cap_mask + 1) - 1;
+}
+
+__global__ void lattice_reset_kernel(int *counters, int first_chunk) {
+  counters[4] = first_chunk ? 0 : counters[4] + counters[0];
+  counters[0] = 0;
+  if (first_chunk) { counters[1] = 0; counters[2] = 0; }
+  counters[5] = 0;
+  counters[6] = 0;
+}
+
+__device__ __forceinline__ unsigned tile_hash64(unsigned long long k) {
+  const unsigned lo = (unsigned)k, hi = (unsigned)(k >> 32);
+  return ((lo ^ (hi * 0x9E3779B1u)) * 2654435761u) >> 21;      // 11 bits: kTileHS = 2048
+}
+constexpr int kTileHS = 2048;
+
+// Find-or-insert in the tile's shared-memory table; most keys of a tile are already there (a plain load decides),
+// only an empty slot costs a CAS.
+__device__ __forceinline__ int tile_insert64(unsigned long long *hkey, unsigned long long key) {
+  unsigned h = tile_hash64(key);
+  for (;;) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(hkey + h);
+    if (cur == key) return (int)h;
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(hkey + h, kEmptyKey, key);
+      if (cur == kEmptyKey || cur == key) return (int)h;
+    }
+    h = (h + 1) & (kTileHS - 1);
   }
 }
 
-__global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const float *__restrict__ images,
-                                                            EmbedConst ec, int N, int H, int W, int n_pad,
-                                                            float sigmargb, float sigmaxy) {
-  __shared__ int s_new, s_base;
-  if (threadIdx.x == 0) s_new = 0;
-  __syncthreads();
-  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long total = (long long)N * n_pad;
-  const bool in_range = g < total;        // out-of-range threads stay for the block collectives
-  const int n = H * W;
-  const int b = in_range ? (int)(g / n_pad) : 0, p = in_range ? (int)(g % n_pad) : 0;
-  const bool real = in_range && p < n;   // the SSE loop also embeds zero-feature padding pixels (permutohedral.cpp:168-173)
+__device__ __forceinline__ void point_keys(const int q0[kLatD + 1], const int rank[kLatD + 1], int b,
+                                           unsigned long long key[kLatD + 1], int *bad) {
+#pragma unroll
+  for (int r = 0; r <= kLatD; ++r) {
+    int q[kLatD];
+#pragma unroll
+    for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
+    key[r] = pack_key(q, r, b, bad);
+  }
+}
 
+__global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBufs L, const float *__restrict__ images,
+                                                                      EmbedConst ec, int H, int W, int n_pad,
+                                                                      float sigmargb, float sigmaxy) {
+  __shared__ unsigned long long hkey[kTileHS];      // 16 KB
+  __shared__ int hinfo[kTileHS];                    //  8 KB  pair count, then (list index << 16) | first pair
+  __shared__ __align__(16) unsigned short plist_s[kTilePairs];
+  __shared__ int s_warp[kTilePix / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+  const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
+  const int n = H * W;
+  const bool ok = x < W && y < H;
+  for (int i = tid; i < kTileHS; i += kTilePix) { hkey[i] = kEmptyKey; hinfo[i] = 0; }
+  for (int i = tid; i < kTilePairs / 2; i += kTilePix) reinterpret_cast<unsigned *>(plist_s)[i] = 0;
+
+  const int p = y * W + x;
   float f[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (real) {
+  if (ok) {
     const float *img = images + (size_t)b * 3 * n;
-    f[0] = __fdiv_rn((float)(p % W), sigmaxy);               // bilateralfilter.cpp:9-13
-    f[1] = __fdiv_rn((float)(p / W), sigmaxy);
+    f[0] = __fdiv_rn((float)x, sigmaxy);               // bilateralfilter.cpp:9-13
+    f[1] = __fdiv_rn((float)y, sigmaxy);
     f[2] = __fdiv_rn(__ldg(img + p), sigmargb);
     f[3] = __fdiv_rn(__ldg(img + n + p), sigmargb);
     f[4] = __fdiv_rn(__ldg(img + 2 * n + p), sigmargb);
@@ -155,104 +195,159 @@ __global__ void __launch_bounds__(256) lattice_build_kernel(LatticeBufs L, const
   int q0[kLatD + 1], rank[kLatD + 1];
   float bary[kLatD + 1];
   embed_point(f, ec, q0, rank, bary);
+  int bad = 0;
+  unsigned long long key[kLatD + 1];
+  point_keys(q0, rank, b, key, &bad);
+  if (!ok) bad = 0;
+  __syncthreads();
 
-  const long long gp = (long long)b * n + p;   // compact pixel index
-  int bad = 0, max_probe = 0;
-  unsigned new_mask = 0;                        // bit r: this thread created the table entry of vertex r
-  unsigned long long key[kLatD + 1], slot[kLatD + 1], cur[kLatD + 1];
-  // Nine out of ten look-ups find a vertex that an earlier pixel created (M is ~0.5 n for 6 n look-ups), so the
-  // table is probed with plain L2 loads - all six in flight at once - and only an empty slot costs a CAS.  A stale
-  // "empty" is harmless (the CAS decides); an occupied slot never changes again.
+  int hs[kLatD + 1], pos[kLatD + 1];
 #pragma unroll
   for (int r = 0; r <= kLatD; ++r) {
-    int q[kLatD];
-#pragma unroll
-    for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
-    key[r] = pack_key(q, r, b, &bad);
-    slot[r] = hash_key(key[r]) & L.cap_mask;
-    cur[r] = in_range ? __ldcg(L.table_keys + slot[r]) : key[r];
+    hs[r] = 0; pos[r] = 0;
+    if (ok) {
+      hs[r] = tile_insert64(hkey, key[r]);
+      pos[r] = atomicAdd(hinfo + hs[r], 1);
+    }
   }
+  // the SSE loop of the reference also embeds the zero-feature pixels that pad n to a multiple of four
+  // (permutohedral.cpp:168-173): their vertices exist (they count in M and take part in the blur) but receive nothing
+  if (n_pad > n && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+    const float fz[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    int qz[kLatD + 1], rz[kLatD + 1];
+    float bz[kLatD + 1];
+    unsigned long long kz[kLatD + 1];
+    int badz = 0;
+    embed_point(fz, ec, qz, rz, bz);
+    point_keys(qz, rz, b, kz, &badz);
 #pragma unroll
-  for (int r = 0; r <= kLatD; ++r) {
-    if (in_range) {
-      unsigned long long s = slot[r], c = cur[r];
+    for (int r = 0; r <= kLatD; ++r) tile_insert64(hkey, kz[r]);
+  }
+  __syncthreads();
+
+  // one scan over the 2048 slots gives every occupied slot its list index and the start of its pair bucket
+  constexpr int PER = kTileHS / kTilePix;   // 8 consecutive slots per thread
+  int packed[PER], sum = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int s = tid * PER + i;
+    packed[i] = hkey[s] != kEmptyKey ? ((1 << 16) | hinfo[s]) : 0;
+    sum += packed[i];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lx >= o) incl += t;
+  }
+  if (lx == 31) s_warp[ly] = incl;
+  __syncthreads();
+  int run = incl - sum, total = 0;
+#pragma unroll
+  for (int wv = 0; wv < kTilePix / 32; ++wv) {
+    const int t = s_warp[wv];
+    if (wv < ly) run += t;
+    total += t;
+  }
+  const int U = total >> 16;
+  const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tid == 0) {
+    int base = atomicAdd(L.counters + 5, U);
+    if ((long long)base + U > L.t_cap) { atomicOr(L.counters + 1, 2); base = -1; }
+    s_base = base;
+    L.tile_info[tile] = make_int2(max(base, 0), base < 0 ? 0 : U);
+  }
+  __syncthreads();
+  const int base = s_base;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    if (packed[i]) {
+      const int s = tid * PER + i;
+      const int u = run >> 16, start = run & 0xffff, cnt = packed[i] & 0xffff;
+      if (base >= 0) {
+        L.tkeys[base + u] = hkey[s];
+        L.tseg[base + u] = ((unsigned)start << 16) | (unsigned)cnt;
+      }
+      hinfo[s] = run;
+      run += packed[i];
+    }
+  }
+  __syncthreads();
+  if (ok) {
+    const long long gp = (long long)b * n + p;
+#pragma unroll
+    for (int r = 0; r <= kLatD; ++r) {
+      const int info = hinfo[hs[r]];
+      plist_s[(info & 0xffff) + pos[r]] = (unsigned short)((tid << 3) | r);
+      L.lidx[(size_t)r * L.P + gp] = (unsigned short)(info >> 16);
+      L.bary[(size_t)r * L.P + gp] = bary[r];
+    }
+  }
+  __syncthreads();
+  if (tid < kTilePairs / 8)
+    reinterpret_cast<uint4 *>(L.plist + (size_t)tile * kTilePairs)[tid] = reinterpret_cast<const uint4 *>(plist_s)[tid];
+  if (bad) atomicOr(L.counters + 1, 1);
+}
+
+__global__ void lattice_table_clear_kernel(LatticeBufs L) {
+  const unsigned long long cap = live_mask(L) + 1;   // a power of two >= 1024
+  for (unsigned long long i = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) * 2; i < cap;
+       i += (unsigned long long)gridDim.x * blockDim.x * 2)
+    *reinterpret_cast<ulonglong2 *>(L.table_keys + i) = make_ulonglong2(kEmptyKey, kEmptyKey);
+}
+
+// The T distinct-per-tile keys into the global table.  A vertex is shared by ~2.6 tiles, so most look-ups find
+// the key (plain L2 load); only an empty slot costs a CAS.  A stale "empty" is harmless (the CAS decides); an
+// occupied slot never changes again.  New vertices get dense ids: one global atomic per CTA and round.
+__global__ void __launch_bounds__(256) lattice_insert_kernel(LatticeBufs L) {
+  __shared__ int s_new, s_base;
+  const int T = (int)min((long long)L.counters[5], L.t_cap);
+  const unsigned long long mask = live_mask(L);
+  int max_probe = 0;
+  for (int e0 = blockIdx.x * 256; e0 < T; e0 += gridDim.x * 256) {
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    const int e = e0 + threadIdx.x;
+    bool is_new = false;
+    unsigned long long key = 0, s = 0;
+    if (e < T) {
+      key = L.tkeys[e];
+      s = hash_key(key) & mask;
+      unsigned long long c = __ldcg(L.table_keys + s);
       int probes = 0;
       for (;;) {
-        if (c == key[r]) break;
+        if (c == key) break;
         if (c == kEmptyKey) {
-          c = atomicCAS(L.table_keys + s, kEmptyKey, key[r]);
-          if (c == kEmptyKey) { new_mask |= 1u << r; break; }
-          if (c == key[r]) break;
+          c = atomicCAS(L.table_keys + s, kEmptyKey, key);
+          if (c == kEmptyKey) { is_new = true; break; }
+          if (c == key) break;
         }
-        s = (s + 1) & L.cap_mask;
+        s = (s + 1) & mask;
         c = __ldcg(L.table_keys + s);
         ++probes;
       }
-      slot[r] = s;
       max_probe = max(max_probe, probes);
-      if (real) {
-        L.offsets[(size_t)r * L.P + gp] = (int)s;
-        L.bary[(size_t)r * L.P + gp] = bary[r];
-      }
+      L.tvid[e] = (int)s;
     }
-  }
-  // dense vertex ids: one global atomic per CTA instead of one per new vertex (a single hot address otherwise)
-  const int mine = __popc(new_mask);
-  int local = 0;
-  if (mine) local = atomicAdd(&s_new, mine);
-  __syncthreads();
-  if (threadIdx.x == 0) s_base = s_new ? atomicAdd(L.counters, s_new) : 0;
-  __syncthreads();
-  if (mine) {
-    int id = s_base + local;
+    const int local = is_new ? atomicAdd(&s_new, 1) : 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && s_new) s_base = atomicAdd(L.counters, s_new);
+    __syncthreads();
+    if (is_new) {
+      const long long id = (long long)s_base + local;
+      if (id < L.m_cap) {
+        L.vkeys[id] = key;
+        L.table_ids[s] = (int)id + 1;
+        // every neighbour entry starts as "absent"; lattice_finish_kernel fills in the ones that exist
 #pragma unroll
-    for (int r = 0; r <= kLatD; ++r) {
-      if (new_mask & (1u << r)) {
-        L.vkeys[id] = key[r];
-        L.table_ids[slot[r]] = id + 1;
-        ++id;
+        for (int j = 0; j <= kLatD; ++j) L.nbr[(size_t)j * L.m_cap + id] = make_int2(0, 0);
+      } else {
+        L.table_ids[s] = 0;
+        atomicOr(L.counters + 1, 2);
       }
     }
   }
-  if (bad) atomicExch(L.counters + 1, 1);
   if (max_probe > 0) atomicMax(L.counters + 2, max_probe);
-}
-
-__global__ void lattice_resolve_kernel(LatticeBufs L) {
-  const long long total = 6 * L.P;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x)
-    L.offsets[i] = L.table_ids[L.offsets[i]];
-}
-
-// After the build the vertex count M is known on the device.  The neighbour look-ups (12 per vertex) would be
-// DRAM-latency bound in the worst-case-sized build table, so the M keys are re-inserted into a compact table of
-// 2^k >= 2M slots that reuses the head of the build table's storage and stays L2-resident.
-__device__ __forceinline__ unsigned long long compact_mask(const LatticeBufs &L) {
-  const unsigned m2 = 2u * (unsigned)max(L.counters[0], 512);
-  const unsigned long long cap = 1ULL << (32 - __clz(m2 - 1));
-  return min(cap, L.cap_mask + 1) - 1;
-}
-
-__global__ void lattice_compact_clear_kernel(LatticeBufs L) {
-  const unsigned long long cap = compact_mask(L) + 1;
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < cap;
-       i += (unsigned long long)gridDim.x * blockDim.x)
-    L.table_keys[i] = kEmptyKey;
-}
-
-__global__ void lattice_compact_insert_kernel(LatticeBufs L) {
-  const unsigned long long mask = compact_mask(L);
-  const long long M = L.counters[0];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long key = L.vkeys[i];
-    unsigned long long slot = hash_key(key) & mask;
-    while (atomicCAS(L.table_keys + slot, kEmptyKey, key) != kEmptyKey) slot = (slot + 1) & mask;   // keys are distinct
-    L.table_ids[slot] = (int)i + 1;
-    // every neighbour entry starts as "absent"; lattice_neighbours_kernel fills in the ones that exist
-#pragma unroll
-    for (int j = 0; j <= kLatD; ++j) L.nbr[(size_t)j * L.m_cap + i] = make_int2(0, 0);
-  }
 }
 
 __device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long long mask, unsigned long long key) {
@@ -265,19 +360,25 @@ __device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long lo
   }
 }
 
-// Blur neighbours (permutohedral.cpp:282-294): n1 = key - 1 on every stored coordinate and key[j] + 5 on axis j,
-// n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q carries when it wraps.
-// The relation is symmetric - u = n1_j(v) exactly when v = n2_j(u) - so a thread looks up only n1 (6 instead of 12
-// table walks per vertex) and, when it finds u, also records itself as u's n2.  Entries start as "absent" (0).
-__global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) {
-  const long long M = L.counters[0];
+// (a) list entries: table slot -> vertex row.  (b) blur neighbours (permutohedral.cpp:282-294): n1 = key - 1 on every
+// stored coordinate and key[j] + 5 on axis j, n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q
+// carries when it wraps.  The relation is symmetric - u = n1_j(v) exactly when v = n2_j(u) - so a thread looks up only
+// n1 (6 instead of 12 table walks per vertex) and, when it finds u, also records itself as u's n2.  Entries start as
+// "absent" (0).  (c) the value rows the splat accumulates into are zeroed: thread (vertex, j) owns quads j, j+6, ...
+__global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
+  const long long M = min((long long)L.counters[0], L.m_cap);
+  const int T = (int)min((long long)L.counters[5], L.t_cap);
   const long long total = M * (kLatD + 1);
   const unsigned long long qmask = (1ULL << kQBits) - 1;
-  const unsigned long long tmask = compact_mask(L);
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  const unsigned long long tmask = live_mask(L);
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gstride = (long long)gridDim.x * blockDim.x;
+  for (long long e = gtid; e < T; e += gstride) L.tvid[e] = L.table_ids[L.tvid[e]];
+  const int kq = L.Kp / 4;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long idx = gtid; idx < total; idx += gstride) {
     const long long i = idx / (kLatD + 1);
     const int j = (int)(idx % (kLatD + 1));
+    for (int q = j; q < kq; q += kLatD + 1) reinterpret_cast<float4 *>(L.val0 + (size_t)(i + 1) * L.Kp)[q] = z;
     const unsigned long long key = L.vkeys[i];
     const int r = (int)((key >> (kQBits * kLatD)) & 7);
     const unsigned long long bbits = key >> (kQBits * kLatD + 3);
@@ -297,50 +398,96 @@ __global__ void __launch_bounds__(256) lattice_neighbours_kernel(LatticeBufs L) 
       base[2 * (size_t)(u - 1) + 1] = (int)i + 1;   // vertex i is the n2 of vertex u - 1
     }
   }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < kq) {
+      reinterpret_cast<float4 *>(L.val0)[threadIdx.x] = z;
+      reinterpret_cast<float4 *>(L.val1)[threadIdx.x] = z;
+    }
+    if (threadIdx.x == 0) {
+      L.counters[3] = (int)min(tmask + 1, (unsigned long long)0x7fffffff);
+      L.counters[6] = 1;
+    }
+  }
 }
 
 // ---- compute -------------------------------------------------------------------------------------
+// Only needed when a lattice is splatted a second time: the build leaves val0 zeroed (counters[6]).
 __global__ void lattice_zero_values_kernel(LatticeBufs L) {
-  const long long rows = (long long)L.counters[0] + 1;
+  if (L.counters[6]) return;
+  const long long rows = min((long long)L.counters[0], L.m_cap) + 1;
   const long long total4 = rows * (L.Kp / 4);
   float4 *v0 = reinterpret_cast<float4 *>(L.val0);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
        i += (long long)gridDim.x * blockDim.x)
     v0[i] = z;
-  if (blockIdx.x == 0 && threadIdx.x < L.Kp / 4) reinterpret_cast<float4 *>(L.val1)[threadIdx.x] = z;
 }
 
-__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
+constexpr int kChunk = 24;                       // channels per pass (K = 21 -> one pass)
+constexpr int kPlane = kTilePix + 1;             // odd plane pitch: channel-strided reads hit distinct banks
 
-// Splat (permutohedral.cpp:526-534).  One thread per pixel; the channels of a vertex are contiguous so each
-// (pixel, vertex, 4 channels) is one 128-bit vector reduction in L2.
-__global__ void __launch_bounds__(256) lattice_splat_kernel(LatticeBufs L, const float *__restrict__ ins, int K,
-                                                            int n) {
-  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < L.P;
-       gp += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(gp / n), p = (int)(gp % n);
-    int off[kLatD + 1];
-    float w[kLatD + 1];
+// Splat (permutohedral.cpp:526-534), one CTA per tile.  The tile's pair list, weights and input channels are staged
+// in shared memory; a quarter-warp per distinct vertex walks the vertex's pairs (lane cl sums channels cl, cl + 8,
+// cl + 16) and issues one reduction per vertex row and channel pass.
+__global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins,
+                                                                      int K, int H, int W) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float *in_s = reinterpret_cast<float *>(s_raw);                         // [kChunk][kPlane]
+  float *bary_s = in_s + kChunk * kPlane;                                 // [6][256]
+  unsigned *seg_s = reinterpret_cast<unsigned *>(bary_s + 6 * kTilePix);  // [kTileMaxU]
+  int *vid_s = reinterpret_cast<int *>(seg_s + kTileMaxU);                // [kTileMaxU]
+  unsigned short *plist_s = reinterpret_cast<unsigned short *>(vid_s + kTileMaxU);   // [kTilePairs], 16-byte aligned
+
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+  const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
+  const int n = H * W;
+  const bool ok = x < W && y < H;
+  const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int2 info = L.tile_info[tile];
+  const int U = info.y;
+  const long long gp = (long long)b * n + (long long)y * W + x;
 #pragma unroll
-    for (int r = 0; r <= kLatD; ++r) {
-      off[r] = L.offsets[(size_t)r * L.P + gp];
-      w[r] = L.bary[(size_t)r * L.P + gp];
+  for (int r = 0; r <= kLatD; ++r) bary_s[r * kTilePix + tid] = ok ? L.bary[(size_t)r * L.P + gp] : 0.0f;
+  if (tid < kTilePairs / 8)
+    reinterpret_cast<uint4 *>(plist_s)[tid] = reinterpret_cast<const uint4 *>(L.plist + (size_t)tile * kTilePairs)[tid];
+  for (int u = tid; u < U; u += kTilePix) {
+    seg_s[u] = L.tseg[info.x + u];
+    vid_s[u] = L.tvid[info.x + u];
+  }
+  if (tile == 0 && tid == 0) L.counters[6] = 0;   // val0 is being written
+
+  const int sub = lx >> 3, cl = tid & 7;
+  const float *src0 = ins + (size_t)b * K * n + (size_t)y * W + x;
+  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
+    const int kc = min(kChunk, L.Kp - c0);
+    __syncthreads();   // the previous pass has read in_s
+    {
+      float v[kChunk];
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) v[c] = (ok && c0 + c < K) ? __ldg(src0 + (size_t)(c0 + c) * n) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < kChunk; ++c) in_s[c * kPlane + tid] = v[c];
     }
-    const float *src = ins + (size_t)b * K * n + p;
-    for (int c0 = 0; c0 < L.Kp; c0 += 4) {
-      float4 x;
-      x.x = c0 + 0 < K ? __ldg(src + (size_t)(c0 + 0) * n) : 0.f;
-      x.y = c0 + 1 < K ? __ldg(src + (size_t)(c0 + 1) * n) : 0.f;
-      x.z = c0 + 2 < K ? __ldg(src + (size_t)(c0 + 2) * n) : 0.f;
-      x.w = c0 + 3 < K ? __ldg(src + (size_t)(c0 + 3) * n) : 0.f;
-#pragma unroll
-      for (int r = 0; r <= kLatD; ++r)
-        red_add_v4(L.val0 + (size_t)off[r] * L.Kp + c0,
-                   make_float4(__fmul_rn(w[r], x.x), __fmul_rn(w[r], x.y), __fmul_rn(w[r], x.z), __fmul_rn(w[r], x.w)));
+    __syncthreads();
+    for (int u = ly * 4 + sub; u < U; u += 32) {
+      const unsigned seg = seg_s[u];
+      const int start = seg >> 16, cnt = seg & 0xffff;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+      for (int e = 0; e < cnt; ++e) {
+        const int code = plist_s[start + e];
+        const int pix = code >> 3;
+        const float wv = bary_s[(code & 7) * kTilePix + pix];
+        const float *src = in_s + cl * kPlane + pix;
+        a0 = fmaf(wv, src[0], a0);
+        a1 = fmaf(wv, src[8 * kPlane], a1);
+        a2 = fmaf(wv, src[16 * kPlane], a2);
+      }
+      if (cnt && vid_s[u] > 0) {
+        float *dst = L.val0 + (size_t)vid_s[u] * L.Kp + c0 + cl;
+        if (cl < kc) atomicAdd(dst, a0);
+        if (cl + 8 < kc) atomicAdd(dst + 8, a1);
+        if (cl + 16 < kc) atomicAdd(dst + 16, a2);
+      }
     }
   }
 }
@@ -349,7 +496,7 @@ __global__ void __launch_bounds__(256) lattice_splat_kernel(LatticeBufs L, const
 __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const float *__restrict__ src,
                                                            float *__restrict__ dst, int axis) {
   const int kq = L.Kp / 4;
-  const long long total = (long long)L.counters[0] * kq;
+  const long long total = min((long long)L.counters[0], L.m_cap) * kq;
   const int2 *nb = L.nbr + (size_t)axis * L.m_cap;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -368,301 +515,62 @@ __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const 
   }
 }
 
-// Slice (permutohedral.cpp:554-567) with the optional dense-CRF epilogue (seg_helper.py:888-890).
-template <bool ENERGY>
-__global__ void __launch_bounds__(256) lattice_slice_kernel(LatticeBufs L, const float *__restrict__ values,
-                                                            const float *__restrict__ ins,
-                                                            const float *__restrict__ gate, double *loss_acc,
-                                                            float *__restrict__ outs, int K, int n) {
-  const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
-  float local = 0.0f;
-  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < L.P;
-       gp += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(gp / n), p = (int)(gp % n);
-    int off[kLatD + 1];
-    float w[kLatD + 1];
-#pragma unroll
-    for (int r = 0; r <= kLatD; ++r) {
-      off[r] = L.offsets[(size_t)r * L.P + gp];
-      w[r] = __fmul_rn(L.bary[(size_t)r * L.P + gp], alpha);
-    }
-    const float gt = ENERGY ? __ldg(gate + gp) : 1.0f;
-    float *dst = outs + (size_t)b * K * n + p;
-    const float *src = ins + (size_t)b * K * n + p;
-    // two adjacent quads (one 32-byte sector of each vertex row; rows are 32-byte aligned, Kp % 4 == 0) per pass, so
-    // that a sector is requested by one pair of back-to-back loads instead of twice, five other rows apart
-    for (int c0 = 0; c0 < L.Kp; c0 += 8) {
-      const bool two = c0 + 4 < L.Kp;
-      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-#pragma unroll
-      for (int r = 0; r <= kLatD; ++r) {
-        const float *row = values + (size_t)off[r] * L.Kp + c0;
-        const float4 v0 = *reinterpret_cast<const float4 *>(row);
-        const float4 v1 = two ? *reinterpret_cast<const float4 *>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        acc0.x = __fadd_rn(acc0.x, __fmul_rn(w[r], v0.x)); acc0.y = __fadd_rn(acc0.y, __fmul_rn(w[r], v0.y));
-        acc0.z = __fadd_rn(acc0.z, __fmul_rn(w[r], v0.z)); acc0.w = __fadd_rn(acc0.w, __fmul_rn(w[r], v0.w));
-        acc1.x = __fadd_rn(acc1.x, __fmul_rn(w[r], v1.x)); acc1.y = __fadd_rn(acc1.y, __fmul_rn(w[r], v1.y));
-        acc1.z = __fadd_rn(acc1.z, __fmul_rn(w[r], v1.z)); acc1.w = __fadd_rn(acc1.w, __fmul_rn(w[r], v1.w));
-      }
-      const float a8[8] = {acc0.x, acc0.y, acc0.z, acc0.w, acc1.x, acc1.y, acc1.z, acc1.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (c0 + k < K) {
-          float o = a8[k];
-          if (ENERGY) {
-            o = __fmul_rn(o, gt);
-            local = fmaf(__ldg(src + (size_t)(c0 + k) * n), o, local);
-          }
-          dst[(size_t)(c0 + k) * n] = o;
-        }
-      }
-    }
-  }
-  if (ENERGY) {
-    __shared__ float s_part[8];
-    local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float t = threadIdx.x < (blockDim.x >> 5) ? s_part[threadIdx.x] : 0.0f;
-      t = warp_sum(t);
-      if (threadIdx.x == 0) atomicAdd(loss_acc, (double)t);
-    }
-  }
-}
-
-// ---- tile-local vertex sharing ---------------------------------------------------------------------
-// A 32 x 8 pixel tile touches 6 * 256 (pixel, vertex) pairs but only ~22 % as many distinct vertices (the lattice
-// cells are sigma_xy = 50 pixels wide; measured on the synthetic VOC images: 0.22 at 32 x 8, 0.15 at 32 x 32).  The
-// tile kernels below therefore dedup the vertex ids of a tile in a shared-memory hash table first and touch every
-// distinct vertex row in L2 once per tile instead of once per pair:
-//   splat  pairs are bucketed per vertex (count -> scan -> fill), each vertex sums its contributions from a
-//          shared-memory copy of the tile's input channels and issues ONE sector-wide reduction per 8 channels
-//   slice  the distinct vertex rows are staged in shared memory once and the pixels gather from there
-constexpr int kTileW = 32;
-constexpr int kChunk = 24;                       // channels per pass (K = 21 -> one pass)
-
-__device__ __forceinline__ unsigned tile_hash(int id, int bits) { return ((unsigned)id * 2654435761u) >> (32 - bits); }
-
-// Inserts `id` into the open-addressing table hkey[1 << bits] (-1 = empty); returns the slot.  *won is set for the
-// thread whose CAS created the entry.
-__device__ __forceinline__ int tile_insert(int *hkey, int bits, int id, bool *won) {
-  const unsigned mask = (1u << bits) - 1;
-  unsigned h = tile_hash(id, bits);
-  for (;;) {
-    const int old = atomicCAS(hkey + h, -1, id);
-    if (old == -1) { *won = true; return (int)h; }
-    if (old == id) { *won = false; return (int)h; }
-    h = (h + 1) & mask;
-  }
-}
-
-// Splat (permutohedral.cpp:526-534) with tile-local pre-reduction.  CTA = 256 threads = TH/8 pixels per thread of a
-// 32 x TH tile.  Shared memory: hash keys + (start | count) words, the pair list bucketed by vertex, the list of
-// occupied slots and the tile's input channels [kChunk][pixels + 1].
-template <int TH>
-__global__ void __launch_bounds__(256) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins, int K,
-                                                                 int H, int W) {
-  constexpr int PPT = TH / 8, PIX = kTileW * TH, PAIRS = 6 * PIX;
-  constexpr int BITS = PPT == 1 ? 11 : 12, HS = 1 << BITS;   // load factor <= 0.75 when every pair is distinct
-  constexpr int PLANE = PIX + 1;                               // odd plane pitch: channel-strided reads hit distinct banks
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  int *hkey = reinterpret_cast<int *>(s_raw);                  // [HS]
-  int *hinfo = hkey + HS;                                      // [HS] count, then (start << 16) | count
-  int2 *plist = reinterpret_cast<int2 *>(hinfo + HS);          // [PAIRS] (pixel, weight bits) bucketed by vertex
-  unsigned short *ulist = reinterpret_cast<unsigned short *>(plist + PAIRS);   // [PAIRS] occupied slots
-  float *in_s = reinterpret_cast<float *>(ulist + PAIRS);      // [kChunk][PLANE]
-  __shared__ int s_scan[8];
-  __shared__ int s_U;
-
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int n = H * W;
-  const int tid = threadIdx.x, lx = tid & 31, ly0 = tid >> 5;
-  for (int i = tid; i < HS; i += 256) { hkey[i] = -1; hinfo[i] = 0; }
-  if (tid == 0) s_U = 0;
-  __syncthreads();
-
-  int hslot[PPT][6], hpos[PPT][6];
-  float wgt[PPT][6];
-  // every vertex id and weight of the thread's pixels is requested before the first shared-memory atomic (the
-  // compiler does not move loads across atomics)
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int x = x0 + lx, y = y0 + ly0 + 8 * j;
-    const bool ok = x < W && y < H;
-    const long long gp = (long long)b * n + (long long)y * W + x;
-#pragma unroll
-    for (int r = 0; r <= kLatD; ++r) {
-      hslot[j][r] = ok ? L.offsets[(size_t)r * L.P + gp] : -1;
-      wgt[j][r] = ok ? L.bary[(size_t)r * L.P + gp] : 0.0f;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-#pragma unroll
-    for (int r = 0; r <= kLatD; ++r) {
-      if (hslot[j][r] >= 0) {
-        bool won;
-        const int h = tile_insert(hkey, BITS, hslot[j][r], &won);
-        hslot[j][r] = h;
-        hpos[j][r] = atomicAdd(hinfo + h, 1);
-      }
-    }
-  }
-  __syncthreads();
-  // exclusive scan of the counts (HS / 256 consecutive slots per thread) + list of the occupied slots
-  {
-    constexpr int PER = HS / 256;
-    int cnt[PER], sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { cnt[i] = hinfo[tid * PER + i]; sum += cnt[i]; }
-    int incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((tid & 31) >= o) incl += t;
-    }
-    if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
-    __syncthreads();
-    int base = incl - sum;
-    for (int wv = 0; wv < (tid >> 5); ++wv) base += s_scan[wv];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      if (cnt[i]) {
-        hinfo[tid * PER + i] = (base << 16) | cnt[i];
-        ulist[atomicAdd(&s_U, 1)] = (unsigned short)(tid * PER + i);
-        base += cnt[i];
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < PPT; ++j)
-#pragma unroll
-    for (int r = 0; r <= kLatD; ++r)
-      if (hslot[j][r] >= 0)
-        plist[(hinfo[hslot[j][r]] >> 16) + hpos[j][r]] = make_int2((ly0 + 8 * j) * kTileW + lx, __float_as_int(wgt[j][r]));
-  const int U = s_U;
-
-  const int sub = (tid & 31) >> 3, cl = tid & 7, wv = tid >> 5;
-  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
-    const int kc = min(kChunk, L.Kp - c0);
-    __syncthreads();   // the pair list is complete / the previous pass has read in_s
-    for (int i0 = tid; i0 < kc * PIX; i0 += 4 * 256) {   // four loads in flight per thread
-      float v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * 256;
-        const int c = i / PIX, pl = i - c * PIX;
-        const int x = x0 + (pl & 31), y = y0 + (pl >> 5);
-        v[k] = 0.0f;
-        if (i < kc * PIX && c0 + c < K && x < W && y < H) v[k] = __ldg(ins + ((size_t)b * K + c0 + c) * n + (size_t)y * W + x);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * 256;
-        const int c = i / PIX, pl = i - c * PIX;
-        if (i < kc * PIX) in_s[c * PLANE + pl] = v[k];
-      }
-    }
-    __syncthreads();
-    // a quarter-warp per vertex: lane cl sums channels cl, cl + 8, cl + 16 over the vertex's pairs
-    for (int u = wv * 4 + sub; u < U; u += 32) {
-      const int slot = ulist[u];
-      const int info = hinfo[slot];
-      const int start = info >> 16, cnt = info & 0xffff;
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-      for (int e = 0; e < cnt; ++e) {
-        const int2 pw = plist[start + e];
-        const float wv_ = __int_as_float(pw.y);
-        const float *src = in_s + cl * PLANE + pw.x;
-        a0 = fmaf(wv_, src[0], a0);
-        a1 = fmaf(wv_, src[8 * PLANE], a1);
-        a2 = fmaf(wv_, src[16 * PLANE], a2);
-      }
-      float *dst = L.val0 + (size_t)hkey[slot] * L.Kp + c0 + cl;
-      if (cl < kc) atomicAdd(dst, a0);
-      if (cl + 8 < kc) atomicAdd(dst + 8, a1);
-      if (cl + 16 < kc) atomicAdd(dst + 16, a2);
-    }
-  }
-}
-
-// Slice (permutohedral.cpp:554-567) + optional dense-CRF epilogue with the distinct vertex rows of a 32 x 8 tile staged
-// in shared memory (up to kSliceRows of them; pairs beyond that read L2 directly).
+// Slice (permutohedral.cpp:554-567) + optional dense-CRF epilogue (seg_helper.py:888-890), one CTA per tile.  The
+// tile's distinct vertex rows (up to kSliceRows of them; list entries beyond that are read from L2 directly) are staged
+// in shared memory once per channel pass and the pixels gather from there through their 16-bit list indices.
 constexpr int kSliceRows = 512;
+constexpr int kRowPitch = kChunk + 4;             // 28 floats: row starts fall on 8 different bank quads
 template <bool ENERGY>
-__global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
-                                                                 const float *__restrict__ ins,
-                                                                 const float *__restrict__ gate, double *loss_acc,
-                                                                 float *__restrict__ outs, int K, int H, int W) {
-  constexpr int BITS = 11, HS = 1 << BITS, TH = 8;
-  __shared__ int hkey[HS];
-  __shared__ int hval[HS];                      // local row index of the slot's vertex
-  __shared__ int urow_id[kSliceRows];           // vertex id of local row u
+__global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
+                                                                         const float *__restrict__ ins,
+                                                                         const float *__restrict__ gate, double *loss_acc,
+                                                                         float *__restrict__ outs, int K, int H, int W) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  float *rows = reinterpret_cast<float *>(s_raw);   // [kSliceRows][kChunk]
-  __shared__ int s_U;
-  __shared__ float s_part[8];
+  float *rows = reinterpret_cast<float *>(s_raw);   // [kSliceRows][kRowPitch]
+  __shared__ int vid_s[kSliceRows];
+  __shared__ float s_part[kTilePix / 32];
   const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * TH, b = blockIdx.z;
-  const int n = H * W;
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-  for (int i = tid; i < HS; i += 256) hkey[i] = -1;
-  if (tid == 0) s_U = 0;
-  __syncthreads();
-  const int x = x0 + lx, y = y0 + ly;
+  const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
+  const int n = H * W;
   const bool ok = x < W && y < H;
+  const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int2 info = L.tile_info[tile];
+  const int Us = min(info.y, kSliceRows);
   const long long gp = (long long)b * n + (long long)y * W + x;
-  int id[kLatD + 1], hs[kLatD + 1];
+  const bool poisoned = L.counters[1] != 0;      // key range / capacity error: fail loudly, never alias silently
+  int u_r[kLatD + 1];
   float w[kLatD + 1];
 #pragma unroll
-  for (int r = 0; r <= kLatD; ++r) {   // all loads first: the compiler does not move loads across the atomics below
-    id[r] = ok ? L.offsets[(size_t)r * L.P + gp] : 0;
+  for (int r = 0; r <= kLatD; ++r) {
+    u_r[r] = ok ? (int)L.lidx[(size_t)r * L.P + gp] : 0;
     w[r] = ok ? __fmul_rn(L.bary[(size_t)r * L.P + gp], alpha) : 0.0f;
-    hs[r] = 0;
   }
+  for (int u = tid; u < Us; u += kTilePix) vid_s[u] = L.tvid[info.x + u];
   const float gt = (ENERGY && ok) ? __ldg(gate + gp) : 1.0f;
+  const size_t at0 = (size_t)b * K * n + (size_t)y * W + x;
   float s_in[kChunk];                   // energy epilogue: the pixel's own inputs of the first channel pass
   if (ENERGY) {
 #pragma unroll
-    for (int c = 0; c < kChunk; ++c)
-      s_in[c] = (ok && c < K) ? __ldg(ins + ((size_t)b * K + c) * n + (size_t)y * W + x) : 0.0f;
+    for (int c = 0; c < kChunk; ++c) s_in[c] = (ok && c < K) ? __ldg(ins + at0 + (size_t)c * n) : 0.0f;
   }
-#pragma unroll
-  for (int r = 0; r <= kLatD; ++r) {
-    if (ok) {
-      bool won;
-      hs[r] = tile_insert(hkey, BITS, id[r], &won);
-      if (won) {
-        const int u = atomicAdd(&s_U, 1);
-        hval[hs[r]] = u;
-        if (u < kSliceRows) urow_id[u] = id[r];
-      }
-    }
-  }
-  __syncthreads();
-  int u_r[kLatD + 1];
-#pragma unroll
-  for (int r = 0; r <= kLatD; ++r) u_r[r] = ok ? hval[hs[r]] : 0;
-  const int U = min(s_U, kSliceRows);
   float local = 0.0f;
   for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
     const int kc = min(kChunk, L.Kp - c0), kq = kc >> 2;
-    __syncthreads();
-    for (int i0 = tid; i0 < U * kq; i0 += 4 * 256) {   // four row quads in flight per thread
+    __syncthreads();                     // vid_s is complete / the previous pass has read `rows`
+    for (int i0 = tid; i0 < Us * kq; i0 += 4 * kTilePix) {   // four row quads in flight per thread
       float4 v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * 256;
+        const int i = i0 + k * kTilePix;
         const int u = i / kq, q = i - u * kq;
-        if (i < U * kq) v[k] = *reinterpret_cast<const float4 *>(values + (size_t)urow_id[u] * L.Kp + c0 + 4 * q);
+        if (i < Us * kq) v[k] = *reinterpret_cast<const float4 *>(values + (size_t)vid_s[u] * L.Kp + c0 + 4 * q);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * 256;
+        const int i = i0 + k * kTilePix;
         const int u = i / kq, q = i - u * kq;
-        if (i < U * kq) reinterpret_cast<float4 *>(rows)[u * (kChunk / 4) + q] = v[k];
+        if (i < Us * kq) *reinterpret_cast<float4 *>(rows + u * kRowPitch + 4 * q) = v[k];
       }
     }
     __syncthreads();
@@ -674,8 +582,8 @@ __global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs 
 #pragma unroll
         for (int r = 0; r <= kLatD; ++r) {
           const float4 v = u_r[r] < kSliceRows
-                               ? reinterpret_cast<const float4 *>(rows)[u_r[r] * (kChunk / 4) + q]
-                               : *reinterpret_cast<const float4 *>(values + (size_t)id[r] * L.Kp + c0 + 4 * q);
+                               ? *reinterpret_cast<const float4 *>(rows + u_r[r] * kRowPitch + 4 * q)
+                               : *reinterpret_cast<const float4 *>(values + (size_t)L.tvid[info.x + u_r[r]] * L.Kp + c0 + 4 * q);
           acc.x = __fadd_rn(acc.x, __fmul_rn(w[r], v.x));
           acc.y = __fadd_rn(acc.y, __fmul_rn(w[r], v.y));
           acc.z = __fadd_rn(acc.z, __fmul_rn(w[r], v.z));
@@ -686,13 +594,12 @@ __global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs 
         for (int k = 0; k < 4; ++k) {
           const int c = c0 + 4 * q + k;
           if (c < K) {
-            float o = a4[k];
-            const size_t at = ((size_t)b * K + c) * n + (size_t)y * W + x;
+            float o = poisoned ? __int_as_float(0x7fc00000) : a4[k];
             if (ENERGY) {
               o = __fmul_rn(o, gt);
-              local = fmaf(c0 == 0 ? s_in[4 * q + k] : __ldg(ins + at), o, local);
+              local = fmaf(c0 == 0 ? s_in[4 * q + k] : __ldg(ins + at0 + (size_t)c * n), o, local);
             }
-            outs[at] = o;
+            outs[at0 + (size_t)c * n] = o;
           }
         }
       }
@@ -700,10 +607,10 @@ __global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs 
   }
   if (ENERGY) {
     local = warp_sum(local);
-    if ((tid & 31) == 0) s_part[tid >> 5] = local;
+    if (lx == 0) s_part[ly] = local;
     __syncthreads();
     if (tid < 32) {
-      float t = tid < 8 ? s_part[tid] : 0.0f;
+      float t = tid < kTilePix / 32 ? s_part[tid] : 0.0f;
       t = warp_sum(t);
       if (tid == 0) atomicAdd(loss_acc, (double)t);
     }
@@ -711,125 +618,117 @@ __global__ void __launch_bounds__(256, 3) lattice_slice_tile_kernel(LatticeBufs 
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static unsigned long long table_capacity(long long m_cap) {
+static unsigned long long table_capacity(long long t_cap) {
   unsigned long long cap = 1024;
-  // m_cap is the worst case (six new vertices per pixel; natural images stay below 2.5 n), so the load factor is
-  // at most 0.8 and in practice below 0.1
-  while (cap < (unsigned long long)m_cap + (unsigned long long)m_cap / 4) cap <<= 1;
+  // t_cap is the worst case (six new list entries per pixel); the build uses the first 2^k >= 2T slots, so the
+  // allocation only bounds the load factor in the worst case (<= 0.8)
+  while (cap < (unsigned long long)t_cap + (unsigned long long)t_cap / 4) cap <<= 1;
   return cap;
 }
 
 // Images per lattice: up to kMaxImagesPerLattice (the key's image field).  Smaller chunks whose two value buffers fit
-// in L2 were measured and are slower at every size (VOC B = 32: 2.73 ms per step at 64, 2.80 at 16, 2.95 at 8 - the
-// blur passes are not HBM-bound and the smaller launches fill the GPU worse).  COSA_LATTICE_CHUNK overrides (A/B).
+// in L2 were measured in round 1 and are slower at every size (the blur passes are not HBM-bound and smaller launches
+// fill the GPU worse).
 int lattice_chunk_images(int N, int K, int H, int W) {
   (void)K; (void)H; (void)W;
-  static int forced = -1;
-  if (forced < 0) {
-    const char *e = getenv("COSA_LATTICE_CHUNK");
-    forced = e ? atoi(e) : 0;
-  }
-  int c = forced > 0 ? min(forced, kMaxImagesPerLattice) : kMaxImagesPerLattice;
-  c = min(c, N);
+  const int c = min(kMaxImagesPerLattice, N);
   const int chunks = (N + c - 1) / c;
   return (N + chunks - 1) / chunks;   // even chunks
 }
 
+struct LatticeDims {
+  long long n, n_pad, P, m_cap, t_cap, tiles;
+  unsigned long long cap;
+  int tiles_x, tiles_y, Kp;
+};
+
+static LatticeDims lattice_dims(int N, int K, int H, int W) {
+  LatticeDims d;
+  d.n = (long long)H * W;
+  d.n_pad = (d.n + 3) & ~3LL;
+  d.P = (long long)N * d.n;
+  d.t_cap = 6LL * N * d.n_pad;
+  d.m_cap = d.t_cap;
+  d.cap = table_capacity(d.t_cap);
+  d.tiles_x = ceil_div(W, kTileW);
+  d.tiles_y = ceil_div(H, kTileH);
+  d.tiles = (long long)N * d.tiles_x * d.tiles_y;
+  d.Kp = (K + 3) & ~3;
+  return d;
+}
+
+template <typename F>
+static void lattice_layout(const LatticeDims &d, F &&take) {
+  take(0, (size_t)8 * sizeof(int));                                   // counters first: same place for every chunk size
+  take(1, (size_t)d.cap * sizeof(unsigned long long));                // table_keys
+  take(2, (size_t)d.cap * sizeof(int));                               // table_ids
+  take(3, (size_t)d.m_cap * sizeof(unsigned long long));              // vkeys
+  take(4, (size_t)d.tiles * sizeof(int2));                            // tile_info
+  take(5, (size_t)d.t_cap * sizeof(unsigned long long));              // tkeys
+  take(6, (size_t)d.t_cap * sizeof(int));                             // tvid
+  take(7, (size_t)d.t_cap * sizeof(unsigned));                        // tseg
+  take(8, (size_t)d.tiles * kTilePairs * sizeof(unsigned short));     // plist
+  take(9, (size_t)6 * d.P * sizeof(unsigned short));                  // lidx
+  take(10, (size_t)6 * d.P * sizeof(float));                          // bary
+  take(11, (size_t)6 * d.m_cap * sizeof(int2));                       // nbr
+  take(12, (size_t)(d.m_cap + 1) * d.Kp * sizeof(float));             // val0
+  take(13, (size_t)(d.m_cap + 1) * d.Kp * sizeof(float));             // val1
+}
+
 size_t lattice_ws_bytes(int N, int K, int H, int W) {
-  const long long n = (long long)H * W, n_pad = (n + 3) & ~3LL;
-  const long long P = (long long)N * n, m_cap = 6LL * N * n_pad;
-  const unsigned long long cap = table_capacity(m_cap);
-  const int Kp = (K + 3) & ~3;
   size_t b = 0;
-  b += align_up(cap * sizeof(unsigned long long), 256);
-  b += align_up(cap * sizeof(int), 256);
-  b += align_up((size_t)m_cap * sizeof(unsigned long long), 256);
-  b += align_up(8 * sizeof(int), 256);
-  b += 2 * align_up((size_t)6 * P * sizeof(float), 256);
-  b += align_up((size_t)6 * m_cap * sizeof(int2), 256);
-  b += 2 * align_up((size_t)(m_cap + 1) * Kp * sizeof(float), 256);
+  lattice_layout(lattice_dims(N, K, H, W), [&](int, size_t bytes) { b += align_up(bytes, 256); });
   return b;
 }
 
 void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
-  const long long n = (long long)H * W, n_pad = (n + 3) & ~3LL;
-  L->P = (long long)N * n;
-  L->m_cap = 6LL * N * n_pad;
-  const unsigned long long cap = table_capacity(L->m_cap);
-  L->cap_mask = cap - 1;
-  L->Kp = (K + 3) & ~3;
-  Arena a(ws);
-  L->counters = a.take<int>(8);   // first: the same place for every chunk size (cosa_bilateral_stats)
-  L->table_keys = a.take<unsigned long long>(cap);
-  L->table_ids = a.take<int>(cap);
-  L->vkeys = a.take<unsigned long long>((size_t)L->m_cap);
-  L->offsets = a.take<int>((size_t)6 * L->P);
-  L->bary = a.take<float>((size_t)6 * L->P);
-  L->nbr = a.take<int2>((size_t)6 * L->m_cap);
-  L->val0 = a.take<float>((size_t)(L->m_cap + 1) * L->Kp);
-  L->val1 = a.take<float>((size_t)(L->m_cap + 1) * L->Kp);
-}
-
-static int persistent_blocks(long long work_items, int per_block) {
-  return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(work_items, per_block)));
+  const LatticeDims d = lattice_dims(N, K, H, W);
+  L->P = d.P; L->m_cap = d.m_cap; L->t_cap = d.t_cap; L->cap_mask = d.cap - 1;
+  L->tiles_x = d.tiles_x; L->tiles_y = d.tiles_y; L->Kp = d.Kp;
+  char *p = (char *)ws;
+  void *slot[14];
+  lattice_layout(d, [&](int i, size_t bytes) { slot[i] = p; p += align_up(bytes, 256); });
+  L->counters = (int *)slot[0];
+  L->table_keys = (unsigned long long *)slot[1];
+  L->table_ids = (int *)slot[2];
+  L->vkeys = (unsigned long long *)slot[3];
+  L->tile_info = (int2 *)slot[4];
+  L->tkeys = (unsigned long long *)slot[5];
+  L->tvid = (int *)slot[6];
+  L->tseg = (unsigned *)slot[7];
+  L->plist = (unsigned short *)slot[8];
+  L->lidx = (unsigned short *)slot[9];
+  L->bary = (float *)slot[10];
+  L->nbr = (int2 *)slot[11];
+  L->val0 = (float *)slot[12];
+  L->val1 = (float *)slot[13];
 }
 
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
                   bool first_chunk, cudaStream_t stream) {
   if (N < 1 || N > kMaxImagesPerLattice) return COSA_E_ARG;
+  if (L.tiles_y > 65535) return COSA_E_ARG;
   const long long n = (long long)H * W;
   const int n_pad = (int)((n + 3) & ~3LL);
-  const unsigned long long cap = L.cap_mask + 1;
-  COSA_LAUNCH(lattice_clear_kernel, persistent_blocks((long long)(cap / 2), 256), 256, 0, stream, L.table_keys, cap,
-              L.counters, first_chunk ? 1 : 0);
-  const long long total = (long long)N * n_pad;
-  COSA_LAUNCH(lattice_build_kernel, (unsigned)ceil_div_ll(total, 256), 256, 0, stream, L, images, make_embed_const(),
-              N, H, W, n_pad, sigmargb, sigmaxy);
-  COSA_LAUNCH(lattice_resolve_kernel, persistent_blocks(6 * L.P, 256), 256, 0, stream, L);
-  // the vertex count lives on the device: size the grid for the SMs and let the kernel read it
-  COSA_LAUNCH(lattice_compact_clear_kernel, sm_count() * 8, 256, 0, stream, L);
-  COSA_LAUNCH(lattice_compact_insert_kernel, sm_count() * 8, 256, 0, stream, L);
-  COSA_LAUNCH(lattice_neighbours_kernel, sm_count() * 8, 256, 0, stream, L);
+  COSA_LAUNCH(lattice_reset_kernel, 1, 1, 0, stream, L.counters, first_chunk ? 1 : 0);
+  const dim3 grid(L.tiles_x, L.tiles_y, N);
+  COSA_LAUNCH(lattice_tile_build_kernel, grid, kTilePix, 0, stream, L, images, make_embed_const(), H, W, n_pad,
+              sigmargb, sigmaxy);
+  // T and M live on the device: size the grids for the SMs and let the kernels read the counts
+  COSA_LAUNCH(lattice_table_clear_kernel, sm_count() * 8, 256, 0, stream, L);
+  COSA_LAUNCH(lattice_insert_kernel, sm_count() * 8, 256, 0, stream, L);
+  COSA_LAUNCH(lattice_finish_kernel, sm_count() * 8, 256, 0, stream, L);
   return 0;
 }
 
-// COSA_LATTICE_PIXEL=1 selects the one-thread-per-pixel splat / slice kernels (A/B runs); COSA_SPLAT_TH=16 the
-// 32 x 16 splat tile.
-static int lattice_env(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-static bool lattice_per_pixel() {
-  static int v = -1;
-  if (v < 0) v = lattice_env("COSA_LATTICE_PIXEL", 0) ? 1 : 0;
-  return v == 1;
-}
-
-template <int TH>
-static int launch_splat_tile(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
-  constexpr int PIX = kTileW * TH, PAIRS = 6 * PIX, HS = TH == 8 ? 2048 : 4096;
-  const size_t smem = (size_t)HS * 8 + (size_t)PAIRS * 8 + (size_t)PAIRS * 2 + (size_t)kChunk * (PIX + 1) * 4;
-  static bool attr = false;
-  if (!attr) {
-    COSA_CUDA(cudaFuncSetAttribute(lattice_splat_tile_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  const dim3 grid(ceil_div(W, kTileW), ceil_div(H, TH), N);
-  COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<TH>, grid, 256, smem, stream, L, ins, K, H, W);
-  return 0;
+static size_t splat_smem_bytes() {
+  return (size_t)kChunk * kPlane * 4 + (size_t)6 * kTilePix * 4 + (size_t)kTileMaxU * 8 + (size_t)kTilePairs * 2;
 }
 
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
-  const int n = H * W;
   COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
-  if (lattice_per_pixel()) {
-    COSA_LAUNCH(lattice_splat_kernel, persistent_blocks(L.P, 256), 256, 0, stream, L, ins, K, n);
-  } else {
-    static int th = 0;
-    if (!th) th = lattice_env("COSA_SPLAT_TH", 8) == 16 ? 16 : 8;
-    if (th == 16) COSA_CHECK(launch_splat_tile<16>(L, ins, N, K, H, W, stream));
-    else COSA_CHECK(launch_splat_tile<8>(L, ins, N, K, H, W, stream));
-  }
+  const dim3 grid(L.tiles_x, L.tiles_y, N);
+  COSA_LAUNCH(lattice_splat_tile_kernel, grid, kTilePix, splat_smem_bytes(), stream, L, ins, K, H, W);
   float *src = L.val0, *dst = L.val1;
   for (int axis = 0; axis <= kLatD; ++axis) {
     COSA_LAUNCH(lattice_blur_kernel, sm_count() * 8, 256, 0, stream, L, src, dst, axis);
@@ -840,32 +739,22 @@ int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int
 
 int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, double *loss_acc, float *outs, int N,
                   int K, int H, int W, cudaStream_t stream) {
-  const int n = H * W;
-  static int slice_tile = -1;
-  if (slice_tile < 0) slice_tile = lattice_env("COSA_SLICE_TILE", 0) ? 1 : 0;   // measured equal: the simple one is the default
-  if (lattice_per_pixel() || !slice_tile) {
-    const int blocks = persistent_blocks(L.P, 256);
-    if (gate) {
-      COSA_LAUNCH(lattice_slice_kernel<true>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
-    } else {
-      COSA_LAUNCH(lattice_slice_kernel<false>, blocks, 256, 0, stream, L, L.val0, ins, gate, loss_acc, outs, K, n);
-    }
-    return 0;
-  }
-  const size_t smem = (size_t)kSliceRows * kChunk * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  const size_t smem = (size_t)kSliceRows * kRowPitch * sizeof(float);   // 56 KB: opt-in, per device
+  static bool attr_done[64] = {};
+  int dev = 0;
+  COSA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  const dim3 grid(ceil_div(W, kTileW), ceil_div(H, 8), N);
+  const dim3 grid(L.tiles_x, L.tiles_y, N);
   if (gate) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<true>, grid, 256, smem, stream, L, L.val0, ins,
-                  gate, loss_acc, outs, K, H, W);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<true>, grid, kTilePix, smem, stream, L, L.val0,
+                  ins, gate, loss_acc, outs, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<false>, grid, 256, smem, stream, L, L.val0, ins,
-                  gate, loss_acc, outs, K, H, W);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<false>, grid, kTilePix, smem, stream, L, L.val0,
+                  ins, gate, loss_acc, outs, K, H, W);
   }
   return 0;
 }
@@ -903,11 +792,12 @@ extern "C" int cosa_bilateral_stats(const void *ws, int N, int K, int H, int W, 
   cudaStream_t s = (cudaStream_t)stream;
   LatticeBufs L;
   lattice_carve(const_cast<void *>(ws), lattice_chunk_images(N, K, H, W), K, H, W, &L);
-  int h[5];
+  int h[6];
   COSA_CUDA(cudaMemcpyAsync(h, L.counters, sizeof(h), cudaMemcpyDeviceToHost, s));
   COSA_CUDA(cudaStreamSynchronize(s));
   stats[0] = (long long)h[0] + h[4];   // vertices of all chunks of the last call
-  stats[1] = h[1]; stats[2] = (long long)(L.cap_mask + 1); stats[3] = h[2];
+  stats[1] = h[1]; stats[2] = h[3]; stats[3] = h[2];
+  if (h[1] & 2) return COSA_E_WORKSPACE;
   return h[1] ? COSA_E_KEYRANGE : 0;
 }
 
@@ -931,6 +821,10 @@ extern "C" int cosa_bilateralfilter_batch_host(const float *images, const float 
     cudaMemcpy(d_in, ins, (size_t)N * K * n * sizeof(float), cudaMemcpyHostToDevice);
     rc = cosa_bilateralfilter_batch(d_img, d_in, d_out, N, K, H, W, sigmargb, sigmaxy, d_ws, ws_bytes, nullptr);
     if (rc == 0) rc = (int)cudaMemcpy(outs, d_out, (size_t)N * K * n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (rc == 0) {   // the host form is synchronous: report a key-range / capacity error instead of returning NaNs
+      long long st[4];
+      rc = cosa_bilateral_stats(d_ws, N, K, H, W, st, nullptr);
+    }
   }
   cudaFree(d_img); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
   return rc;

@@ -19,8 +19,11 @@ import torch
 import torch.nn.functional as F
 from torch.autograd import Function
 
-from . import _lib
+from . import _lazy, _lib
 from .par import PAR
+
+IMAGENET_MEAN = (123.675, 116.28, 103.53)
+IMAGENET_STD = (58.395, 57.12, 57.375)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -121,33 +124,62 @@ def multi_scale_camseg(model, imgs, scales):
     return cam, cam_aux, seg
 
 
-def denormalize_img(imgs, mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375)):
+def denormalize_img(imgs, mean=IMAGENET_MEAN, std=IMAGENET_STD, lazy=True):
     """[0,1] image from the ImageNet-normalised network input, ``(uint8)(imgs * std + mean) / 255``
-    (utils/torch_helper.py:354-367; main.py:117 feeds the result to cam2mask / PAR)."""
-    import ctypes
-    lib = _lib.load()
+    (utils/torch_helper.py:354-367; main.py:117 feeds the result to cam2mask / PAR).
+
+    Returns a :class:`cosa_b200._lazy.LazyTensor` by default: ``cam2mask`` de-normalises inside its first kernel and
+    the [B,3,H,W] image is never written; any other use computes it with the stand-alone kernel first (same values
+    either way).  ``lazy=False`` computes it at once."""
     imgs = _lib.dev_f32(imgs, "imgs")
     b, c, h, w = imgs.shape
     if c != 3:
         raise ValueError("denormalize_img expects [B,3,H,W]")
-    out = torch.empty_like(imgs)
-    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
-    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
-    with torch.cuda.device(imgs.device):
-        _lib.check(lib.cosa_denormalize_img(_lib.ptr(imgs), _lib.ptr(out), b, h * w, m, sd, _lib.stream_ptr()))
-    return out
+    mean_t, std_t = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+
+    def produce():
+        lib = _lib.load()
+        out = torch.empty_like(imgs)
+        m = (ctypes.c_float * 3)(*mean_t)
+        sd = (ctypes.c_float * 3)(*std_t)
+        with torch.cuda.device(imgs.device):
+            _lib.check(lib.cosa_denormalize_img(_lib.ptr(imgs), _lib.ptr(out), b, h * w, m, sd, _lib.stream_ptr()))
+        return out
+
+    if not lazy:
+        return produce()
+    return _lazy.LazyTensor("denormalize_img", (imgs, mean_t, std_t), produce, imgs)
 
 
-def cam_validation(cam, cls_label):
-    lib = _lib.load()
+def cam_validation(cam, cls_label, lazy=True):
+    """``cam * cls_label[:, :, None, None]`` (utils/seg_helper.py:547-551).
+
+    Returns a :class:`cosa_b200._lazy.LazyTensor` by default: ``cam2mask`` (its only consumer in main.py:137-166) reads
+    only the planes of present classes and applies the label factor itself, so the B*(C-1) planes (18 of 20 all-zero
+    at VOC) are never written; any other use computes the product with the stand-alone kernel first.  ``lazy=False``
+    computes it at once."""
     cam = _lib.dev_f32(cam, "cam")
     cls_label = _lib.dev_f32(cls_label.to(cam.device), "cls_label")
     b, c, h, w = cam.shape
-    out = torch.empty_like(cam)
-    with torch.cuda.device(cam.device):
-        _lib.check(lib.cosa_cam_validation(_lib.ptr(cam), _lib.ptr(cls_label), _lib.ptr(out), b, c, h * w,
-                                           _lib.stream_ptr()))
-    return out
+    assert cls_label.shape == (b, c), "cls_label must be [B, C-1]"
+
+    def produce():
+        lib = _lib.load()
+        out = torch.empty_like(cam)
+        with torch.cuda.device(cam.device):
+            _lib.check(lib.cosa_cam_validation(_lib.ptr(cam), _lib.ptr(cls_label), _lib.ptr(out), b, c, h * w,
+                                               _lib.stream_ptr()))
+        return out
+
+    if not lazy:
+        return produce()
+    return _lazy.LazyTensor("cam_validation", (cam, cls_label), produce, cam)
+
+
+def _same_labels(a, b):
+    """True when two cls_label tensors are the same device data (what lets a pending cam_validation be folded in)."""
+    return (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+            and a.stride() == b.stride())
 
 
 def cam_to_label(cam,
@@ -188,11 +220,15 @@ def cam_to_label(cam,
 # ----------------------------------------------------------------------------------------------------
 # cam2mask
 # ----------------------------------------------------------------------------------------------------
+_PROPAGATE_ALL = [bool(os.environ.get("COSA_CAM2MASK_ALL_CHANNELS"))]
+
+
 def cam2mask_propagate_all_channels(on):
-    """``True``: PAR propagates every live channel of both threshold stacks, as the reference does.  ``False``
-    (default): the last live channel of each stack is derived from the channel sum (see include/cosa_b200.h,
-    ``cosa_cam2mask_set_all_channels``)."""
-    _lib.check(_lib.load().cosa_cam2mask_set_all_channels(int(bool(on))))
+    """Default of ``cam2mask(..., propagate_all_channels=None)``.  ``True``: PAR propagates every live channel of
+    both threshold stacks, as the reference does.  ``False`` (default): the last live channel of each stack is
+    derived from the channel sum (include/cosa_b200.h, ``COSA_CAM2MASK_ALL_CHANNELS``); labels then differ from the
+    all-channel evaluation only at numerical ties of the reference's own argmax (margin ~1e-7)."""
+    _PROPAGATE_ALL[0] = bool(on)
 
 
 def cam2mask(
@@ -206,6 +242,7 @@ def cam2mask(
         ignore_index=255,
         downscale=2,
         return_parts=False,
+        propagate_all_channels=None,
 ):
     """Pseudo-label map [B,H,W] float32 with values {0..C-1, ignore_index} (seg_helper.py:721-785).
 
@@ -214,15 +251,31 @@ def cam2mask(
     per image exactly like the reference; only the resize/argmax tail then runs in this package's kernels).
     """
     lib = _lib.load()
+    generic = refine_model is not None and refine_model is not False and not isinstance(refine_model, PAR)
+    flags = 0
+    denorm = None
+    # pending producers (denormalize_img / cam_validation of this package) are folded into the first kernel
+    src = None if generic else _lazy.pending(images, "denormalize_img")
+    if src is not None:
+        images, denorm = src[0], (src[1], src[2])
+    src = None if generic else _lazy.pending(cams, "cam_validation")
+    if src is not None and isinstance(cls_labels, torch.Tensor) and cls_labels.is_cuda \
+            and _same_labels(_lib.dev_f32(cls_labels, "cls_labels"), src[1]):
+        cams = src[0]
+        flags |= 4                                                          # COSA_CAM2MASK_CAMS_UNVALIDATED
     images = _lib.dev_f32(images, "images")
     cams = _lib.dev_f32(cams, "cams")
     cls_labels = _lib.dev_f32(cls_labels.to(cams.device), "cls_labels")
     b, _, h, w = images.shape
     c1 = cams.shape[1]
-    if refine_model is not None and refine_model is not False and not isinstance(refine_model, PAR):
+    if generic:
         return _cam2mask_generic(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model,
                                  ignore_index, downscale)
     use_par = isinstance(refine_model, PAR)
+    if propagate_all_channels is None:
+        propagate_all_channels = _PROPAGATE_ALL[0]
+    if propagate_all_channels:
+        flags |= 2                                                          # COSA_CAM2MASK_ALL_CHANNELS
     dev = cams.device
     boxes = _lib.resolve_boxes(img_boxes, b, h, w, dev)
     out = torch.empty((b, h, w), dtype=torch.float32, device=dev)
@@ -231,7 +284,6 @@ def cam2mask(
     n_dil = len(refine_model.dilations) if use_par else 0
     with torch.cuda.device(dev):
         nbytes = lib.cosa_cam2mask_ws_bytes(b, c1, h, w, int(downscale or 0), int(use_par), n_dil)
-        flags = 0
         share = refine_model._shared if use_par else None
         uses_before = _lib.workspace_uses(dev)
         ws = _lib.workspace(nbytes, dev)
@@ -240,16 +292,18 @@ def cam2mask(
             # buffer, and nobody else was handed the buffer since the call that left the affinity there
             key = (tuple(images.shape), c1, int(downscale or 0), tuple(refine_model.dilations),
                    int(refine_model.num_iter) > 0, ws.data_ptr(), int(nbytes),
-                   torch.cuda.current_stream(dev).cuda_stream)
+                   torch.cuda.current_stream(dev).cuda_stream, denorm)
             if share["key"] == key and share["uses"] == uses_before:
-                flags = 1                                                   # COSA_CAM2MASK_REUSE_AFFINITY
+                flags |= 1                                                  # COSA_CAM2MASK_REUSE_AFFINITY
             share["key"], share["uses"] = key, uses_before + 1
-        _lib.check(lib.cosa_cam2mask_flags(_lib.ptr(images), _lib.ptr(boxes), _lib.ptr(cams), _lib.ptr(cls_labels),
-                                           float(threshold_high), float(threshold_low), float(ignore_index),
-                                           int(downscale or 0), int(use_par), refine_model._dil if use_par else None,
-                                           n_dil, int(refine_model.num_iter) if use_par else 0, _lib.ptr(out),
-                                           _lib.ptr(hi), _lib.ptr(lo), b, c1, h, w, _lib.ptr(ws), nbytes, flags,
-                                           _lib.stream_ptr()))
+        mean_c = (ctypes.c_float * 3)(*denorm[0]) if denorm else None
+        std_c = (ctypes.c_float * 3)(*denorm[1]) if denorm else None
+        _lib.check(lib.cosa_cam2mask_ex(_lib.ptr(images), _lib.ptr(boxes), _lib.ptr(cams), _lib.ptr(cls_labels),
+                                        float(threshold_high), float(threshold_low), float(ignore_index),
+                                        int(downscale or 0), int(use_par), refine_model._dil if use_par else None,
+                                        n_dil, int(refine_model.num_iter) if use_par else 0, _lib.ptr(out),
+                                        _lib.ptr(hi), _lib.ptr(lo), b, c1, h, w, _lib.ptr(ws), nbytes, flags,
+                                        mean_c, std_c, _lib.stream_ptr()))
     if return_parts:
         return out, hi, lo
     return out
@@ -433,7 +487,10 @@ class DenseEnergyLoss(torch.nn.Module):
                     float(self.sigma_xy * self.scale_factor), B, C, H, W, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
                 done = torch.cuda.Event()
                 done.record(side)
-        self.__dict__["_prebuilt"] = dict(img_ptr=img.data_ptr(), shape=(B, C, H, W), mean=mean_t, std=std_t,
+        # identity of the image: address, shape AND the tensor's version counter (an in-place update of `img`, or a new
+        # tensor that the caching allocator placed at the same address, must not pick this lattice up)
+        self.__dict__["_prebuilt"] = dict(img_ptr=img.data_ptr(), img_version=img._version, img_ref=img,
+                                          shape=(B, C, H, W), mean=mean_t, std=std_t,
                                           sigmas=(float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor)),
                                           ws=ws, nbytes=nbytes, done=done, device=dev)
         return True
@@ -450,7 +507,8 @@ class DenseEnergyLoss(torch.nn.Module):
         pre = self.__dict__.pop("_prebuilt", None)
         if pre is None:
             return None
-        if (pre["img_ptr"] != img.data_ptr() or pre["shape"] != tuple(shape) or pre["device"] != img.device
+        if (pre["img_ref"] is not img or pre["img_version"] != img._version
+                or pre["img_ptr"] != img.data_ptr() or pre["shape"] != tuple(shape) or pre["device"] != img.device
                 or pre["mean"] != tuple(float(v) for v in mean) or pre["std"] != tuple(float(v) for v in std)
                 or pre["sigmas"] != (float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor))):
             return None

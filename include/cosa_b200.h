@@ -20,13 +20,15 @@
 extern "C" {
 #endif
 
-#define COSA_B200_ABI_VERSION 1
+#define COSA_B200_ABI_VERSION 2
 
 enum {
   COSA_OK = 0,
   COSA_E_ARG = -1,        /* bad shape / null pointer / unsupported parameter            */
   COSA_E_WORKSPACE = -2,  /* ws_bytes smaller than *_ws_bytes() for the same arguments  */
-  COSA_E_KEYRANGE = -3    /* lattice coordinate outside the packed-key range */
+  COSA_E_KEYRANGE = -3    /* lattice coordinate outside the packed-key range: |coordinate| <= 6143 here,
+                             the reference stores `short`; the filter output and the energy loss are NaN when this
+                             happens, and cosa_bilateral_stats / the _host form return this code */
 };
 
 int cosa_abi_version(void);
@@ -138,12 +140,25 @@ int cosa_cam2mask_flags(const float *images, const int *boxes, const float *cams
                         float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, int flags,
                         void *stream);
 
-/* cosa_cam2mask with PAR refines softmax stacks whose channels sum to 1, and a PAR step multiplies that sum by the
- * constant row sum of its weights (PAR.py:85-89), so by default the last live channel of each stack is not
- * propagated but evaluated as row_sum^num_iter - (sum of the others) by the labelling kernel (one third of the
- * propagation work at two foreground classes; labels identical on every fixture).  on != 0 propagates every
- * channel like the reference does; the environment variable COSA_CAM2MASK_ALL_CHANNELS sets the initial choice. */
-int cosa_cam2mask_set_all_channels(int on);
+/* cosa_cam2mask_flags plus two producers folded into its first kernel, so that neither main.py:117's [0,1] image
+ * nor main.py:137's validated CAM tensor has to exist in HBM:
+ *   denorm_mean / denorm_std (HOST float[3], both or neither): `images` is the ImageNet-normalised network input and
+ *     every source pixel is de-normalised exactly as cosa_denormalize_img does (utils/torch_helper.py:354-367);
+ *   COSA_CAM2MASK_CAMS_UNVALIDATED: `cams` has not been through cam_validation; every source value is multiplied by
+ *     cls_labels[b,c] (utils/seg_helper.py:547-551).  Only planes of present classes are read either way.
+ * COSA_CAM2MASK_ALL_CHANNELS: with PAR, cosa_cam2mask refines softmax stacks whose channels sum to 1, and a PAR step
+ *   multiplies that sum by the constant row sum of its weights (PAR.py:85-89), so by default the last live channel of
+ *   each stack is not propagated but evaluated as row_sum^num_iter - (sum of the others) by the labelling kernel (one
+ *   third of the propagation work at two foreground classes; the value differs from a propagated one by ~1e-6, so a
+ *   label can differ only where the reference's own top-1/top-2 margin is a numerical tie).  This flag propagates
+ *   every channel like the reference does. */
+#define COSA_CAM2MASK_ALL_CHANNELS 2
+#define COSA_CAM2MASK_CAMS_UNVALIDATED 4
+int cosa_cam2mask_ex(const float *images, const int *boxes, const float *cams, const float *cls_labels,
+                     float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
+                     const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
+                     float *label_low_out, int B, int C1, int H, int W, void *ws, size_t ws_bytes, int flags,
+                     const float *denorm_mean, const float *denorm_std, void *stream);
 
 /* _refine_cams tail: bilinear (align_corners=False) resize of refined [B,nc,h,w] to (H,W), argmax over
  * channels (first max wins), label = valid_key[argmax].      utils/seg_helper.py:793-795 */
@@ -164,8 +179,8 @@ int cosa_bilateralfilter_batch_host(const float *images, const float *ins, float
                                     int W, float sigmargb, float sigmaxy);
 /* Lattice statistics of the last build in `ws` (same N,K,H,W as that call; for the dense-energy entry points
  * the lattice is the tail of their workspace), copied to host after synchronising `stream`:
- * stats[0] = M (vertices over the whole batch), stats[1] = key-range error flag, stats[2] = table
- * capacity, stats[3] = max probe length. */
+ * stats[0] = M (vertices over the whole batch), stats[1] = error flags (1 = key range, 2 = capacity), stats[2] = table
+ * capacity in use, stats[3] = max probe length.  Returns COSA_E_KEYRANGE / COSA_E_WORKSPACE when a flag is set. */
 int cosa_bilateral_stats(const void *ws, int N, int K, int H, int W, long long stats[4], void *stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -168,14 +168,20 @@ def cam_to_label(cam, cls_label, img_box=None, bkg_thre=None, high_thre=None, lo
     return valid_cam, out
 
 
-def refine_cams(refine_model, images, cams, valid_key, orig_size):
+def refine_cams(refine_model, images, cams, valid_key, orig_size, margin_out=None):
     refined = refine_model(images, cams) if refine_model else cams
     refined = F.interpolate(refined, size=orig_size, mode="bilinear", align_corners=False)
+    if margin_out is not None and refined.shape[1] > 1:      # checker bookkeeping, not part of the reference
+        top = refined[0].topk(2, dim=0).values
+        torch.minimum(margin_out, top[0] - top[1], out=margin_out)
     return valid_key[refined.argmax(dim=1)]
 
 
 def cam2mask(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model=None,
-             ignore_index=255, downscale=2, return_parts=False):
+             ignore_index=255, downscale=2, return_parts=False, return_margins=False):
+    """cam2mask (seg_helper.py:721-785).  ``return_margins`` additionally returns, per pixel, the smaller top-1/top-2
+    margin of the two up-sampled stacks the argmax decides on (inf outside the boxes): the near-tie protocol of the
+    parity tests accepts a differing label only where this margin is a numerical tie."""
     b, _, h, w = images.shape
     if downscale:
         size = [h // downscale, w // downscale]
@@ -192,19 +198,22 @@ def cam2mask(images, img_boxes, cams, cls_labels, threshold_high, threshold_low,
     present = torch.cat([torch.ones((b, 1)), cls_labels], dim=1)
     lab_hi = torch.full((b, h, w), float(ignore_index))
     lab_lo = lab_hi.clone()
+    margins = torch.full((b, h, w), float("inf")) if return_margins else None
     for i, coord in enumerate(img_boxes):
         keys = torch.nonzero(present[i])[:, 0]
         ys, xs = _box_slices(coord, h, w)
         for stack, dst in ((stacks[0], lab_hi), (stacks[1], lab_lo)):
             active = stack[i, keys].unsqueeze(0).softmax(dim=1)
-            lab = refine_cams(refine_model, small[[i]], active, keys, (h, w))
+            lab = refine_cams(refine_model, small[[i]], active, keys, (h, w),
+                              margin_out=margins[i] if return_margins else None)
             dst[i, ys, xs] = lab[0, ys, xs].to(dst.dtype)
     out = lab_hi.clone()
     out[lab_hi == 0] = ignore_index
     out[(lab_hi + lab_lo) == 0] = 0
-    if return_parts:
-        return out, lab_hi, lab_lo
-    return out
+    res = (out, lab_hi, lab_lo) if return_parts else (out,)
+    if return_margins:
+        res = res + (margins,)
+    return res if len(res) > 1 else res[0]
 
 
 # ----------------------------------------------------------------------------------------------

@@ -31,37 +31,11 @@ from cosa_b200 import synthetic as port  # noqa: E402  (the shared synthetic-inp
 
 
 def load_reference():
-    olat.build()
-    shim = types.ModuleType("bilateralfilter")
-    shim.bilateralfilter_batch = olat.ref_bilateralfilter_batch
-    shim.bilateralfilter = None
-    sys.modules["bilateralfilter"] = shim
-    for name in ("pydensecrf", "pydensecrf.densecrf", "pydensecrf.utils"):
-        sys.modules[name] = types.ModuleType(name)
-    sys.modules["pydensecrf.utils"].unary_from_softmax = None
-    sys.modules["pydensecrf"].densecrf = sys.modules["pydensecrf.densecrf"]
-    torch.Tensor.cuda = lambda self, *a, **k: self
-
-    def by_path(name, path):
-        spec = importlib.util.spec_from_file_location(name, path)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        return mod
-
-    # utils/torch_helper.py (denormalize_img) imports its sibling ``misc`` and texttable (absent): both unused here
-    pkg = types.ModuleType("utils")
-    pkg.__path__ = []
-    sys.modules.setdefault("utils", pkg)
-    sys.modules.setdefault("utils.misc", types.ModuleType("utils.misc"))
-    tt = types.ModuleType("texttable")
-    tt.Texttable = None
-    sys.modules.setdefault("texttable", tt)
+    """The reference's own modules (oracle/reference_import.py holds the import shim shared with bench.py)."""
+    from oracle import reference_import
     global ref_torch_helper
-    ref_torch_helper = by_path("utils.torch_helper", os.path.join(REF, "utils", "torch_helper.py"))
-    par = by_path("ref_PAR", os.path.join(REF, "models", "PAR.py"))
-    sh = by_path("ref_seg_helper", os.path.join(REF, "utils", "seg_helper.py"))
-    rrm = None
-    return par, sh, rrm
+    par, sh, ref_torch_helper = reference_import.load_reference()
+    return par, sh, None
 
 
 ONLY = set(sys.argv[1:])        # optional: names of the fixtures to (re)write; default all

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(raw, n), "libcosa_b200.so does not export " + n
     assert set(_lib._SIGNATURES) == set(names), set(_lib._SIGNATURES) ^ set(names)
-    assert lib.cosa_abi_version() == 1
+    assert lib.cosa_abi_version() == _lib.ABI_VERSION == 2
     assert b"workspace" in lib.cosa_strerror(-2)
 
 

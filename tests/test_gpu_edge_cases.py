@@ -75,7 +75,9 @@ def test_boxes_empty_missing_and_no_foreground(cosa, port):
                         threshold_high=0.7, threshold_low=0.25, refine_model=par)
     want = port.cam2mask(images=host["img_denorm"], img_boxes=boxes, cams=host["cams"], cls_labels=host["cls_label"],
                          threshold_high=0.7, threshold_low=0.25, refine_model=port.ParOracle())
-    assert int((got.cpu() != want).sum()) <= 1
+    margins = _oracle_margin(port, dict(images=host["img_denorm"], cams=host["cams"], cls_label=host["cls_label"]),
+                             port.ParOracle())
+    check_labels_near_tie(got, want, margins, "cam2mask with empty / missing / negative boxes")
     assert bool((got[1] == 255).all()) and bool((got[3] == 255).all())          # empty box / no box: all ignore
     assert set(got[2].unique().tolist()) <= {0.0, 255.0}
     # the same boxes through cam_to_label and get_energy_loss
@@ -150,8 +152,23 @@ def test_lattice_key_range_guard(cosa):
     out = torch.empty_like(x)
     bf.bilateralfilter_batch(img, x, out, N, K, H, W, 15.0, 50.0)
     assert bf.lattice_stats(N, K, H, W)[1] == 0
+    assert bool(torch.isfinite(out).all())
     bf.bilateralfilter_batch(img, x, out, N, K, H, W, 0.001, 50.0)       # sigma_rgb = 0.001 -> coordinates ~ 1e6
     assert bf.lattice_stats(N, K, H, W)[1] == 1
+    assert bool(torch.isnan(out).all()), "an out-of-range lattice must poison the output, not alias vertices"
+    # ... the dense-CRF loss built on it is NaN as well (fail loudly on the production path) ...
+    segs = torch.rand((N, K, H, W), device="cuda").softmax(dim=1)
+    loss = cosa.DenseEnergyLossFunction.apply(img, segs, 0.001, 50.0, torch.ones((N, H, W), device="cuda"),
+                                              torch.zeros((N, H, W), dtype=torch.bool, device="cuda"))
+    assert bool(torch.isnan(loss).all())
+    # ... and the synchronous host form (the SWIG drop-in) reports it as an error
+    import numpy as np
+    outs = np.zeros(N * K * H * W, dtype=np.float32)
+    with pytest.raises(cosa._lib.CosaError):
+        bf.bilateralfilter_batch(img.cpu().numpy().ravel(), x.cpu().numpy().ravel(), outs, N, K, H, W, 0.001, 50.0)
+    # the reference's own range (short) is wider: sigma_rgb = 0.05 is fine there and flagged here, 0.5 is fine in both
+    bf.bilateralfilter_batch(img, x, out, N, K, H, W, 0.5, 50.0)
+    assert bf.lattice_stats(N, K, H, W)[1] == 0 and bool(torch.isfinite(out).all())
 
 
 def test_high_resolution_energy_matches_oracle(cosa, port):
@@ -171,7 +188,8 @@ def test_high_resolution_energy_matches_oracle(cosa, port):
     assert_close(logit.grad, o_logit.grad, "512^2 energy grad")
     got = cosa.cam2mask(images=d["img_denorm"], img_boxes=host["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
                         threshold_high=0.7, threshold_low=0.25)
-    assert int((got.cpu() != label).sum()) <= 1e-5 * label.numel()
+    margins = _oracle_margin(port, dict(images=host["img_denorm"], cams=host["cams"], cls_label=host["cls_label"]), None)
+    print("512^2 cam2mask (no refine model): %d label flips" % check_labels_near_tie(got, label, margins, "512^2 cam2mask"))
 
 
 def test_host_pipeline_matches_device_path(cosa, port):
@@ -347,7 +365,7 @@ def test_prebuilt_lattice_matches_the_single_stream_call(cosa):
     label0, loss0, grad0, M0, launches0 = run(None, d["simg"])
     label1, loss1, grad1, M1, launches1 = run(d["simg"], d["simg"])
     assert torch.equal(label0, label1) and M0 == M1 and M0 > 0
-    assert launches1 == launches0 - 6, "the forward must skip exactly the six build launches"
+    assert launches1 == launches0 - 5, "the forward must skip exactly the five build launches"
     assert_close(loss1, loss0, "prebuilt loss", tol=1e-5)
     assert_close(grad1, grad0, "prebuilt gradient", tol=1e-5)
     # a lattice prebuilt for another image tensor is not picked up ...

@@ -302,15 +302,18 @@ def test_cam_to_label_vs_oracle(cosa, port, shape):
 
 
 # ---- cam2mask ------------------------------------------------------------------------------------------
-def _oracle_margin(port, d, refine_model, downscale=2):
-    """Oracle label map plus, per pixel, the smaller top-1/top-2 margin of the two up-sampled stacks."""
+def _oracle_margin(port, d, refine_model, downscale=2, thr=(0.7, 0.25)):
+    """Per pixel, the smaller top-1/top-2 margin of the oracle's two up-sampled stacks (seg_helper.py:793-794): where it
+    is below NEAR_TIE the argmax is a numerical tie and a differing label is accepted (and counted)."""
     images, cams, cls = d["images"], d["cams"], d["cls_label"]
     b, _, h, w = images.shape
     margins = torch.full((b, h, w), float("inf"))
-    small = F.interpolate(images, size=[h // downscale, w // downscale], mode="bilinear", align_corners=False)
-    for thr in (0.7, 0.25):
-        stack = torch.cat([torch.ones((b, 1, h, w)) * thr, cams], dim=1)
-        stack = F.interpolate(stack, size=[h // downscale, w // downscale], mode="bilinear", align_corners=False)
+    size = [h // downscale, w // downscale] if downscale else [h, w]
+    small = F.interpolate(images, size=size, mode="bilinear", align_corners=False) if downscale else images
+    for t in thr:
+        stack = torch.cat([torch.ones((b, 1, h, w)) * t, cams], dim=1)
+        if downscale:
+            stack = F.interpolate(stack, size=size, mode="bilinear", align_corners=False)
         for i in range(b):
             keys = torch.nonzero(torch.cat([torch.ones(1), cls[i]]))[:, 0]
             active = stack[i, keys].unsqueeze(0).softmax(dim=1)
@@ -350,10 +353,9 @@ def test_cam2mask_golden(cosa, port, tag):
     evalbox = dict(args, img_boxes=[[0, -1, 0, -1]] * d["images"].shape[0])
     n2 = check_labels_near_tie(cosa.cam2mask(refine_model=par, **evalbox), t(g["out_par_evalbox"]), m_par,
                                "cam2mask + PAR, eval-style boxes")
-    got = cosa.cam2mask(downscale=0, **args)
-    n3 = int((got.cpu() != t(g["out_nodownscale"])).sum())
+    n3 = check_labels_near_tie(cosa.cam2mask(downscale=0, **args), t(g["out_nodownscale"]),
+                               _oracle_margin(port, d, None, downscale=0), "cam2mask, downscale=0")
     print("cam2mask_%s label mismatches vs reference: none=%d par=%d evalbox=%d nodownscale=%d" % (tag, n0, n1, n2, n3))
-    assert n3 <= 1e-4 * got.numel()
 
 
 def test_cam2mask_generic_refine_model_matches_fused(cosa):
@@ -361,9 +363,11 @@ def test_cam2mask_generic_refine_model_matches_fused(cosa):
     args = dict(images=cu(g["images"]), img_boxes=t(g["boxes"]), cams=cu(g["cams"]), cls_labels=cu(g["cls_label"]),
                 threshold_high=0.7, threshold_low=0.25)
     par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
-    fused = cosa.cam2mask(refine_model=par, **args)
+    fused = cosa.cam2mask(refine_model=par, propagate_all_channels=True, **args)
     generic = cosa.cam2mask(refine_model=lambda im, cm: par(im, cm), **args)     # any callable: per-image path
-    assert int((fused != generic).sum()) <= 1e-4 * fused.numel()
+    n = int((fused != generic).sum())
+    print("fused (all channels propagated) vs per-image generic path: %d labels differ" % n)
+    assert n == 0
 
 
 def test_cam2mask_derived_channel_vs_all_channels(cosa, port):
@@ -384,12 +388,13 @@ def test_cam2mask_derived_channel_vs_all_channels(cosa, port):
     margins = _oracle_margin(port, dict(images=d["img_denorm"], cams=cams, cls_label=cls), port.ParOracle())
     args = dict(images=d["img_denorm"].cuda(), cams=cams.cuda(), cls_labels=cls.cuda(),
                 refine_model=cosa.PAR(num_iter=10, dilations=DIL).cuda(), return_parts=True, **kw)
-    try:
+    full = [x.clone() for x in cosa.cam2mask(propagate_all_channels=True, **args)]
+    derived = cosa.cam2mask(**args)
+    try:        # the module-level default is what `propagate_all_channels=None` resolves to
         seg_helper.cam2mask_propagate_all_channels(True)
-        full = [x.clone() for x in cosa.cam2mask(**args)]
+        assert all(torch.equal(a_, b_) for a_, b_ in zip(cosa.cam2mask(**args), full))
     finally:
         seg_helper.cam2mask_propagate_all_channels(False)
-    derived = cosa.cam2mask(**args)
     n_full = check_labels_near_tie(full[0], want, margins, "cam2mask + PAR, every channel propagated")
     n_der = check_labels_near_tie(derived[0], want, margins, "cam2mask + PAR, last channel derived")
     between = [int((a_ != b_).sum()) for a_, b_ in zip(derived, full)]
