@@ -162,7 +162,7 @@ def cpu_path_step(d, n_images, full=False):
                                 sigma_xy=100.0, scale_factor=0.5)
     loss.backward()
     if full:
-        return float(loss.detach()), label, margins, logit.grad
+        return float(loss.detach()), label, margins, logit.grad, port.last_loss_exact_over_reference()
     return float(loss.detach())
 
 
@@ -363,7 +363,7 @@ def run_cosa_arm(args):
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_path_step(host, 1)
         t0 = time.perf_counter()
-        cpu_loss, cpu_label, cpu_margin, cpu_grad = cpu_path_step(host, n_img, full=True)
+        cpu_loss, cpu_label, cpu_margin, cpu_grad, exact_ratio = cpu_path_step(host, n_img, full=True)
         dt = time.perf_counter() - t0
         cpu = {"value": n_img / dt, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "first %d images of the same batch, 1 warm-up image + 1 timed pass (%.1f s); %s"
@@ -378,12 +378,19 @@ def run_cosa_arm(args):
         l2 = cosa_b200.get_energy_loss(img=sub["simg"], logit=logit, label=cpu_label.to(dev),
                                        img_box=host["img_box"][:n_img], loss_layer=layer)
         l2.backward()
+        # the reference accumulates <S, AS> with a float32 np.dot (seg_helper.py:890) that is itself ~1e-4 away from
+        # the exact sum at these sizes; the product accumulates in double.  Both distances are reported: against the
+        # CPU leg's own value, and against the same maths accumulated in float64 (oracle/reference_port.py: LAST_DOT)
         loss_rel = abs(float(l2.detach()) - cpu_loss) / abs(cpu_loss)
+        loss_rel_exact = abs(float(l2.detach()) - cpu_loss * exact_ratio) / abs(cpu_loss * exact_ratio)
+        drift = abs(exact_ratio - 1.0)
         grad_rel = float((logit.grad.cpu() - cpu_grad).abs().max() / cpu_grad.abs().max())
         parity = {"images": n_img, "label_pixels": int(cpu_label.numel()), "label_flips": flips,
-                  "worst_flip_margin": worst, "near_tie_margin": 1e-5, "loss_rel": loss_rel, "grad_rel": grad_rel,
-                  "tolerance": 1e-4, "against": cpu["kind"]}
-        ok = (flips == 0 or (worst <= 1e-5 and flips <= 1e-5 * cpu_label.numel())) and loss_rel <= 1e-4 and grad_rel <= 1e-4
+                  "worst_flip_margin": worst, "near_tie_margin": 1e-5, "loss_rel": loss_rel,
+                  "loss_rel_vs_float64_accumulation": loss_rel_exact, "cpu_float32_dot_drift": drift,
+                  "grad_rel": grad_rel, "tolerance": 1e-4, "against": cpu["kind"]}
+        ok = ((flips == 0 or (worst <= 1e-5 and flips <= 1e-5 * cpu_label.numel())) and loss_rel_exact <= 1e-4
+              and loss_rel <= drift + 1e-4 and grad_rel <= 1e-4)
         parity["ok"] = bool(ok)
         if not ok:
             emit({"metric": METRIC, "error": "parity gate failed - nothing was timed", "parity": parity})
@@ -555,7 +562,7 @@ def run_cosa_arm(args):
             "config": {"workload": wl["name"] % B, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
                        "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "thresholds": [thr_high, thr_low],
                        "par_step": "1 affinity launch + 10 step launches (programmatic dependent launches); the "
-                                   "single cooperative launch of north_star exists (COSA_PAR_STEP=coop) and is slower",
+                                   "single cooperative launch of north_star exists (cosa_par_set_step_mode('coop')) and is slower",
                        "fused_producers": "denormalize_img and cam_validation are folded into cam2mask's first kernel "
                                           "(cosa_cam2mask_ex); their tensors are never written",
                        "streams": ("CRF lattice build (image-only) on a second stream under cam2mask "

@@ -589,11 +589,6 @@ __global__ void __launch_bounds__(128, 2) energy_logit_grad_pair_kernel(const fl
   }
 }
 
-static bool energy_force_generic() {   // COSA_ENERGY_GENERIC=1: two-pass kernels for every class count (A/B runs)
-  static int v = -1;
-  if (v < 0) v = getenv("COSA_ENERGY_GENERIC") ? 1 : 0;
-  return v == 1;
-}
 static int grid1d(long long items) { return (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(items, 256))); }
 
 }  // namespace cosa
@@ -761,11 +756,11 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
   void *lws = a.base + a.off;
   Affine3 aff;
   for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
-  if (C == 21 && !energy_force_generic()) {   // VOC: register-resident single pass
+  if (C == 21) {   // VOC: register-resident single pass
     const long long threads = (long long)B * h * w;
     COSA_LAUNCH(energy_prepare_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label, boxes,
                 aff, img_half, s_roi, gate, roi_half, B, H, W);
-  } else if (C == 81 && W % 32 == 0 && !energy_force_generic()) {   // COCO: register-resident, two pixels per thread
+  } else if (C == 81 && W % 32 == 0) {   // COCO: register-resident, two pixels per thread
     const long long threads = (long long)B * h * (W / 32) * 32;
     COSA_LAUNCH(energy_prepare_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label,
                 boxes, aff, img_half, s_roi, gate, roi_half, B, H, W);
@@ -792,11 +787,11 @@ extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, 
   const float *roi_half = sv.take<float>((size_t)B * hw);
   dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (C == 21 && W % 4 == 0 && !energy_force_generic()) {
+  if (C == 21 && W % 4 == 0) {
     const long long threads = (long long)B * H * (W / 4);
     COSA_LAUNCH(energy_logit_grad_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
                 roi_half, grad_out, weight, grad_logit, B, H, W);
-  } else if (C == 81 && !energy_force_generic()) {
+  } else if (C == 81) {
     const long long threads = (long long)B * H * (W / 2);
     COSA_LAUNCH(energy_logit_grad_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
                 roi_half, grad_out, weight, grad_logit, B, H, W);

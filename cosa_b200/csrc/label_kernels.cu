@@ -1124,13 +1124,15 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   // row_sum^num_iter minus the sum of the others, evaluated by the labelling kernel at every tap (|error| ~ 1e-6,
   // the same order as the summation-order differences between two fp32 evaluations of the reference).
   // COSA_CAM2MASK_ALL_CHANNELS (a per-call flag) propagates every channel instead.
-  if (refine) COSA_CHECK(par_upload_constants(dilations, n_dil, s));
+  ParConst pc;
+  pc.row_sum = 1.0;
+  if (refine) COSA_CHECK(par_make_constants(dilations, n_dil, &pc));
   const int derive = (refine && !(flags & COSA_CAM2MASK_ALL_CHANNELS)) ? 1 : 0;
   Denorm dn;
   dn.on = denorm_mean != nullptr;
   for (int c = 0; c < 3; ++c) { dn.mean[c] = dn.on ? denorm_mean[c] : 0.0f; dn.std[c] = dn.on ? denorm_std[c] : 1.0f; }
   const float *cam_scale = (flags & COSA_CAM2MASK_CAMS_UNVALIDATED) ? cls_labels : nullptr;
-  const float derive_total = derive ? (float)pow(par_weight_row_sum(), (double)num_iter) : 0.0f;
+  const float derive_total = derive ? (float)pow(pc.row_sum, (double)num_iter) : 0.0f;
   COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
   if (refine) {
@@ -1160,10 +1162,9 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
   if (refine) {
     if (reuse_aff) {
-      COSA_CHECK(par_launch_iterations(aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
-                                       num_iter, s));
+      COSA_CHECK(par_launch_iterations(pc, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, num_iter, s));
     } else {
-      COSA_CHECK(par_refine_batch(img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, n_dil,
+      COSA_CHECK(par_refine_batch(pc, img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w,
                                   num_iter, s));
     }
     refined = fin;
@@ -1211,9 +1212,7 @@ static int cam_merge_impl(const float *const *raw, const int *hs, const int *ws,
   int *mm = (int *)minmax_ws;
   COSA_LAUNCH(minmax_init_kernel, ceil_div(planes, 256), 256, 0, s, mm, planes);
   if (W % 4 == 0 && n_scales <= 5) {
-    static int two_eval = -1;
-    if (two_eval < 0) two_eval = getenv("COSA_MERGE_TWO_EVAL") ? 1 : 0;   // A/B: evaluate the merge twice, store once
-    if (two_eval || ((uintptr_t)out % 16) != 0) {
+    if (((uintptr_t)out % 16) != 0) {   // unaligned output: evaluate the merge twice (extrema, then store)
       COSA_CHECK(launch_merge_rows<0>(rs, out, mm, B, C1, H, W, cls_label, s));
       return launch_merge_rows<1>(rs, out, mm, B, C1, H, W, cls_label, s);
     }

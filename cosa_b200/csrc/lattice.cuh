@@ -15,9 +15,10 @@
 // Tile-local vertex lists.  The image is cut into 32 x 8 pixel tiles.  The 1536 (pixel, vertex) pairs of a tile
 // touch only ~22 % as many distinct vertices (the lattice cells are sigma_xy pixels wide), so the build
 // de-duplicates a tile's keys ONCE in shared memory and writes
-//     tile_info[t]          (first list entry, U = number of distinct vertices of the tile)
-//     tkeys / tvid / tseg   per list entry: packed key, vertex row (id + 1), (first pair << 16 | pairs) in plist
-//     plist[t][1536]        the tile's pairs bucketed by list entry: (pixel in tile << 3 | r)
+//     tile_info[t]          (first list entry, U | pairs << 16: distinct vertices and pairs of the tile)
+//     tkeys / tvid          per list entry: packed key, vertex row (id + 1)
+//     plist[t][1536 + 32]   the tile's pairs bucketed by list entry: (pixel in tile << 3 | r | first-of-vertex << 11),
+//                           then for each block of 48 pairs the list entry its first pair belongs to
 //     lidx[r][P], bary[r][P] per pixel: 16-bit index into the tile's list and the barycentric weight
 // Only the distinct keys of a tile go to the global hash table (4-5x fewer probes); the splat reduces a tile's pairs
 // per vertex from shared memory without hashing, and the slice stages the tile's vertex rows once.
@@ -35,7 +36,8 @@ constexpr unsigned long long kEmptyKey = ~0ULL;
 constexpr int kTileW = 32, kTileH = 8;
 constexpr int kTilePix = kTileW * kTileH;           // 256 = threads per tile CTA
 constexpr int kTilePairs = (kLatD + 1) * kTilePix;  // 1536
-constexpr int kTileMaxU = kTilePairs + kLatD + 1;   // + the keys of the SSE padding pixels (first tile of an image)
+constexpr int kPairBlock = kTilePairs / 32;         // 48: pairs per quarter-warp of the splat
+constexpr int kTileListStride = kTilePairs + 32;    // u16 per tile: the pair list + the first list entry of each block
 
 // counters[]: 0: M   1: error flags (1 = key range, 2 = list / vertex capacity)   2: max probe length
 //             3: table capacity in use   4: M of the earlier chunks of this call   5: T = list entries
@@ -45,11 +47,10 @@ struct LatticeBufs {
   int *table_ids;                   // [cap]   vertex id + 1 of an occupied slot
   unsigned long long *vkeys;        // [m_cap] packed key of vertex id
   int *counters;                    // [8]
-  int2 *tile_info;                  // [tiles] (first list entry, U)
+  int2 *tile_info;                  // [tiles] (first list entry, U | pairs << 16)
   unsigned long long *tkeys;        // [t_cap] packed key of a list entry
   int *tvid;                        // [t_cap] table slot during the build, then vertex id + 1 (row of val0 / val1)
-  unsigned *tseg;                   // [t_cap] (first pair << 16) | pairs
-  unsigned short *plist;            // [tiles][kTilePairs]
+  unsigned short *plist;            // [tiles][kTileListStride]
   unsigned short *lidx;             // [6][P]  index into the tile's list
   float *bary;                      // [6][P]
   int2 *nbr;                        // [6][m_cap]  (n1, n2) as vertex id + 1, 0 = absent

@@ -156,23 +156,39 @@ __device__ __forceinline__ int tile_insert64(unsigned long long *hkey, unsigned 
   }
 }
 
+// The six vertex keys of a point.  canonical[r][rank] is r or r-6 (permutohedral.cpp:148-153), i.e. in (q, r) form
+// vertex r has q[i] = q0[i] - [rank[i] >= 6 - r]: going from vertex r-1 to r, exactly the coordinate whose rank is
+// 6 - r loses one (the sixth coordinate is not stored), and the residue field gains one.
 __device__ __forceinline__ void point_keys(const int q0[kLatD + 1], const int rank[kLatD + 1], int b,
                                            unsigned long long key[kLatD + 1], int *bad) {
+  unsigned long long k = 0;
 #pragma unroll
-  for (int r = 0; r <= kLatD; ++r) {
-    int q[kLatD];
+  for (int i = 0; i < kLatD; ++i) {
+    const int v = q0[i] + kQBias;
+    if (v < 1 || v >= (1 << kQBits)) *bad = 1;      // v - 1 (the decremented coordinate) must fit as well
+    k |= (unsigned long long)(v & ((1 << kQBits) - 1)) << (kQBits * i);
+  }
+  k |= (unsigned long long)b << (kQBits * kLatD + 3);
+  key[0] = k;
 #pragma unroll
-    for (int i = 0; i < kLatD; ++i) q[i] = q0[i] - (rank[i] > kLatD - r ? 1 : 0);   // canonical[r][rank] = r or r-6
-    key[r] = pack_key(q, r, b, bad);
+  for (int r = 1; r <= kLatD; ++r) {
+    unsigned long long dec = 0;
+#pragma unroll
+    for (int i = 0; i < kLatD; ++i)
+      if (rank[i] == kLatD + 1 - r) dec = 1ULL << (kQBits * i);
+    k = k - dec + (1ULL << (kQBits * kLatD));
+    key[r] = k;
   }
 }
+
+constexpr int kPairFirst = 1 << 11;    // plist code: (pixel in tile << 3) | r, bit 11 = first pair of its vertex
 
 __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBufs L, const float *__restrict__ images,
                                                                       EmbedConst ec, int H, int W, int n_pad,
                                                                       float sigmargb, float sigmaxy) {
   __shared__ unsigned long long hkey[kTileHS];      // 16 KB
   __shared__ int hinfo[kTileHS];                    //  8 KB  pair count, then (list index << 16) | first pair
-  __shared__ __align__(16) unsigned short plist_s[kTilePairs];
+  __shared__ __align__(16) unsigned short plist_s[kTileListStride];   // pairs bucketed by vertex + the block table
   __shared__ int s_warp[kTilePix / 32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
@@ -180,7 +196,7 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
   const int n = H * W;
   const bool ok = x < W && y < H;
   for (int i = tid; i < kTileHS; i += kTilePix) { hkey[i] = kEmptyKey; hinfo[i] = 0; }
-  for (int i = tid; i < kTilePairs / 2; i += kTilePix) reinterpret_cast<unsigned *>(plist_s)[i] = 0;
+  for (int i = tid; i < kTileListStride / 2; i += kTilePix) reinterpret_cast<unsigned *>(plist_s)[i] = 0;
 
   const int p = y * W + x;
   float f[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -210,19 +226,6 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
       pos[r] = atomicAdd(hinfo + hs[r], 1);
     }
   }
-  // the SSE loop of the reference also embeds the zero-feature pixels that pad n to a multiple of four
-  // (permutohedral.cpp:168-173): their vertices exist (they count in M and take part in the blur) but receive nothing
-  if (n_pad > n && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-    const float fz[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    int qz[kLatD + 1], rz[kLatD + 1];
-    float bz[kLatD + 1];
-    unsigned long long kz[kLatD + 1];
-    int badz = 0;
-    embed_point(fz, ec, qz, rz, bz);
-    point_keys(qz, rz, b, kz, &badz);
-#pragma unroll
-    for (int r = 0; r <= kLatD; ++r) tile_insert64(hkey, kz[r]);
-  }
   __syncthreads();
 
   // one scan over the 2048 slots gives every occupied slot its list index and the start of its pair bucket
@@ -230,8 +233,8 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
   int packed[PER], sum = 0;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
-    const int s = tid * PER + i;
-    packed[i] = hkey[s] != kEmptyKey ? ((1 << 16) | hinfo[s]) : 0;
+    const int c = hinfo[tid * PER + i];
+    packed[i] = c ? ((1 << 16) | c) : 0;    // every occupied slot has at least one pair
     sum += packed[i];
   }
   int incl = sum;
@@ -249,13 +252,29 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
     if (wv < ly) run += t;
     total += t;
   }
-  const int U = total >> 16;
+  const int U = total >> 16, pairs = total & 0xffff;
   const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  // The SSE loop of the reference also embeds the zero-feature pixels that pad n to a multiple of four
+  // (permutohedral.cpp:168-173): their vertices exist (they count in M and take part in the blur) but receive nothing.
+  // The first tile of an image appends their six keys behind its own list entries: the insert kernel sees them, the
+  // splat and the slice (which walk U entries) do not.
+  const bool pad_tile = n_pad > n && blockIdx.x == 0 && blockIdx.y == 0;
   if (tid == 0) {
-    int base = atomicAdd(L.counters + 5, U);
-    if ((long long)base + U > L.t_cap) { atomicOr(L.counters + 1, 2); base = -1; }
+    const int take = U + (pad_tile ? kLatD + 1 : 0);
+    int base = atomicAdd(L.counters + 5, take);
+    if ((long long)base + take > L.t_cap) { atomicOr(L.counters + 1, 2); base = -1; }
     s_base = base;
-    L.tile_info[tile] = make_int2(max(base, 0), base < 0 ? 0 : U);
+    L.tile_info[tile] = make_int2(max(base, 0), base < 0 ? 0 : (U | (pairs << 16)));
+    if (pad_tile && base >= 0) {
+      const float fz[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      int qz[kLatD + 1], rz[kLatD + 1], badz = 0;
+      float bz[kLatD + 1];
+      unsigned long long kz[kLatD + 1];
+      embed_point(fz, ec, qz, rz, bz);
+      point_keys(qz, rz, b, kz, &badz);
+#pragma unroll
+      for (int r = 0; r <= kLatD; ++r) L.tkeys[base + U + r] = kz[r];
+    }
   }
   __syncthreads();
   const int base = s_base;
@@ -264,11 +283,11 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
     if (packed[i]) {
       const int s = tid * PER + i;
       const int u = run >> 16, start = run & 0xffff, cnt = packed[i] & 0xffff;
-      if (base >= 0) {
-        L.tkeys[base + u] = hkey[s];
-        L.tseg[base + u] = ((unsigned)start << 16) | (unsigned)cnt;
-      }
+      if (base >= 0) L.tkeys[base + u] = hkey[s];
       hinfo[s] = run;
+      // block table: the splat walks the pair list in blocks of kPairBlock pairs; block j starts inside vertex u
+      for (int j = (start + kPairBlock - 1) / kPairBlock; j * kPairBlock < start + cnt; ++j)
+        plist_s[kTilePairs + j] = (unsigned short)u;
       run += packed[i];
     }
   }
@@ -278,14 +297,14 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
 #pragma unroll
     for (int r = 0; r <= kLatD; ++r) {
       const int info = hinfo[hs[r]];
-      plist_s[(info & 0xffff) + pos[r]] = (unsigned short)((tid << 3) | r);
+      plist_s[(info & 0xffff) + pos[r]] = (unsigned short)((tid << 3) | r | (pos[r] == 0 ? kPairFirst : 0));
       L.lidx[(size_t)r * L.P + gp] = (unsigned short)(info >> 16);
       L.bary[(size_t)r * L.P + gp] = bary[r];
     }
   }
   __syncthreads();
-  if (tid < kTilePairs / 8)
-    reinterpret_cast<uint4 *>(L.plist + (size_t)tile * kTilePairs)[tid] = reinterpret_cast<const uint4 *>(plist_s)[tid];
+  if (tid < kTileListStride / 8)
+    reinterpret_cast<uint4 *>(L.plist + (size_t)tile * kTileListStride)[tid] = reinterpret_cast<const uint4 *>(plist_s)[tid];
   if (bad) atomicOr(L.counters + 1, 1);
 }
 
@@ -426,68 +445,87 @@ __global__ void lattice_zero_values_kernel(LatticeBufs L) {
 constexpr int kChunk = 24;                       // channels per pass (K = 21 -> one pass)
 constexpr int kPlane = kTilePix + 1;             // odd plane pitch: channel-strided reads hit distinct banks
 
-// Splat (permutohedral.cpp:526-534), one CTA per tile.  The tile's pair list, weights and input channels are staged
-// in shared memory; a quarter-warp per distinct vertex walks the vertex's pairs (lane cl sums channels cl, cl + 8,
-// cl + 16) and issues one reduction per vertex row and channel pass.
+// Splat (permutohedral.cpp:526-534), one CTA per tile.  The tile's pair list (bucketed by vertex in the build), the
+// weights and the input channels are staged in shared memory.  The 32 quarter-warps of the CTA each take one block of
+// kPairBlock consecutive pairs of the list - the same amount of work whatever the vertex degrees - and lane cl sums
+// channels cl, cl + 8, cl + 16; a quarter-warp flushes its partial sum with one reduction per vertex row whenever the
+// list moves on to the next vertex (kPairFirst).  KT > 0: compile-time channel count (one pass); 0: run-time K.
+template <int KT>
 __global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins,
-                                                                      int K, int H, int W) {
+                                                                      int Krt, int H, int W) {
+  static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
   extern __shared__ __align__(16) unsigned char s_raw[];
   float *in_s = reinterpret_cast<float *>(s_raw);                         // [kChunk][kPlane]
   float *bary_s = in_s + kChunk * kPlane;                                 // [6][256]
-  unsigned *seg_s = reinterpret_cast<unsigned *>(bary_s + 6 * kTilePix);  // [kTileMaxU]
-  int *vid_s = reinterpret_cast<int *>(seg_s + kTileMaxU);                // [kTileMaxU]
-  unsigned short *plist_s = reinterpret_cast<unsigned short *>(vid_s + kTileMaxU);   // [kTilePairs], 16-byte aligned
+  int *vid_s = reinterpret_cast<int *>(bary_s + 6 * kTilePix);            // [kTilePairs]
+  unsigned short *plist_s = reinterpret_cast<unsigned short *>(vid_s + kTilePairs);   // [kTileListStride], 16-byte aligned
 
+  const int K = KT ? KT : Krt, Kp = (K + 3) & ~3;
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
   const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
   const int n = H * W;
   const bool ok = x < W && y < H;
   const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const int2 info = L.tile_info[tile];
-  const int U = info.y;
+  const int U = info.y & 0xffff, pairs = info.y >> 16;
   const long long gp = (long long)b * n + (long long)y * W + x;
+  {
+    const float *bp = L.bary + gp;
 #pragma unroll
-  for (int r = 0; r <= kLatD; ++r) bary_s[r * kTilePix + tid] = ok ? L.bary[(size_t)r * L.P + gp] : 0.0f;
-  if (tid < kTilePairs / 8)
-    reinterpret_cast<uint4 *>(plist_s)[tid] = reinterpret_cast<const uint4 *>(L.plist + (size_t)tile * kTilePairs)[tid];
-  for (int u = tid; u < U; u += kTilePix) {
-    seg_s[u] = L.tseg[info.x + u];
-    vid_s[u] = L.tvid[info.x + u];
+    for (int r = 0; r <= kLatD; ++r) { bary_s[r * kTilePix + tid] = ok ? __ldg(bp) : 0.0f; bp += L.P; }
   }
+  if (tid < kTileListStride / 8)
+    reinterpret_cast<uint4 *>(plist_s)[tid] = reinterpret_cast<const uint4 *>(L.plist + (size_t)tile * kTileListStride)[tid];
+  for (int u = tid; u < U; u += kTilePix) vid_s[u] = L.tvid[info.x + u];
   if (tile == 0 && tid == 0) L.counters[6] = 0;   // val0 is being written
 
   const int sub = lx >> 3, cl = tid & 7;
+  const int j = ly * 4 + sub;                     // this quarter-warp's block of the pair list
+  const int e0 = j * kPairBlock, e1 = min(e0 + kPairBlock, pairs);
   const float *src0 = ins + (size_t)b * K * n + (size_t)y * W + x;
-  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
-    const int kc = min(kChunk, L.Kp - c0);
-    __syncthreads();   // the previous pass has read in_s
+  for (int c0 = 0; c0 < Kp; c0 += kChunk) {
+    const int kc = min(kChunk, Kp - c0);
+    if (c0) __syncthreads();   // the previous pass has read in_s
     {
       float v[kChunk];
+      const float *sp = src0 + (size_t)c0 * n;
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) v[c] = (ok && c0 + c < K) ? __ldg(src0 + (size_t)(c0 + c) * n) : 0.0f;
+      for (int c = 0; c < kChunk; ++c) {
+        v[c] = (ok && c0 + c < K) ? __ldg(sp) : 0.0f;
+        sp += n;
+      }
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) in_s[c * kPlane + tid] = v[c];
     }
     __syncthreads();
-    for (int u = ly * 4 + sub; u < U; u += 32) {
-      const unsigned seg = seg_s[u];
-      const int start = seg >> 16, cnt = seg & 0xffff;
+    if (e0 < e1) {
+      int u = plist_s[kTilePairs + j];
       float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-      for (int e = 0; e < cnt; ++e) {
-        const int code = plist_s[start + e];
-        const int pix = code >> 3;
+      auto flush = [&]() {
+        const int vid = vid_s[u];
+        if (vid > 0) {
+          float *dst = L.val0 + (size_t)vid * Kp + c0 + cl;
+          if (cl < kc) atomicAdd(dst, a0);
+          if (cl + 8 < kc) atomicAdd(dst + 8, a1);
+          if (cl + 16 < kc) atomicAdd(dst + 16, a2);
+        }
+      };
+      const float *inl = in_s + cl * kPlane;
+#pragma unroll 4
+      for (int e = e0; e < e1; ++e) {
+        const int code = plist_s[e];
+        if ((code & kPairFirst) && e != e0) {
+          flush();
+          ++u;
+          a0 = a1 = a2 = 0.0f;
+        }
+        const int pix = (code >> 3) & 0xff;
         const float wv = bary_s[(code & 7) * kTilePix + pix];
-        const float *src = in_s + cl * kPlane + pix;
-        a0 = fmaf(wv, src[0], a0);
-        a1 = fmaf(wv, src[8 * kPlane], a1);
-        a2 = fmaf(wv, src[16 * kPlane], a2);
+        a0 = fmaf(wv, inl[pix], a0);
+        a1 = fmaf(wv, inl[8 * kPlane + pix], a1);
+        a2 = fmaf(wv, inl[16 * kPlane + pix], a2);
       }
-      if (cnt && vid_s[u] > 0) {
-        float *dst = L.val0 + (size_t)vid_s[u] * L.Kp + c0 + cl;
-        if (cl < kc) atomicAdd(dst, a0);
-        if (cl + 8 < kc) atomicAdd(dst + 8, a1);
-        if (cl + 16 < kc) atomicAdd(dst + 16, a2);
-      }
+      flush();
     }
   }
 }
@@ -518,17 +556,21 @@ __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const 
 // Slice (permutohedral.cpp:554-567) + optional dense-CRF epilogue (seg_helper.py:888-890), one CTA per tile.  The
 // tile's distinct vertex rows (up to kSliceRows of them; list entries beyond that are read from L2 directly) are staged
 // in shared memory once per channel pass and the pixels gather from there through their 16-bit list indices.
+// KT > 0: compile-time channel count; 0: run-time K.
 constexpr int kSliceRows = 512;
 constexpr int kRowPitch = kChunk + 4;             // 28 floats: row starts fall on 8 different bank quads
-template <bool ENERGY>
+template <bool ENERGY, int KT>
 __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
                                                                          const float *__restrict__ ins,
                                                                          const float *__restrict__ gate, double *loss_acc,
-                                                                         float *__restrict__ outs, int K, int H, int W) {
+                                                                         float *__restrict__ outs, int Krt, int H, int W) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float *rows = reinterpret_cast<float *>(s_raw);   // [kSliceRows][kRowPitch]
   __shared__ int vid_s[kSliceRows];
   __shared__ float s_part[kTilePix / 32];
+  static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
+  constexpr int KQ = KT ? (KT + 3) / 4 : 1;       // row quads per vertex (compile-time form of kq)
+  const int K = KT ? KT : Krt, Kp = (K + 3) & ~3;
   const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
   const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
@@ -536,45 +578,46 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
   const bool ok = x < W && y < H;
   const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const int2 info = L.tile_info[tile];
-  const int Us = min(info.y, kSliceRows);
+  const int Us = min(info.y & 0xffff, kSliceRows);
   const long long gp = (long long)b * n + (long long)y * W + x;
-  const bool poisoned = L.counters[1] != 0;      // key range / capacity error: fail loudly, never alias silently
   int u_r[kLatD + 1];
   float w[kLatD + 1];
+  {
+    const unsigned short *ip = L.lidx + gp;
+    const float *bp = L.bary + gp;
 #pragma unroll
-  for (int r = 0; r <= kLatD; ++r) {
-    u_r[r] = ok ? (int)L.lidx[(size_t)r * L.P + gp] : 0;
-    w[r] = ok ? __fmul_rn(L.bary[(size_t)r * L.P + gp], alpha) : 0.0f;
+    for (int r = 0; r <= kLatD; ++r) {
+      u_r[r] = ok ? (int)__ldg(ip) : 0;
+      w[r] = ok ? __fmul_rn(__ldg(bp), alpha) : 0.0f;
+      ip += L.P; bp += L.P;
+    }
   }
   for (int u = tid; u < Us; u += kTilePix) vid_s[u] = L.tvid[info.x + u];
   const float gt = (ENERGY && ok) ? __ldg(gate + gp) : 1.0f;
   const size_t at0 = (size_t)b * K * n + (size_t)y * W + x;
-  float s_in[kChunk];                   // energy epilogue: the pixel's own inputs of the first channel pass
-  if (ENERGY) {
-#pragma unroll
-    for (int c = 0; c < kChunk; ++c) s_in[c] = (ok && c < K) ? __ldg(ins + at0 + (size_t)c * n) : 0.0f;
-  }
   float local = 0.0f;
-  for (int c0 = 0; c0 < L.Kp; c0 += kChunk) {
-    const int kc = min(kChunk, L.Kp - c0), kq = kc >> 2;
+  for (int c0 = 0; c0 < Kp; c0 += kChunk) {
+    const int kc = min(kChunk, Kp - c0), kq = kc >> 2;
     __syncthreads();                     // vid_s is complete / the previous pass has read `rows`
     for (int i0 = tid; i0 < Us * kq; i0 += 4 * kTilePix) {   // four row quads in flight per thread
       float4 v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = i0 + k * kTilePix;
-        const int u = i / kq, q = i - u * kq;
-        if (i < Us * kq) v[k] = *reinterpret_cast<const float4 *>(values + (size_t)vid_s[u] * L.Kp + c0 + 4 * q);
+        const int u = KT ? i / KQ : i / kq, q = i - u * kq;
+        if (i < Us * kq) v[k] = *reinterpret_cast<const float4 *>(values + (size_t)vid_s[u] * Kp + c0 + 4 * q);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = i0 + k * kTilePix;
-        const int u = i / kq, q = i - u * kq;
+        const int u = KT ? i / KQ : i / kq, q = i - u * kq;
         if (i < Us * kq) *reinterpret_cast<float4 *>(rows + u * kRowPitch + 4 * q) = v[k];
       }
     }
     __syncthreads();
     if (ok) {
+      const float *ip = ins + at0 + (size_t)c0 * n;
+      float *op = outs + at0 + (size_t)c0 * n;
 #pragma unroll
       for (int q = 0; q < kChunk / 4; ++q) {
         if (q >= kq) break;
@@ -583,7 +626,7 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
         for (int r = 0; r <= kLatD; ++r) {
           const float4 v = u_r[r] < kSliceRows
                                ? *reinterpret_cast<const float4 *>(rows + u_r[r] * kRowPitch + 4 * q)
-                               : *reinterpret_cast<const float4 *>(values + (size_t)L.tvid[info.x + u_r[r]] * L.Kp + c0 + 4 * q);
+                               : *reinterpret_cast<const float4 *>(values + (size_t)L.tvid[info.x + u_r[r]] * Kp + c0 + 4 * q);
           acc.x = __fadd_rn(acc.x, __fmul_rn(w[r], v.x));
           acc.y = __fadd_rn(acc.y, __fmul_rn(w[r], v.y));
           acc.z = __fadd_rn(acc.z, __fmul_rn(w[r], v.z));
@@ -592,18 +635,25 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
         const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int c = c0 + 4 * q + k;
-          if (c < K) {
-            float o = poisoned ? __int_as_float(0x7fc00000) : a4[k];
+          if (c0 + 4 * q + k < K) {
+            float o = a4[k];
             if (ENERGY) {
               o = __fmul_rn(o, gt);
-              local = fmaf(c0 == 0 ? s_in[4 * q + k] : __ldg(ins + at0 + (size_t)c * n), o, local);
+              local = fmaf(__ldg(ip), o, local);
             }
-            outs[at0 + (size_t)c * n] = o;
+            *op = o;
+            ip += n; op += n;
           }
         }
       }
     }
+  }
+  // key range / capacity error: fail loudly, never alias silently - every output and the energy become NaN
+  if (L.counters[1] != 0) {
+    const float qnan = __int_as_float(0x7fc00000);
+    if (ok)
+      for (int c = 0; c < K; ++c) outs[at0 + (size_t)c * n] = qnan;
+    local = qnan;
   }
   if (ENERGY) {
     local = warp_sum(local);
@@ -647,7 +697,7 @@ static LatticeDims lattice_dims(int N, int K, int H, int W) {
   d.n = (long long)H * W;
   d.n_pad = (d.n + 3) & ~3LL;
   d.P = (long long)N * d.n;
-  d.t_cap = 6LL * N * d.n_pad;
+  d.t_cap = 6LL * N * d.n_pad + 6LL * N;   // + the keys of the padding pixels, appended once per image
   d.m_cap = d.t_cap;
   d.cap = table_capacity(d.t_cap);
   d.tiles_x = ceil_div(W, kTileW);
@@ -666,8 +716,8 @@ static void lattice_layout(const LatticeDims &d, F &&take) {
   take(4, (size_t)d.tiles * sizeof(int2));                            // tile_info
   take(5, (size_t)d.t_cap * sizeof(unsigned long long));              // tkeys
   take(6, (size_t)d.t_cap * sizeof(int));                             // tvid
-  take(7, (size_t)d.t_cap * sizeof(unsigned));                        // tseg
-  take(8, (size_t)d.tiles * kTilePairs * sizeof(unsigned short));     // plist
+  take(7, (size_t)256);                                               // (unused)
+  take(8, (size_t)d.tiles * kTileListStride * sizeof(unsigned short));  // plist + block table
   take(9, (size_t)6 * d.P * sizeof(unsigned short));                  // lidx
   take(10, (size_t)6 * d.P * sizeof(float));                          // bary
   take(11, (size_t)6 * d.m_cap * sizeof(int2));                       // nbr
@@ -695,7 +745,6 @@ void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
   L->tile_info = (int2 *)slot[4];
   L->tkeys = (unsigned long long *)slot[5];
   L->tvid = (int *)slot[6];
-  L->tseg = (unsigned *)slot[7];
   L->plist = (unsigned short *)slot[8];
   L->lidx = (unsigned short *)slot[9];
   L->bary = (float *)slot[10];
@@ -722,13 +771,19 @@ int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W
 }
 
 static size_t splat_smem_bytes() {
-  return (size_t)kChunk * kPlane * 4 + (size_t)6 * kTilePix * 4 + (size_t)kTileMaxU * 8 + (size_t)kTilePairs * 2;
+  return (size_t)kChunk * kPlane * 4 + (size_t)6 * kTilePix * 4 + (size_t)kTilePairs * 4 + (size_t)kTileListStride * 2;
 }
 
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
   COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
   const dim3 grid(L.tiles_x, L.tiles_y, N);
-  COSA_LAUNCH(lattice_splat_tile_kernel, grid, kTilePix, splat_smem_bytes(), stream, L, ins, K, H, W);
+  if (K == 21) {
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<21>, grid, kTilePix, splat_smem_bytes(), stream,
+                  L, ins, K, H, W);
+  } else {
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<0>, grid, kTilePix, splat_smem_bytes(), stream,
+                  L, ins, K, H, W);
+  }
   float *src = L.val0, *dst = L.val1;
   for (int axis = 0; axis <= kLatD; ++axis) {
     COSA_LAUNCH(lattice_blur_kernel, sm_count() * 8, 256, 0, stream, L, src, dst, axis);
@@ -744,17 +799,21 @@ int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, dou
   int dev = 0;
   COSA_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const dim3 grid(L.tiles_x, L.tiles_y, N);
-  if (gate) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<true>, grid, kTilePix, smem, stream, L, L.val0,
-                  ins, gate, loss_acc, outs, K, H, W);
+  if (gate && K == 21) {
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 21>), grid, kTilePix, smem, stream, L,
+                  L.val0, ins, gate, loss_acc, outs, K, H, W);
+  } else if (gate) {
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 0>), grid, kTilePix, smem, stream, L,
+                  L.val0, ins, gate, loss_acc, outs, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", lattice_slice_tile_kernel<false>, grid, kTilePix, smem, stream, L, L.val0,
-                  ins, gate, loss_acc, outs, K, H, W);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0>), grid, kTilePix, smem, stream, L,
+                  L.val0, ins, gate, loss_acc, outs, K, H, W);
   }
   return 0;
 }

@@ -6,16 +6,21 @@ namespace cosa {
 
 constexpr int kMaxDil = 8;   // up to 64 neighbours
 
-// Uploads the dilation list and the constant position term (PAR.py:51-62,82) for subsequent launches.
-int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream);
-
-// Sum over the neighbours of the weights of one pixel for the last uploaded dilation list: 1 (softmax) + w2 (the
-// position term), evaluated from the float constants the kernels use.  A propagation step multiplies the channel
-// sum of a stack by this factor (PAR.py:85-89; replicate padding keeps all 8*n_dil taps).
-double par_weight_row_sum();
+// The dilation list and the constant position term w2 * softmax(pos_aff) (PAR.py:51-62,82), evaluated on the host and
+// passed to the kernels by value.  row_sum: sum over the neighbours of the weights of one pixel, 1 (softmax) + w2 (the
+// position term), from the float constants the kernels use - a propagation step multiplies the channel sum of a stack
+// by this factor (PAR.py:85-89; replicate padding keeps all 8*n_dil taps).  std_dilations: the list is the reference's
+// {1,2,4,8,12,24} (PAR.py:94), which the compile-time tile kernels serve.
+struct ParConst {
+  int dil[kMaxDil];
+  float pos_term[kMaxDil * 8];
+  int n_dil, std_dilations;
+  double row_sum;
+};
+int par_make_constants(const int *dilations, int n_dil, ParConst *pc);
 
 // aff [B, 8*n_dil, h, w] from imgs [B,3,h,w].
-int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream);
+int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, cudaStream_t stream);
 
 // Row layout of a mask buffer [B, c_stride, h, pitch]: the w interior columns start at column `off`; `padn`
 // replicated columns on either side make every neighbour load of the vectorised kernel an unclamped, 16-byte
@@ -35,15 +40,15 @@ inline size_t layout_floats(const MaskLayout &l, int B, int c_stride, int h) {
 // num_iter propagation steps src0 -> ... -> final_dst.  The two scratch buffers use layout `lay`; src0 must use
 // `lay` too (use par_launch_pack for a plain tensor); final_dst has its own layout (plain for user tensors).
 // Live channels per image: nch_dev[b] when given, else nch_uniform.
-int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
-                          float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
-                          int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream);
+int par_launch_iterations(const ParConst &pc, const float *aff, const float *src0, float *scratch_a, float *scratch_b,
+                          MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
+                          int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream);
 
 // Affinity (into aff [B, 8*n_dil, h, w]) + num_iter steps for the whole batch.  Buffer conventions as in
 // par_launch_iterations.
-int par_refine_batch(const float *imgs, float *aff, const float *src0, float *scratch_a, float *scratch_b,
-                     MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                     int c_stride, int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream);
+int par_refine_batch(const ParConst &pc, const float *imgs, float *aff, const float *src0, float *scratch_a,
+                     float *scratch_b, MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev,
+                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream);
 
 // plain [planes, h, w] -> layout `lay` (interior + replicated pads)
 int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, int h, int w, cudaStream_t stream);

@@ -7,35 +7,28 @@
 //
 // Neighbour n = 8*k + m: dilation k in ctor order, direction m in get_kernel() order (PAR.py:10-24):
 // (-,-) (-,0) (-,+) (0,-) (0,+) (+,-) (+,0) (+,+), borders replicated (PAR.py:44).
+//
+// Step kernels: `par_iterate_tile_kernel` (the reference dilation set, TMA-staged 32 x 32 tiles, one launch per step:
+// the default), `par_propagate_kernel` (the same tiles, ALL steps in one cooperative launch with grid barriers:
+// north_star's single launch; measured slower, selectable), `par_iterate_smem_kernel` / `par_iterate_kernel` (any
+// dilation set: padded rows with the near neighbourhood staged / plain NCHW).  The variants that were measured and
+// dropped (scalar 512-thread tiles, double-buffered persistent CTAs, deeper register prefetch, rolling affinity
+// refill, L2 tensor prefetch of the affinity tile) are described in DESIGN.md section 4.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <math.h>
-#include <stdlib.h>
+
+#include <atomic>
 
 #include "common.cuh"
 #include "par.cuh"
 
 namespace cosa {
 
-__constant__ int c_dil[kMaxDil];
-__constant__ float c_pos_term[kMaxDil * 8];   // w2 * softmax(pos_aff), filled by par_upload_constants
-static bool g_std_dilations = false;          // the last uploaded list is the reference's {1,2,4,8,12,24} (PAR.py:94)
-static double g_row_sum = 1.01;               // sum over the neighbours of softmax + w2 * softmax(pos_aff)
-double par_weight_row_sum() { return g_row_sum; }
-
-// Host: the position term is a constant vector (PAR.py:51-62,77,82); evaluate it in double.
-int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
-  if (n_dil < 1 || n_dil > kMaxDil) return COSA_E_ARG;
-  // the constants of the last dilation list stay on the device: nothing to do for the same list again (this also
-  // keeps the call free of host-to-device copies, which a stream capture of the step could not record)
-  static int last_n = 0, last_dil[kMaxDil], last_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev == last_dev && n_dil == last_n) {
-    bool same = true;
-    for (int k = 0; k < n_dil; ++k) same = same && dilations[k] == last_dil[k];
-    if (same) return 0;
-  }
+// The dilation list and the constant position term (PAR.py:51-62,77,82), evaluated on the host in double and handed to
+// the kernels BY VALUE: no __constant__ upload, hence nothing to order between streams and nothing cached per device.
+int par_make_constants(const int *dilations, int n_dil, ParConst *pc) {
+  if (!dilations || n_dil < 1 || n_dil > kMaxDil) return COSA_E_ARG;
   const int nd = 8 * n_dil;
   double pos[kMaxDil * 8], mean = 0.0;
   for (int k = 0; k < n_dil; ++k) {
@@ -58,22 +51,33 @@ int par_upload_constants(const int *dilations, int n_dil, cudaStream_t stream) {
     mx = fmax(mx, logit[n]);
   }
   for (int n = 0; n < nd; ++n) sum += exp(logit[n] - mx);
-  float term[kMaxDil * 8];
-  for (int n = 0; n < nd; ++n) term[n] = 0.01f * (float)(exp(logit[n] - mx) / sum);
-  g_row_sum = 1.0;
-  for (int n = 0; n < nd; ++n) g_row_sum += (double)term[n];
-  int dil[kMaxDil] = {0};
-  for (int k = 0; k < n_dil; ++k) dil[k] = dilations[k];
-  static const int kStd[6] = {1, 2, 4, 8, 12, 24};
-  g_std_dilations = n_dil == 6;
-  for (int k = 0; k < 6 && g_std_dilations; ++k) g_std_dilations = dil[k] == kStd[k];
-  COSA_CUDA(cudaMemcpyToSymbolAsync(c_dil, dil, sizeof(dil), 0, cudaMemcpyHostToDevice, stream));
-  COSA_CUDA(cudaMemcpyToSymbolAsync(c_pos_term, term, sizeof(float) * nd, 0, cudaMemcpyHostToDevice, stream));
-  last_dev = dev;
-  last_n = n_dil;
-  for (int k = 0; k < n_dil; ++k) last_dil[k] = dilations[k];
+  // row_sum: sum over the neighbours of softmax + w2 * softmax(pos_aff), from the float constants the kernels use
+  pc->row_sum = 1.0;
+  for (int n = 0; n < kMaxDil * 8; ++n) pc->pos_term[n] = 0.0f;
+  for (int n = 0; n < nd; ++n) {
+    pc->pos_term[n] = 0.01f * (float)(exp(logit[n] - mx) / sum);
+    pc->row_sum += (double)pc->pos_term[n];
+  }
+  for (int k = 0; k < kMaxDil; ++k) pc->dil[k] = k < n_dil ? dilations[k] : 0;
+  pc->n_dil = n_dil;
+  static const int kStd[6] = {1, 2, 4, 8, 12, 24};   // the reference's list (PAR.py:94): the compile-time tile kernels
+  pc->std_dilations = n_dil == 6;
+  for (int k = 0; k < 6 && pc->std_dilations; ++k) pc->std_dilations = pc->dil[k] == kStd[k];
   return 0;
 }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) belongs to the current device's context: once per (kernel, device).
+template <typename F>
+static int opt_in_smem(F kernel, int bytes, std::atomic<unsigned long long> &done) {
+  int dev = 0;
+  COSA_CUDA(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ULL << (dev & 63);
+  if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return 0;
+  COSA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev < 64) done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Affinity.  One thread per pixel; per colour channel the 8*NDIL neighbour differences live in registers
@@ -91,7 +95,7 @@ __device__ __forceinline__ float div3_rn(float x) {
 
 template <int NDIL>
 __global__ void __launch_bounds__(128) par_affinity_kernel(const float *__restrict__ imgs, float *__restrict__ aff,
-                                                           int h, int w) {
+                                                           int h, int w, const ParConst pc) {
   constexpr int ND = 8 * NDIL;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(128) par_affinity_kernel(const float *__restri
     float sum = 0.0f;
 #pragma unroll
     for (int k = 0; k < NDIL; ++k) {
-      const int d = c_dil[k];
+      const int d = pc.dil[k];
       const int ym = max(y - d, 0), yp = min(y + d, h - 1);
       const int xm = max(x - d, 0), xp = min(x + d, w - 1);
       const float *r0 = ch + (size_t)ym * w, *r1 = ch + (size_t)y * w, *r2 = ch + (size_t)yp * w;
@@ -153,12 +157,13 @@ __global__ void __launch_bounds__(128) par_affinity_kernel(const float *__restri
   const float rden = 1.0f / den;
   float *out = aff + (size_t)b * ND * plane + (size_t)y * w + x;
 #pragma unroll
-  for (int n = 0; n < ND; ++n) out[(size_t)n * plane] = fmaf(logit[n], rden, c_pos_term[n]);
+  for (int n = 0; n < ND; ++n) out[(size_t)n * plane] = fmaf(logit[n], rden, pc.pos_term[n]);
 }
 
 // Generic (any n_dil <= kMaxDil) three-pass variant: neighbours are re-read instead of kept in registers.
 __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *__restrict__ imgs,
-                                                                   float *__restrict__ aff, int h, int w, int n_dil) {
+                                                                   float *__restrict__ aff, int h, int w, int n_dil,
+                                                                   const ParConst pc) {
   const int nd = 8 * n_dil;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *
   const float *img = imgs + (size_t)b * 3 * plane;
   float *out = aff + (size_t)b * nd * plane + (size_t)y * w + x;
   auto nbr = [&](const float *ch, int n) {
-    const int d = c_dil[n >> 3], m = n & 7;
+    const int d = pc.dil[n >> 3], m = n & 7;
     const int dy = (m < 3) ? -d : (m < 5 ? 0 : d);
     const int dx = (m == 0 || m == 3 || m == 5) ? -d : ((m == 1 || m == 6) ? 0 : d);
     return __ldg(ch + (size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1));
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *
   for (int n = 0; n < nd; ++n) den += expf(out[(size_t)n * plane] - mx);
   const float rden = 1.0f / den;
   for (int n = 0; n < nd; ++n)
-    out[(size_t)n * plane] = fmaf(expf(out[(size_t)n * plane] - mx), rden, c_pos_term[n]);
+    out[(size_t)n * plane] = fmaf(expf(out[(size_t)n * plane] - mx), rden, pc.pos_term[n]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(128) par_affinity_generic_kernel(const float *
 template <int CH>
 __global__ void __launch_bounds__(256) par_iterate_kernel(const float *__restrict__ aff, const float *__restrict__ in,
                                                           float *__restrict__ out, const int *__restrict__ nch_dev,
-                                                          int nch_uniform, int c_stride, int h, int w, int n_dil) {
+                                                          int nch_uniform, int c_stride, int h, int w, int n_dil,
+                                                          const ParConst pc) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(256) par_iterate_kernel(const float *__restric
     const int live = min(CH, nch - c0);
 #pragma unroll 1
     for (int kd = 0; kd < n_dil; ++kd) {
-      const int d = c_dil[kd];
+      const int d = pc.dil[kd];
       const int ym = max(y - d, 0) * w, y0 = y * w, yp = min(y + d, h - 1) * w;
       const int xm = max(x - d, 0), xp = min(x + d, w - 1);
       const int off[8] = {ym + xm, ym + x, ym + xp, y0 + xm, y0 + xp, yp + xm, yp + x, yp + xp};
@@ -256,12 +262,11 @@ __global__ void __launch_bounds__(256) par_iterate_kernel(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// One propagation step, vectorised form (w % 4 == 0, padded rows).  A thread owns 4 horizontally adjacent pixels
-// and CH channels: per dilation it streams the 8 affinity quads (128-bit, no L1 allocation) and, per channel and
-// neighbour row, three aligned 128-bit loads that cover the column offsets -d, 0, +d of all four pixels
-// (d % 4 == 0: the quads at x-d, x, x+d; d < 4: the quads left/centre/right, recombined in registers).
-// The replicated column pads make every load unclamped; rows are clamped by index.  A warp covers 4 rows x
-// 8 quads, i.e. one 128-byte line per row when the interior is 128-byte aligned.
+// Vectorised step kernels (w % 4 == 0, padded rows).  A thread owns 4 horizontally adjacent pixels and CH channels:
+// per dilation it streams the 8 affinity quads (128-bit, no L1 allocation) and, per channel and neighbour row, three
+// aligned 128-bit loads that cover the column offsets -d, 0, +d of all four pixels (d % 4 == 0: the quads at x-d, x,
+// x+d; d < 4: the quads left/centre/right, recombined in registers).  The replicated column pads make every load
+// unclamped; rows are clamped by index.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
@@ -286,126 +291,10 @@ __device__ __forceinline__ void shifted_quads(const float4 &L, const float4 &C, 
     p = make_float4(C.w, R.x, R.y, R.z);
   }
 }
-
-static int par_tile_log2() {   // width of the CTA tile in quads (log2); COSA_PAR_TILE_LOG2 overrides
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("COSA_PAR_TILE_LOG2");
-    v = e ? atoi(e) : 3;
-    if (v < 0 || v > 8) v = 3;
-  }
-  return v;
-}
-
-template <int CH>
-__global__ void __launch_bounds__(256, 2)
-    par_iterate_vec_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
-                           float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
-                           int c_stride, int h, int w, int n_dil, int tq_log2) {
-  // CTA tile = 2^tq_log2 quads x (256 >> tq_log2) rows; a warp then covers 4 rows x 8 quads (one 128-byte line per row)
-  const int wq = w >> 2;
-  const int xq = (blockIdx.x << tq_log2) + (threadIdx.x & ((1 << tq_log2) - 1));
-  const int y = blockIdx.y * (256 >> tq_log2) + (threadIdx.x >> tq_log2);
-  const int b = blockIdx.z;
-  if (xq >= wq || y >= h) return;
-  const int x = xq << 2;
-  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
-  const size_t plane = (size_t)h * w;
-  const size_t iplane = (size_t)h * li.pitch, oplane = (size_t)h * lo.pitch;
-  const float *A = aff + (size_t)b * (8 * n_dil) * plane + (size_t)y * w + x;
-  const float *src = in + (size_t)b * c_stride * iplane + li.off + x;
-  float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
-
-  for (int c0 = 0; c0 < nch; c0 += CH) {
-    float4 acc[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int live = min(CH, nch - c0);
-#pragma unroll 1
-    for (int kd = 0; kd < n_dil; ++kd) {
-      const int d = c_dil[kd];
-      float4 a[8];
-#pragma unroll
-      for (int m = 0; m < 8; ++m) a[m] = ldg_stream4(A + (size_t)(8 * kd + m) * plane);
-      const size_t rm = (size_t)max(y - d, 0) * li.pitch, r0 = (size_t)y * li.pitch,
-                   rp = (size_t)min(y + d, h - 1) * li.pitch;
-      if ((d & 3) == 0) {
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            const float *ch = src + (size_t)(c0 + k) * iplane;
-            fma4(acc[k], a[0], ldg4(ch + rm - d));
-            fma4(acc[k], a[1], ldg4(ch + rm));
-            fma4(acc[k], a[2], ldg4(ch + rm + d));
-            fma4(acc[k], a[3], ldg4(ch + r0 - d));
-            fma4(acc[k], a[4], ldg4(ch + r0 + d));
-            fma4(acc[k], a[5], ldg4(ch + rp - d));
-            fma4(acc[k], a[6], ldg4(ch + rp));
-            fma4(acc[k], a[7], ldg4(ch + rp + d));
-          }
-        }
-      } else if (d < 4) {
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            const float *ch = src + (size_t)(c0 + k) * iplane;
-            float4 m, p;
-            float4 C = ldg4(ch + rm);
-            shifted_quads(ldg4(ch + rm - 4), C, ldg4(ch + rm + 4), d, m, p);
-            fma4(acc[k], a[0], m); fma4(acc[k], a[1], C); fma4(acc[k], a[2], p);
-            C = ldg4(ch + r0);
-            shifted_quads(ldg4(ch + r0 - 4), C, ldg4(ch + r0 + 4), d, m, p);
-            fma4(acc[k], a[3], m); fma4(acc[k], a[4], p);
-            C = ldg4(ch + rp);
-            shifted_quads(ldg4(ch + rp - 4), C, ldg4(ch + rp + 4), d, m, p);
-            fma4(acc[k], a[5], m); fma4(acc[k], a[6], C); fma4(acc[k], a[7], p);
-          }
-        }
-      } else {   // unaligned large dilation: scalar loads, still unclamped thanks to the pads
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            const float *ch = src + (size_t)(c0 + k) * iplane;
-            const size_t rows[3] = {rm, r0, rp};
-#pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-              const float *q = ch + rows[rr];
-#pragma unroll
-              for (int cc = 0; cc < 3; ++cc) {
-                if (rr == 1 && cc == 1) continue;
-                const int mi = rr * 3 + cc - (rr * 3 + cc > 4 ? 1 : 0);
-                const float *qq = q + (cc - 1) * d;
-                fma4(acc[k], a[mi], make_float4(__ldg(qq), __ldg(qq + 1), __ldg(qq + 2), __ldg(qq + 3)));
-              }
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < CH; ++k) {
-      if (k < live) {
-        float *o = dst + (size_t)(c0 + k) * oplane;
-        *reinterpret_cast<float4 *>(o) = acc[k];
-        if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
-          if (xq == 0) {
-            const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
-            for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
-          }
-          if (xq == wq - 1) {
-            const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
-            for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
-          }
-        }
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // One propagation step with the near neighbourhood staged in shared memory by the TMA unit.
 //
-// CTA tile: 32 rows x 32 pixels (256 threads, 4 pixels x CH channels each, as in the vector kernel).  The mask tile
+// CTA tile: 32 rows x 32 pixels (256 threads, 4 pixels x CH channels each).  The mask tile
 // of every live channel, with a halo of kHalo = 8 pixels, is brought into shared memory by cp.async.bulk row copies
 // (one 192-byte copy per tile row and channel, completion on an mbarrier): 32 of the 48 neighbours (dilations
 // 1, 2, 4, 8) are then served by conflict-free 128-bit shared-memory loads; only dilations > 8 go to L1/L2.
@@ -453,7 +342,7 @@ template <int CH>
 __global__ void __launch_bounds__(256, 2)
     par_iterate_smem_kernel(const float *__restrict__ aff, const float *__restrict__ in, MaskLayout li,
                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
-                            int c_stride, int h, int w, int n_dil) {
+                            int c_stride, int h, int w, int n_dil, const ParConst pc) {
   extern __shared__ __align__(128) float s_tile[];   // [CH][kSmemH][kSmemW]
   __shared__ __align__(8) unsigned long long s_bar;
   const int wq = w >> 2;
@@ -490,7 +379,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll 1
     for (int it = 0; it < 2 * n_dil; ++it) {
       const int kd = it < n_dil ? it : it - n_dil;
-      const int d = c_dil[kd];
+      const int d = pc.dil[kd];
       if ((d <= kHalo) != (it >= n_dil)) continue;
       float4 a[8];
 #pragma unroll
@@ -650,8 +539,8 @@ __device__ __forceinline__ void load_aff8(float4 (&a)[8], const float *&A, size_
   }
 }
 
-// TMA: one 3-D box {80 columns, 16 rows, 1 plane} of the mask tensor [B*c_stride, h, pitch] per request; rows outside
-// the image are zero-filled by the unit and replaced by the replicated border row afterwards.
+// One dilation with ROLLING affinity refill: as soon as the taps of one neighbour row have been consumed by every
+// channel, their registers are reloaded with the same taps of the dilation two ahead (A walks the planes in order), so
 __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *tmap, int x, int y, int z,
                                              unsigned long long *bar) {
   asm volatile(
@@ -701,7 +590,8 @@ __device__ __forceinline__ void replicate_border(float *tile, int planes, int r_
 }
 
 __global__ void __launch_bounds__(256, 2)
-    par_affinity_tile_kernel(const __grid_constant__ CUtensorMap tm_img, float *__restrict__ aff, int h, int w) {
+    par_affinity_tile_kernel(const __grid_constant__ CUtensorMap tm_img, float *__restrict__ aff, int h, int w,
+                             const ParConst pc) {
   extern __shared__ __align__(128) float s_tile[];   // [3][80][80]
   __shared__ __align__(8) unsigned long long s_bar;
   constexpr int ND = 48;
@@ -776,7 +666,7 @@ __global__ void __launch_bounds__(256, 2)
     float *out = aff + (size_t)b * ND * plane + (size_t)y * w + x;
 #pragma unroll
     for (int n = 0; n < ND; ++n) {
-      *out = fmaf(logit[n], rden, c_pos_term[n]);
+      *out = fmaf(logit[n], rden, pc.pos_term[n]);
       // walk the planes with one opaque 64-bit add: `out[n * plane]` costs a wide multiply and four more integer
       // instructions per store in a kernel that is bound by instruction issue
       asm volatile("add.u64 %0, %0, %1;" : "+l"(out) : "l"(plane * sizeof(float)));
@@ -786,8 +676,8 @@ __global__ void __launch_bounds__(256, 2)
 
 // Tile-mode step kernel (default): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
 // passes of its tile.  The hardware CTA scheduler balances the load; 2 CTAs per SM overlap staging and compute.
-template <int CH, int DEPTH, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int CH>
+__global__ void __launch_bounds__(256, 2)
     par_iterate_tile_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
                             int c_stride, int h, int w, int gsplit) {
@@ -845,8 +735,8 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float *Ap = A;
-    // affinity quads DEPTH - 1 dilations ahead of their use (DEPTH = 2 leaves 32 more registers to the
-    // shared-memory loads in flight)
+    // affinity quads one dilation ahead of their use: two sets of 8 quads in registers (a third set spills at 128
+    // registers, and one CTA per SM with deeper prefetch loses more to occupancy than it gains: DESIGN.md section 4)
     float4 a0[8], a1[8];
     load_aff8(a0, Ap, plane);
     load_aff8(a1, Ap, plane);
@@ -855,58 +745,17 @@ __global__ void __launch_bounds__(256, MINB)
       mbar_wait(&s_bar[1], phase);
       replicate_border_rows(s_tile, live, r_lo, r_hi);
     }
-    if constexpr (DEPTH == 6) {          // every affinity quad of the pixel quad in flight before the first FFMA
-      float4 a2[8], a3[8], a4[8], a5[8];
-      load_aff8(a2, Ap, plane);
-      load_aff8(a3, Ap, plane);
-      load_aff8(a4, Ap, plane);
-      load_aff8(a5, Ap, plane);
-      tile_dilation<1, CH>(acc, a0, q, live);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      tile_dilation<4, CH>(acc, a2, q, live);
-      tile_dilation<8, CH>(acc, a3, q, live);
-      if (!edge) mbar_wait(&s_bar[1], phase);
-      tile_dilation<12, CH>(acc, a4, q, live);
-      tile_dilation<24, CH>(acc, a5, q, live);
-    } else if constexpr (DEPTH == 4) {
-      float4 a2[8], a3[8];
-      load_aff8(a2, Ap, plane);
-      load_aff8(a3, Ap, plane);
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      tile_dilation<4, CH>(acc, a2, q, live);
-      tile_dilation<8, CH>(acc, a3, q, live);
-      if (!edge) mbar_wait(&s_bar[1], phase);
-      tile_dilation<12, CH>(acc, a0, q, live);
-      tile_dilation<24, CH>(acc, a1, q, live);
-    } else if constexpr (DEPTH == 3) {
-      float4 a2[8];
-      load_aff8(a2, Ap, plane);
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      tile_dilation<4, CH>(acc, a2, q, live);
-      load_aff8(a2, Ap, plane);
-      tile_dilation<8, CH>(acc, a0, q, live);
-      if (!edge) mbar_wait(&s_bar[1], phase);
-      tile_dilation<12, CH>(acc, a1, q, live);
-      tile_dilation<24, CH>(acc, a2, q, live);
-    } else {
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      tile_dilation<4, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<8, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      if (!edge) mbar_wait(&s_bar[1], phase);
-      tile_dilation<12, CH>(acc, a0, q, live);
-      tile_dilation<24, CH>(acc, a1, q, live);
-    }
+    tile_dilation<1, CH>(acc, a0, q, live);
+    load_aff8(a0, Ap, plane);
+    tile_dilation<2, CH>(acc, a1, q, live);
+    load_aff8(a1, Ap, plane);
+    tile_dilation<4, CH>(acc, a0, q, live);
+    load_aff8(a0, Ap, plane);
+    tile_dilation<8, CH>(acc, a1, q, live);
+    load_aff8(a1, Ap, plane);
+    if (!edge) mbar_wait(&s_bar[1], phase);
+    tile_dilation<12, CH>(acc, a0, q, live);
+    tile_dilation<24, CH>(acc, a1, q, live);
     phase ^= 1;
     if (active) {
 #pragma unroll
@@ -933,147 +782,6 @@ __global__ void __launch_bounds__(256, MINB)
     }
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Scalar tile-mode step kernel: the same TMA-staged (32+48)^2 tiles, but 512 threads per CTA with one pixel COLUMN
-// position and two rows (ty, ty + 16) each instead of 256 threads with a pixel quad.  A warp reads 32 consecutive
-// floats of a staged row (one conflict-free wavefront per LDS.32: the same bytes per wavefront as the quad
-// kernel's LDS.128), every offset is an immediate for every dilation, and a thread needs ~60 registers instead of
-// 128, so 32 warps per SM hide the shared-memory latency the 16-warp quad kernel stalls on (ncu: 63 % of its issue
-// slots wait on the short scoreboard with the LSU data pipe at 48 %).
-// ------------------------------------------------------------------------------------------------
-constexpr int kRowsPerPass = 16;   // 512 threads = 32 columns x 16 rows; two passes cover the 32-row tile
-
-template <int D, int CH>
-__device__ __forceinline__ void tile_dilation1(float (&acc)[2][CH], const float (&a)[2][8], const float *q, int live) {
-  constexpr int R = D * kFS;
-#pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    if (k < live) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float *p = q + k * (kFS * kFS) + j * (kRowsPerPass * kFS);
-        float t = acc[j][k];
-        t = fmaf(a[j][0], p[-R - D], t); t = fmaf(a[j][1], p[-R], t); t = fmaf(a[j][2], p[-R + D], t);
-        t = fmaf(a[j][3], p[-D], t);                                   t = fmaf(a[j][4], p[D], t);
-        t = fmaf(a[j][5], p[R - D], t);  t = fmaf(a[j][6], p[R], t);  t = fmaf(a[j][7], p[R + D], t);
-        acc[j][k] = t;
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ float ldg_stream1(const float *p) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-
-// the 8 affinities of one dilation for the thread's two pixels; A walks through the planes
-__device__ __forceinline__ void load_aff8x2(float (&a)[2][8], const float *&A, size_t plane, size_t row16) {
-#pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    a[0][m] = ldg_stream1(A);
-    a[1][m] = ldg_stream1(A + row16);
-    asm volatile("add.u64 %0, %0, %1;" : "+l"(A) : "l"(plane * sizeof(float)));
-  }
-}
-
-template <int CH>
-__global__ void __launch_bounds__(512, 2)
-    par_iterate_tile1_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
-                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
-                             int c_stride, int h, int w, int gsplit) {
-  extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-  const int x = x0 + tx, y = y0 + ty;
-  const int b = blockIdx.z / gsplit, g = blockIdx.z - b * gsplit;
-  const int nch = nch_dev ? nch_dev[b] : nch_uniform;
-  if (nch <= 0) return;   // an image without live channels (cam2mask: no foreground class)
-  const int n_groups = nch <= CH ? 1 : gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
-  const int chunk = (nch + n_groups - 1) / n_groups;
-  if (g * chunk >= nch) return;
-  const size_t plane = (size_t)h * w;
-  const size_t oplane = (size_t)h * lo.pitch;
-  // second row clamped into the image for the affinity reads of inactive threads
-  const int ya = min(y, h - 1), yb = min(y + kRowsPerPass, h - 1);
-  const float *A = aff + (size_t)b * 48 * plane + (size_t)ya * w + min(x, w - 1);
-  const size_t row16 = (size_t)(yb - ya) * w;
-  const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
-  const bool edge = r_lo > 0 || r_hi < kFS;
-  const float *q = s_tile + (ty + kFH) * kFS + tx + kFH;   // this thread's first pixel in staged channel 0
-
-  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-  __syncthreads();
-  unsigned phase = 0;
-  for (int c0 = g * chunk; c0 < nch; c0 += gsplit * chunk) {
-    const int live = min(chunk, nch - c0);
-    constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&s_bar[0], (unsigned)(live * kNear * kFS * sizeof(float)));
-      mbar_expect_tx(&s_bar[1], (unsigned)(live * kFar * kFS * sizeof(float)));
-      const int gx = li.off + x0 - kFH, gz = b * c_stride + c0;
-      for (int r = kFNear0; r < kFNear1; r += kBoxRows)
-        for (int k = 0; k < live; ++k)
-          tma_load_box(s_tile + (k * kFS + r) * kFS, &tmap_in, gx, y0 - kFH + r, gz + k, &s_bar[0]);
-      for (int k = 0; k < live; ++k) {
-        tma_load_box(s_tile + (k * kFS) * kFS, &tmap_in, gx, y0 - kFH, gz + k, &s_bar[1]);
-        tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, &tmap_in, gx, y0 - kFH + kFNear1, gz + k, &s_bar[1]);
-      }
-    }
-    float acc[2][CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[0][k] = acc[1][k] = 0.0f;
-    const float *Ap = A;
-    float a0[2][8], a1[2][8];   // affinities one dilation ahead of their use
-    load_aff8x2(a0, Ap, plane, row16);
-    load_aff8x2(a1, Ap, plane, row16);
-    mbar_wait(&s_bar[0], phase);
-    if (edge) {
-      mbar_wait(&s_bar[1], phase);
-      replicate_border_rows(s_tile, live, r_lo, r_hi);
-    }
-    tile_dilation1<1, CH>(acc, a0, q, live);
-    load_aff8x2(a0, Ap, plane, row16);
-    tile_dilation1<2, CH>(acc, a1, q, live);
-    load_aff8x2(a1, Ap, plane, row16);
-    tile_dilation1<4, CH>(acc, a0, q, live);
-    load_aff8x2(a0, Ap, plane, row16);
-    tile_dilation1<8, CH>(acc, a1, q, live);
-    load_aff8x2(a1, Ap, plane, row16);
-    if (!edge) mbar_wait(&s_bar[1], phase);
-    tile_dilation1<12, CH>(acc, a0, q, live);
-    tile_dilation1<24, CH>(acc, a1, q, live);
-    phase ^= 1;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int yy = y + j * kRowsPerPass;
-      if (x < w && yy < h) {
-        float *dst = out + ((size_t)b * c_stride + c0) * oplane + (size_t)yy * lo.pitch + lo.off + x;
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            float *o = dst + (size_t)k * oplane;
-            *o = acc[j][k];
-            if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
-              if (x == 0)
-                for (int i = 1; i <= lo.padn; ++i) o[-i] = acc[j][k];
-              if (x == w - 1)
-                for (int i = 1; i <= lo.padn; ++i) o[i] = acc[j][k];
-            }
-          }
-        }
-      }
-    }
-    if (c0 + gsplit * chunk < nch) {   // the tile is re-staged (async proxy) for the next channel group
-      __syncthreads();
-      if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-  }
-}
-
 // One work unit of the persistent kernel: an image tile and a group of <= CH live channels.
 struct PropUnit {
   int u;            // linear unit index (>= n_units: none left)
@@ -1122,9 +830,9 @@ __device__ __forceinline__ PropUnit prop_find_unit(const PropArgs &p, const int 
 // ------------------------------------------------------------------------------------------------
 // Persistent propagation kernel: <= 2 CTAs per SM stride over the work units (image tile x channel group) of a step
 // and - with a cooperative launch - over ALL num_iter steps in ONE launch, separated by grid barriers (the masks
-// ping-pong between two scratch buffers in L2).  Measured slower than the tile-mode kernel above on B200
-// (profiles/README.md: static unit assignment, deeper affinity prefetch runs into the scoreboard limit), so it is
-// selectable (COSA_PAR_STEP=coop | persist, cosa_par_set_step_mode) rather than the default.
+// ping-pong between two scratch buffers in L2): north_star's "all propagation iterations in one launch".  Measured
+// slower than the tile-mode kernel above on B200 (profiles/README.md: static unit assignment, grid barriers), so it is
+// selectable (cosa_par_set_step_mode("coop")) rather than the default.
 // The affinity quads of the next unit's first two dilations are requested while the far dilations of the current
 // unit are computed, and the next tile is staged by TMA once the last shared-memory read of the current one retired.
 // ------------------------------------------------------------------------------------------------
@@ -1261,199 +969,6 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Double-buffered persistent step kernel (COSA_PAR_STEP=db; measured slower than the default, kept selectable).
-// <= 2 CTAs per SM stride over the work units (image tile x group of <= CH channels) of one step and each CTA owns
-// TWO tile buffers: the TMA boxes of unit i+1 are requested before unit i is computed and land while it runs, and
-// the affinity quads of unit i+1's first two dilations are requested while the last dilation of unit i is computed,
-// so after the first unit of a launch a CTA never waits for a tile.  Units that share an image tile (channel
-// groups) are adjacent in the unit order, so the second reader of the tile's affinity planes finds them in L2.
-// Result (VOC B = 32): 1.34 ms for the ten steps against 0.95 ms.  The ncu source view shows why hiding the tile
-// staging does not help: the long-scoreboard stalls sit on the first FFMA of every dilation, i.e. on the affinity
-// quads, whose prefetch distance (one dilation = 16 LDS + 64 FFMA at two channels) is far shorter than an L2 round
-// trip.  With one set of 8 quads effectively in flight per warp, 16 warps per SM keep 64 KB in flight, which at a
-// ~1.2 us loaded latency is ~8 TB/s over the GPU - about what the step moves.  The step is bound by affinity bytes
-// in flight; more of them need registers the kernel does not have.
-// ------------------------------------------------------------------------------------------------
-template <int CH>
-__device__ __forceinline__ PropUnit db_find_unit(const PropArgs &p, const int *s_nch, int n_pass, long long u,
-                                                 long long n_units) {
-  const int tiles = p.tiles_x * p.tiles_y;
-  PropUnit r;
-  for (; u < n_units; u += gridDim.x) {
-    const int pass = (int)(u % n_pass);
-    const long long bt = u / n_pass;
-    const int b = (int)(bt / tiles), t = (int)(bt - (long long)b * tiles);
-    const int nch = !p.nch_dev ? p.nch_uniform : (b < kPropMaxCachedB ? s_nch[b] : p.nch_dev[b]);
-    if (nch <= 0) continue;
-    const int n_groups = (nch + CH - 1) / CH;              // even split, at most CH channels per unit
-    const int chunk = (nch + n_groups - 1) / n_groups;
-    const int c0 = pass * chunk;
-    if (c0 < nch) {
-      r.u = (int)min(u, (long long)0x7fffffff); r.b = b; r.y0 = (t / p.tiles_x) * kTileH; r.x0 = (t % p.tiles_x) * kTileW;
-      r.c0 = c0; r.live = min(chunk, nch - c0);
-      return r;
-    }
-  }
-  r.u = -1; r.b = 0; r.x0 = 0; r.y0 = 0; r.c0 = 0; r.live = 0;
-  return r;
-}
-
-template <int CH, int DEEP>
-__global__ void __launch_bounds__(256, DEEP ? 1 : 2)
-    par_iterate_db_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_in, float *__restrict__ out,
-                          MaskLayout lo) {
-  extern __shared__ __align__(128) float s_tile[];   // [2][CH][80][80]
-  __shared__ __align__(8) unsigned long long s_bar[2][2];   // [buffer][near | far]
-  __shared__ int s_nch[kPropMaxCachedB];
-  __shared__ int s_max_nch;
-  constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
-  constexpr int kBuf = CH * kFS * kFS;
-  const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
-  const int wq = p.w >> 2;
-  const size_t plane = (size_t)p.h * p.w;
-  const size_t oplane = (size_t)p.h * lo.pitch;
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0][0], 1); mbar_init(&s_bar[0][1], 1);
-    mbar_init(&s_bar[1][0], 1); mbar_init(&s_bar[1][1], 1);
-    s_max_nch = 0;
-  }
-  __syncthreads();
-  int n_pass = p.n_pass;
-  if (p.nch_dev) {
-    int mx = 0;
-    for (int b = threadIdx.x; b < p.B; b += 256) {
-      const int v = p.nch_dev[b];
-      if (b < kPropMaxCachedB) s_nch[b] = v;
-      mx = max(mx, v);
-    }
-    if (mx > 0) atomicMax(&s_max_nch, mx);
-    __syncthreads();
-    n_pass = max(1, min(p.n_pass, (s_max_nch + CH - 1) / CH));
-  }
-  const long long n_units = (long long)p.B * p.tiles_x * p.tiles_y * n_pass;
-
-  auto stage = [&](const PropUnit &un, int buf) {   // one thread
-    float *tile = s_tile + buf * kBuf;
-    mbar_expect_tx(&s_bar[buf][0], (unsigned)(un.live * kNear * kFS * sizeof(float)));
-    mbar_expect_tx(&s_bar[buf][1], (unsigned)(un.live * kFar * kFS * sizeof(float)));
-    const int gx = p.li.off + un.x0 - kFH, gz = un.b * p.c_stride + un.c0;
-    for (int r = kFNear0; r < kFNear1; r += kBoxRows)
-      for (int k = 0; k < un.live; ++k)
-        tma_load_box(tile + (k * kFS + r) * kFS, &tm_in, gx, un.y0 - kFH + r, gz + k, &s_bar[buf][0]);
-    for (int k = 0; k < un.live; ++k) {
-      tma_load_box(tile + (k * kFS) * kFS, &tm_in, gx, un.y0 - kFH, gz + k, &s_bar[buf][1]);
-      tma_load_box(tile + (k * kFS + kFNear1) * kFS, &tm_in, gx, un.y0 - kFH + kFNear1, gz + k, &s_bar[buf][1]);
-    }
-  };
-  auto aff_ptr = [&](const PropUnit &un) {
-    return p.aff + (size_t)un.b * 48 * plane + (size_t)min(un.y0 + tr, p.h - 1) * p.w + min(un.x0 + (tq << 2), p.w - 4);
-  };
-
-  unsigned phase0 = 0, phase1 = 0;   // parity of the next completion of each buffer's barriers
-  int buf = 0;
-  PropUnit cur = db_find_unit<CH>(p, s_nch, n_pass, blockIdx.x, n_units);
-  float4 a0[8], a1[8];
-  float4 a2[DEEP ? 8 : 1], a3[DEEP ? 8 : 1];   // DEEP: four dilations of affinity quads in flight (one CTA per SM)
-  const float *Ap = aff_ptr(cur);
-  if (cur.u >= 0) {
-    if (threadIdx.x == 0) stage(cur, 0);
-    load_aff8(a0, Ap, plane);
-    load_aff8(a1, Ap, plane);
-    if constexpr (DEEP) {
-      load_aff8(a2, Ap, plane);
-      load_aff8(a3, Ap, plane);
-    }
-  }
-  while (cur.u >= 0) {
-    const PropUnit nxt = db_find_unit<CH>(p, s_nch, n_pass, (long long)cur.u + gridDim.x, n_units);
-    const bool more = nxt.u >= 0;
-    // the other buffer's last reader retired before the barrier that ended the previous unit: stage the next tile now
-    if (more && threadIdx.x == 0) stage(nxt, buf ^ 1);
-    const int live = cur.live;
-    const float *tile = s_tile + buf * kBuf;
-    const float *q = tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
-    // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
-    const int r_lo = max(0, kFH - cur.y0), r_hi = min(kFS, p.h - cur.y0 + kFH);
-    const bool edge = r_lo > 0 || r_hi < kFS;
-    float4 acc[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const unsigned ph = buf ? phase1 : phase0;
-    mbar_wait(&s_bar[buf][0], ph);
-    if (edge) {
-      mbar_wait(&s_bar[buf][1], ph);
-      replicate_border_rows(const_cast<float *>(tile), live, r_lo, r_hi);
-    }
-    if constexpr (DEEP) {
-      // a0..a3 hold d = 1, 2, 4, 8 on entry; a set is refilled as soon as its dilation is done: first with this
-      // unit's d = 12, 24, then with the next unit's d = 1, 2, 4, 8 (which therefore are four dilations ahead)
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);                       // d = 12
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);                       // d = 24
-      tile_dilation<4, CH>(acc, a2, q, live);
-      Ap = aff_ptr(nxt);
-      if (more) load_aff8(a2, Ap, plane);             // next unit, d = 1
-      tile_dilation<8, CH>(acc, a3, q, live);
-      if (more) load_aff8(a3, Ap, plane);             // next unit, d = 2
-      if (!edge) mbar_wait(&s_bar[buf][1], ph);
-      tile_dilation<12, CH>(acc, a0, q, live);
-      if (more) load_aff8(a0, Ap, plane);             // next unit, d = 4
-      tile_dilation<24, CH>(acc, a1, q, live);
-      if (more) load_aff8(a1, Ap, plane);             // next unit, d = 8
-      // rotate the names so that the next unit finds d = 1, 2, 4, 8 in a0..a3 again
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const float4 t0 = a0[m], t1 = a1[m];
-        a0[m] = a2[m]; a1[m] = a3[m]; a2[m] = t0; a3[m] = t1;
-      }
-    } else {
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      tile_dilation<4, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<8, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      if (!edge) mbar_wait(&s_bar[buf][1], ph);
-      tile_dilation<12, CH>(acc, a0, q, live);
-      // the next unit's first affinity quads travel while the last dilation of this one is computed
-      Ap = aff_ptr(nxt);
-      if (more) load_aff8(a0, Ap, plane);
-      tile_dilation<24, CH>(acc, a1, q, live);
-      if (more) load_aff8(a1, Ap, plane);
-    }
-    __syncthreads();                       // every shared-memory read of this buffer has retired
-    if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int xq = (cur.x0 >> 2) + tq, y = cur.y0 + tr;
-    if (xq < wq && y < p.h) {
-      float *dst = out + ((size_t)cur.b * p.c_stride + cur.c0) * oplane + (size_t)y * lo.pitch + lo.off + (xq << 2);
-#pragma unroll
-      for (int k = 0; k < CH; ++k) {
-        if (k < live) {
-          float *o = dst + (size_t)k * oplane;
-          *reinterpret_cast<float4 *>(o) = acc[k];
-          if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
-            if (xq == 0) {
-              const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
-              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
-            }
-            if (xq == wq - 1) {
-              const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
-              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
-            }
-          }
-        }
-      }
-    }
-    if (buf) phase1 ^= 1; else phase0 ^= 1;
-    buf ^= 1;
-    cur = nxt;
-  }
-}
-
 // plain [planes, h, w] -> padded layout (interior + replicated column pads)
 __global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
                                 int h, int w) {
@@ -1524,27 +1039,21 @@ MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
   return l;
 }
 
-int par_launch_affinity(const float *imgs, float *aff, int B, int h, int w, int n_dil, cudaStream_t stream) {
+int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, cudaStream_t stream) {
   dim3 grid(ceil_div(w, 32), ceil_div(h, 4), B), block(128);
-  static int force_generic = -1;
-  if (force_generic < 0) force_generic = getenv("COSA_PAR_AFF_GENERIC") ? 1 : 0;
-  static int use_tile = -1;
-  if (use_tile < 0) use_tile = getenv("COSA_PAR_AFF_L1") ? 0 : 1;
-  if (n_dil == 6 && g_std_dilations && w % 4 == 0 && use_tile && !force_generic) {
-    static bool attr = false;
+  const int n_dil = pc.n_dil;
+  if (pc.std_dilations && w % 4 == 0) {
+    static std::atomic<unsigned long long> done{0};
     const int smem = 3 * kFS * kFS * (int)sizeof(float);
-    if (!attr) {
-      COSA_CUDA(cudaFuncSetAttribute(par_affinity_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr = true;
-    }
+    COSA_CHECK(opt_in_smem(par_affinity_tile_kernel, smem, done));
     CUtensorMap tm;
     COSA_CHECK(make_tmap3(&tm, imgs, (long long)B * 3, h, w, kFS, kBoxRows, 1));
     COSA_LAUNCH(par_affinity_tile_kernel, dim3(ceil_div(w, kTileW), ceil_div(h, kTileH), B), 256, smem, stream, tm, aff,
-                h, w);
-  } else if (n_dil == 6 && !force_generic) {
-    COSA_LAUNCH(par_affinity_kernel<6>, grid, block, 0, stream, imgs, aff, h, w);
+                h, w, pc);
+  } else if (n_dil == 6) {
+    COSA_LAUNCH(par_affinity_kernel<6>, grid, block, 0, stream, imgs, aff, h, w, pc);
   } else {
-    COSA_LAUNCH(par_affinity_generic_kernel, grid, block, 0, stream, imgs, aff, h, w, n_dil);
+    COSA_LAUNCH(par_affinity_generic_kernel, grid, block, 0, stream, imgs, aff, h, w, n_dil, pc);
   }
   return 0;
 }
@@ -1556,154 +1065,29 @@ int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, in
   return 0;
 }
 
-// Step-kernel selection (COSA_PAR_STEP in the environment, or cosa_par_set_step_mode at run time):
-//   tile (default)  TMA-tile kernel, one CTA per tile and channel split, one launch per step
+// Step-kernel selection (cosa_par_set_step_mode; process-wide, meant for A/B runs and tests - results are identical):
+//   tile (default)  TMA-tile kernel, one CTA per tile and channel split, one launch per step (steps 2..T as
+//                   programmatic dependent launches)
 //   coop            persistent TMA-tile kernel, every step in ONE cooperative launch (grid barriers)
-//   persist         persistent TMA-tile kernel, one launch per step
-//   smem | vec      the generic per-step kernels (any dilation set): near neighbourhood staged / L1 only
-enum { kStepTile = 0, kStepCoop = 1, kStepPersist = 2, kStepSmem = 3, kStepVec = 4, kStepDb = 5 };
-static int g_step_mode = -1;
+//   smem            the generic per-step kernel (what non-reference dilation sets use)
+enum { kStepTile = 0, kStepCoop = 1, kStepSmem = 2 };
+static std::atomic<int> g_step_mode{kStepTile};
 static int parse_step_mode(const char *e) {
-  if (!e) return kStepTile;
+  if (!e) return -1;
   switch (e[0]) {
-    case 'd': return kStepDb;
     case 't': return kStepTile;
     case 'c': return kStepCoop;
-    case 'p': return kStepPersist;
     case 's': return kStepSmem;
-    case 'v': return kStepVec;
     default: return -1;
   }
 }
-static int par_step_mode() {
-  if (g_step_mode < 0) {
-    g_step_mode = parse_step_mode(getenv("COSA_PAR_STEP"));
-    if (g_step_mode < 0) g_step_mode = kStepTile;
-  }
-  return g_step_mode;
-}
 
-template <int CH>
-static int par_launch_propagate_t(PropArgs a, const CUtensorMap &t0, const CUtensorMap &ta, const CUtensorMap &tb,
-                                  int max_nch, cudaStream_t stream) {
-  const size_t smem = (size_t)CH * kFS * kFS * sizeof(float);
-  static bool attr = false;
-  static int occ = 0, coop_ok = 0;
-  if (!attr) {
-    COSA_CUDA(cudaFuncSetAttribute(par_propagate_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, par_propagate_kernel<CH>, 256, smem));
-    int dev = 0;
-    COSA_CUDA(cudaGetDevice(&dev));
-    COSA_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
-    attr = true;
-  }
-  if (occ < 1) return COSA_E_ARG;
-  // two CTAs per tile share the channels of an image with more than CH live ones (the kernel keeps <= CH
-  // channels in one CTA, where the affinity quads are loaded once)
-  a.gsplit = 2;
-  if (const char *e = getenv("COSA_PAR_GSPLIT")) a.gsplit = max(1, atoi(e));
-  a.n_pass = ceil_div(max_nch, a.gsplit * CH);
-  const long long per_pass = (long long)a.B * a.tiles_x * a.tiles_y * a.gsplit;
-  const int mode = par_step_mode();
-  if (mode == kStepCoop && coop_ok && a.num_iter > 1) {   // every step in one cooperative launch
-    const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
-    a.it_begin = 0;
-    a.it_end = a.num_iter;
-    void *args[] = {(void *)&a, (void *)&t0, (void *)&ta, (void *)&tb};
-    if (g_prof_on) prof_mark("par_propagate_kernel", stream, true);
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)par_propagate_kernel<CH>, dim3(grid), dim3(256), args,
-                                                      smem, stream);
-    ++g_launches;
-    if (g_prof_on) prof_mark("par_propagate_kernel", stream, false);
-    return e == cudaSuccess ? 0 : (int)e;
-  }
-  if (mode == kStepTile) {
-    static bool attr_tile = false;
-    static int depth = 0, minb = 2;
-    if (!attr_tile) {
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile_kernel<CH, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const char *e = getenv("COSA_PAR_DEPTH");
-      depth = e ? atoi(e) : 2;
-      if (depth != 3 && depth != 4 && depth != 6) depth = 2;
-      e = getenv("COSA_PAR_MINB");
-      minb = (e && atoi(e) == 3) ? 3 : ((e && atoi(e) == 1) ? 1 : 2);
-      attr_tile = true;
-    }
-    static int pdl = -1;
-    if (pdl < 0) {
-      const char *e = getenv("COSA_PAR_PDL");
-      pdl = e ? atoi(e) : 1;
-    }
-    static int scalar = -1;
-    if (scalar < 0) {
-      const char *e = getenv("COSA_PAR_SCALAR");
-      scalar = e ? atoi(e) : 0;   // measured slower than the quad kernel (1.05 vs 0.95 ms per ten steps at VOC B = 32)
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_tile1_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
-    for (int it = 0; it < a.num_iter; ++it) {
-      const bool last = it == a.num_iter - 1;
-      const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
-      float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
-      if (scalar) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", par_iterate_tile1_kernel<CH>, grid, 512, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else if (depth == 6) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 6, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else if (depth == 4) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 4, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else if (depth == 3 && minb == 1) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 3, 1>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else if (depth == 2 && minb == 3) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 3>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else if (depth == 2 && it > 0 && pdl && !g_prof_on) {
-        // steps 2..T: programmatic dependent launch behind the previous step (see the kernel's prologue)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(256);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        const MaskLayout lo_it = last ? a.lo_final : a.li;
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, par_iterate_tile_kernel<CH, 2, 2>, a.aff, tm, a.li, dst, lo_it,
-                                                 a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-        ++g_launches;
-        if (e != cudaSuccess) return (int)e;
-      } else if (depth == 2) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 2, 2>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      } else {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_tile_kernel<CH, 3, 2>), grid, 256, smem, stream, a.aff, tm, a.li,
-                      dst, last ? a.lo_final : a.li, a.nch_dev, a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
-      }
-    }
-    return 0;
-  }
-  const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
-  for (int it = 0; it < a.num_iter; ++it) {
-    a.it_begin = it;
-    a.it_end = it + 1;
-    COSA_LAUNCH(par_propagate_kernel<CH>, grid, 256, smem, stream, a, t0, ta, tb);
-  }
-  return 0;
-}
+constexpr int kStepCH = 3;   // channels per CTA pass of the tile kernels
 
 static int par_launch_propagate(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
                                 float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                                int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
+                                int c_stride, int B, int h, int w, int num_iter, int mode, cudaStream_t stream) {
+  constexpr int CH = kStepCH;
   PropArgs a;
   a.aff = aff;
   a.out_a = scratch_a; a.out_b = scratch_b; a.out_final = final_dst;
@@ -1718,102 +1102,99 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
   COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
   const int max_nch = nch_dev ? c_stride : nch_uniform;
-  if (par_step_mode() == kStepDb) {
-    static int deep = -1;
-    if (deep < 0) {
-      const char *e = getenv("COSA_PAR_DB_DEEP");
-      deep = e ? atoi(e) : 1;
+  const size_t smem = (size_t)CH * kFS * kFS * sizeof(float);
+  // two CTAs per tile share the channels of an image with more than CH live ones (the kernel keeps <= CH channels in
+  // one CTA, where the affinity quads are loaded once)
+  a.gsplit = 2;
+  a.n_pass = ceil_div(max_nch, a.gsplit * CH);
+  if (mode == kStepCoop && num_iter > 1) {   // every step in one cooperative launch
+    static std::atomic<unsigned long long> done{0};
+    COSA_CHECK(opt_in_smem(par_propagate_kernel<CH>, (int)smem, done));
+    int dev = 0, occ = 0, coop_ok = 0;
+    COSA_CUDA(cudaGetDevice(&dev));
+    COSA_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
+    COSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, par_propagate_kernel<CH>, 256, smem));
+    if (coop_ok && occ >= 1) {
+      const long long per_pass = (long long)a.B * a.tiles_x * a.tiles_y * a.gsplit;
+      const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
+      a.it_begin = 0;
+      a.it_end = a.num_iter;
+      void *args[] = {(void *)&a, (void *)&t0, (void *)&ta, (void *)&tb};
+      if (g_prof_on) prof_mark("par_propagate_kernel", stream, true);
+      const cudaError_t e = cudaLaunchCooperativeKernel((const void *)par_propagate_kernel<CH>, dim3(grid), dim3(256),
+                                                        args, smem, stream);
+      ++g_launches;
+      if (g_prof_on) prof_mark("par_propagate_kernel", stream, false);
+      return e == cudaSuccess ? 0 : (int)e;
     }
-    const int CHv = deep ? 4 : 2;
-    const size_t smem = (size_t)2 * CHv * kFS * kFS * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)2 * 2 * kFS * kFS * sizeof(float))));
-      COSA_CUDA(cudaFuncSetAttribute(par_iterate_db_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)2 * 4 * kFS * kFS * sizeof(float))));
-      attr = true;
-    }
-    a.gsplit = 1;
-    a.n_pass = ceil_div(max_nch, CHv);
-    const long long n_units = (long long)a.B * a.tiles_x * a.tiles_y * a.n_pass;
-    const int grid = (int)max(1LL, min(n_units, (deep ? 1LL : 2LL) * sm_count()));
-    for (int it = 0; it < a.num_iter; ++it) {
-      const bool last = it == a.num_iter - 1;
-      const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
-      float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
-      if (deep) {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_db_kernel<4, 1>), grid, 256, smem, stream, a, tm, dst,
-                      last ? a.lo_final : a.li);
-      } else {
-        COSA_LAUNCH_T("par_iterate_tile_kernel", (par_iterate_db_kernel<2, 0>), grid, 256, smem, stream, a, tm, dst,
-                      last ? a.lo_final : a.li);
-      }
-    }
-    return 0;
   }
-  static int ch = 0;
-  if (!ch) {
-    const char *e = getenv("COSA_PAR_CH");
-    ch = e ? atoi(e) : 3;
+  static std::atomic<unsigned long long> done_tile{0};
+  COSA_CHECK(opt_in_smem(par_iterate_tile_kernel<CH>, (int)smem, done_tile));
+  const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
+  for (int it = 0; it < a.num_iter; ++it) {
+    const bool last = it == a.num_iter - 1;
+    const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
+    float *dst = last ? a.out_final : ((it & 1) ? a.out_b : a.out_a);
+    const MaskLayout lo_it = last ? a.lo_final : a.li;
+    // steps 2..T: programmatic dependent launch behind the previous step (see the kernel's prologue); plain launches
+    // while the per-kernel event timing is on, so that a step's events bracket that step alone
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (it > 0 && !g_prof_on) ? 1 : 0;
+    if (g_prof_on) prof_mark("par_iterate_tile_kernel", stream, true);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, par_iterate_tile_kernel<CH>, a.aff, tm, a.li, dst, lo_it, a.nch_dev,
+                                             a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+    ++g_launches;
+    if (g_prof_on) prof_mark("par_iterate_tile_kernel", stream, false);
+    if (e != cudaSuccess) return (int)e;
   }
-  if (ch == 2) return par_launch_propagate_t<2>(a, t0, ta, tb, max_nch, stream);
-  if (ch == 3) return par_launch_propagate_t<3>(a, t0, ta, tb, max_nch, stream);
-  return par_launch_propagate_t<4>(a, t0, ta, tb, max_nch, stream);
+  return 0;
 }
 
-int par_launch_iterations(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
-                          float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform, int c_stride,
-                          int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream) {
+int par_launch_iterations(const ParConst &pc, const float *aff, const float *src0, float *scratch_a, float *scratch_b,
+                          MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
+                          int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
   if (num_iter <= 0) return COSA_E_ARG;   // callers handle the zero-iteration copy themselves
+  const int n_dil = pc.n_dil;
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
   const bool vec = lay.padn > 0;
-  if (vec && g_std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) &&
-      (par_step_mode() <= kStepPersist || par_step_mode() == kStepDb))
+  const int mode = g_step_mode.load(std::memory_order_relaxed);
+  if (vec && pc.std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) && mode != kStepSmem)
     return par_launch_propagate(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
-                                c_stride, B, h, w, num_iter, stream);
+                                c_stride, B, h, w, num_iter, mode, stream);
   const float *src = src0;
   for (int it = 0; it < num_iter; ++it) {
     const bool last = it == num_iter - 1;
     float *dst = last ? final_dst : ((it & 1) ? scratch_b : scratch_a);
     const MaskLayout lo = last ? lay_final : lay;
-    const int step_kind = par_step_mode() == kStepVec ? 1 : 0;
-    if (vec && step_kind != 1) {
+    if (vec) {
       dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileH), B), block(256);
-      static bool attr_set = false;
-      if (!attr_set) {
-        COSA_CUDA(cudaFuncSetAttribute(par_iterate_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       8 * kSmemH * kSmemW * (int)sizeof(float)));
-        COSA_CUDA(cudaFuncSetAttribute(par_iterate_smem_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       4 * kSmemH * kSmemW * (int)sizeof(float)));
-        attr_set = true;
-      }
+      static std::atomic<unsigned long long> done8{0}, done4{0};
       if (wide) {
+        COSA_CHECK(opt_in_smem(par_iterate_smem_kernel<8>, 8 * kSmemH * kSmemW * (int)sizeof(float), done8));
         COSA_LAUNCH(par_iterate_smem_kernel<8>, grid, block, 8 * kSmemH * kSmemW * sizeof(float), stream, aff, src, lay,
-                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil);
+                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil, pc);
       } else {
+        COSA_CHECK(opt_in_smem(par_iterate_smem_kernel<4>, 4 * kSmemH * kSmemW * (int)sizeof(float), done4));
         COSA_LAUNCH(par_iterate_smem_kernel<4>, grid, block, 4 * kSmemH * kSmemW * sizeof(float), stream, aff, src, lay,
-                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil);
-      }
-    } else if (vec) {
-      const int tq = par_tile_log2();
-      dim3 grid(ceil_div(w / 4, 1 << tq), ceil_div(h, 256 >> tq), B), block(256);
-      if (wide) {
-        COSA_LAUNCH(par_iterate_vec_kernel<8>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
-                    c_stride, h, w, n_dil, tq);
-      } else {
-        COSA_LAUNCH(par_iterate_vec_kernel<4>, grid, block, 0, stream, aff, src, lay, dst, lo, nch_dev, nch_uniform,
-                    c_stride, h, w, n_dil, tq);
+                    dst, lo, nch_dev, nch_uniform, c_stride, h, w, n_dil, pc);
       }
     } else {
       if (lo.pitch != w || lo.off != 0) return COSA_E_ARG;   // the generic kernel writes plain NCHW only
       dim3 grid(ceil_div(w, 32), ceil_div(h, 8), B), block(256);
       if (wide) {
         COSA_LAUNCH(par_iterate_kernel<8>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h,
-                    w, n_dil);
+                    w, n_dil, pc);
       } else {
         COSA_LAUNCH(par_iterate_kernel<4>, grid, block, 0, stream, aff, src, dst, nch_dev, nch_uniform, c_stride, h,
-                    w, n_dil);
+                    w, n_dil, pc);
       }
     }
     src = dst;
@@ -1824,12 +1205,12 @@ int par_launch_iterations(const float *aff, const float *src0, float *scratch_a,
 // Affinity + num_iter propagation steps for the whole batch.  (Splitting the batch into L2-sized chunks so that
 // the affinity planes are re-read from L2 was measured and is slower: the step is bound by the L1 path of the
 // neighbour loads, not by the affinity stream - see profiles/README.md.)
-int par_refine_batch(const float *imgs, float *aff, const float *src0, float *scratch_a, float *scratch_b,
-                     MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                     int c_stride, int B, int h, int w, int n_dil, int num_iter, cudaStream_t stream) {
-  COSA_CHECK(par_launch_affinity(imgs, aff, B, h, w, n_dil, stream));
-  return par_launch_iterations(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
-                               c_stride, B, h, w, n_dil, num_iter, stream);
+int par_refine_batch(const ParConst &pc, const float *imgs, float *aff, const float *src0, float *scratch_a,
+                     float *scratch_b, MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev,
+                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
+  COSA_CHECK(par_launch_affinity(pc, imgs, aff, B, h, w, stream));
+  return par_launch_iterations(pc, aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
+                               c_stride, B, h, w, num_iter, stream);
 }
 
 }  // namespace cosa
@@ -1847,17 +1228,17 @@ extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
 
 extern "C" int cosa_par_set_step_mode(const char *name) {
   const int m = parse_step_mode(name);
-  if (!name || m < 0) return COSA_E_ARG;
-  g_step_mode = m;
+  if (m < 0) return COSA_E_ARG;
+  g_step_mode.store(m, std::memory_order_relaxed);
   return 0;
 }
 
 extern "C" int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const int *dilations, int n_dil,
                                  void *stream) {
   if (!imgs || !aff || B < 1 || h < 1 || w < 1) return COSA_E_ARG;
-  cudaStream_t s = (cudaStream_t)stream;
-  COSA_CHECK(par_upload_constants(dilations, n_dil, s));
-  return par_launch_affinity(imgs, aff, B, h, w, n_dil, s);
+  ParConst pc;
+  COSA_CHECK(par_make_constants(dilations, n_dil, &pc));
+  return par_launch_affinity(pc, imgs, aff, B, h, w, (cudaStream_t)stream);
 }
 
 extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out, int B, int C, int h, int w,
@@ -1867,7 +1248,8 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
     return COSA_E_ARG;
   if (ws_bytes < cosa_par_ws_bytes(B, C, h, w, n_dil)) return COSA_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
-  COSA_CHECK(par_upload_constants(dilations, n_dil, s));
+  ParConst pc;
+  COSA_CHECK(par_make_constants(dilations, n_dil, &pc));
   const size_t plane = (size_t)h * w;
   MaskLayout lay = padded_layout(w, dilations, n_dil);
   if (lay.padn > 24) lay = plain_layout(w);   // keeps the scratch within cosa_par_ws_bytes
@@ -1903,6 +1285,5 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
   }
   // step 0 reads src0 (buf_b or the caller's tensor) and writes buf_a, step 1 writes buf_b, ...
   // (src0 is the caller's tensor only in the plain layout, whose strides equal the scratch strides)
-  return par_refine_batch(imgs, aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, n_dil, num_iter,
-                          s);
+  return par_refine_batch(pc, imgs, aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, num_iter, s);
 }

@@ -53,14 +53,14 @@ size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil);
 int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out, int B, int C, int h, int w,
                      int hm, int wm, const int *dilations, int n_dil, int num_iter, void *ws, size_t ws_bytes,
                      void *stream);
-/* The affinity alone, [B, 8*n_dil, h, w] (PAR.py:69-85); used by tests and by cam2mask internally. */
-/* Selects the propagation kernel used by cosa_par_forward / cosa_cam2mask from now on (process-wide; results are
- * identical, only the launch structure differs): "tile" (default; TMA-staged 32x32 tiles, one launch per step),
- * "coop" (persistent kernel, ALL steps in one cooperative launch with grid barriers), "persist" (persistent kernel,
- * one launch per step), "db" (persistent kernel with two tile buffers per CTA), "smem" / "vec" (generic per-step kernels, also used for non-reference dilation sets).
- * The environment variable COSA_PAR_STEP sets the initial choice.  Returns COSA_E_ARG for an unknown name. */
+/* Selects the propagation kernel used by cosa_par_forward / cosa_cam2mask from now on (process-wide, meant for A/B
+ * runs and tests; results are identical, only the launch structure differs): "tile" (default; TMA-staged 32x32 tiles,
+ * one launch per step, steps 2..T as programmatic dependent launches), "coop" (persistent kernel, ALL steps in one
+ * cooperative launch with grid barriers), "smem" (the generic per-step kernel that non-reference dilation sets use).
+ * Returns COSA_E_ARG for an unknown name. */
 int cosa_par_set_step_mode(const char *name);
 
+/* The affinity alone, [B, 8*n_dil, h, w] (PAR.py:69-85); used by tests and by cam2mask internally. */
 int cosa_par_affinity(const float *imgs, float *aff, int B, int h, int w, const int *dilations, int n_dil,
                       void *stream);
 

@@ -379,3 +379,26 @@ def test_prebuilt_lattice_matches_the_single_stream_call(cosa):
     # geometries the fused path does not take are refused quietly
     assert layer.prebuild_lattice(d["simg"].cpu(), C) is False
     assert cosa.DenseEnergyLoss(1e-7, 15, 100, 1.0).prebuild_lattice(d["simg"], C) is False
+
+
+def test_par_two_streams_two_dilation_sets(cosa, port):
+    """Two PAR instances with different dilation lists running concurrently on two streams: the dilations and the
+    position term travel with each launch (kernel arguments), so neither call can see the other's constants."""
+    gen = torch.Generator().manual_seed(77)
+    imgs = torch.rand((2, 3, 64, 96), generator=gen)
+    masks = torch.rand((2, 4, 64, 96), generator=gen).softmax(dim=1)
+    sets = ([1, 2, 4, 8, 12, 24], [3, 5, 7])
+    want = [port.par_forward(imgs, masks, tuple(d), 6) for d in sets]
+    pars = [cosa.PAR(num_iter=6, dilations=d).cuda() for d in sets]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    di, dm = imgs.cuda(), masks.cuda()
+    torch.cuda.synchronize()
+    outs = [[], []]
+    for _ in range(5):
+        for k in (0, 1):
+            with torch.cuda.stream(streams[k]):
+                outs[k].append(pars[k](di, dm))
+    torch.cuda.synchronize()
+    for k in (0, 1):
+        for o in outs[k]:
+            assert_close(o, want[k], "PAR dilations %s on its own stream" % sets[k])

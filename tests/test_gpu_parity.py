@@ -46,6 +46,21 @@ def assert_close(got, want, what, tol=TOL):
     return r
 
 
+def assert_loss_close(port, got, want, what):
+    """CRF loss scalar against the oracle's.  The reference accumulates <S, AS> with a float32 np.dot
+    (seg_helper.py:890), whose own distance from the exact sum grows with the batch (~1e-4 at the BASELINE sizes,
+    BLAS-dependent); the product accumulates in double.  The bar is therefore: within TOL of the reference's maths
+    evaluated exactly (float64 dot of the oracle's own S and AS), and no further from the reference's float32 value
+    than that value is from the exact one (+ TOL).  Returns (rel vs float64, rel vs float32, the reference's drift)."""
+    g = float(got.detach().cpu().reshape(-1)[0]) if isinstance(got, torch.Tensor) else float(np.asarray(got).reshape(-1)[0])
+    w32 = float(want.detach().cpu().reshape(-1)[0]) if isinstance(want, torch.Tensor) else float(np.asarray(want).reshape(-1)[0])
+    w64 = w32 * port.last_loss_exact_over_reference()
+    r64, r32, drift = abs(g - w64) / abs(w64), abs(g - w32) / abs(w32), abs(w32 - w64) / abs(w64)
+    assert r64 <= TOL, "%s: rel = %.3g > %g against the float64-accumulated oracle" % (what, r64, TOL)
+    assert r32 <= drift + TOL, "%s: rel = %.3g against the reference's float32 value (its own drift: %.3g)" % (what, r32, drift)
+    return r64, r32, drift
+
+
 def assert_same(got, want, what):
     got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
     want = want.detach().cpu().numpy() if isinstance(want, torch.Tensor) else np.asarray(want)
@@ -109,10 +124,10 @@ def test_par_tile_path_shapes(cosa, port, shape):
     assert_close(aff, port.par_affinity(imgs)[:, 0], "affinity %s" % (shape,))
 
 
-@pytest.mark.parametrize("mode", ["coop", "persist", "smem", "vec", "tile", "db"])
+@pytest.mark.parametrize("mode", ["coop", "smem", "tile"])
 def test_par_step_kernels_agree(cosa, port, mode):
-    """Every propagation kernel (single cooperative launch, persistent, double-buffered persistent, generic, and
-    the default one CTA per tile) against the oracle, on a
+    """Every propagation kernel (single cooperative launch, the generic per-step kernel, and the default one CTA
+    per tile) against the oracle, on a
     ragged batch shape (partial tiles in both directions) and on the cam2mask path with per-image channel counts."""
     from cosa_b200 import par as par_mod
     g = torch.Generator().manual_seed(11)
