@@ -514,7 +514,7 @@ def run_cosa_arm(args):
         sync_all()
         e2e_ms = sharding.all_reduce_max(ev0.elapsed_time(ev1))
         ref_loss = float(loss.detach())
-        assert abs(float(res[-1][1]) - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-12, "e2e loss differs from the device path"
+        assert abs(float(res[-1][1].detach()) - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-12, "e2e loss differs from the device path"
         e2e = {"value": sharding.all_reduce_sum(B * e2e_steps) / (e2e_ms / 1e3), "unit": "images/s",
                "h2d_bytes_per_step": (pipe.h2d_bytes - h2d0) // e2e_steps,
                "d2h_bytes_per_step": (pipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
@@ -534,7 +534,7 @@ def run_cosa_arm(args):
             npipe.submit_native(nbatch)
         npipe.drain()
         sync_all()
-        h2d0, d2h0, l0 = npipe.h2d_bytes, npipe.d2h_bytes, _lib.launch_count()
+        h2d0, d2h0, l0 = npipe.h2d_bytes, npipe.d2h_bytes, _lib.launch_count() + npipe.graph_kernels
         ev0.record()
         for _ in range(e2e_steps):
             npipe.submit_native(nbatch)
@@ -546,7 +546,7 @@ def run_cosa_arm(args):
                       "h2d_bytes_per_step": (npipe.h2d_bytes - h2d0) // e2e_steps,
                       "d2h_bytes_per_step": (npipe.d2h_bytes - d2h0) // e2e_steps, "steps": e2e_steps,
                       "ms_per_step": n_ms / e2e_steps,
-                      "gpu_launches_per_step": (_lib.launch_count() - l0) / e2e_steps,
+                      "gpu_launches_per_step": (_lib.launch_count() + npipe.graph_kernels - l0) / e2e_steps,
                       "note": "HostPipeline.submit_native: host buffers at the resolution the networks emit them "
                               "(raw CAMs on the 28/14/42 token grids for images and flips, logits 28x28); "
                               "multi_scale_cam_merge + cam_validation and the main.py:167 enlargement (with its "
