@@ -11,17 +11,19 @@ by hand-written sm_100a CUDA kernels behind the C-ABI in ``include/cosa_b200.h``
   ``get_energy_loss, DenseEnergyLoss, DenseEnergyLossFunction``   utils/seg_helper.py:191-230, 864-903
   ``multi_scale_camseg`` (merge fused), ``seg_loss``, ``seg_refine_by_label``, ``cam_loss``   :232-275, 800-813, 553-602
   ``bilateralfilter.bilateralfilter_batch``         utils/bilateralfilter (SWIG module)
+  ``DenseCRF, crf_inference_infv2, crf_inference_inf``   utils/seg_helper.py:905-922, 961-996 (dense-CRF inference)
 
 Everything requires CUDA tensors; there is no CPU fallback and no second backend.
 """
 from . import _lib  # noqa: F401
 from .host_pipeline import GraphedStep, HostPipeline
 from .par import PAR, get_kernel
-from .seg_helper import (DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
+from .seg_helper import (DenseCRF, crf_inference_batch, crf_inference_inf, crf_inference_infv2, DenseEnergyLoss, DenseEnergyLossFunction, _refine_cams, cam2mask, cam_normalize,
                          cam_to_label, cam_validation, denormalize_img, get_energy_loss, multi_scale_cam_merge, multi_scale_camseg,
                          multi_scale_seg_merge, cam_loss, seg_loss, seg_refine_by_label, upsample_bilinear)
 
 __all__ = ["PAR", "get_kernel", "cam_validation", "cam_to_label", "cam2mask", "_refine_cams", "cam_normalize",
            "get_energy_loss", "DenseEnergyLoss", "DenseEnergyLossFunction", "multi_scale_camseg", "multi_scale_cam_merge",
            "multi_scale_seg_merge", "HostPipeline", "GraphedStep", "seg_loss",
-           "seg_refine_by_label", "cam_loss", "denormalize_img", "upsample_bilinear"]
+           "seg_refine_by_label", "cam_loss", "denormalize_img", "upsample_bilinear", "DenseCRF", "crf_inference_infv2",
+           "crf_inference_inf", "crf_inference_batch"]

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "cosa_bilateralfilter_batch": (_c_int, [_vp, _vp, _vp] + [_c_int] * 4 + [_c_float] * 2 + [_vp, _c_size_t, _vp]),
     "cosa_bilateralfilter_batch_host": (_c_int, [_vp, _vp, _vp] + [_c_int] * 4 + [_c_float] * 2),
     "cosa_bilateral_stats": (_c_int, [_vp] + [_c_int] * 4 + [ctypes.POINTER(_c_ll), _vp]),
+    "cosa_crf_inference_ws_bytes": (_c_size_t, [_c_int] * 4),
+    "cosa_crf_inference": (_c_int, [_vp] * 3 + [_c_int] * 5 + [_c_float] * 5 + [_vp, _c_size_t, _vp]),
     "cosa_dense_energy_ws_bytes": (_c_size_t, [_c_int] * 4),
     "cosa_dense_energy_forward": (_c_int, [_vp] * 4 + [_c_float] * 2 + [_vp, _vp] + [_c_int] * 4 +
                                   [_vp, _c_size_t, _vp]),

@@ -27,17 +27,22 @@
 
 namespace cosa {
 
-constexpr int kLatD = 5;
+constexpr int kLatD = 5;                            // the path's lattice: (x, y, R, G, B)
+constexpr int kMaxLatD = 5;                         // kernels are instantiated for D = 5 and D = 2 (the dense CRF's
+                                                    // spatial kernel, utils/seg_helper.py:961-996)
 constexpr int kQBits = 11;
 constexpr int kQBias = 1 << (kQBits - 1);          // 1024
+constexpr int kKeyRShift = kQBits * kMaxLatD;       // 55: residue field (the same place for every D)
+constexpr int kKeyBShift = kKeyRShift + 3;          // 58: image index
 constexpr int kMaxImagesPerLattice = 64;
 constexpr unsigned long long kEmptyKey = ~0ULL;
 
 constexpr int kTileW = 32, kTileH = 8;
 constexpr int kTilePix = kTileW * kTileH;           // 256 = threads per tile CTA
-constexpr int kTilePairs = (kLatD + 1) * kTilePix;  // 1536
-constexpr int kPairBlock = kTilePairs / 32;         // 48: pairs per quarter-warp of the splat
-constexpr int kTileListStride = kTilePairs + 32;    // u16 per tile: the pair list + the first list entry of each block
+constexpr int tile_pairs(int d) { return (d + 1) * kTilePix; }      // 1536 at D = 5
+constexpr int pair_block(int d) { return tile_pairs(d) / 32; }      // 48: pairs per quarter-warp of the splat
+constexpr int list_stride(int d) { return tile_pairs(d) + 32; }     // u16 per tile: the pair list + the first list
+                                                                    // entry of each block
 
 // counters[]: 0: M   1: error flags (1 = key range, 2 = list / vertex capacity)   2: max probe length
 //             3: table capacity in use   4: M of the earlier chunks of this call   5: T = list entries
@@ -50,10 +55,10 @@ struct LatticeBufs {
   int2 *tile_info;                  // [tiles] (first list entry, U | pairs << 16)
   unsigned long long *tkeys;        // [t_cap] packed key of a list entry
   int *tvid;                        // [t_cap] table slot during the build, then vertex id + 1 (row of val0 / val1)
-  unsigned short *plist;            // [tiles][kTileListStride]
-  unsigned short *lidx;             // [6][P]  index into the tile's list
-  float *bary;                      // [6][P]
-  int2 *nbr;                        // [6][m_cap]  (n1, n2) as vertex id + 1, 0 = absent
+  unsigned short *plist;            // [tiles][list_stride(d)]
+  unsigned short *lidx;             // [d + 1][P]  index into the tile's list
+  float *bary;                      // [d + 1][P]
+  int2 *nbr;                        // [d + 1][m_cap]  (n1, n2) as vertex id + 1, 0 = absent
   float *val0, *val1;               // [m_cap + 1][Kp]   row 0 is the all-zero "absent" row
   long long P;                      // N * H * W
   long long m_cap;                  // upper bound on the number of vertices
@@ -61,13 +66,15 @@ struct LatticeBufs {
   unsigned long long cap_mask;      // allocated table capacity - 1 (power of two)
   int tiles_x, tiles_y;             // tiles per image
   int Kp;                           // channels rounded up to a multiple of 4
+  int d;                            // lattice dimension: 5 (bilateral) or 2 (spatial)
 };
 
-size_t lattice_ws_bytes(int N, int K, int H, int W);
+size_t lattice_ws_bytes(int N, int K, int H, int W, int d = kLatD);
 // Carves `ws` (>= lattice_ws_bytes) into the buffers above.
-void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L);
+void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int d = kLatD);
 
-// Build the lattice of N (<= kMaxImagesPerLattice) planar RGB images [N,3,H,W].
+// Build the lattice (dimension L.d) of N (<= kMaxImagesPerLattice) planar RGB images [N,3,H,W] (d = 2: the images are
+// not read, the features are the pixel coordinates alone).
 // first_chunk: this is the first lattice of a call (resets the per-call counters: total vertices, error flag).
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
                   bool first_chunk, cudaStream_t stream);

@@ -23,22 +23,25 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "lattice.cuh"
 
 namespace cosa {
 
 // ---- packed keys ---------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long pack_key(const int q[kLatD], int r, int b, int *bad) {
+template <int D>
+__device__ __forceinline__ unsigned long long pack_key(const int q[D], int r, int b, int *bad) {
   unsigned long long k = 0;
 #pragma unroll
-  for (int i = 0; i < kLatD; ++i) {
+  for (int i = 0; i < D; ++i) {
     const int v = q[i] + kQBias;
     if (v < 0 || v >= (1 << kQBits)) *bad = 1;
     k |= (unsigned long long)(v & ((1 << kQBits) - 1)) << (kQBits * i);
   }
-  k |= (unsigned long long)r << (kQBits * kLatD);
-  k |= (unsigned long long)b << (kQBits * kLatD + 3);
+  k |= (unsigned long long)r << kKeyRShift;
+  k |= (unsigned long long)b << kKeyBShift;
   return k;
 }
 
@@ -53,22 +56,23 @@ __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
 // Scale factors of the elevation (permutohedral.cpp:156-159): double arithmetic with a float inv_std_dev,
 // stored as float.  Evaluated on the host, passed by value.
 struct EmbedConst {
-  float sf[kLatD];
+  float sf[kMaxLatD];
 };
 
-static EmbedConst make_embed_const() {
+static EmbedConst make_embed_const(int d) {
   EmbedConst c;
-  const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (kLatD + 1));
-  for (int i = 0; i < kLatD; ++i) c.sf[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev);
+  const float inv_std_dev = (float)(sqrt(2.0 / 3.0) * (d + 1));
+  for (int i = 0; i < kMaxLatD; ++i) c.sf[i] = i < d ? (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev) : 0.0f;
   return c;
 }
 
-// One point of Permutohedral::init (permutohedral.cpp:176-252).  Outputs q0[i] = rem0[i]/6 (after the wrap),
-// rank[i] and the six barycentric weights.
-__device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedConst &ec, int q0[kLatD + 1],
-                                            int rank[kLatD + 1], float bary[kLatD + 1]) {
-  constexpr int D = kLatD;
-  const float inv6 = 1.0f / 6.0f;
+// One point of Permutohedral::init (permutohedral.cpp:176-252), any dimension D.  Outputs q0[i] = rem0[i]/(D+1) (after
+// the wrap), rank[i] and the D+1 barycentric weights.  ("6" in the names below is D+1; the path's lattice has D = 5.)
+template <int D>
+__device__ __forceinline__ void embed_point(const float f[D], const EmbedConst &ec, int q0[D + 1], int rank[D + 1],
+                                            float bary[D + 1]) {
+  const float inv6 = 1.0f / (float)(D + 1);
+  constexpr float six = (float)(D + 1);
   float el[D + 1], rem0[D + 1];
   float sm = 0.0f;
 #pragma unroll
@@ -82,7 +86,7 @@ __device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedCon
 #pragma unroll
   for (int i = 0; i <= D; ++i) {
     const float v = rintf(__fmul_rn(inv6, el[i]));     // _mm_cvtps_epi32: round half to even
-    rem0[i] = __fmul_rn(v, 6.0f);
+    rem0[i] = __fmul_rn(v, six);
     sum = __fadd_rn(sum, v);
   }
   float diff[D + 1];
@@ -100,8 +104,8 @@ __device__ __forceinline__ void embed_point(const float f[kLatD], const EmbedCon
 #pragma unroll
   for (int i = 0; i <= D; ++i) {
     rank[i] += isum;
-    if (rank[i] < 0) { rank[i] += D + 1; rem0[i] = __fadd_rn(rem0[i], 6.0f); }
-    else if (rank[i] > D) { rank[i] -= D + 1; rem0[i] = __fsub_rn(rem0[i], 6.0f); }
+    if (rank[i] < 0) { rank[i] += D + 1; rem0[i] = __fadd_rn(rem0[i], six); }
+    else if (rank[i] > D) { rank[i] -= D + 1; rem0[i] = __fsub_rn(rem0[i], six); }
   }
   // barycentric (permutohedral.cpp:222-241): b[5-rank] += v, b[6-rank] -= v, then b[0] += 1 + b[6].
   // rank is a permutation, so b[s] = v(rank = 5-s) - v(rank = 6-s) whatever the visiting order.
@@ -159,33 +163,51 @@ __device__ __forceinline__ int tile_insert64(unsigned long long *hkey, unsigned 
 // The six vertex keys of a point.  canonical[r][rank] is r or r-6 (permutohedral.cpp:148-153), i.e. in (q, r) form
 // vertex r has q[i] = q0[i] - [rank[i] >= 6 - r]: going from vertex r-1 to r, exactly the coordinate whose rank is
 // 6 - r loses one (the sixth coordinate is not stored), and the residue field gains one.
-__device__ __forceinline__ void point_keys(const int q0[kLatD + 1], const int rank[kLatD + 1], int b,
-                                           unsigned long long key[kLatD + 1], int *bad) {
+template <int D>
+__device__ __forceinline__ void point_keys(const int q0[D + 1], const int rank[D + 1], int b,
+                                           unsigned long long key[D + 1], int *bad) {
   unsigned long long k = 0;
 #pragma unroll
-  for (int i = 0; i < kLatD; ++i) {
+  for (int i = 0; i < D; ++i) {
     const int v = q0[i] + kQBias;
     if (v < 1 || v >= (1 << kQBits)) *bad = 1;      // v - 1 (the decremented coordinate) must fit as well
     k |= (unsigned long long)(v & ((1 << kQBits) - 1)) << (kQBits * i);
   }
-  k |= (unsigned long long)b << (kQBits * kLatD + 3);
+  k |= (unsigned long long)b << kKeyBShift;
   key[0] = k;
 #pragma unroll
-  for (int r = 1; r <= kLatD; ++r) {
+  for (int r = 1; r <= D; ++r) {
     unsigned long long dec = 0;
 #pragma unroll
-    for (int i = 0; i < kLatD; ++i)
-      if (rank[i] == kLatD + 1 - r) dec = 1ULL << (kQBits * i);
-    k = k - dec + (1ULL << (kQBits * kLatD));
+    for (int i = 0; i < D; ++i)
+      if (rank[i] == D + 1 - r) dec = 1ULL << (kQBits * i);
+    k = k - dec + (1ULL << kKeyRShift);
     key[r] = k;
+  }
+}
+
+// Features of pixel (x, y) of image plane set `img` (bilateralfilter.cpp:9-13): D = 5: (x, y) / sigma_xy and
+// (R, G, B) / sigma_rgb; D = 2 (the spatial kernel of the dense CRF, densecrf addPairwiseGaussian): (x, y) / sigma_xy.
+template <int D>
+__device__ __forceinline__ void point_features(float f[D], const float *img, int n, int p, int x, int y, float sigmargb,
+                                               float sigmaxy) {
+  f[0] = __fdiv_rn((float)x, sigmaxy);
+  f[1] = __fdiv_rn((float)y, sigmaxy);
+  if constexpr (D == 5) {
+    f[2] = __fdiv_rn(__ldg(img + p), sigmargb);
+    f[3] = __fdiv_rn(__ldg(img + n + p), sigmargb);
+    f[4] = __fdiv_rn(__ldg(img + 2 * n + p), sigmargb);
   }
 }
 
 constexpr int kPairFirst = 1 << 11;    // plist code: (pixel in tile << 3) | r, bit 11 = first pair of its vertex
 
+template <int D>
 __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBufs L, const float *__restrict__ images,
                                                                       EmbedConst ec, int H, int W, int n_pad,
                                                                       float sigmargb, float sigmaxy) {
+  constexpr int kLatD = D;                           // (shadows the path's default inside this kernel)
+  constexpr int kTilePairs = tile_pairs(D), kPairBlock = pair_block(D), kTileListStride = list_stride(D);
   __shared__ unsigned long long hkey[kTileHS];      // 16 KB
   __shared__ int hinfo[kTileHS];                    //  8 KB  pair count, then (list index << 16) | first pair
   __shared__ __align__(16) unsigned short plist_s[kTileListStride];   // pairs bucketed by vertex + the block table
@@ -199,21 +221,16 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
   for (int i = tid; i < kTileListStride / 2; i += kTilePix) reinterpret_cast<unsigned *>(plist_s)[i] = 0;
 
   const int p = y * W + x;
-  float f[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (ok) {
-    const float *img = images + (size_t)b * 3 * n;
-    f[0] = __fdiv_rn((float)x, sigmaxy);               // bilateralfilter.cpp:9-13
-    f[1] = __fdiv_rn((float)y, sigmaxy);
-    f[2] = __fdiv_rn(__ldg(img + p), sigmargb);
-    f[3] = __fdiv_rn(__ldg(img + n + p), sigmargb);
-    f[4] = __fdiv_rn(__ldg(img + 2 * n + p), sigmargb);
-  }
+  float f[kLatD];
+#pragma unroll
+  for (int i = 0; i < kLatD; ++i) f[i] = 0.0f;
+  if (ok) point_features<D>(f, images + (size_t)b * 3 * n, n, p, x, y, sigmargb, sigmaxy);
   int q0[kLatD + 1], rank[kLatD + 1];
   float bary[kLatD + 1];
-  embed_point(f, ec, q0, rank, bary);
+  embed_point<D>(f, ec, q0, rank, bary);
   int bad = 0;
   unsigned long long key[kLatD + 1];
-  point_keys(q0, rank, b, key, &bad);
+  point_keys<D>(q0, rank, b, key, &bad);
   if (!ok) bad = 0;
   __syncthreads();
 
@@ -266,12 +283,14 @@ __global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBuf
     s_base = base;
     L.tile_info[tile] = make_int2(max(base, 0), base < 0 ? 0 : (U | (pairs << 16)));
     if (pad_tile && base >= 0) {
-      const float fz[kLatD] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      float fz[kLatD];
+#pragma unroll
+      for (int i = 0; i < kLatD; ++i) fz[i] = 0.0f;
       int qz[kLatD + 1], rz[kLatD + 1], badz = 0;
       float bz[kLatD + 1];
       unsigned long long kz[kLatD + 1];
-      embed_point(fz, ec, qz, rz, bz);
-      point_keys(qz, rz, b, kz, &badz);
+      embed_point<D>(fz, ec, qz, rz, bz);
+      point_keys<D>(qz, rz, b, kz, &badz);
 #pragma unroll
       for (int r = 0; r <= kLatD; ++r) L.tkeys[base + U + r] = kz[r];
     }
@@ -359,7 +378,7 @@ __global__ void __launch_bounds__(256) lattice_insert_kernel(LatticeBufs L) {
         L.table_ids[s] = (int)id + 1;
         // every neighbour entry starts as "absent"; lattice_finish_kernel fills in the ones that exist
 #pragma unroll
-        for (int j = 0; j <= kLatD; ++j) L.nbr[(size_t)j * L.m_cap + id] = make_int2(0, 0);
+        for (int j = 0; j <= L.d; ++j) L.nbr[(size_t)j * L.m_cap + id] = make_int2(0, 0);
       } else {
         L.table_ids[s] = 0;
         atomicOr(L.counters + 1, 2);
@@ -384,7 +403,9 @@ __device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long lo
 // carries when it wraps.  The relation is symmetric - u = n1_j(v) exactly when v = n2_j(u) - so a thread looks up only
 // n1 (6 instead of 12 table walks per vertex) and, when it finds u, also records itself as u's n2.  Entries start as
 // "absent" (0).  (c) the value rows the splat accumulates into are zeroed: thread (vertex, j) owns quads j, j+6, ...
+template <int D>
 __global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
+  constexpr int kLatD = D;
   const long long M = min((long long)L.counters[0], L.m_cap);
   const int T = (int)min((long long)L.counters[5], L.t_cap);
   const long long total = M * (kLatD + 1);
@@ -399,8 +420,8 @@ __global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
     const int j = (int)(idx % (kLatD + 1));
     for (int q = j; q < kq; q += kLatD + 1) reinterpret_cast<float4 *>(L.val0 + (size_t)(i + 1) * L.Kp)[q] = z;
     const unsigned long long key = L.vkeys[i];
-    const int r = (int)((key >> (kQBits * kLatD)) & 7);
-    const unsigned long long bbits = key >> (kQBits * kLatD + 3);
+    const int r = (int)((key >> kKeyRShift) & 7);
+    const unsigned long long bbits = key >> kKeyBShift;
     // n1: coordinates -1, axis +5
     const int r2 = r == 0 ? kLatD : r - 1;
     const int dq = r == 0 ? -1 : 0;
@@ -409,7 +430,7 @@ __global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
 #pragma unroll
     for (int k = 0; k < kLatD; ++k)
       qq[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias + dq + (k == j ? 1 : 0);
-    const unsigned long long nk = pack_key(qq, r2, 0, &bad) | (bbits << (kQBits * kLatD + 3));
+    const unsigned long long nk = pack_key<D>(qq, r2, 0, &bad) | (bbits << kKeyBShift);
     const int u = bad ? 0 : table_find(L, tmask, nk);
     if (u > 0) {
       int *base = reinterpret_cast<int *>(L.nbr + (size_t)j * L.m_cap);
@@ -450,14 +471,16 @@ constexpr int kPlane = kTilePix + 1;             // odd plane pitch: channel-str
 // kPairBlock consecutive pairs of the list - the same amount of work whatever the vertex degrees - and lane cl sums
 // channels cl, cl + 8, cl + 16; a quarter-warp flushes its partial sum with one reduction per vertex row whenever the
 // list moves on to the next vertex (kPairFirst).  KT > 0: compile-time channel count (one pass); 0: run-time K.
-template <int KT>
+template <int KT, int D>
 __global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins,
                                                                       int Krt, int H, int W) {
   static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
+  constexpr int kLatD = D;
+  constexpr int kTilePairs = tile_pairs(D), kPairBlock = pair_block(D), kTileListStride = list_stride(D);
   extern __shared__ __align__(16) unsigned char s_raw[];
   float *in_s = reinterpret_cast<float *>(s_raw);                         // [kChunk][kPlane]
-  float *bary_s = in_s + kChunk * kPlane;                                 // [6][256]
-  int *vid_s = reinterpret_cast<int *>(bary_s + 6 * kTilePix);            // [kTilePairs]
+  float *bary_s = in_s + kChunk * kPlane;                                 // [D + 1][256]
+  int *vid_s = reinterpret_cast<int *>(bary_s + (D + 1) * kTilePix);      // [kTilePairs]
   unsigned short *plist_s = reinterpret_cast<unsigned short *>(vid_s + kTilePairs);   // [kTileListStride], 16-byte aligned
 
   const int K = KT ? KT : Krt, Kp = (K + 3) & ~3;
@@ -559,7 +582,7 @@ __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const 
 // KT > 0: compile-time channel count; 0: run-time K.
 constexpr int kSliceRows = 512;
 constexpr int kRowPitch = kChunk + 4;             // 28 floats: row starts fall on 8 different bank quads
-template <bool ENERGY, int KT>
+template <bool ENERGY, int KT, int D>
 __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
                                                                          const float *__restrict__ ins,
                                                                          const float *__restrict__ gate, double *loss_acc,
@@ -569,9 +592,10 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
   __shared__ int vid_s[kSliceRows];
   __shared__ float s_part[kTilePix / 32];
   static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
+  constexpr int kLatD = D;
   constexpr int KQ = KT ? (KT + 3) / 4 : 1;       // row quads per vertex (compile-time form of kq)
   const int K = KT ? KT : Krt, Kp = (K + 3) & ~3;
-  const float alpha = 1.0f / (1.0f + 0.03125f);   // 1 / (1 + 2^-d)
+  const float alpha = 1.0f / (1.0f + 1.0f / (float)(1 << D));   // 1 / (1 + 2^-d), exact
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
   const int x = blockIdx.x * kTileW + lx, y = blockIdx.y * kTileH + ly, b = blockIdx.z;
   const int n = H * W;
@@ -689,15 +713,17 @@ int lattice_chunk_images(int N, int K, int H, int W) {
 struct LatticeDims {
   long long n, n_pad, P, m_cap, t_cap, tiles;
   unsigned long long cap;
-  int tiles_x, tiles_y, Kp;
+  int tiles_x, tiles_y, Kp, d;
 };
 
-static LatticeDims lattice_dims(int N, int K, int H, int W) {
+static LatticeDims lattice_dims(int N, int K, int H, int W, int dim) {
   LatticeDims d;
+  d.d = dim;
+  const long long V = dim + 1;             // vertices of a simplex
   d.n = (long long)H * W;
   d.n_pad = (d.n + 3) & ~3LL;
   d.P = (long long)N * d.n;
-  d.t_cap = 6LL * N * d.n_pad + 6LL * N;   // + the keys of the padding pixels, appended once per image
+  d.t_cap = V * N * d.n_pad + V * N;       // + the keys of the padding pixels, appended once per image
   d.m_cap = d.t_cap;
   d.cap = table_capacity(d.t_cap);
   d.tiles_x = ceil_div(W, kTileW);
@@ -717,24 +743,24 @@ static void lattice_layout(const LatticeDims &d, F &&take) {
   take(5, (size_t)d.t_cap * sizeof(unsigned long long));              // tkeys
   take(6, (size_t)d.t_cap * sizeof(int));                             // tvid
   take(7, (size_t)256);                                               // (unused)
-  take(8, (size_t)d.tiles * kTileListStride * sizeof(unsigned short));  // plist + block table
-  take(9, (size_t)6 * d.P * sizeof(unsigned short));                  // lidx
-  take(10, (size_t)6 * d.P * sizeof(float));                          // bary
-  take(11, (size_t)6 * d.m_cap * sizeof(int2));                       // nbr
+  take(8, (size_t)d.tiles * list_stride(d.d) * sizeof(unsigned short));  // plist + block table
+  take(9, (size_t)(d.d + 1) * d.P * sizeof(unsigned short));          // lidx
+  take(10, (size_t)(d.d + 1) * d.P * sizeof(float));                  // bary
+  take(11, (size_t)(d.d + 1) * d.m_cap * sizeof(int2));               // nbr
   take(12, (size_t)(d.m_cap + 1) * d.Kp * sizeof(float));             // val0
   take(13, (size_t)(d.m_cap + 1) * d.Kp * sizeof(float));             // val1
 }
 
-size_t lattice_ws_bytes(int N, int K, int H, int W) {
+size_t lattice_ws_bytes(int N, int K, int H, int W, int dim) {
   size_t b = 0;
-  lattice_layout(lattice_dims(N, K, H, W), [&](int, size_t bytes) { b += align_up(bytes, 256); });
+  lattice_layout(lattice_dims(N, K, H, W, dim), [&](int, size_t bytes) { b += align_up(bytes, 256); });
   return b;
 }
 
-void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
-  const LatticeDims d = lattice_dims(N, K, H, W);
+void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int dim) {
+  const LatticeDims d = lattice_dims(N, K, H, W, dim);
   L->P = d.P; L->m_cap = d.m_cap; L->t_cap = d.t_cap; L->cap_mask = d.cap - 1;
-  L->tiles_x = d.tiles_x; L->tiles_y = d.tiles_y; L->Kp = d.Kp;
+  L->tiles_x = d.tiles_x; L->tiles_y = d.tiles_y; L->Kp = d.Kp; L->d = d.d;
   char *p = (char *)ws;
   void *slot[14];
   lattice_layout(d, [&](int i, size_t bytes) { slot[i] = p; p += align_up(bytes, 256); });
@@ -756,64 +782,87 @@ void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L) {
 int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W, float sigmargb, float sigmaxy,
                   bool first_chunk, cudaStream_t stream) {
   if (N < 1 || N > kMaxImagesPerLattice) return COSA_E_ARG;
-  if (L.tiles_y > 65535) return COSA_E_ARG;
+  if (L.tiles_y > 65535 || (L.d != 5 && L.d != 2)) return COSA_E_ARG;
   const long long n = (long long)H * W;
   const int n_pad = (int)((n + 3) & ~3LL);
   COSA_LAUNCH(lattice_reset_kernel, 1, 1, 0, stream, L.counters, first_chunk ? 1 : 0);
   const dim3 grid(L.tiles_x, L.tiles_y, N);
-  COSA_LAUNCH(lattice_tile_build_kernel, grid, kTilePix, 0, stream, L, images, make_embed_const(), H, W, n_pad,
-              sigmargb, sigmaxy);
+  if (L.d == 5) {
+    COSA_LAUNCH_T("lattice_tile_build_kernel", lattice_tile_build_kernel<5>, grid, kTilePix, 0, stream, L, images,
+                  make_embed_const(5), H, W, n_pad, sigmargb, sigmaxy);
+  } else {
+    COSA_LAUNCH_T("lattice_tile_build_kernel", lattice_tile_build_kernel<2>, grid, kTilePix, 0, stream, L, images,
+                  make_embed_const(2), H, W, n_pad, sigmargb, sigmaxy);
+  }
   // T and M live on the device: size the grids for the SMs and let the kernels read the counts
   COSA_LAUNCH(lattice_table_clear_kernel, sm_count() * 8, 256, 0, stream, L);
   COSA_LAUNCH(lattice_insert_kernel, sm_count() * 8, 256, 0, stream, L);
-  COSA_LAUNCH(lattice_finish_kernel, sm_count() * 8, 256, 0, stream, L);
+  if (L.d == 5) {
+    COSA_LAUNCH_T("lattice_finish_kernel", lattice_finish_kernel<5>, sm_count() * 8, 256, 0, stream, L);
+  } else {
+    COSA_LAUNCH_T("lattice_finish_kernel", lattice_finish_kernel<2>, sm_count() * 8, 256, 0, stream, L);
+  }
   return 0;
 }
 
-static size_t splat_smem_bytes() {
-  return (size_t)kChunk * kPlane * 4 + (size_t)6 * kTilePix * 4 + (size_t)kTilePairs * 4 + (size_t)kTileListStride * 2;
+static size_t splat_smem_bytes(int d) {
+  return (size_t)kChunk * kPlane * 4 + (size_t)(d + 1) * kTilePix * 4 + (size_t)tile_pairs(d) * 4 +
+         (size_t)list_stride(d) * 2;
 }
 
 int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int H, int W, cudaStream_t stream) {
+  if (L.Kp != ((K + 3) & ~3)) return COSA_E_ARG;   // the view must have been carved for this channel count
   COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
   const dim3 grid(L.tiles_x, L.tiles_y, N);
-  if (K == 21) {
-    COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<21>, grid, kTilePix, splat_smem_bytes(), stream,
-                  L, ins, K, H, W);
+  if (L.d == 2) {
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 2>), grid, kTilePix, splat_smem_bytes(2),
+                  stream, L, ins, K, H, W);
+  } else if (K == 21) {
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<21, 5>), grid, kTilePix, splat_smem_bytes(5),
+                  stream, L, ins, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_splat_tile_kernel", lattice_splat_tile_kernel<0>, grid, kTilePix, splat_smem_bytes(), stream,
-                  L, ins, K, H, W);
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 5>), grid, kTilePix, splat_smem_bytes(5),
+                  stream, L, ins, K, H, W);
   }
   float *src = L.val0, *dst = L.val1;
-  for (int axis = 0; axis <= kLatD; ++axis) {
+  for (int axis = 0; axis <= L.d; ++axis) {
     COSA_LAUNCH(lattice_blur_kernel, sm_count() * 8, 256, 0, stream, L, src, dst, axis);
     float *t = src; src = dst; dst = t;
   }
-  return 0;   // six swaps: the result is back in val0
+  // d + 1 swaps: for d = 5 the result is back in val0; for d = 2 (three passes) it is in val1 - the slice reads `src`
+  return 0;
 }
 
 int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, double *loss_acc, float *outs, int N,
                   int K, int H, int W, cudaStream_t stream) {
   const size_t smem = (size_t)kSliceRows * kRowPitch * sizeof(float);   // 56 KB: opt-in, per device
-  static bool attr_done[64] = {};
+  static std::atomic<unsigned long long> attr_done{0};
   int dev = 0;
   COSA_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  const unsigned long long bit = 1ULL << (dev & 63);
+  if (dev >= 64 || !(attr_done.load(std::memory_order_acquire) & bit)) {
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 21, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev < 64) attr_done.fetch_or(bit, std::memory_order_release);
   }
   const dim3 grid(L.tiles_x, L.tiles_y, N);
-  if (gate && K == 21) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 21>), grid, kTilePix, smem, stream, L,
-                  L.val0, ins, gate, loss_acc, outs, K, H, W);
+  // d + 1 blur passes ping-pong between val0 and val1: the result is in val0 for odd d, in val1 for even d
+  const float *values = ((L.d + 1) & 1) ? L.val1 : L.val0;
+  if (L.d == 2) {
+    if (gate) return COSA_E_ARG;   // the energy epilogue belongs to the bilateral (d = 5) filter
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 2>), grid, kTilePix, smem, stream, L,
+                  values, ins, gate, loss_acc, outs, K, H, W);
+  } else if (gate && K == 21) {
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 21, 5>), grid, kTilePix, smem, stream, L,
+                  values, ins, gate, loss_acc, outs, K, H, W);
   } else if (gate) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 0>), grid, kTilePix, smem, stream, L,
-                  L.val0, ins, gate, loss_acc, outs, K, H, W);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 0, 5>), grid, kTilePix, smem, stream, L,
+                  values, ins, gate, loss_acc, outs, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0>), grid, kTilePix, smem, stream, L,
-                  L.val0, ins, gate, loss_acc, outs, K, H, W);
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 5>), grid, kTilePix, smem, stream, L,
+                  values, ins, gate, loss_acc, outs, K, H, W);
   }
   return 0;
 }

@@ -11,6 +11,7 @@ kernels of ``csrc/`` through the C-ABI (``include/cosa_b200.h``).  Inputs must b
   DenseEnergyLossFunction  utils/seg_helper.py:864-903
   DenseEnergyLoss          utils/seg_helper.py:191-208
   get_energy_loss          utils/seg_helper.py:210-230
+  DenseCRF, crf_inference_infv2, crf_inference_inf   utils/seg_helper.py:905-922, 961-996 (evaluation-time dense CRF)
 """
 import ctypes
 import os
@@ -623,6 +624,81 @@ def last_energy_lattice_stats(B, C, H, W, device=None):
     if rc not in (0, -3):
         _lib.check(rc)
     return tuple(int(v) for v in stats)
+
+
+# ---- dense-CRF mean-field inference at evaluation time --------------------------------------
+def crf_inference_batch(images, probs, iter_max, pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std):
+    """Mean-field marginals [N,C,H,W] of the fully connected CRF for a batch of CUDA tensors: ``images`` [N,3,H,W]
+    planar RGB 0..255, ``probs`` [N,C,H,W] softmax output.  One lattice pair for the whole batch (N <= 64)."""
+    lib = _lib.load()
+    images = _lib.dev_f32(images, "images")
+    probs = _lib.dev_f32(probs.to(images.device), "probs")
+    N, C, H, W = probs.shape
+    if images.shape != (N, 3, H, W):
+        raise ValueError("images must be [N,3,H,W] matching probs [N,C,H,W]")
+    out = torch.empty_like(probs)
+    with torch.cuda.device(probs.device):
+        nbytes = lib.cosa_crf_inference_ws_bytes(N, C, H, W)
+        if nbytes == 0:
+            raise _lib.CosaError("cosa_b200: unsupported dense-CRF geometry (N must be 1..64)")
+        ws = _lib.workspace(nbytes, probs.device)
+        _lib.check(lib.cosa_crf_inference(_lib.ptr(images), _lib.ptr(probs), _lib.ptr(out), N, C, H, W, int(iter_max),
+                                          float(pos_w), float(pos_xy_std), float(bi_w), float(bi_xy_std),
+                                          float(bi_rgb_std), _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+    return out
+
+
+def _crf_one(image, probmap, iter_max, pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std):
+    """The reference's calling convention: ``image`` HWC uint8 (numpy array or tensor), ``probmap`` [C,H,W] float32.
+    Returns what the reference returns - a numpy array [C,H,W] - unless ``probmap`` is a CUDA tensor (then a CUDA
+    tensor, and nothing leaves the device)."""
+    import numpy as np
+    if not torch.cuda.is_available():
+        raise _lib.CosaError("cosa_b200: dense-CRF inference needs a CUDA device - this package has no CPU fallback")
+    on_device = isinstance(probmap, torch.Tensor) and probmap.is_cuda
+    dev = probmap.device if on_device else torch.device("cuda", torch.cuda.current_device())
+    img = torch.as_tensor(np.ascontiguousarray(image) if not isinstance(image, torch.Tensor) else image)
+    img = img.to(dev).float().permute(2, 0, 1).unsqueeze(0).contiguous()
+    p = torch.as_tensor(np.ascontiguousarray(probmap) if not isinstance(probmap, torch.Tensor) else probmap)
+    q = crf_inference_batch(img, p.to(dev).float().unsqueeze(0), iter_max, pos_w, pos_xy_std, bi_w, bi_xy_std,
+                            bi_rgb_std)[0]
+    return q if on_device else q.cpu().numpy()
+
+
+class DenseCRF(object):
+    """Same ctor / call as the reference's wrapper around pydensecrf (seg_helper.py:961-987): ``__call__(image,
+    probmap)`` with ``image`` HWC uint8 and ``probmap`` [C,H,W] softmax output returns the marginals Q [C,H,W] after
+    ``iter_max`` mean-field iterations with a Gaussian (``pos_*``) and a bilateral (``bi_*``) Potts kernel."""
+
+    def __init__(self, iter_max, pos_w, pos_xy_std, bi_w, bi_xy_std, bi_rgb_std):
+        self.iter_max = iter_max
+        self.pos_w = pos_w
+        self.pos_xy_std = pos_xy_std
+        self.bi_w = bi_w
+        self.bi_xy_std = bi_xy_std
+        self.bi_rgb_std = bi_rgb_std
+
+    def __call__(self, image, probmap):
+        return _crf_one(image, probmap, self.iter_max, self.pos_w, self.pos_xy_std, self.bi_w, self.bi_xy_std,
+                        self.bi_rgb_std)
+
+
+crf_inference_infv2 = DenseCRF(            # seg_helper.py:988-996, used by evaluation_engine.py:208
+    iter_max=1,
+    pos_xy_std=1,
+    pos_w=1,
+    bi_xy_std=121,
+    bi_rgb_std=5,
+    bi_w=4,
+)
+
+
+def crf_inference_inf(img, probs, t=10, scale_factor=1, labels=21):
+    """seg_helper.py:905-922: Gaussian sxy = 4 / scale_factor, bilateral sxy = 83 / scale_factor, srgb = 5, both with
+    compatibility 3, ``t`` iterations.  ``labels`` must equal ``probs.shape[0]`` (the reference reshapes with it)."""
+    if int(labels) != int(probs.shape[0]):
+        raise ValueError("labels must equal probs.shape[0]")
+    return _crf_one(img, probs, t, 3, 4 / scale_factor, 3, 83 / scale_factor, 5)
 
 
 # ---- the consumers either side of the path (SURVEY.md 8(f) ranks 2, 3) ------------------------------------------

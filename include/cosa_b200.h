@@ -231,6 +231,22 @@ int cosa_energy_loss_backward(const float *logit, const void *saved, const float
                               float *grad_logit, int B, int C, int H, int W, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense-CRF mean-field inference (evaluation-time post-processing).
+ *   replaces utils/seg_helper.py:961-996 (class DenseCRF.__call__ / crf_inference_infv2, evaluation_engine.py:205-211)
+ *   and :905-922 (crf_inference_inf), i.e. pydensecrf's DenseCRF2D with setUnaryEnergy(unary_from_softmax(probs)),
+ *   addPairwiseGaussian(sxy=pos_xy_std, compat=pos_w), addPairwiseBilateral(sxy=bi_xy_std, srgb=bi_rgb_std,
+ *   compat=bi_w) and inference(iter_max), kernel normalisation NORMALIZE_SYMMETRIC (pydensecrf's default).
+ *   images [N,3,H,W] planar RGB 0..255 (the reference passes HWC uint8: the host mirror converts), probs [N,C,H,W]
+ *   (softmax output), q_out [N,C,H,W] the mean-field marginals after iter_max iterations.  N <= 64.
+ *   pydensecrf is not vendored by the reference (README.md:104 installs its git master): parity of this function is
+ *   pinned on the reference's own permutohedral C++ for the two filters and on the published update rule - DESIGN.md.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cosa_crf_inference_ws_bytes(int N, int C, int H, int W);
+int cosa_crf_inference(const float *images, const float *probs, float *q_out, int N, int C, int H, int W, int iter_max,
+                       float pos_w, float pos_xy_std, float bi_w, float bi_xy_std, float bi_rgb_std, void *ws,
+                       size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The consumers either side of the path.
  *
  * seg_loss: fg/bg-balanced cross-entropy of seg_pred [B,C,H,W] against the pseudo-label map mask_label [B,H,W]

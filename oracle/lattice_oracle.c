@@ -10,8 +10,10 @@
  * legs may load this library.  The product (cosa_b200/) never does.
  *
  * Parity pin: bit-exact against the unmodified reference C++ built into
- * oracle/_ref/libbf_ref.so (tests/test_oracle_lattice.py) and against the committed
- * golden vectors tests/golden/bilateral_*.npz generated from that build.
+ * oracle/_ref/libbf_ref.so (tests/test_oracle_golden.py::test_c_oracle_is_bit_exact_against_reference_build) and
+ * against the committed golden vectors tests/golden/bilateral_*.npz generated from that build; the generic-feature
+ * entry (any D) against the reference's own Permutohedral class driven through oracle/ref_lattice_shim.cpp
+ * (tests/golden/crf_inference.npz).
  *
  * Reference map (all under /root/reference/utils/bilateralfilter/):
  *   features            bilateralfilter.cpp:4-19
@@ -27,8 +29,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Lattice dimension: 5 for the path's bilateral filter (liblattice_oracle.so); the Makefile also builds the file with
+ * -DD=2 (liblattice_oracle_d2.so) for the spatial kernel of the dense-CRF inference oracle (oracle/crf_oracle.py). */
+#ifndef D
 #define D 5
-#define D1 6
+#endif
+#define D1 (D + 1)
 
 typedef struct {
   int16_t *keys;   /* [filled][D] */
@@ -142,8 +148,8 @@ static void scale_factors(float sf[D]) {
   for (int i = 0; i < D; i++) sf[i] = (float)(1.0 / sqrt((double)((i + 2) * (i + 1))) * inv_std_dev);
 }
 
-static void lattice_build(Lattice *L, const float *image, int H, int W, float sigmargb, float sigmaxy) {
-  const int n = H * W;
+/* features [n][D] (point-major, as Permutohedral::init takes them) */
+static void lattice_build_features(Lattice *L, const float *feat, int n) {
   const int n_pad = (n + 3) & ~3;   /* the SSE loop also embeds the zero-feature padding pixels (:168-173, :241) */
   float sf[D];
   scale_factors(sf);
@@ -154,16 +160,7 @@ static void lattice_build(Lattice *L, const float *image, int H, int W, float si
   kt_init(&kt, (size_t)n_pad * D1);
   for (int p = 0; p < n_pad; p++) {
     float f[D];
-    if (p < n) {
-      int i = p % W, j = p / W;
-      f[0] = (float)i / sigmaxy;                  /* bilateralfilter.cpp:9-13 */
-      f[1] = (float)j / sigmaxy;
-      f[2] = image[0 * n + p] / sigmargb;
-      f[3] = image[1 * n + p] / sigmargb;
-      f[4] = image[2 * n + p] / sigmargb;
-    } else {
-      for (int k = 0; k < D; k++) f[k] = 0.0f;
-    }
+    for (int k = 0; k < D; k++) f[k] = p < n ? feat[(size_t)p * D + k] : 0.0f;
     int16_t keys[D1][D];
     float bw[D1];
     embed_point(f, sf, keys, bw);
@@ -190,6 +187,23 @@ static void lattice_build(Lattice *L, const float *image, int H, int W, float si
   }
   kt_free(&kt);
 }
+
+#if D == 5
+static void lattice_build(Lattice *L, const float *image, int H, int W, float sigmargb, float sigmaxy) {
+  const int n = H * W;
+  float *feat = (float *)malloc((size_t)n * D * sizeof(float));
+  for (int p = 0; p < n; p++) {
+    int i = p % W, j = p / W;
+    feat[(size_t)p * D + 0] = (float)i / sigmaxy;                  /* bilateralfilter.cpp:9-13 */
+    feat[(size_t)p * D + 1] = (float)j / sigmaxy;
+    feat[(size_t)p * D + 2] = image[0 * n + p] / sigmargb;
+    feat[(size_t)p * D + 3] = image[1 * n + p] / sigmargb;
+    feat[(size_t)p * D + 4] = image[2 * n + p] / sigmargb;
+  }
+  lattice_build_features(L, feat, n);
+  free(feat);
+}
+#endif
 
 static void lattice_free(Lattice *L) { free(L->offset); free(L->bary); free(L->nbr); free(L->vkeys); }
 
@@ -223,6 +237,22 @@ static void lattice_filter(const Lattice *L, float *out, const float *in, float 
   }
 }
 
+/* Generic entry (any D): lattice of n points with features [n][D], K planes of n values filtered with it
+ * (Permutohedral::init + compute per plane, un-normalised).  Returns M. */
+int cosa_oracle_filter_features(const float *features, int n, const float *in, float *out, int K) {
+  Lattice L;
+  lattice_build_features(&L, features, n);
+  float *values = (float *)malloc((size_t)(L.M + 2) * sizeof(float));
+  float *new_values = (float *)malloc((size_t)(L.M + 2) * sizeof(float));
+  for (int k = 0; k < K; k++) lattice_filter(&L, out + (size_t)k * n, in + (size_t)k * n, values, new_values);
+  free(values); free(new_values);
+  int M = L.M;
+  lattice_free(&L);
+  return M;
+}
+int cosa_oracle_lattice_dim(void) { return D; }
+
+#if D == 5
 /* bilateralfilter(): bilateralfilter.cpp:22-40.  Returns M. */
 int cosa_oracle_bilateralfilter(const float *image, const float *in, float *out, int K, int H, int W,
                                 float sigmargb, float sigmaxy) {
@@ -261,3 +291,4 @@ int cosa_oracle_lattice_embed(const float *image, int H, int W, float sigmargb, 
   lattice_free(&L);
   return M;
 }
+#endif /* D == 5 */

@@ -225,6 +225,29 @@ def main():
          cam_pred=cam_pred, cam_loss=cl, cam_loss_grad=cam_pred.grad, cam_loss_norelu=cl2,
          cam_loss_norelu_grad=cam_pred2.grad)
 
+    # ---- dense-CRF inference (seg_helper.py:961-996): pydensecrf is absent, so what the reference CAN pin here is its
+    # own Permutohedral class (the code base pydensecrf wraps) for the two filters of the mean-field update, driven
+    # through oracle/ref_lattice_shim.cpp: filter responses on the 2-D and 5-D lattices, and the marginals of the
+    # update rule restated in oracle/crf_oracle.py evaluated WITH the reference class as the filter ------------------
+    from oracle import crf_oracle as co
+    rng = np.random.default_rng(2024)
+    Hc, Wc, Cc = 45, 61, 6                                  # H*W % 4 != 0: the SSE padding points take part
+    yy, xx = np.mgrid[0:Hc, 0:Wc].astype(np.float32)
+    base = np.stack([127 + 100 * np.sin(0.05 * xx + c) * np.cos(0.07 * yy) for c in range(3)], -1)
+    crf_img = np.clip(np.floor(base + 12 * rng.standard_normal((Hc, Wc, 3))), 0, 255).astype(np.uint8)
+    logits_c = 2.5 * rng.standard_normal((Cc, Hc // 4 + 1, Wc // 4 + 1)).astype(np.float32)
+    logits_c = torch.nn.functional.interpolate(torch.from_numpy(logits_c)[None], size=(Hc, Wc), mode="bilinear",
+                                               align_corners=False)[0]
+    crf_probs = logits_c.softmax(dim=0).numpy().astype(np.float32)
+    vals = rng.random((3, Hc * Wc)).astype(np.float32)
+    f_g1, f_g4 = co.gaussian_features(Hc, Wc, 1.0), co.gaussian_features(Hc, Wc, 4.0)
+    f_b = co.bilateral_features(crf_img, 121, 5)
+    save("crf_inference", image=crf_img, probs=crf_probs, vals=vals,
+         filt_gauss1=co.ref_filter(f_g1, vals), filt_gauss4=co.ref_filter(f_g4, vals), filt_bilateral=co.ref_filter(f_b, vals),
+         q_infv2=co.crf_inference(crf_img, crf_probs, 1, 1, 1, 4, 121, 5, filter_fn=co.ref_filter),
+         q_inf_t10=co.crf_inference(crf_img, crf_probs, 10, 3, 4, 3, 83, 5, filter_fn=co.ref_filter),
+         q_iter0=co.crf_inference(crf_img, crf_probs, 0, 1, 1, 4, 121, 5, filter_fn=co.ref_filter))
+
     with open(os.path.join(HERE, "META.txt"), "w") as f:
         for k, v in meta.items():
             f.write("%s: %s\n" % (k, v))
