@@ -617,44 +617,56 @@ __global__ void __launch_bounds__(256, 2)
     const int yl = ty + 8 * rr;
     const int x = x0 + tx, y = y0 + yl;
     if (x >= w || y >= h) continue;
-    float logit[ND];
+    // packed fp32: neighbour pairs (2i, 2i + 1) share one FADD2 / FMUL2 / FFMA2
+    float2 logit2[ND / 2];
 #pragma unroll
-    for (int n = 0; n < ND; ++n) logit[n] = 0.0f;
+    for (int i = 0; i < ND / 2; ++i) logit2[i] = make_float2(0.0f, 0.0f);
 #pragma unroll 1
     for (int c = 0; c < 3; ++c) {
       const float *q = s_tile + (c * kFS + kFH + yl) * kFS + kFH + tx;
       const float ctr = q[0];
-      float v[ND];
+      float2 v2[ND / 2];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const int d = kD[k], R = kD[k] * kFS;
-        v[8 * k + 0] = q[-R - d]; v[8 * k + 1] = q[-R]; v[8 * k + 2] = q[-R + d];
-        v[8 * k + 3] = q[-d];                           v[8 * k + 4] = q[d];
-        v[8 * k + 5] = q[R - d];  v[8 * k + 6] = q[R];  v[8 * k + 7] = q[R + d];
+        v2[4 * k + 0] = make_float2(q[-R - d], q[-R]);
+        v2[4 * k + 1] = make_float2(q[-R + d], q[-d]);
+        v2[4 * k + 2] = make_float2(q[d], q[R - d]);
+        v2[4 * k + 3] = make_float2(q[R], q[R + d]);
       }
-      float sum = 0.0f;
+      float2 s2 = v2[0];
 #pragma unroll
-      for (int n = 0; n < ND; ++n) sum += v[n];
-      const float mean = div3_rn(sum) * 0.0625f;   // sum / 48, correctly rounded (ND = 48)
-      float ss = 0.0f;
+      for (int i = 1; i < ND / 2; ++i) s2 = fadd2(s2, v2[i]);
+      const float mean = div3_rn(s2.x + s2.y) * 0.0625f;   // sum / 48, correctly rounded (ND = 48)
+      const float2 nmean = splat2(-mean);
+      float2 ss2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-      for (int n = 0; n < ND; ++n) {
-        const float t = v[n] - mean;
-        ss = fmaf(t, t, ss);
+      for (int i = 0; i < ND / 2; ++i) {
+        const float2 t = fadd2(v2[i], nmean);
+        ss2 = ffma2(t, t, ss2);
       }
-      const float sd = sqrtf(ss / (float)(ND - 1));
-      const float inv = 1.0f / ((sd + 1e-8f) * 0.3f);
+      const float sd = sqrtf((ss2.x + ss2.y) / (float)(ND - 1));
+      const float2 inv = splat2(1.0f / ((sd + 1e-8f) * 0.3f)), nctr = splat2(-ctr);
 #pragma unroll
-      for (int n = 0; n < ND; ++n) {
-        const float t = fabsf(v[n] - ctr) * inv;
-        logit[n] = fmaf(t, t, logit[n]);
+      for (int i = 0; i < ND / 2; ++i) {
+        const float2 t = fmul2(fadd2(v2[i], nctr), inv);   // (|v - ctr| * inv)^2 == ((v - ctr) * inv)^2 bit for bit
+        logit2[i] = ffma2(t, t, logit2[i]);
       }
     }
+    // aff = -(sum_c t^2) / 3 (div3_rn, packed: q = RN(x c), RN(q + RN(x - 3 q) c)); softmax over the 48 neighbours
+    float logit[ND];
     float mx = -INFINITY;
+    {
+      const float2 c3 = splat2(0.333333343267440796f), m3 = splat2(-3.0f);
 #pragma unroll
-    for (int n = 0; n < ND; ++n) {
-      logit[n] = div3_rn(-logit[n]);
-      mx = fmaxf(mx, logit[n]);
+      for (int i = 0; i < ND / 2; ++i) {
+        const float2 xneg = make_float2(-logit2[i].x, -logit2[i].y);
+        const float2 qq = fmul2(xneg, c3);
+        const float2 r = ffma2(ffma2(m3, qq, xneg), c3, qq);
+        logit[2 * i] = r.x;
+        logit[2 * i + 1] = r.y;
+        mx = fmaxf(mx, fmaxf(r.x, r.y));
+      }
     }
     float den = 0.0f;
 #pragma unroll
