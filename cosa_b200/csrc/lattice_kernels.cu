@@ -111,11 +111,12 @@ __device__ __forceinline__ void embed_point(const float f[D], const EmbedConst &
   // rank is a permutation, so b[s] = v(rank = 5-s) - v(rank = 6-s) whatever the visiting order.
   float vr[D + 1];
 #pragma unroll
+  for (int k = 0; k <= D; ++k) vr[k] = 0.0f;
+#pragma unroll
   for (int i = 0; i <= D; ++i) {
     const float v = __fmul_rn(__fsub_rn(el[i], rem0[i]), inv6);
 #pragma unroll
-    for (int k = 0; k <= D; ++k)
-      if (rank[i] == k) vr[k] = v;
+    for (int k = 0; k <= D; ++k) vr[k] = (rank[i] == k) ? v : vr[k];   // selects: no dynamically indexed local array
     q0[i] = (int)rintf(__fmul_rn(rem0[i], inv6));   // exact: rem0 is a small multiple of 6
   }
 #pragma unroll
@@ -124,9 +125,12 @@ __device__ __forceinline__ void embed_point(const float f[D], const EmbedConst &
 }
 
 // ---- build ---------------------------------------------------------------------------------------
-// Table capacity of this build: 2^k >= 2T (T = distinct keys summed over the tiles >= M), at most what was allocated.
+// Table capacity of this build: 2^k >= 1.25 T (T = distinct keys summed over the tiles; a vertex is shared by ~2.6
+// tiles, so the load factor M / 2^k is ~0.2-0.4, and at most 0.8 when no two tiles share a vertex - there is always an
+// empty slot to end a probe sequence), at most what was allocated.
 __device__ __forceinline__ unsigned long long live_mask(const LatticeBufs &L) {
-  const unsigned t2 = 2u * (unsigned)max(L.counters[5], 512);
+  const unsigned t = (unsigned)max(L.counters[5], 1024);
+  const unsigned t2 = t + t / 4;
   const unsigned long long cap = 1ULL << (32 - __clz(t2 - 1));
   return min(cap, L.cap_mask + 1) - 1;
 }
@@ -376,9 +380,6 @@ __global__ void __launch_bounds__(256) lattice_insert_kernel(LatticeBufs L) {
       if (id < L.m_cap) {
         L.vkeys[id] = key;
         L.table_ids[s] = (int)id + 1;
-        // every neighbour entry starts as "absent"; lattice_finish_kernel fills in the ones that exist
-#pragma unroll
-        for (int j = 0; j <= L.d; ++j) L.nbr[(size_t)j * L.m_cap + id] = make_int2(0, 0);
       } else {
         L.table_ids[s] = 0;
         atomicOr(L.counters + 1, 2);
@@ -399,10 +400,12 @@ __device__ __forceinline__ int table_find(const LatticeBufs &L, unsigned long lo
 }
 
 // (a) list entries: table slot -> vertex row.  (b) blur neighbours (permutohedral.cpp:282-294): n1 = key - 1 on every
-// stored coordinate and key[j] + 5 on axis j, n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q
-// carries when it wraps.  The relation is symmetric - u = n1_j(v) exactly when v = n2_j(u) - so a thread looks up only
-// n1 (6 instead of 12 table walks per vertex) and, when it finds u, also records itself as u's n2.  Entries start as
-// "absent" (0).  (c) the value rows the splat accumulates into are zeroed: thread (vertex, j) owns quads j, j+6, ...
+// stored coordinate and key[j] + D on axis j, n2 the opposite.  In (q, r) form the residue moves to r-1 / r+1 and q
+// carries when it wraps.  Thread (vertex, axis) looks both up in the L2-resident table and writes its own (n1, n2)
+// pair: one coalesced 8-byte store per entry.  (Looking up n1 only and recording the symmetric n2 through a scattered
+// 4-byte store halved the table walks but made every scattered store a DRAM read-modify-write of its sector: 250 MB
+// of reads per build at VOC B = 32.)  Absent neighbours are 0.  (c) the value rows the splat accumulates into are
+// zeroed: thread (vertex, j) owns quads j, j + D + 1, ...
 template <int D>
 __global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
   constexpr int kLatD = D;
@@ -422,21 +425,27 @@ __global__ void __launch_bounds__(256) lattice_finish_kernel(LatticeBufs L) {
     const unsigned long long key = L.vkeys[i];
     const int r = (int)((key >> kKeyRShift) & 7);
     const unsigned long long bbits = key >> kKeyBShift;
-    // n1: coordinates -1, axis +5
-    const int r2 = r == 0 ? kLatD : r - 1;
-    const int dq = r == 0 ? -1 : 0;
-    int qq[kLatD];
-    int bad = 0;
+    int q0[kLatD];
 #pragma unroll
-    for (int k = 0; k < kLatD; ++k)
-      qq[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias + dq + (k == j ? 1 : 0);
-    const unsigned long long nk = pack_key<D>(qq, r2, 0, &bad) | (bbits << kKeyBShift);
-    const int u = bad ? 0 : table_find(L, tmask, nk);
-    if (u > 0) {
-      int *base = reinterpret_cast<int *>(L.nbr + (size_t)j * L.m_cap);
-      base[2 * i] = u;                       // n1 of vertex i
-      base[2 * (size_t)(u - 1) + 1] = (int)i + 1;   // vertex i is the n2 of vertex u - 1
+    for (int k = 0; k < kLatD; ++k) q0[k] = (int)((key >> (kQBits * k)) & qmask) - kQBias;
+    int2 nn;
+    {   // n1: coordinates -1, axis +D: residue r - 1 (q carries down when r wraps), axis coordinate one q up
+      const int r2 = r == 0 ? kLatD : r - 1, dq = r == 0 ? -1 : 0;
+      int qq[kLatD], bad = 0;
+#pragma unroll
+      for (int k = 0; k < kLatD; ++k) qq[k] = q0[k] + dq + (k == j ? 1 : 0);
+      const unsigned long long nk = pack_key<D>(qq, r2, 0, &bad) | (bbits << kKeyBShift);
+      nn.x = bad ? 0 : table_find(L, tmask, nk);
     }
+    {   // n2: coordinates +1, axis -D: residue r + 1 (q carries up when r wraps), axis coordinate one q down
+      const int r2 = r == kLatD ? 0 : r + 1, dq = r == kLatD ? 1 : 0;
+      int qq[kLatD], bad = 0;
+#pragma unroll
+      for (int k = 0; k < kLatD; ++k) qq[k] = q0[k] + dq - (k == j ? 1 : 0);
+      const unsigned long long nk = pack_key<D>(qq, r2, 0, &bad) | (bbits << kKeyBShift);
+      nn.y = bad ? 0 : table_find(L, tmask, nk);
+    }
+    L.nbr[(size_t)j * L.m_cap + i] = nn;
   }
   if (blockIdx.x == 0) {
     if (threadIdx.x < kq) {
@@ -559,6 +568,9 @@ __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const 
   const int kq = L.Kp / 4;
   const long long total = min((long long)L.counters[0], L.m_cap) * kq;
   const int2 *nb = L.nbr + (size_t)axis * L.m_cap;
+  // row 0 of `dst` is the "absent neighbour" row of the next pass: zero it here, so that no pass depends on what a
+  // buffer held before (views of one lattice carved for different channel counts place val1 at different offsets)
+  if (blockIdx.x == 0 && threadIdx.x < kq) reinterpret_cast<float4 *>(dst)[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const long long i = idx / kq;
@@ -642,9 +654,24 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
     if (ok) {
       const float *ip = ins + at0 + (size_t)c0 * n;
       float *op = outs + at0 + (size_t)c0 * n;
+      // energy epilogue: the pixel's own inputs, requested one channel quad ahead of their use
+      float nxt[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ENERGY) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < K) nxt[k] = __ldg(ip + (size_t)k * n);
+      }
 #pragma unroll
       for (int q = 0; q < kChunk / 4; ++q) {
         if (q >= kq) break;
+        float cur[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cur[k] = nxt[k];
+        if (ENERGY && q + 1 < kq) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + 4 * (q + 1) + k < K) nxt[k] = __ldg(ip + (size_t)(4 + k) * n);
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r <= kLatD; ++r) {
@@ -663,7 +690,7 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
             float o = a4[k];
             if (ENERGY) {
               o = __fmul_rn(o, gt);
-              local = fmaf(__ldg(ip), o, local);
+              local = fmaf(cur[k], o, local);
             }
             *op = o;
             ip += n; op += n;
@@ -694,7 +721,7 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
 // ---- host side -----------------------------------------------------------------------------------
 static unsigned long long table_capacity(long long t_cap) {
   unsigned long long cap = 1024;
-  // t_cap is the worst case (six new list entries per pixel); the build uses the first 2^k >= 2T slots, so the
+  // t_cap is the worst case (six new list entries per pixel); the build uses the first 2^k >= 1.25 T slots, so the
   // allocation only bounds the load factor in the worst case (<= 0.8)
   while (cap < (unsigned long long)t_cap + (unsigned long long)t_cap / 4) cap <<= 1;
   return cap;

@@ -402,3 +402,37 @@ def test_par_two_streams_two_dilation_sets(cosa, port):
     for k in (0, 1):
         for o in outs[k]:
             assert_close(o, want[k], "PAR dilations %s on its own stream" % sets[k])
+
+
+def test_results_do_not_depend_on_stale_scratch(cosa, port):
+    """Every entry point must initialise what it reads: the cached scratch buffers are filled with 0xFF bytes (NaN
+    floats, -1 indices, all-ones keys) between two runs of the whole path and of the dense-CRF inference, and the
+    results must be the ones of the first run."""
+    from cosa_b200 import _lib
+    host = batch(B=3, C=21, H=90, W=122, n_fg=2, seed=211)        # h*w % 4 != 0 at half resolution: padding keys
+    d = to_cuda(host)
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+    probs = d["logits"].softmax(dim=1)
+    img255 = (d["img_denorm"] * 255).contiguous()
+
+    def run():
+        label = cosa.cam2mask(images=cosa.denormalize_img(d["simg"]), img_boxes=host["img_box"],
+                              cams=cosa.cam_validation(d["cams"], d["cls_label"]), cls_labels=d["cls_label"],
+                              threshold_high=0.7, threshold_low=0.25, refine_model=par)
+        logit = d["logits"].clone().requires_grad_(True)
+        loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=host["img_box"], loss_layer=layer)
+        loss.backward()
+        q = cosa.crf_inference_batch(img255, probs, 2, 1, 1, 4, 121, 5)
+        torch.cuda.synchronize()
+        return label.clone(), loss.detach().clone(), logit.grad.clone(), q.clone()
+
+    first = run()
+    for buf in list(_lib._scratch.values()):
+        buf.fill_(255)
+    torch.cuda.synchronize()
+    second = run()
+    assert torch.equal(first[0], second[0])
+    assert_close(second[1], first[1], "loss after poisoning the scratch", tol=1e-6)
+    assert_close(second[2], first[2], "gradient after poisoning the scratch", tol=1e-5)
+    assert_close(second[3], first[3], "dense-CRF marginals after poisoning the scratch", tol=1e-5)
