@@ -7,6 +7,7 @@
     seg_loss forward + backward                   utils/seg_helper.py:800-813
     seg_refine_by_label                           utils/seg_helper.py:553-568
     cam_loss forward + backward                   utils/seg_helper.py:593-602
+    dense-CRF mean-field inference (rank 4)       utils/seg_helper.py:961-996 (evaluation_engine.py:205-211)
 
     python bench_stages.py [--batch 32] [--steps 20] [--warmup 5] [--no-cpu]
 
@@ -81,7 +82,7 @@ def main():
 
     stages = [
         # name, device fn, cpu fn (on n images), algorithmic bytes per call
-        ("denormalize_img", lambda: cosa_b200.denormalize_img(d["simg"]), lambda n: port.denormalize_img(simg[:n]),
+        ("denormalize_img", lambda: cosa_b200.denormalize_img(d["simg"], lazy=False), lambda n: port.denormalize_img(simg[:n]),
          f32 * B * 3 * H * W * 2),
         ("upsample_bilinear fwd (28^2 -> 448^2)", lambda: cosa_b200.upsample_bilinear(d["seg_low"], (H, W)), None,
          f32 * B * C * H * W),
@@ -104,6 +105,26 @@ def main():
          lambda n: cam_loss_fb(dict(cam_pred=cam_pred[:n]), port, valid_seg[:n].cpu()),
          f32 * B * (C - 1) * 28 * 28 * (4 * 1 + 4)),                       # 4 taps + cam, target, grad (token grid)
     ]
+    # dense-CRF mean-field inference at evaluation time (seg_helper.py:961-996): one VOC-sized image
+    # as evaluation_engine.py:205-211 calls it, and a batch of 16 through one lattice pair.  Algorithmic bytes: the two
+    # lattice filters over K = 21 channels (build + norm filter + splat / blur / slice) are data dependent (M); the
+    # figure charged here is the floor of the mean-field update itself: probabilities in, marginals out, image in.
+    from oracle import crf_oracle
+    img_u8 = (torch.rand((16, 3, 448, 448), generator=g) * 255).floor()
+    probs16 = logits[:16].softmax(dim=1).to(dev)
+    img16 = img_u8.to(dev)
+    img1 = img16[:1, :, :366, :].contiguous()
+    img1 = torch.nn.functional.pad(img1, (0, 52))[:, :, :, :500].contiguous()
+    probs1 = torch.nn.functional.pad(probs16[:1, :, :366, :], (0, 52), value=1.0 / C)[:, :, :, :500].contiguous()
+    stages += [
+        ("crf_inference_infv2 (1 image 366x500, 21 classes, 1 iteration)",
+         lambda: cosa_b200.crf_inference_batch(img1, probs1, 1, 1, 1, 4, 121, 5),
+         lambda n: crf_oracle.crf_inference(img1[0].permute(1, 2, 0).cpu().numpy(), probs1[0].cpu().numpy(), 1, 1, 1, 4, 121, 5),
+         f32 * 366 * 500 * (2 * C + 3)),
+        ("crf_inference_infv2 (16 images 448x448, 21 classes, 1 iteration)",
+         lambda: cosa_b200.crf_inference_batch(img16, probs16, 1, 1, 1, 4, 121, 5), None,
+         f32 * 16 * 448 * 448 * (2 * C + 3)),
+    ]
     for name, fn, cpu_fn, alg in stages:
         for _ in range(max(3, args.warmup)):
             fn()
@@ -123,7 +144,7 @@ def main():
                 "config": "VOC shape B=%d, %dx%d, %d classes" % (B, H, W, C), "cpu": None}
         if cpu_fn is not None and not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
-            n = min(4, B)
+            n = 1 if name.startswith("crf_inference") else min(4, B)
             cpu_fn(1)
             t0 = time.perf_counter()
             cpu_fn(n)

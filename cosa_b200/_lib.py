@@ -44,6 +44,7 @@ _SIGNATURES = {
     "cosa_cam_validation": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_ll, _vp]),
     "cosa_cam_to_label": (_c_int, [_vp] * 5 + [_c_int] * 4 + [_c_float] * 3 + [_c_int, _c_ll, _vp]),
     "cosa_cam2mask_ws_bytes": (_c_size_t, [_c_int] * 7),
+    "cosa_cam2mask_ws_bytes_ex": (_c_size_t, [_c_int] * 8),
     "cosa_cam2mask": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
                       [_c_int] * 4 + [_vp, _c_size_t, _vp]),
     "cosa_cam2mask_flags": (_c_int, [_vp] * 4 + [_c_float] * 3 + [_c_int, _c_int, _vp, _c_int, _c_int] + [_vp] * 3 +
@@ -63,6 +64,9 @@ _SIGNATURES = {
     "cosa_dense_energy_backward": (_c_int, [_vp] * 4 + [_c_int] * 4 + [_vp]),
     "cosa_energy_loss_ws_bytes": (_c_size_t, [_c_int] * 4),
     "cosa_energy_loss_saved_bytes": (_c_size_t, [_c_int] * 4),
+    "cosa_energy_loss_ws_bytes_ex": (_c_size_t, [_c_int] * 5),
+    "cosa_energy_loss_lattice_offset": (_c_size_t, [_c_int] * 4),
+    "cosa_energy_loss_prebuild_ex": (_c_int, [_vp] * 3 + [_c_float] * 2 + [_c_int] * 4 + [_vp, _c_size_t, _c_int, _vp]),
     "cosa_energy_loss_forward": (_c_int, [_vp] * 6 + [_c_float] * 3 + [_vp, _vp] + [_c_int] * 4 +
                                  [_vp, _c_size_t, _vp]),
     "cosa_energy_loss_prebuild": (_c_int, [_vp] * 3 + [_c_float] * 2 + [_c_int] * 4 + [_vp, _c_size_t, _vp]),

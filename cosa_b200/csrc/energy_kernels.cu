@@ -603,9 +603,11 @@ extern "C" size_t cosa_dense_energy_ws_bytes(int N, int K, int H, int W) {
          lattice_ws_bytes(lattice_chunk_images(N, K, H, W), K, H, W);
 }
 
+static float budget_of(int flags) { return (float)((flags >> 8) & 0xff) / 16.0f; }   // COSA_ENERGY_VERTEX_BUDGET
+
 static int energy_core(const float *images, const float *s_roi, const float *gate, float *as_out, float *loss_out,
                        double *acc, int N, int K, int H, int W, float sigmargb, float sigmaxy, float weight,
-                       int apply_weight, void *lattice_ws, cudaStream_t s, bool prebuilt = false) {
+                       int apply_weight, void *lattice_ws, cudaStream_t s, bool prebuilt = false, float vpp = 0.0f) {
   const size_t n = (size_t)H * W;
   COSA_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
   const int chunk = lattice_chunk_images(N, K, H, W);
@@ -613,7 +615,7 @@ static int energy_core(const float *images, const float *s_roi, const float *gat
   for (int n0 = 0; n0 < N; n0 += chunk) {   // chunks reuse the lattice workspace, stream-ordered
     const int nb = min(chunk, N - n0);
     LatticeBufs L;
-    lattice_carve(lattice_ws, nb, K, H, W, &L);
+    lattice_carve(lattice_ws, nb, K, H, W, &L, kLatD, vpp);
     if (!prebuilt)
       COSA_CHECK(lattice_build(L, images + (size_t)n0 * 3 * n, nb, H, W, sigmargb, sigmaxy, n0 == 0, s));
     COSA_CHECK(lattice_splat_blur(L, s_roi + (size_t)n0 * K * n, nb, K, H, W, s));
@@ -660,12 +662,22 @@ extern "C" size_t cosa_energy_loss_saved_bytes(int B, int C, int H, int W) {
   return align_up((size_t)B * C * hw * sizeof(float), 256) + align_up((size_t)B * hw * sizeof(float), 256);
 }
 
-extern "C" size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W) {
+// bytes in front of the lattice in the workspace of the fused calls (independent of the vertex budget)
+extern "C" size_t cosa_energy_loss_lattice_offset(int B, int C, int H, int W) {
   if (B < 1 || C < 1 || H < 2 || W < 2) return 0;
   const size_t hw = (size_t)(H / 2) * (W / 2);
   return align_up((size_t)B * 3 * hw * sizeof(float), 256) + align_up((size_t)B * C * hw * sizeof(float), 256) +
-         align_up((size_t)B * hw * sizeof(float), 256) + 256 +
-         lattice_ws_bytes(lattice_chunk_images(B, C, H / 2, W / 2), C, H / 2, W / 2);
+         align_up((size_t)B * hw * sizeof(float), 256) + 256;
+}
+
+extern "C" size_t cosa_energy_loss_ws_bytes_ex(int B, int C, int H, int W, int flags) {
+  if (B < 1 || C < 1 || H < 2 || W < 2) return 0;
+  return cosa_energy_loss_lattice_offset(B, C, H, W) +
+         lattice_ws_bytes(lattice_chunk_images(B, C, H / 2, W / 2), C, H / 2, W / 2, kLatD, budget_of(flags));
+}
+
+extern "C" size_t cosa_energy_loss_ws_bytes(int B, int C, int H, int W) {
+  return cosa_energy_loss_ws_bytes_ex(B, C, H, W, 0);
 }
 
 // The image-only half of the forward: de-normalised nearest 2:1 image (the same two roundings as the prepare kernels)
@@ -700,9 +712,16 @@ __global__ void __launch_bounds__(256) energy_img_half_scalar_kernel(const float
 extern "C" int cosa_energy_loss_prebuild(const float *simg, const float *mean, const float *std, float sigmargb,
                                          float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes,
                                          void *stream) {
+  return cosa_energy_loss_prebuild_ex(simg, mean, std, sigmargb, sigmaxy_scaled, B, C, H, W, ws, ws_bytes, 0, stream);
+}
+
+extern "C" int cosa_energy_loss_prebuild_ex(const float *simg, const float *mean, const float *std, float sigmargb,
+                                            float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+                                            int flags, void *stream) {
+  if (flags & ~COSA_ENERGY_VERTEX_BUDGET_MASK) return COSA_E_ARG;
   if (!simg || !mean || !std || !ws || B < 1 || C < 1) return COSA_E_ARG;
   if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
-  if (ws_bytes < cosa_energy_loss_ws_bytes(B, C, H, W)) return COSA_E_WORKSPACE;
+  if (ws_bytes < cosa_energy_loss_ws_bytes_ex(B, C, H, W, flags)) return COSA_E_WORKSPACE;
   const int h = H / 2, w = W / 2;
   if (lattice_chunk_images(B, C, h, w) < B) return COSA_E_ARG;   // more than one lattice chunk: nothing to prebuild
   cudaStream_t s = (cudaStream_t)stream;
@@ -721,7 +740,7 @@ extern "C" int cosa_energy_loss_prebuild(const float *simg, const float *mean, c
     COSA_LAUNCH(energy_img_half_scalar_kernel, grid1d((long long)B * 3 * hw), 256, 0, s, simg, aff, img_half, B * 3, H, W);
   }
   LatticeBufs L;
-  lattice_carve(lws, B, C, h, w, &L);
+  lattice_carve(lws, B, C, h, w, &L, kLatD, budget_of(flags));
   return lattice_build(L, img_half, B, h, w, sigmargb, sigmaxy_scaled, true, s);
 }
 
@@ -737,11 +756,11 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
                                               const int *boxes, const float *mean, const float *std, float weight,
                                               float sigmargb, float sigmaxy_scaled, float *loss_out, void *saved, int B,
                                               int C, int H, int W, void *ws, size_t ws_bytes, int flags, void *stream) {
-  if (flags & ~COSA_ENERGY_LATTICE_PREBUILT) return COSA_E_ARG;
+  if (flags & ~(COSA_ENERGY_LATTICE_PREBUILT | COSA_ENERGY_VERTEX_BUDGET_MASK)) return COSA_E_ARG;
   if (!simg || !logit || !label || !boxes || !mean || !std || !loss_out || !saved || !ws || B < 1 || C < 1)
     return COSA_E_ARG;
   if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
-  if (ws_bytes < cosa_energy_loss_ws_bytes(B, C, H, W)) return COSA_E_WORKSPACE;
+  if (ws_bytes < cosa_energy_loss_ws_bytes_ex(B, C, H, W, flags)) return COSA_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   const int h = H / 2, w = W / 2;
   const size_t hw = (size_t)h * w;
@@ -774,7 +793,7 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
                 roi_half, C, H, W);
   }
   return energy_core(img_half, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1, lws,
-                     s, (flags & COSA_ENERGY_LATTICE_PREBUILT) != 0);
+                     s, (flags & COSA_ENERGY_LATTICE_PREBUILT) != 0, budget_of(flags));
 }
 
 extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,

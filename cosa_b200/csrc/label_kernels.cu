@@ -284,14 +284,17 @@ __global__ void __launch_bounds__(256) cam_to_label_kernel(const float *__restri
 // ------------------------------------------------------------------------------------------------
 __global__ void cam2mask_keys_kernel(const float *__restrict__ cls_labels, int *__restrict__ keys,
                                      int *__restrict__ nc_out, int *__restrict__ nch_out, int B, int C1,
-                                     int derive) {
+                                     int derive, int cap, int *__restrict__ err) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int *k = keys + (size_t)b * (C1 + 1);
   int n = 0;
   k[n++] = 0;
   for (int c = 0; c < C1; ++c)
-    if (cls_labels[(size_t)b * C1 + c] != 0.0f) k[n++] = c + 1;
+    if (cls_labels[(size_t)b * C1 + c] != 0.0f) {
+      if (n <= cap) k[n++] = c + 1;
+      else atomicExch(err, 1);      // more present classes than the mask buffers were sized for (COSA_CAM2MASK_MAX_CLASSES)
+    }
   nc_out[b] = n;
   nch_out[b] = 2 * (n - derive);   // stored channels: both stacks, minus the derived one of each
 }
@@ -344,7 +347,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
                                                                float *__restrict__ img_small,
                                                                float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
                                                                int C1, float thr_high, float thr_low, int derive,
-                                                               Denorm dn, const float *__restrict__ cam_scale) {
+                                                               Denorm dn, const float *__restrict__ cam_scale,
+                                                               int cstride) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -368,7 +372,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_kernel(const float *__re
   const float *cam_b = cams + (size_t)b * C1 * HW;
   // mask rows may be padded (MaskLayout): interior at column ml.off, ml.padn replicated columns either side
   const size_t mplane = (size_t)g.h * ml.pitch;
-  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * mplane + (size_t)y * ml.pitch + ml.off + x;
+  float *m_hi = masks + (size_t)b * cstride * mplane + (size_t)y * ml.pitch + ml.off + x;
   const int ns = nc - derive;   // channels stored per stack (the last live one is derived, see cosa_cam2mask)
   float *m_lo = m_hi + (size_t)ns * mplane;
   auto put = [&](float *dst, float val) {
@@ -447,7 +451,8 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
                                                                   float *__restrict__ img_small,
                                                                   float *__restrict__ masks, MaskLayout ml, ResizeGeom g,
                                                                   int C1, float thr_high, float thr_low, int derive,
-                                                                  Denorm dn, const float *__restrict__ cam_scale) {
+                                                                  Denorm dn, const float *__restrict__ cam_scale,
+                                                                  int cstride) {
   const int xp = blockIdx.x * 32 + (threadIdx.x & 31);     // pair index: half-resolution columns 2 xp, 2 xp + 1
   const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(256) cam2mask_prepare_x2_kernel(const float *_
   const int *key = keys + (size_t)b * (C1 + 1);
   const float *cam_b = cams + (size_t)b * C1 * HW;
   const size_t mplane = (size_t)g.h * ml.pitch;
-  float *m_hi = masks + (size_t)b * 2 * (C1 + 1) * mplane + (size_t)y * ml.pitch + ml.off + x;
+  float *m_hi = masks + (size_t)b * cstride * mplane + (size_t)y * ml.pitch + ml.off + x;
   const int ns = nc - derive;
   float *m_lo = m_hi + (size_t)ns * mplane;
   auto put = [&](float *dst, float v0, float v1) {
@@ -550,7 +555,8 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
                                                                 float *__restrict__ label_hi_out,
                                                                 float *__restrict__ label_lo_out, MaskLayout ml,
                                                                 ResizeGeom g, int C1, float ignore_index,
-                                                                float derive_total) {
+                                                                float derive_total, int cstride,
+                                                                const int *__restrict__ err) {
   const int X = blockIdx.x * 32 + (threadIdx.x & 31);
   const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -565,7 +571,7 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
     // up-sampling scale = reduced / full (area_pixel_compute_scale with the output size given)
     const Tap ty = tap_half_pixel(Y, g.identity ? 1.0f : (float)g.h / (float)g.H, g.h);
     const Tap tx = tap_half_pixel(X, g.identity ? 1.0f : (float)g.w / (float)g.W, g.w);
-    const float *st = refined + (size_t)b * 2 * (C1 + 1) * mplane + ml.off;
+    const float *st = refined + (size_t)b * cstride * mplane + ml.off;
     const int ns = derive_total > 0.0f ? nc - 1 : nc;   // channels stored per stack
     hi = (float)key[upsampled_argmax(st, nc, mplane, ml.pitch, ty, tx, derive_total)];
     lo = (float)key[upsampled_argmax(st + (size_t)ns * mplane, nc, mplane, ml.pitch, ty, tx, derive_total)];
@@ -574,6 +580,7 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
   float out = hi;
   if (hi == 0.0f) out = ignore_index;
   if (hi + lo == 0.0f) out = 0.0f;
+  if (*err) out = hi = lo = __int_as_float(0x7fc00000);   // class budget exceeded: fail loudly
   label_out[out_idx] = out;
   if (label_hi_out) label_hi_out[out_idx] = hi;
   if (label_lo_out) label_lo_out[out_idx] = lo;
@@ -591,7 +598,8 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
                                                                    float *__restrict__ label_hi_out,
                                                                    float *__restrict__ label_lo_out, MaskLayout ml,
                                                                    ResizeGeom g, int C1, float ignore_index,
-                                                                   float derive_total) {
+                                                                   float derive_total, int cstride,
+                                                                   const int *__restrict__ err) {
   const int xs = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ys = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
     const Tap tx[2] = {tap_half_pixel(X0, 0.5f, g.w), tap_half_pixel(X0 + 1, 0.5f, g.w)};
     const size_t r[3] = {(size_t)max(ys - 1, 0) * ml.pitch, (size_t)ys * ml.pitch, (size_t)min(ys + 1, g.h - 1) * ml.pitch};
     const int c[3] = {max(xs - 1, 0), xs, min(xs + 1, g.w - 1)};
-    const float *st = refined + (size_t)b * 2 * (C1 + 1) * mplane + ml.off;
+    const float *st = refined + (size_t)b * cstride * mplane + ml.off;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {                       // high stack, low stack
       const bool derive = derive_total > 0.0f;
@@ -660,6 +668,7 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
           if (in[dy][dx]) (s == 0 ? hi : lo)[dy][dx] = (float)key[arg[dy][dx]];
     }
   }
+  const bool poisoned = *err != 0;      // class budget exceeded: fail loudly
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
     float o[2];
@@ -668,6 +677,7 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
       float out = hi[dy][dx];
       if (hi[dy][dx] == 0.0f) out = ignore_index;
       if (hi[dy][dx] + lo[dy][dx] == 0.0f) out = 0.0f;
+      if (poisoned) out = hi[dy][dx] = lo[dy][dx] = __int_as_float(0x7fc00000);
       o[dx] = out;
     }
     const size_t idx = (size_t)b * HW + (size_t)(Y0 + dy) * g.W + X0;
@@ -1054,14 +1064,27 @@ static MaskLayout cam2mask_layout(int w, int use_par, const int *dilations, int 
   return l.padn > 24 ? plain_layout(w) : l;
 }
 
+// mask planes per image: both threshold stacks of (1 + present classes) channels; COSA_CAM2MASK_MAX_CLASSES caps the
+// present classes the buffers are sized for (0 = all C1)
+static int cam2mask_class_cap(int C1, int flags) {
+  const int cap = (flags >> 8) & 0xff;
+  return cap > 0 ? min(cap, C1) : C1;
+}
+
 extern "C" size_t cosa_cam2mask_ws_bytes(int B, int C1, int H, int W, int downscale, int use_par, int n_dil) {
+  return cosa_cam2mask_ws_bytes_ex(B, C1, H, W, downscale, use_par, n_dil, 0);
+}
+
+extern "C" size_t cosa_cam2mask_ws_bytes_ex(int B, int C1, int H, int W, int downscale, int use_par, int n_dil,
+                                            int flags) {
   ResizeGeom g;
   cam2mask_geom(H, W, downscale, &g);
   const size_t hw = (size_t)g.h * g.w;
   const size_t pitch = use_par ? (size_t)max_padded_pitch(g.w) : (size_t)g.w;
-  size_t bytes = align_up((size_t)B * (C1 + 1) * sizeof(int), 256) + 2 * align_up((size_t)B * sizeof(int), 256);
+  const int cstride = 2 * (cam2mask_class_cap(C1, flags) + 1);
+  size_t bytes = align_up((size_t)B * (C1 + 1) * sizeof(int), 256) + 3 * align_up((size_t)B * sizeof(int), 256);
   const int n_mask_bufs = use_par ? 4 : 1;
-  bytes += n_mask_bufs * align_up((size_t)B * 2 * (C1 + 1) * g.h * pitch * sizeof(float), 256);
+  bytes += n_mask_bufs * align_up((size_t)B * cstride * g.h * pitch * sizeof(float), 256);
   if (use_par) {
     bytes += align_up((size_t)B * 3 * hw * sizeof(float), 256);
     bytes += align_up((size_t)B * 8 * n_dil * hw * sizeof(float), 256);
@@ -1095,7 +1118,8 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
                                 float *label_high_out, float *label_low_out, int B, int C1, int H, int W, void *ws,
                                 size_t ws_bytes, int flags, const float *denorm_mean, const float *denorm_std,
                                 void *stream) {
-  if (flags & ~(COSA_CAM2MASK_REUSE_AFFINITY | COSA_CAM2MASK_ALL_CHANNELS | COSA_CAM2MASK_CAMS_UNVALIDATED))
+  if (flags & ~(COSA_CAM2MASK_REUSE_AFFINITY | COSA_CAM2MASK_ALL_CHANNELS | COSA_CAM2MASK_CAMS_UNVALIDATED |
+                COSA_CAM2MASK_MAX_CLASSES_MASK))
     return COSA_E_ARG;
   if ((denorm_mean == nullptr) != (denorm_std == nullptr)) return COSA_E_ARG;
   if (!images || !boxes || !cams || !cls_labels || !label_out || !ws || B < 1 || C1 < 1 || H < 1 || W < 1 ||
@@ -1105,17 +1129,20 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   ResizeGeom g;
   cam2mask_geom(H, W, downscale, &g);
   if (g.h < 1 || g.w < 1) return COSA_E_ARG;
-  if (ws_bytes < cosa_cam2mask_ws_bytes(B, C1, H, W, downscale, use_par, n_dil)) return COSA_E_WORKSPACE;
+  if (ws_bytes < cosa_cam2mask_ws_bytes_ex(B, C1, H, W, downscale, use_par, n_dil, flags)) return COSA_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t hw = (size_t)g.h * g.w;
   const int C = C1 + 1;
   const bool refine = use_par && num_iter > 0;
   const MaskLayout lay = cam2mask_layout(g.w, refine, dilations, n_dil);
-  const size_t mfloats = layout_floats(lay, B, 2 * C, g.h);
+  const int class_cap = cam2mask_class_cap(C1, flags);
+  const int cstride = 2 * (class_cap + 1);
+  const size_t mfloats = layout_floats(lay, B, cstride, g.h);
   Arena arena(ws);
   int *keys = arena.take<int>((size_t)B * C);
   int *nc = arena.take<int>(B);
   int *nch = arena.take<int>(B);
+  int *err = arena.take<int>(B);   // [0]: an image had more present classes than the buffers were sized for
   float *masks = arena.take<float>(mfloats);
 
   // The stacks PAR refines are softmax outputs: their channels sum to 1 at every pixel, and one propagation step
@@ -1133,7 +1160,8 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   for (int c = 0; c < 3; ++c) { dn.mean[c] = dn.on ? denorm_mean[c] : 0.0f; dn.std[c] = dn.on ? denorm_std[c] : 1.0f; }
   const float *cam_scale = (flags & COSA_CAM2MASK_CAMS_UNVALIDATED) ? cls_labels : nullptr;
   const float derive_total = derive ? (float)pow(pc.row_sum, (double)num_iter) : 0.0f;
-  COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive);
+  COSA_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
+  COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive, class_cap, err);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
   if (refine) {
     sa = arena.take<float>(mfloats);
@@ -1151,20 +1179,21 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   if (exact2) {
     dim3 gs(ceil_div(g.w / 2, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH_T("cam2mask_prepare_kernel", cam2mask_prepare_x2_kernel, gs, 256, 0, s, images, cams, keys, nc,
-                  reuse_aff ? nullptr : img_small, masks, lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale);
+                  reuse_aff ? nullptr : img_small, masks, lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale,
+                  cstride);
   } else {
     dim3 gs(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH(cam2mask_prepare_kernel, gs, 256, 0, s, images, cams, keys, nc, reuse_aff ? nullptr : img_small, masks,
-                lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale);
+                lay, g, C1, threshold_high, threshold_low, derive, dn, cam_scale, cstride);
   }
   const float *refined = masks;
   MaskLayout lay_fin = lay;
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
   if (refine) {
     if (reuse_aff) {
-      COSA_CHECK(par_launch_iterations(pc, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w, num_iter, s));
+      COSA_CHECK(par_launch_iterations(pc, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, cstride, B, g.h, g.w, num_iter, s));
     } else {
-      COSA_CHECK(par_refine_batch(pc, img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, 2 * C, B, g.h, g.w,
+      COSA_CHECK(par_refine_batch(pc, img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, cstride, B, g.h, g.w,
                                   num_iter, s));
     }
     refined = fin;
@@ -1172,11 +1201,11 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   if (!g.identity && H == 2 * g.h && W == 2 * g.w) {
     dim3 gf(ceil_div(g.w, 32), ceil_div(g.h, 8), B);
     COSA_LAUNCH(cam2mask_finalize_x2_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
-                label_low_out, lay_fin, g, C1, ignore_index, derive_total);
+                label_low_out, lay_fin, g, C1, ignore_index, derive_total, cstride, err);
   } else {
     dim3 gf(ceil_div(W, 32), ceil_div(H, 8), B);
     COSA_LAUNCH(cam2mask_finalize_kernel, gf, 256, 0, s, refined, keys, nc, boxes, label_out, label_high_out,
-                label_low_out, lay_fin, g, C1, ignore_index, derive_total);
+                label_low_out, lay_fin, g, C1, ignore_index, derive_total, cstride, err);
   }
   return 0;
 }

@@ -69,9 +69,14 @@ struct LatticeBufs {
   int d;                            // lattice dimension: 5 (bilateral) or 2 (spatial)
 };
 
-size_t lattice_ws_bytes(int N, int K, int H, int W, int d = kLatD);
-// Carves `ws` (>= lattice_ws_bytes) into the buffers above.
-void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int d = kLatD);
+// vpp: vertex budget in vertices per pixel.  0 = the worst case (d + 1 new vertices per pixel: every size bound is then
+// a guarantee).  A positive value sizes the vertex arrays (keys, neighbour table, the two value buffers - the bulk of
+// the workspace) for vpp * N * H * W vertices and the per-tile lists for twice as many entries; natural images need
+// 0.2 - 0.6 (the synthetic VOC batch: 0.50), uniform noise 2.4.  A lattice that outgrows its budget raises the sticky
+// error flag 2: outputs and loss become NaN and cosa_bilateral_stats returns COSA_E_WORKSPACE - never a silent overrun.
+size_t lattice_ws_bytes(int N, int K, int H, int W, int d = kLatD, float vpp = 0.0f);
+// Carves `ws` (>= lattice_ws_bytes for the same arguments) into the buffers above.
+void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int d = kLatD, float vpp = 0.0f);
 
 // Build the lattice (dimension L.d) of N (<= kMaxImagesPerLattice) planar RGB images [N,3,H,W] (d = 2: the images are
 // not read, the features are the pixel coordinates alone).

@@ -743,7 +743,7 @@ struct LatticeDims {
   int tiles_x, tiles_y, Kp, d;
 };
 
-static LatticeDims lattice_dims(int N, int K, int H, int W, int dim) {
+static LatticeDims lattice_dims(int N, int K, int H, int W, int dim, float vpp) {
   LatticeDims d;
   d.d = dim;
   const long long V = dim + 1;             // vertices of a simplex
@@ -752,6 +752,10 @@ static LatticeDims lattice_dims(int N, int K, int H, int W, int dim) {
   d.P = (long long)N * d.n;
   d.t_cap = V * N * d.n_pad + V * N;       // + the keys of the padding pixels, appended once per image
   d.m_cap = d.t_cap;
+  if (vpp > 0.0f) {                        // a vertex budget instead of the worst case (lattice.cuh)
+    d.m_cap = min(d.m_cap, (long long)ceil((double)vpp * (double)d.P) + V * N + 1024);
+    d.t_cap = min(d.t_cap, 2 * d.m_cap);
+  }
   d.cap = table_capacity(d.t_cap);
   d.tiles_x = ceil_div(W, kTileW);
   d.tiles_y = ceil_div(H, kTileH);
@@ -778,14 +782,14 @@ static void lattice_layout(const LatticeDims &d, F &&take) {
   take(13, (size_t)(d.m_cap + 1) * d.Kp * sizeof(float));             // val1
 }
 
-size_t lattice_ws_bytes(int N, int K, int H, int W, int dim) {
+size_t lattice_ws_bytes(int N, int K, int H, int W, int dim, float vpp) {
   size_t b = 0;
-  lattice_layout(lattice_dims(N, K, H, W, dim), [&](int, size_t bytes) { b += align_up(bytes, 256); });
+  lattice_layout(lattice_dims(N, K, H, W, dim, vpp), [&](int, size_t bytes) { b += align_up(bytes, 256); });
   return b;
 }
 
-void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int dim) {
-  const LatticeDims d = lattice_dims(N, K, H, W, dim);
+void lattice_carve(void *ws, int N, int K, int H, int W, LatticeBufs *L, int dim, float vpp) {
+  const LatticeDims d = lattice_dims(N, K, H, W, dim, vpp);
   L->P = d.P; L->m_cap = d.m_cap; L->t_cap = d.t_cap; L->cap_mask = d.cap - 1;
   L->tiles_x = d.tiles_x; L->tiles_y = d.tiles_y; L->Kp = d.Kp; L->d = d.d;
   char *p = (char *)ws;

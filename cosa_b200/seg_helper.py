@@ -244,12 +244,15 @@ def cam2mask(
         downscale=2,
         return_parts=False,
         propagate_all_channels=None,
+        max_classes=None,
 ):
     """Pseudo-label map [B,H,W] float32 with values {0..C-1, ignore_index} (seg_helper.py:721-785).
 
     ``refine_model`` may be ``None`` (the shipped default), a :class:`cosa_b200.PAR` (whole batch, both
     threshold stacks, one fused kernel sequence) or any other callable ``(images, cams) -> cams`` (called
     per image exactly like the reference; only the resize/argmax tail then runs in this package's kernels).
+    ``max_classes`` (optional) sizes the scratch for at most that many present classes per image instead of all of
+    them (VOC B = 32 with PAR: 1.7 GB -> 0.8 GB at 6); an image with more makes every label of the call NaN.
     """
     lib = _lib.load()
     generic = refine_model is not None and refine_model is not False and not isinstance(refine_model, PAR)
@@ -283,8 +286,12 @@ def cam2mask(
     hi = torch.empty_like(out) if return_parts else None
     lo = torch.empty_like(out) if return_parts else None
     n_dil = len(refine_model.dilations) if use_par else 0
+    if max_classes is not None:
+        if not 1 <= int(max_classes) <= 255:
+            raise ValueError("max_classes must be between 1 and 255")
+        flags |= (int(max_classes) & 0xff) << 8                             # COSA_CAM2MASK_MAX_CLASSES
     with torch.cuda.device(dev):
-        nbytes = lib.cosa_cam2mask_ws_bytes(b, c1, h, w, int(downscale or 0), int(use_par), n_dil)
+        nbytes = lib.cosa_cam2mask_ws_bytes_ex(b, c1, h, w, int(downscale or 0), int(use_par), n_dil, flags)
         share = refine_model._shared if use_par else None
         uses_before = _lib.workspace_uses(dev)
         ws = _lib.workspace(nbytes, dev)
@@ -414,6 +421,11 @@ class DenseEnergyLoss(torch.nn.Module):
 
     # the seg_helper copy passes recompute_scale_factor=True to F.interpolate, the rrm_utils copy does not
     recompute_scale_factor = True
+    # Scratch sizing of the fused path: ``None`` sizes the lattice for the worst case (6 vertices per half-resolution
+    # pixel: 2.9 GB at VOC B = 32); a number sizes its vertex arrays for that many vertices per pixel (1.5 -> 0.8 GB;
+    # natural images need 0.2 - 0.6).  A batch that outgrows the budget makes the loss NaN (never a silent overrun)
+    # and ``cosa_b200.seg_helper.last_energy_lattice_stats`` reports error flag 2.  Set it on the class or an instance.
+    vertex_budget = None
 
     def __init__(self, weight, sigma_rgb, sigma_xy, scale_factor):
         super(DenseEnergyLoss, self).__init__()
@@ -421,6 +433,14 @@ class DenseEnergyLoss(torch.nn.Module):
         self.sigma_rgb = sigma_rgb
         self.sigma_xy = sigma_xy
         self.scale_factor = scale_factor
+
+    def _budget_flags(self):
+        b = self.vertex_budget
+        if b is None:
+            return 0
+        if not (0.0625 <= float(b) <= 15.9):
+            raise ValueError("vertex_budget must be None or between 1/16 and 15.9 vertices per pixel")
+        return (int(float(b) * 16.0 + 0.5) & 0xff) << 8          # COSA_ENERGY_VERTEX_BUDGET
 
     def _kw(self):
         kw = dict(scale_factor=self.scale_factor)
@@ -471,7 +491,8 @@ class DenseEnergyLoss(torch.nn.Module):
         mean_t, std_t = tuple(float(v) for v in mean), tuple(float(v) for v in std)
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
-            nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+            bflags = self._budget_flags()
+            nbytes = lib.cosa_energy_loss_ws_bytes_ex(B, C, H, W, bflags)
             st = self.__dict__.setdefault("_pre_state", {})
             side = st.get(("stream", dev.index))
             if side is None:
@@ -483,9 +504,10 @@ class DenseEnergyLoss(torch.nn.Module):
                 ws = st[("ws", dev.index)] = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=dev)
             side.wait_stream(main)          # img is ready; the previous step's filter no longer reads the workspace
             with torch.cuda.stream(side):
-                _lib.check(lib.cosa_energy_loss_prebuild(
+                _lib.check(lib.cosa_energy_loss_prebuild_ex(
                     _lib.ptr(img), (ctypes.c_float * 3)(*mean_t), (ctypes.c_float * 3)(*std_t), float(self.sigma_rgb),
-                    float(self.sigma_xy * self.scale_factor), B, C, H, W, _lib.ptr(ws), nbytes, _lib.stream_ptr()))
+                    float(self.sigma_xy * self.scale_factor), B, C, H, W, _lib.ptr(ws), nbytes, bflags,
+                    _lib.stream_ptr()))
                 done = torch.cuda.Event()
                 done.record(side)
         # identity of the image: address, shape AND the tensor's version counter (an in-place update of `img`, or a new
@@ -493,7 +515,7 @@ class DenseEnergyLoss(torch.nn.Module):
         self.__dict__["_prebuilt"] = dict(img_ptr=img.data_ptr(), img_version=img._version, img_ref=img,
                                           shape=(B, C, H, W), mean=mean_t, std=std_t,
                                           sigmas=(float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor)),
-                                          ws=ws, nbytes=nbytes, done=done, device=dev)
+                                          ws=ws, nbytes=nbytes, done=done, device=dev, bflags=bflags)
         return True
 
     def __getstate__(self):
@@ -511,7 +533,8 @@ class DenseEnergyLoss(torch.nn.Module):
         if (pre["img_ref"] is not img or pre["img_version"] != img._version
                 or pre["img_ptr"] != img.data_ptr() or pre["shape"] != tuple(shape) or pre["device"] != img.device
                 or pre["mean"] != tuple(float(v) for v in mean) or pre["std"] != tuple(float(v) for v in std)
-                or pre["sigmas"] != (float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor))):
+                or pre["sigmas"] != (float(self.sigma_rgb), float(self.sigma_xy * self.scale_factor))
+                or pre["bflags"] != self._budget_flags()):
             return None
         return pre
 
@@ -521,7 +544,7 @@ class _FusedEnergyLoss(Function):
     ROI / unlabel / gate, lattice filter and the energy, with d loss / d logit computed directly."""
 
     @staticmethod
-    def forward(ctx, logit, simg, label, boxes, mean, std, weight, sigma_rgb, sigma_xy_scaled, pre=None):
+    def forward(ctx, logit, simg, label, boxes, mean, std, weight, sigma_rgb, sigma_xy_scaled, pre=None, bflags=0):
         lib = _lib.load()
         dev = logit.device
         B, C, H, W = logit.shape
@@ -530,13 +553,13 @@ class _FusedEnergyLoss(Function):
         std_c = (ctypes.c_float * 3)(*[float(v) for v in std])
         with torch.cuda.device(dev):
             saved = torch.empty(lib.cosa_energy_loss_saved_bytes(B, C, H, W), dtype=torch.uint8, device=dev)
-            nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+            nbytes = lib.cosa_energy_loss_ws_bytes_ex(B, C, H, W, int(bflags))
             if pre is not None:       # DenseEnergyLoss.prebuild_lattice: the lattice is in the layer's own workspace
                 torch.cuda.current_stream(dev).wait_event(pre["done"])
-                ws, flags = pre["ws"], 1   # COSA_ENERGY_LATTICE_PREBUILT
+                ws, flags = pre["ws"], 1 | int(bflags)   # COSA_ENERGY_LATTICE_PREBUILT
                 _LAST_ENERGY_WS[dev.index] = ws
             else:
-                ws, flags = _lib.workspace(nbytes, dev), 0
+                ws, flags = _lib.workspace(nbytes, dev), int(bflags)
                 _LAST_ENERGY_WS.pop(dev.index, None)
             _lib.check(lib.cosa_energy_loss_forward_flags(
                 _lib.ptr(simg), _lib.ptr(logit), _lib.ptr(label), _lib.ptr(boxes), mean_c, std_c, float(weight),
@@ -557,7 +580,7 @@ class _FusedEnergyLoss(Function):
         with torch.cuda.device(logit.device):
             _lib.check(lib.cosa_energy_loss_backward(_lib.ptr(logit), _lib.ptr(ctx.saved_blob), _lib.ptr(g),
                                                      ctx.weight, _lib.ptr(grad), B, C, H, W, _lib.stream_ptr()))
-        return grad, None, None, None, None, None, None, None, None, None
+        return grad, None, None, None, None, None, None, None, None, None, None
 
 
 _LAST_ENERGY_WS = {}    # device index -> the layer-owned workspace of the last fused call, if it used a prebuilt lattice
@@ -588,7 +611,7 @@ def get_energy_loss(img,
         pre = loss_layer._take_prebuilt(simg, (B, C, H, W), mean, std)
         return _FusedEnergyLoss.apply(logit.contiguous(), simg, _lib.dev_f32(label.to(dev), "label"), boxes, mean, std,
                                       loss_layer.weight, loss_layer.sigma_rgb,
-                                      loss_layer.sigma_xy * loss_layer.scale_factor, pre)
+                                      loss_layer.sigma_xy * loss_layer.scale_factor, pre, loss_layer._budget_flags())
     pred_prob = F.softmax(logit, dim=1)
     crop_mask = torch.zeros_like(pred_prob[:, 0, ...])
     boxes = _lib.resolve_boxes(img_box, B, H, W, torch.device("cpu")).tolist()
@@ -607,21 +630,20 @@ _FUSABLE_LAYERS = {DenseEnergyLoss}
 
 
 def last_energy_lattice_stats(B, C, H, W, device=None):
-    """(M, key_range_error, table_capacity, max_probe) of the lattice built by the last fused
+    """(M, error flags (1 = key range, 2 = vertex budget exceeded), table_capacity, max_probe) of the lattice built by the last fused
     ``get_energy_loss`` call with these logit shapes on the current stream (the lattice is the tail of that
     call's workspace).  Synchronises the stream."""
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     with torch.cuda.device(device):
-        nbytes = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
         ws = _LAST_ENERGY_WS.get(device.index if device.index is not None else torch.cuda.current_device())
         if ws is None:
-            ws = _lib.workspace(nbytes, device)
-        front = nbytes - lib.cosa_bilateral_ws_bytes(B, C, H // 2, W // 2)
+            ws = _lib.workspace(256, device)         # the stream's cached scratch: the last plain call ran in it
+        front = lib.cosa_energy_loss_lattice_offset(B, C, H, W)
         stats = (ctypes.c_longlong * 4)()
         rc = lib.cosa_bilateral_stats(ctypes.c_void_p(ws.data_ptr() + front), B, C, H // 2, W // 2, stats,
                                       _lib.stream_ptr())
-    if rc not in (0, -3):
+    if rc not in (0, -2, -3):        # key-range / capacity errors are reported through stats[1]
         _lib.check(rc)
     return tuple(int(v) for v in stats)
 

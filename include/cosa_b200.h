@@ -154,6 +154,13 @@ int cosa_cam2mask_flags(const float *images, const int *boxes, const float *cams
  *   every channel like the reference does. */
 #define COSA_CAM2MASK_ALL_CHANNELS 2
 #define COSA_CAM2MASK_CAMS_UNVALIDATED 4
+/* Scratch sizing: the mask buffers hold both threshold stacks of (1 + present classes) channels per image, and by
+ * default are sized for every class being present (1.7 GB at VOC B = 32).  COSA_CAM2MASK_MAX_CLASSES(n) (bits 8..15 of
+ * `flags`; give the same flags to cosa_cam2mask_ws_bytes_ex) sizes them for at most n present classes per image (VOC
+ * images have at most 6: 0.8 GB).  An image with more is detected on the device: every label of the call becomes NaN. */
+#define COSA_CAM2MASK_MAX_CLASSES(n) (((n) & 0xff) << 8)
+#define COSA_CAM2MASK_MAX_CLASSES_MASK 0xff00
+size_t cosa_cam2mask_ws_bytes_ex(int B, int C1, int H, int W, int downscale, int use_par, int n_dil, int flags);
 int cosa_cam2mask_ex(const float *images, const int *boxes, const float *cams, const float *cls_labels,
                      float threshold_high, float threshold_low, float ignore_index, int downscale, int use_par,
                      const int *dilations, int n_dil, int num_iter, float *label_out, float *label_high_out,
@@ -220,6 +227,20 @@ int cosa_energy_loss_forward(const float *simg, const float *logit, const float 
  * skips the build; the kernels and their inputs are those of cosa_energy_loss_forward.  Batches that need more than one
  * lattice chunk (B > 64) return COSA_E_ARG from both. */
 #define COSA_ENERGY_LATTICE_PREBUILT 1
+/* Vertex budget (bits 8..15 of `flags`, in sixteenths of a vertex per half-resolution pixel; 0 = worst case).  The
+ * lattice of an image can have up to 6 vertices per pixel, and the default workspace is sized for that (2.9 GB at
+ * VOC B = 32, of which the two value buffers are 1.9 GB); natural images need 0.2 - 0.6 (the synthetic VOC batch: 0.50,
+ * uniform noise: 2.4).  COSA_ENERGY_VERTEX_BUDGET(1.5) sizes the vertex arrays for 1.5 vertices per pixel (0.8 GB at VOC
+ * B = 32).  The same flags must be given to ws_bytes_ex, prebuild_ex and forward_flags.  A batch that outgrows its
+ * budget is detected, not overrun: the loss and its gradient become NaN and cosa_bilateral_stats on the lattice
+ * (cosa_energy_loss_lattice_offset bytes into `ws`) returns COSA_E_WORKSPACE. */
+#define COSA_ENERGY_VERTEX_BUDGET(vertices_per_pixel) (((int)((vertices_per_pixel) * 16.0f + 0.5f) & 0xff) << 8)
+#define COSA_ENERGY_VERTEX_BUDGET_MASK 0xff00
+size_t cosa_energy_loss_ws_bytes_ex(int B, int C, int H, int W, int flags);
+size_t cosa_energy_loss_lattice_offset(int B, int C, int H, int W);
+int cosa_energy_loss_prebuild_ex(const float *simg, const float *mean, const float *std, float sigmargb,
+                                 float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes, int flags,
+                                 void *stream);
 int cosa_energy_loss_prebuild(const float *simg, const float *mean, const float *std, float sigmargb,
                               float sigmaxy_scaled, int B, int C, int H, int W, void *ws, size_t ws_bytes,
                               void *stream);

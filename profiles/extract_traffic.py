@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """dram__bytes_read.sum + dram__bytes_write.sum per launch for every kernel of an `ncu --set full` report
--> profiles/dram_traffic.json (read by bench.py for roofline.traffic).
+-> profiles/dram_traffic.json (read by bench.py for roofline.traffic; the file names the configuration the capture was
+made on, and bench.py reports the traffic only when it runs that configuration).
 
-    python profiles/extract_traffic.py gpurun_out/prof.ncu-rep [more.ncu-rep ...]
+    python profiles/extract_traffic.py <config key, e.g. voc_b32_448x448> gpurun_out/prof.ncu-rep [more.ncu-rep ...]
 """
 import csv
 import io
@@ -14,9 +15,9 @@ import sys
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def main(paths):
+def main(config, paths):
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dram_traffic.json")
-    traffic = json.load(open(out_path)) if os.path.exists(out_path) else {}
+    kernels, sources = {}, {}
     for path in paths:
         raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
@@ -29,11 +30,13 @@ def main(paths):
             wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
             acc.setdefault(name, []).append(rd + wr)
         for name, vals in acc.items():
-            traffic[name] = int(sum(vals) / len(vals))
-        traffic.setdefault("_source", {})[os.path.basename(path)] = sorted(acc)
-    json.dump(traffic, open(out_path, "w"), indent=1, sort_keys=True)
-    print(json.dumps(traffic, indent=1, sort_keys=True))
+            kernels[name] = int(sum(vals) / len(vals))
+        sources[os.path.basename(path)] = sorted(acc)
+    out = {"config": config, "kernels": kernels, "sources": sources,
+           "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches)"}
+    json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(out, indent=1, sort_keys=True))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    main(sys.argv[1], sys.argv[2:])

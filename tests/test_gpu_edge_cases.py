@@ -436,3 +436,60 @@ def test_results_do_not_depend_on_stale_scratch(cosa, port):
     assert_close(second[1], first[1], "loss after poisoning the scratch", tol=1e-6)
     assert_close(second[2], first[2], "gradient after poisoning the scratch", tol=1e-5)
     assert_close(second[3], first[3], "dense-CRF marginals after poisoning the scratch", tol=1e-5)
+
+
+def test_vertex_budget_shrinks_the_scratch_and_overflow_is_loud(cosa, port):
+    """DenseEnergyLoss.vertex_budget: the same loss and gradient from a workspace sized for 1.5 vertices per pixel
+    instead of the worst case 6; a budget the batch outgrows yields NaN and error flag 2, not an overrun."""
+    from cosa_b200 import _lib, seg_helper
+    lib = _lib.load()
+    B, C, H, W = 4, 21, 128, 160
+    d = to_cuda(batch(B=B, C=C, H=H, W=W, n_fg=2, seed=401))
+    label = torch.zeros((B, H, W), device="cuda")
+    full = lib.cosa_energy_loss_ws_bytes(B, C, H, W)
+    small = lib.cosa_energy_loss_ws_bytes_ex(B, C, H, W, (int(1.5 * 16 + 0.5) & 0xff) << 8)
+    assert small < 0.45 * full, (small, full)
+
+    def run(budget, prebuild):
+        layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+        layer.vertex_budget = budget
+        if prebuild:
+            assert layer.prebuild_lattice(d["simg"], C)
+        logit = d["logits"].clone().requires_grad_(True)
+        loss = cosa.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=d["img_box"], loss_layer=layer)
+        loss.backward()
+        return loss.detach().clone(), logit.grad.clone(), seg_helper.last_energy_lattice_stats(B, C, H, W)
+
+    l0, g0, st0 = run(None, False)
+    for pre in (False, True):
+        l1, g1, st1 = run(1.5, pre)
+        assert st1[0] == st0[0] and st1[1] == 0
+        assert_close(l1, l0, "loss with a vertex budget", tol=1e-6)
+        assert_close(g1, g0, "gradient with a vertex budget", tol=1e-5)
+    l2, g2, st2 = run(0.0625, False)                  # 1/16 vertex per pixel: the batch needs ~0.5
+    assert bool(torch.isnan(l2).all()) and st2[1] & 2, (l2, st2)
+    l3, _, st3 = run(None, False)                     # and the next plain call is unaffected
+    assert st3[1] == 0
+    assert_close(l3, l0, "loss after an overflowed call", tol=1e-6)
+    with pytest.raises(ValueError):
+        run(100.0, False)
+
+
+def test_cam2mask_class_budget(cosa):
+    """cam2mask(max_classes=n): same labels from mask buffers sized for n present classes per image; an image with
+    more classes than the budget poisons the call's labels instead of overrunning the scratch."""
+    from cosa_b200 import _lib
+    lib = _lib.load()
+    assert lib.cosa_cam2mask_ws_bytes_ex(32, 20, 448, 448, 2, 1, 6, 6 << 8) < 0.5 * lib.cosa_cam2mask_ws_bytes(32, 20, 448, 448, 2, 1, 6)
+    host = batch(B=3, C=21, H=96, W=128, n_fg=3, seed=77)
+    d = to_cuda(host)
+    par = cosa.PAR(num_iter=10, dilations=DIL).cuda()
+    kw = dict(images=d["img_denorm"], img_boxes=host["img_box"], cams=d["cams"], cls_labels=d["cls_label"],
+              threshold_high=0.7, threshold_low=0.25)
+    for refine in (par, None):
+        want = cosa.cam2mask(refine_model=refine, **kw)
+        assert torch.equal(cosa.cam2mask(refine_model=refine, max_classes=3, **kw), want)
+        assert torch.equal(cosa.cam2mask(refine_model=refine, max_classes=7, **kw), want)
+        over = cosa.cam2mask(refine_model=refine, max_classes=2, **kw)          # three classes present, budget two
+        assert bool(torch.isnan(over).all())
+        assert torch.equal(cosa.cam2mask(refine_model=refine, **kw), want)       # the next call is unaffected
