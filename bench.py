@@ -107,6 +107,16 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    def summary_peek(self):
+        """The clocks seen so far, without ending the sampling."""
+        try:
+            self.file.flush()
+            sm = [float(r.strip().split(", ")[1]) for r in open(self.file.name) if r.count(",") >= 8]
+            busy = [v for v in sm if v >= 0.5 * max(sm)] if sm else []
+            return {"sm_mhz": statistics.median(busy)} if busy else None
+        except Exception:
+            return None
+
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.file is None:
@@ -492,6 +502,23 @@ def run_cosa_arm(args):
                 "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": top["avg_ms"], "alg_bytes_per_launch": top["alg_bytes"],
                 "share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 4)}
+    if top["kernel"] == "par_iterate_tile_kernel":
+        # The PAR step is bound on the SM side, not by HBM: every FMA consumes one neighbour value
+        # through the 128 B/clk shared-memory / L1 load path.  Bytes through that path per launch: per pixel and moved
+        # channel 50 LDS.128 per quad (200 B), plus the 48 affinity quads (192 B per pixel) once per CTA of a tile
+        # (two CTAs share a tile's channels).  Peak = SMs x 128 B/clk x the SM clock seen during the run.
+        h2, w2 = H // 2, W // 2
+        ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
+        n_groups = 1 if ncm <= 3 else 2 * ((ncm + 5) // 6)      # channel groups of a tile: each loads the affinity quads
+        lsu_bytes = B * h2 * w2 * (ncm * 200 + n_groups * 192)
+        sm_mhz = (clocks.summary_peek() or {}).get("sm_mhz") or 1965.0
+        lsu_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * sm_mhz * 1e6 / 1e9
+        lsu_gbs = lsu_bytes / 1e9 / (top["avg_ms"] / 1e3)
+        roofline["secondary"] = {"bound": "shared-memory / L1 load path (LSU)", "achieved": round(lsu_gbs, 1),
+                                 "peak": round(lsu_peak, 1), "unit": "GB/s", "frac": round(lsu_gbs / lsu_peak, 4),
+                                 "bytes_per_launch": lsu_bytes,
+                                 "note": "per pixel: 200 B of mask quads per moved channel + 192 B of affinity quads per "
+                                         "channel group of its tile; peak = SMs x 128 B/clk x SM clock"}
 
     # ---- end to end through the host-buffer API (cosa_b200.HostPipeline): pinned host tensors in, labels + loss in
     # pinned host memory out; every step's uploads and read-backs are inside the timed region ---------------------

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "cosa_cam_normalize": (_c_int, [_vp, _c_int, _vp, _c_int, _c_ll, _vp, _vp]),
     "cosa_multi_scale_cam_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp, _vp]),
     "cosa_multi_scale_cam_merge_valid": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp] + [_c_int] * 4 + [_vp, _vp]),
+    "cosa_multi_scale_cam_merge_present": (_c_int, [_vp, _vp, _vp, _c_int, _vp, _vp] + [_c_int] * 4 + [_vp, _vp]),
     "cosa_multi_scale_seg_merge": (_c_int, [_vp, _vp, _vp, _c_int, _vp] + [_c_int] * 4 + [_vp]),
     "cosa_seg_loss_stats_bytes": (_c_size_t, []),
     "cosa_seg_loss_forward": (_c_int, [_vp, _vp, _c_float, _c_int, _vp, _vp] + [_c_int] * 4 + [_vp]),

@@ -895,12 +895,18 @@ __global__ void __launch_bounds__(128) merge_rows_kernel(RawScales rs, float *__
 // Second pass of the CAM merge: the plane holds the un-normalised scale sum (merge_rows_kernel<.., 3>), the extrema
 // are known; one streaming read-modify-write finishes it (and applies the class label of the fused cam_validation).
 // The bilinear merge is then evaluated once per pixel instead of twice (once for the extrema, once for the store).
+// present_only: planes whose label is 0 are left untouched and no label factor is applied (the caller hands the
+// result to cam2mask as un-validated CAMs: cosa_multi_scale_cam_merge_present).
 __global__ void __launch_bounds__(256) cam_normalize_inplace_kernel(float *__restrict__ out, const int *__restrict__ mm,
                                                                     const float *__restrict__ cls, long long HW4,
-                                                                    long long HW, int planes) {
+                                                                    long long HW, int planes, int present_only) {
   for (int p = blockIdx.y; p < planes; p += gridDim.y) {
-    const float lab = cls ? __ldg(cls + p) : 1.0f;
+    float lab = cls ? __ldg(cls + p) : 1.0f;
     float *dst = out + (size_t)p * HW;
+    if (present_only) {
+      if (lab == 0.0f) continue;
+      lab = 1.0f;
+    }
     if (lab == 0.0f) {
       for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4;
            i += (long long)gridDim.x * blockDim.x)
@@ -1231,8 +1237,10 @@ static int fill_raw_scales(RawScales *rs, const float *const *raw, const int *hs
 }
 
 static int cam_merge_impl(const float *const *raw, const int *hs, const int *ws, int n_scales, const float *cls_label,
-                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream) {
+                          float *out, int B, int C1, int H, int W, float *minmax_ws, void *stream,
+                          int present_only = 0) {
   if (!out || !minmax_ws || B < 1 || C1 < 1 || H < 1 || W < 1) return COSA_E_ARG;
+  if (present_only && !(W % 4 == 0 && n_scales <= 5 && ((uintptr_t)out % 16) == 0)) return COSA_E_ARG;
   RawScales rs;
   COSA_CHECK(fill_raw_scales(&rs, raw, hs, ws, n_scales));
   cudaStream_t s = (cudaStream_t)stream;
@@ -1248,7 +1256,8 @@ static int cam_merge_impl(const float *const *raw, const int *hs, const int *ws,
     COSA_CHECK(launch_merge_rows<3>(rs, out, mm, B, C1, H, W, cls_label, s));
     const int bx = (int)min(ceil_div_ll(HW / 4, 256), 64LL);
     const int by = min(planes, max(1, sm_count() * 16 / bx));
-    COSA_LAUNCH(cam_normalize_inplace_kernel, dim3(bx, by), 256, 0, s, out, mm, cls_label, HW / 4, HW, planes);
+    COSA_LAUNCH(cam_normalize_inplace_kernel, dim3(bx, by), 256, 0, s, out, mm, cls_label, HW / 4, HW, planes,
+                present_only);
     return 0;
   }
   const int bx = (int)max(1LL, min(ceil_div_ll(HW, 256 * 4 * 4), 32LL));
@@ -1268,6 +1277,13 @@ extern "C" int cosa_multi_scale_cam_merge_valid(const float *const *raw, const i
                                                 float *minmax_ws, void *stream) {
   if (!cls_label) return COSA_E_ARG;
   return cam_merge_impl(raw, hs, ws, n_scales, cls_label, out, B, C1, H, W, minmax_ws, stream);
+}
+
+extern "C" int cosa_multi_scale_cam_merge_present(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                                  const float *cls_label, float *out, int B, int C1, int H, int W,
+                                                  float *minmax_ws, void *stream) {
+  if (!cls_label) return COSA_E_ARG;
+  return cam_merge_impl(raw, hs, ws, n_scales, cls_label, out, B, C1, H, W, minmax_ws, stream, 1);
 }
 
 extern "C" int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales,

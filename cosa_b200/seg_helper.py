@@ -62,13 +62,15 @@ def _raw_scale_args(raws, what):
     return raws, ptrs, hs, ws
 
 
-def multi_scale_cam_merge(raw_cams, size, cls_label=None):
+def multi_scale_cam_merge(raw_cams, size, cls_label=None, lazy=True):
     """Normalised CAM [B,C1,H,W] from the per-scale raw maps of ``multi_scale_camseg`` (seg_helper.py:253-270).
 
     ``raw_cams[s]`` is the model output for ``cat([imgs_s, imgs_s.flip(-1)])``: [2B, C1, hs, ws].  Enlargement,
     un-flip, max, ReLU, sum over scales and the per-plane min-max normalisation run in one kernel sequence.
-    With ``cls_label`` [B,C1] the result is ``cam_validation(merged, cls_label)`` (the next call in main.py:137) and
-    the planes of absent classes are zero-filled without being merged.
+    With ``cls_label`` [B,C1] the result is ``cam_validation(merged, cls_label)`` (the next call in main.py:137): the
+    planes of absent classes are not merged, and - like ``cam_validation`` itself - the result is a ``LazyTensor`` whose
+    only written planes are those of present classes until something other than ``cam2mask`` reads it (then the zero
+    planes and the label factor are applied by the stand-alone kernel).  ``lazy=False`` writes the validated tensor.
     """
     lib = _lib.load()
     raws, ptrs, hs, ws = _raw_scale_args(raw_cams, "raw_cam")
@@ -83,6 +85,11 @@ def multi_scale_cam_merge(raw_cams, size, cls_label=None):
         else:
             lab = _lib.dev_f32(cls_label.to(out.device), "cls_label")
             assert lab.shape == (B, C1), "cls_label must be [B, C-1]"
+            if lazy and W % 4 == 0 and len(raws) <= 5 and out.data_ptr() % 16 == 0:
+                _lib.check(lib.cosa_multi_scale_cam_merge_present(ptrs, hs, ws, len(raws), _lib.ptr(lab), _lib.ptr(out),
+                                                                  B, C1, H, W, _lib.ptr(mm), _lib.stream_ptr()))
+                # `out` holds the un-validated planes of the present classes only: a pending cam_validation
+                return cam_validation(out, lab)
             _lib.check(lib.cosa_multi_scale_cam_merge_valid(ptrs, hs, ws, len(raws), _lib.ptr(lab), _lib.ptr(out), B,
                                                             C1, H, W, _lib.ptr(mm), _lib.stream_ptr()))
     return out

@@ -88,6 +88,14 @@ int cosa_multi_scale_cam_merge(const float *const *raw, const int *hs, const int
 int cosa_multi_scale_cam_merge_valid(const float *const *raw, const int *hs, const int *ws, int n_scales,
                                      const float *cls_label, float *out, int B, int C1, int H, int W,
                                      float *minmax_ws, void *stream);
+/* The same for a consumer that reads only the planes of present classes (cosa_cam2mask_ex with
+ * COSA_CAM2MASK_CAMS_UNVALIDATED): planes whose label is 0 are NOT written at all and the planes of present classes
+ * hold the merged, normalised CAM without the label factor.  cosa_cam_validation(out, cls_label, out) turns the result
+ * into what cosa_multi_scale_cam_merge_valid writes.  Requires W % 4 == 0, n_scales <= 5 and a 16-byte aligned `out`
+ * (COSA_E_ARG otherwise: use the _valid form). */
+int cosa_multi_scale_cam_merge_present(const float *const *raw, const int *hs, const int *ws, int n_scales,
+                                       const float *cls_label, float *out, int B, int C1, int H, int W,
+                                       float *minmax_ws, void *stream);
 int cosa_multi_scale_seg_merge(const float *const *raw, const int *hs, const int *ws, int n_scales, float *out, int B,
                                int C, int H, int W, void *stream);
 
