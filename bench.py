@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--aux-labelling", action="store_true",
                     help="also label the auxiliary CAMs of the batch (main.py:171-199, the reference's default); "
                          "reported as a separate workload")
+    ap.add_argument("--par-step", default="tile",
+                    help="PAR step kernel (cosa_b200.par.set_step_mode): tile (default), chain[<images per group>], smem")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
@@ -254,6 +256,16 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ----------------------------------------------------------------------------------------------------
+PAR_STEP_NOTE = {
+    "chain": "1 affinity launch + ONE launch for all 10 propagation steps (par_chain_kernel: one CTA per step x image "
+             "tile, tile-level step counters instead of grid barriers)",
+    "tile": "1 affinity launch + 10 step launches (programmatic dependent launches); north_star's single launch "
+            "exists (--par-step chain: par_chain_kernel, tile-level step counters) - its kernel time equals the ten "
+            "launches', the whole step is slower",
+    "smem": "1 affinity launch + 10 launches of the generic step kernel",
+}
+
+
 def algorithmic_bytes(kernels, B, C, H, W, nc, M):
     """Per-launch algorithmic bytes of every kernel (fp32).  h, w = half resolution."""
     h, w = H // 2, W // 2
@@ -294,10 +306,11 @@ def algorithmic_bytes(kernels, B, C, H, W, nc, M):
                       .replace("_tile_kernel", "_kernel").replace("_x2_kernel", "_kernel"))
     out = {k: per.get(base(k)) for k in kernels}
     design = {k: (4 * B * n * (ND + 2 * ncm) if base(k) == "par_iterate_kernel" else out[k]) for k in kernels}
-    if "par_propagate_kernel" in kernels:      # persistent kernel: launches_per_step steps' worth per launch
-        steps_per_launch = T / max(1.0, kernels["par_propagate_kernel"])
-        out["par_propagate_kernel"] = int(per["par_iterate_kernel"] * steps_per_launch)
-        design["par_propagate_kernel"] = int(4 * B * n * (ND + 2 * ncm) * steps_per_launch)
+    for whole in ("par_chain_kernel",):   # every step of a PAR call in one launch
+        if whole in kernels:
+            steps_per_launch = T / max(1.0, kernels[whole])
+            out[whole] = int(per["par_iterate_kernel"] * steps_per_launch)
+            design[whole] = int(4 * B * n * (ND + 2 * ncm) * steps_per_launch)
     return out, design
 
 
@@ -331,6 +344,7 @@ def run_cosa_arm(args):
         d["cams_aux"] = (0.8 * d["cams"] + 0.2 * d["cams"].flip(0).flip(-1)).contiguous()
     if args.aux_labelling:
         wl["name"] += " + auxiliary CAMs labelled too (x2 labelling, main.py:171-199)"
+    cosa_b200.par.set_step_mode(args.par_step)
     par = cosa_b200.PAR(num_iter=NUM_ITER, dilations=DILATIONS).to(dev)
     layer = cosa_b200.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
 
@@ -502,15 +516,18 @@ def run_cosa_arm(args):
                 "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": top["avg_ms"], "alg_bytes_per_launch": top["alg_bytes"],
                 "share_of_step": round(top["ms_per_step"] / sum(k["ms_per_step"] for k in kernels), 4)}
-    if top["kernel"] == "par_iterate_tile_kernel":
+    if top["kernel"] in ("par_iterate_tile_kernel", "par_chain_kernel"):
         # The PAR step is bound on the SM side, not by HBM: every FMA consumes one neighbour value
         # through the 128 B/clk shared-memory / L1 load path.  Bytes through that path per launch: per pixel and moved
         # channel 50 LDS.128 per quad (200 B), plus the 48 affinity quads (192 B per pixel) once per CTA of a tile
         # (two CTAs share a tile's channels).  Peak = SMs x 128 B/clk x the SM clock seen during the run.
         h2, w2 = H // 2, W // 2
         ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
-        n_groups = 1 if ncm <= 3 else 2 * ((ncm + 5) // 6)      # channel groups of a tile: each loads the affinity quads
-        lsu_bytes = B * h2 * w2 * (ncm * 200 + n_groups * 192)
+        if top["kernel"] == "par_chain_kernel":               # <= 4 channels per pass, all steps in the launch
+            n_groups, steps_in_launch = (ncm + 3) // 4, NUM_ITER / max(1.0, top["launches_per_step"])
+        else:                                                  # channel groups of a tile: each loads the affinity quads
+            n_groups, steps_in_launch = (1 if ncm <= 3 else 2 * ((ncm + 5) // 6)), 1
+        lsu_bytes = int(B * h2 * w2 * (ncm * 200 + n_groups * 192) * steps_in_launch)
         sm_mhz = (clocks.summary_peek() or {}).get("sm_mhz") or 1965.0
         lsu_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * sm_mhz * 1e6 / 1e9
         lsu_gbs = lsu_bytes / 1e9 / (top["avg_ms"] / 1e3)
@@ -518,7 +535,7 @@ def run_cosa_arm(args):
                                  "peak": round(lsu_peak, 1), "unit": "GB/s", "frac": round(lsu_gbs / lsu_peak, 4),
                                  "bytes_per_launch": lsu_bytes,
                                  "note": "per pixel: 200 B of mask quads per moved channel + 192 B of affinity quads per "
-                                         "channel group of its tile; peak = SMs x 128 B/clk x SM clock"}
+                                         "channel group of its tile, per propagation step; peak = SMs x 128 B/clk x SM clock"}
 
     # ---- end to end through the host-buffer API (cosa_b200.HostPipeline): pinned host tensors in, labels + loss in
     # pinned host memory out; every step's uploads and read-backs are inside the timed region ---------------------
@@ -588,8 +605,7 @@ def run_cosa_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"] % B, "par": {"dilations": DILATIONS, "num_iter": NUM_ITER},
                        "crf": "DenseEnergyLoss(1e-7, 15, 100, 0.5)", "thresholds": [thr_high, thr_low],
-                       "par_step": "1 affinity launch + 10 step launches (programmatic dependent launches); the "
-                                   "single cooperative launch of north_star exists (cosa_par_set_step_mode('coop')) and is slower",
+                       "par_step": PAR_STEP_NOTE[args.par_step.rstrip("0123456789")],
                        "fused_producers": "denormalize_img and cam_validation are folded into cam2mask's first kernel "
                                           "(cosa_cam2mask_ex); their tensors are never written",
                        "streams": ("CRF lattice build (image-only) on a second stream under cam2mask "

@@ -1094,6 +1094,7 @@ extern "C" size_t cosa_cam2mask_ws_bytes_ex(int B, int C1, int H, int W, int dow
   if (use_par) {
     bytes += align_up((size_t)B * 3 * hw * sizeof(float), 256);
     bytes += align_up((size_t)B * 8 * n_dil * hw * sizeof(float), 256);
+    bytes += align_up(par_tile_flag_ints(B, g.h, g.w) * sizeof(int), 256);
   }
   return bytes;
 }
@@ -1169,12 +1170,14 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   COSA_CUDA(cudaMemsetAsync(err, 0, sizeof(int), s));
   COSA_LAUNCH(cam2mask_keys_kernel, ceil_div(B, 64), 64, 0, s, cls_labels, keys, nc, nch, B, C1, derive, class_cap, err);
   float *img_small = nullptr, *aff = nullptr, *sa = nullptr, *sb = nullptr, *fin = nullptr;
+  int *tile_flags = nullptr;
   if (refine) {
     sa = arena.take<float>(mfloats);
     sb = arena.take<float>(mfloats);
     fin = arena.take<float>(mfloats);
     img_small = arena.take<float>((size_t)B * 3 * hw);
     aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
+    tile_flags = arena.take<int>(par_tile_flag_ints(B, g.h, g.w));
   }
   // COSA_CAM2MASK_REUSE_AFFINITY: the previous call on this workspace had the same images, geometry and dilations
   // (main.py:158 and :191 label the CAMs and the auxiliary CAMs of one batch): its affinity planes are still in the
@@ -1197,10 +1200,11 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
   lay_fin.padn = 0;   // the labelling kernel never reads the pads
   if (refine) {
     if (reuse_aff) {
-      COSA_CHECK(par_launch_iterations(pc, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, cstride, B, g.h, g.w, num_iter, s));
+      COSA_CHECK(par_launch_iterations(pc, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, cstride, B, g.h, g.w, num_iter,
+                                       tile_flags, s));
     } else {
       COSA_CHECK(par_refine_batch(pc, img_small, aff, masks, sa, sb, lay, fin, lay_fin, nch, 0, cstride, B, g.h, g.w,
-                                  num_iter, s));
+                                  num_iter, tile_flags, s));
     }
     refined = fin;
   }

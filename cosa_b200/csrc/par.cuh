@@ -37,18 +37,23 @@ inline size_t layout_floats(const MaskLayout &l, int B, int c_stride, int h) {
   return (size_t)B * c_stride * h * l.pitch;
 }
 
+// Step counters of the chained step kernel: one int per 32 x 32 tile of every image (part of the caller's workspace).
+inline size_t par_tile_flag_ints(int B, int h, int w) { return (size_t)B * ((h + 31) / 32) * ((w + 31) / 32); }
+
 // num_iter propagation steps src0 -> ... -> final_dst.  The two scratch buffers use layout `lay`; src0 must use
 // `lay` too (use par_launch_pack for a plain tensor); final_dst has its own layout (plain for user tensors).
-// Live channels per image: nch_dev[b] when given, else nch_uniform.
+// Live channels per image: nch_dev[b] when given, else nch_uniform.  tile_flags: par_tile_flag_ints(B, h, w) ints of
+// scratch (nullptr: one launch per step).
 int par_launch_iterations(const ParConst &pc, const float *aff, const float *src0, float *scratch_a, float *scratch_b,
                           MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                          int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream);
+                          int c_stride, int B, int h, int w, int num_iter, int *tile_flags, cudaStream_t stream);
 
 // Affinity (into aff [B, 8*n_dil, h, w]) + num_iter steps for the whole batch.  Buffer conventions as in
 // par_launch_iterations.
 int par_refine_batch(const ParConst &pc, const float *imgs, float *aff, const float *src0, float *scratch_a,
                      float *scratch_b, MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev,
-                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream);
+                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, int *tile_flags,
+                     cudaStream_t stream);
 
 // plain [planes, h, w] -> layout `lay` (interior + replicated pads)
 int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, int h, int w, cudaStream_t stream);

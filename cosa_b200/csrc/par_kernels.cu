@@ -8,15 +8,15 @@
 // Neighbour n = 8*k + m: dilation k in ctor order, direction m in get_kernel() order (PAR.py:10-24):
 // (-,-) (-,0) (-,+) (0,-) (0,+) (+,-) (+,0) (+,+), borders replicated (PAR.py:44).
 //
-// Step kernels: `par_iterate_tile_kernel` (the reference dilation set, TMA-staged 32 x 32 tiles, one launch per step:
-// the default), `par_propagate_kernel` (the same tiles, ALL steps in one cooperative launch with grid barriers:
-// north_star's single launch; measured slower, selectable), `par_iterate_smem_kernel` / `par_iterate_kernel` (any
-// dilation set: padded rows with the near neighbourhood staged / plain NCHW).  The variants that were measured and
-// dropped (scalar 512-thread tiles, double-buffered persistent CTAs, deeper register prefetch, rolling affinity
-// refill, L2 tensor prefetch of the affinity tile) are described in DESIGN.md section 4.
-#include <cooperative_groups.h>
+// Step kernels: `par_chain_kernel` (the reference dilation set, TMA-staged 32 x 32 tiles, ALL steps in one launch
+// chained by tile-level step counters: north_star's single launch, the default), `par_iterate_tile_kernel` (the same
+// tiles, one launch per step), `par_iterate_smem_kernel` / `par_iterate_kernel` (any dilation set: padded rows with
+// the near neighbourhood staged / plain NCHW).  The variants that were measured and dropped (scalar 512-thread tiles,
+// double-buffered persistent CTAs, a cooperative launch with grid barriers, deeper register prefetch, rolling
+// affinity refill, L2 tensor prefetch of the affinity tile) are described in DESIGN.md section 4.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -489,28 +489,29 @@ __global__ void __launch_bounds__(256, 2)
 
 // ------------------------------------------------------------------------------------------------
 // One propagation step for the reference dilation set {1,2,4,8,12,24} with the WHOLE 24-pixel neighbourhood staged in
-// shared memory (the step is bound by the 128 B/clk L1/shared-memory crossbar: every pixel-step consumes
-// 48 x channels neighbour values; from shared memory every 128-bit load costs exactly 4 crossbar cycles, a
-// misaligned global load 5-6 and most far-neighbour loads missed L1).
+// shared memory (every pixel-step consumes 48 x channels neighbour values; from shared memory every 128-bit load
+// costs exactly 4 crossbar cycles, a misaligned global load 5-6 and most far-neighbour loads missed L1).
 //
-// CTA = 32 x 32 pixels (256 threads, one quad x CH channels each).  The (32+48)^2 halo tile of each of the CH staged
-// channels arrives by cp.async.bulk row copies (320 B each, rows clamped = replicate border; columns come from the
-// replicated pads) on two mbarriers: the 48 rows the dilations <= 8 need first, the outer 32 rows second, so the
-// near dilations run while the far rows land.  The dilations are compile-time constants: every shared-memory
-// offset is an immediate and the d = 1, 2 quad recombination is register renaming.  Affinity quads are streamed
-// straight into registers two dilations ahead of their use.
-// blockIdx.z = image * gsplit + g: gsplit CTAs share an image tile and take the channel groups g, g + gsplit, ...
+// CTA = 32 x 32 pixels (256 threads, one quad x CH channels each).  The (32+48)^2 halo tile of each staged channel
+// arrives as ONE TMA box on its own mbarrier (rows outside the image are zero-filled and repaired in place = replicate
+// border; columns come from the replicated pads), so the first dilation of channel 0 starts when 25 KB have landed
+// and the other channels land underneath.  The dilations are compile-time constants: every shared-memory offset is an
+// immediate and the d = 1, 2 quad recombination is register renaming.  Affinity quads are streamed straight into
+// registers one dilation ahead of their use (tile_pass).
 // ------------------------------------------------------------------------------------------------
 constexpr int kFH = 24;                       // halo of the full-neighbourhood tile
 constexpr int kFS = kTileW + 2 * kFH;         // 80 floats per staged row, 80 rows
-constexpr int kFNear0 = kFH - 8, kFNear1 = kFH + kTileH + 8;   // staged rows [16, 64) serve d <= 8
+constexpr unsigned kTileBytes = kFS * kFS * sizeof(float);
 
-template <int D, int CH>
-__device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&a)[8], const float *q, int live) {
+// WAIT: channel k's tile is awaited right before its first use (the first dilation of a pass)
+template <int D, int CH, bool WAIT = false>
+__device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&a)[8], const float *q, int live,
+                                              unsigned long long *bars = nullptr, unsigned phase = 0) {
   constexpr int R = D * kFS;
 #pragma unroll
   for (int k = 0; k < CH; ++k) {
     if (k < live) {
+      if constexpr (WAIT) mbar_wait(&bars[k], phase);
       const float *p = q + k * (kFS * kFS);
       if constexpr ((D & 3) == 0) {
         fma4(acc[k], a[0], lds4(p - R - D)); fma4(acc[k], a[1], lds4(p - R)); fma4(acc[k], a[2], lds4(p - R + D));
@@ -539,8 +540,22 @@ __device__ __forceinline__ void load_aff8(float4 (&a)[8], const float *&A, size_
   }
 }
 
-// One dilation with ROLLING affinity refill: as soon as the taps of one neighbour row have been consumed by every
-// channel, their registers are reloaded with the same taps of the dilation two ahead (A walks the planes in order), so
+// Orders the refill of one affinity register set behind (a) the arrival of the OTHER set and (b) the end of the
+// dilation that used the registers being refilled.  ptxas tracks all global loads of this kernel on ONE scoreboard (the
+// other five pipeline the shared-memory loads), and a scoreboard wait drains everything issued on it: with a refill
+// already in flight, the first FMA of every dilation waited a full memory latency for loads it did not need (ncu r02l:
+// 17 % of all warp stalls).  Making the refill's address depend on a value of the set used next and on the
+// accumulators of the dilation just finished (the select is never taken: affinities and masks are finite) puts the
+// wait for the next set - the only loads in flight, issued a whole dilation earlier - at the dilation boundary and
+// the refill right behind it.
+template <int CH>
+__device__ __forceinline__ const float *issue_after(const float *A, const float4 &next, const float4 (&acc)[CH]) {
+  unsigned bits = __float_as_uint(next.x);
+#pragma unroll
+  for (int k = 0; k < CH; ++k) bits &= __float_as_uint(acc[k].w);
+  return A + (bits == 0xffffffffu ? 4 : 0);
+}
+
 __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *tmap, int x, int y, int z,
                                              unsigned long long *bar) {
   asm volatile(
@@ -686,15 +701,76 @@ __global__ void __launch_bounds__(256, 2)
   }
 }
 
-// Tile-mode step kernel (default): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
+// One pass of a CTA over its tile: <= CH staged channels x the six dilations.  Affinity sets alternate between two
+// register sets; a refill is issued behind the wait for the set used next (issue_after), one dilation ahead of its use.
+template <int CH>
+__device__ __forceinline__ void tile_pass(float4 (&acc)[CH], const float *A, size_t plane, const float *q, int live,
+                                          float *s_tile, unsigned long long *bars, unsigned phase, int r_lo, int r_hi) {
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a0[8], a1[8];
+  load_aff8(a0, A, plane);   // d = 1
+  load_aff8(a1, A, plane);   // d = 2 (in flight together with d = 1: the first wait drains both)
+  if (r_lo > 0 || r_hi < kFS) {   // top / bottom tiles: every channel must have landed before the border rows are repaired
+    for (int k = 0; k < live; ++k) mbar_wait(&bars[k], phase);
+    replicate_border_rows(s_tile, live, r_lo, r_hi);
+  }
+  tile_dilation<1, CH, true>(acc, a0, q, live, bars, phase);
+  load_aff8(a0, A, plane);   // d = 4: nothing else is in flight
+  tile_dilation<2, CH>(acc, a1, q, live);
+  A = issue_after<CH>(A, a0[0], acc);
+  load_aff8(a1, A, plane);   // d = 8
+  tile_dilation<4, CH>(acc, a0, q, live);
+  A = issue_after<CH>(A, a1[0], acc);
+  load_aff8(a0, A, plane);   // d = 12
+  tile_dilation<8, CH>(acc, a1, q, live);
+  A = issue_after<CH>(A, a0[0], acc);
+  load_aff8(a1, A, plane);   // d = 24
+  tile_dilation<12, CH>(acc, a0, q, live);
+  tile_dilation<24, CH>(acc, a1, q, live);
+}
+
+// one thread: stage `live` channel tiles (planes gz .. gz + live - 1, origin (gx, gy)), one TMA box and barrier each
+__device__ __forceinline__ void stage_tiles(float *s_tile, const CUtensorMap *tm, int gx, int gy, int gz, int live,
+                                            unsigned long long *bars) {
+  for (int k = 0; k < live; ++k) {
+    mbar_expect_tx(&bars[k], kTileBytes);
+    tma_load_box(s_tile + (size_t)k * kFS * kFS, tm, gx, gy, gz + k, &bars[k]);
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void store_quads(const float4 (&acc)[CH], float *dst, size_t oplane, int c0, int live,
+                                            const MaskLayout &lo, int xq, int wq) {
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < live) {
+      float *o = dst + (size_t)(c0 + k) * oplane;
+      *reinterpret_cast<float4 *>(o) = acc[k];
+      if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
+        if (xq == 0) {
+          const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
+          for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
+        }
+        if (xq == wq - 1) {
+          const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
+          for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
+        }
+      }
+    }
+  }
+}
+
+// Per-step kernel ("tile" mode): one CTA per (image tile, channel split g of gsplit); the CTA walks the channel
 // passes of its tile.  The hardware CTA scheduler balances the load; 2 CTAs per SM overlap staging and compute.
+// blockIdx.z = image * gsplit + g: gsplit CTAs share an image tile and take the channel groups g, g + gsplit, ...
 template <int CH>
 __global__ void __launch_bounds__(256, 2)
     par_iterate_tile_kernel(const float *__restrict__ aff, const __grid_constant__ CUtensorMap tmap_in, MaskLayout li,
                             float *__restrict__ out, MaskLayout lo, const int *__restrict__ nch_dev, int nch_uniform,
                             int c_stride, int h, int w, int gsplit) {
   extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
-  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ __align__(8) unsigned long long s_bar[CH];
   const int wq = w >> 2;
   const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -714,7 +790,6 @@ __global__ void __launch_bounds__(256, 2)
   float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
   // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
   const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
-  const bool edge = r_lo > 0 || r_hi < kFS;
   const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
 
   // Programmatic dependent launch: the next step's CTAs may become resident as soon as slots free up in this
@@ -722,84 +797,30 @@ __global__ void __launch_bounds__(256, 2)
   // grid's completion (griddepcontrol.wait, below) before they touch the masks.  Without the launch attribute both
   // instructions are no-ops.
   asm volatile("griddepcontrol.launch_dependents;");
-  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) mbar_init(&s_bar[k], 1);
+  }
   __syncthreads();
   unsigned phase = 0;
   for (int c0 = g * chunk; c0 < nch; c0 += gsplit * chunk) {
     const int live = min(chunk, nch - c0);
-    constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
     if (threadIdx.x == 0) {
       // the previous step (the producer of the tiles, and the last reader of the buffer this step overwrites) is
       // complete and its writes are visible; every other thread of the CTA is gated by the mbarriers behind this
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      mbar_expect_tx(&s_bar[0], (unsigned)(live * kNear * kFS * sizeof(float)));
-      mbar_expect_tx(&s_bar[1], (unsigned)(live * kFar * kFS * sizeof(float)));
-      const int gx = li.off + x0 - kFH, gz = b * c_stride + c0;
-      for (int r = kFNear0; r < kFNear1; r += kBoxRows)
-        for (int k = 0; k < live; ++k)
-          tma_load_box(s_tile + (k * kFS + r) * kFS, &tmap_in, gx, y0 - kFH + r, gz + k, &s_bar[0]);
-      for (int k = 0; k < live; ++k) {
-        tma_load_box(s_tile + (k * kFS) * kFS, &tmap_in, gx, y0 - kFH, gz + k, &s_bar[1]);
-        tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, &tmap_in, gx, y0 - kFH + kFNear1, gz + k, &s_bar[1]);
-      }
+      stage_tiles(s_tile, &tmap_in, li.off + x0 - kFH, y0 - kFH, b * c_stride + c0, live, s_bar);
     }
     float4 acc[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float *Ap = A;
-    // affinity quads one dilation ahead of their use: two sets of 8 quads in registers (a third set spills at 128
-    // registers, and one CTA per SM with deeper prefetch loses more to occupancy than it gains: DESIGN.md section 4)
-    float4 a0[8], a1[8];
-    load_aff8(a0, Ap, plane);
-    load_aff8(a1, Ap, plane);
-    mbar_wait(&s_bar[0], phase);
-    if (edge) {
-      mbar_wait(&s_bar[1], phase);
-      replicate_border_rows(s_tile, live, r_lo, r_hi);
-    }
-    tile_dilation<1, CH>(acc, a0, q, live);
-    load_aff8(a0, Ap, plane);
-    tile_dilation<2, CH>(acc, a1, q, live);
-    load_aff8(a1, Ap, plane);
-    tile_dilation<4, CH>(acc, a0, q, live);
-    load_aff8(a0, Ap, plane);
-    tile_dilation<8, CH>(acc, a1, q, live);
-    load_aff8(a1, Ap, plane);
-    if (!edge) mbar_wait(&s_bar[1], phase);
-    tile_dilation<12, CH>(acc, a0, q, live);
-    tile_dilation<24, CH>(acc, a1, q, live);
+    tile_pass<CH>(acc, A, plane, q, live, s_tile, s_bar, phase, r_lo, r_hi);
     phase ^= 1;
-    if (active) {
-#pragma unroll
-      for (int k = 0; k < CH; ++k) {
-        if (k < live) {
-          float *o = dst + (size_t)(c0 + k) * oplane;
-          *reinterpret_cast<float4 *>(o) = acc[k];
-          if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
-            if (xq == 0) {
-              const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
-              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
-            }
-            if (xq == wq - 1) {
-              const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
-              for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
-            }
-          }
-        }
-      }
-    }
+    if (active) store_quads<CH>(acc, dst, oplane, c0, live, lo, xq, wq);
     if (c0 + gsplit * chunk < nch) {   // the tile is re-staged (async proxy) for the next channel group
       __syncthreads();
       if (threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
   }
 }
-// One work unit of the persistent kernel: an image tile and a group of <= CH live channels.
-struct PropUnit {
-  int u;            // linear unit index (>= n_units: none left)
-  int b, x0, y0;    // image, tile origin
-  int c0, live;     // first channel and number of channels of the group
-};
 
 struct PropArgs {
   const float *aff;              // [B, 48, h, w]
@@ -807,179 +828,116 @@ struct PropArgs {
   MaskLayout li, lo_final;       // scratch layout (inputs and intermediate outputs), layout of the last output
   const int *nch_dev;
   int nch_uniform, c_stride, B, h, w;
-  int tiles_x, tiles_y, gsplit, n_pass;   // n_pass: host upper bound of ceil(nch / (gsplit * CH))
-  int it_begin, it_end, num_iter;         // this launch runs steps [it_begin, it_end) of num_iter
+  int tiles_x, tiles_y, num_iter;
 };
 
-constexpr int kPropMaxCachedB = 256;   // per-image channel counts kept in shared memory up to this batch size
-
-template <int CH>
-__device__ __forceinline__ PropUnit prop_find_unit(const PropArgs &p, const int *s_nch, int n_pass, int u) {
-  const int tiles = p.tiles_x * p.tiles_y;
-  const int per_pass = p.B * tiles * p.gsplit;
-  const int n_units = per_pass * n_pass;
-  PropUnit r;
-  for (; u < n_units; u += gridDim.x) {
-    const int pass = u / per_pass, v = u - pass * per_pass;
-    const int g = v % p.gsplit, bt = v / p.gsplit;
-    const int b = bt / tiles, t = bt - b * tiles;
-    const int nch = !p.nch_dev ? p.nch_uniform : (s_nch && b < kPropMaxCachedB ? s_nch[b] : p.nch_dev[b]);
-    // the live channels are split evenly over the gsplit CTAs of a tile, at most CH per pass
-    if (nch <= 0) continue;   // an image without live channels
-    const int n_groups = nch <= CH ? 1 : p.gsplit * ((nch + p.gsplit * CH - 1) / (p.gsplit * CH));
-    const int chunk = (nch + n_groups - 1) / n_groups;
-    const int c0 = (pass * p.gsplit + g) * chunk;
-    if (c0 < nch) {
-      r.u = u; r.b = b; r.y0 = (t / p.tiles_x) * kTileH; r.x0 = (t % p.tiles_x) * kTileW;
-      r.c0 = c0; r.live = min(chunk, nch - c0);
-      return r;
-    }
-  }
-  r.u = n_units; r.b = 0; r.x0 = 0; r.y0 = 0; r.c0 = 0; r.live = 0;
-  return r;
+// ------------------------------------------------------------------------------------------------
+// Chained step kernel (default): ALL num_iter propagation steps in ONE launch - north_star's single launch - without
+// grid barriers.  The grid holds one CTA per (step, image, tile) in step-major order inside groups of `group` images;
+// a CTA of step it > 0 waits (warp 0 polls with ld.acquire.gpu) until the <= 9 tiles of its image that overlap its
+// halo have published step it - 1 in `done` (one counter per image tile: the number of steps that tile has
+// completed), then stages its (32+48)^2 tiles by TMA exactly like par_iterate_tile_kernel.  The same <= 9 tiles are
+// the only readers of the region this CTA overwrites in the ping-pong buffer (halo 24 < tile 32), so the one wait
+// covers the write-after-read hazard too.  CTAs are dispatched in blockIdx order, so every CTA a waiter depends on is
+// already resident or finished: no deadlock, and no wave quantisation at the step boundaries - the SMs stay full over
+// all steps.  The distance between a tile's consecutive steps (group * tiles CTAs) must stay above the number of
+// resident CTAs, or the later one idles its slot until the earlier one is done.
+// One CTA walks ALL live channels of its tile, <= CH per pass (the affinity quads are loaded once per pass).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// Persistent propagation kernel: <= 2 CTAs per SM stride over the work units (image tile x channel group) of a step
-// and - with a cooperative launch - over ALL num_iter steps in ONE launch, separated by grid barriers (the masks
-// ping-pong between two scratch buffers in L2): north_star's "all propagation iterations in one launch".  Measured
-// slower than the tile-mode kernel above on B200 (profiles/README.md: static unit assignment, grid barriers), so it is
-// selectable (cosa_par_set_step_mode("coop")) rather than the default.
-// The affinity quads of the next unit's first two dilations are requested while the far dilations of the current
-// unit are computed, and the next tile is staged by TMA once the last shared-memory read of the current one retired.
-// ------------------------------------------------------------------------------------------------
 template <int CH>
 __global__ void __launch_bounds__(256, 2)
-    par_propagate_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_src0,
-                         const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
+    par_chain_kernel(const PropArgs p, const __grid_constant__ CUtensorMap tm_src0,
+                     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                     int *__restrict__ done, int group) {
   extern __shared__ __align__(128) float s_tile[];   // [CH][80][80]
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  constexpr int kNear = kFNear1 - kFNear0, kFar = kFS - kNear;   // 48 near rows, 32 far rows
+  __shared__ __align__(8) unsigned long long s_bar[CH];
+  const int tiles = p.tiles_x * p.tiles_y;
+  // blockIdx.x -> (image group, step, image of the group, tile)
+  int u = blockIdx.x;
+  const int per_group = p.num_iter * group * tiles;
+  const int grp = u / per_group;
+  u -= grp * per_group;
+  const int b0 = grp * group, bg = min(group, p.B - b0);
+  const int it = u / (bg * tiles);
+  u -= it * bg * tiles;
+  const int bi = u / tiles, t = u - bi * tiles, b = b0 + bi;
+  const int tyi = t / p.tiles_x, txi = t - tyi * p.tiles_x;
+  const int nch = p.nch_dev ? p.nch_dev[b] : p.nch_uniform;
+  if (nch <= 0) return;   // an image without live channels: none of its CTAs runs, none waits
+  const int n_groups = (nch + CH - 1) / CH;
+  const int chunk = (nch + n_groups - 1) / n_groups;
+
+  const CUtensorMap *tm = it == 0 ? &tm_src0 : (((it - 1) & 1) ? &tm_b : &tm_a);
+  const bool last = it == p.num_iter - 1;
+  float *out = last ? p.out_final : ((it & 1) ? p.out_b : p.out_a);
+  const MaskLayout lo = last ? p.lo_final : p.li;
+  const int h = p.h, w = p.w, wq = w >> 2;
   const int tq = threadIdx.x & 7, tr = threadIdx.x >> 3;
-  const int wq = p.w >> 2;
-  const size_t plane = (size_t)p.h * p.w;
+  const int x0 = txi * kTileW, y0 = tyi * kTileH;
+  const int xq = (x0 >> 2) + tq, y = y0 + tr, x = x0 + (tq << 2);
+  const bool active = xq < wq && y < h;
+  const size_t plane = (size_t)h * w;
+  const size_t oplane = (size_t)h * lo.pitch;
+  const float *A = p.aff + (size_t)b * 48 * plane + (size_t)min(y, h - 1) * w + min(x, w - 4);
+  float *dst = out + (size_t)b * p.c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
+  const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
   const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
-  // live channel counts of the batch: cached in shared memory; their maximum bounds the number of passes, so no
-  // CTA scans the empty units the host's worst-case bound (p.n_pass) would imply
-  __shared__ int s_nch[kPropMaxCachedB];
-  __shared__ int s_max_nch;
-  const int per_pass = p.B * p.tiles_x * p.tiles_y * p.gsplit;
-  const bool persistent = (int)gridDim.x < per_pass;   // else: one CTA per (tile, channel split), passes in sequence
-  if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); s_max_nch = 0; }
-  __syncthreads();
-  int n_pass = p.n_pass;
-  if (p.nch_dev && persistent) {
-    int mx = 0;
-    for (int b = threadIdx.x; b < p.B; b += 256) {
-      const int v = p.nch_dev[b];
-      if (b < kPropMaxCachedB) s_nch[b] = v;
-      mx = max(mx, v);
-    }
-    if (mx > 0) atomicMax(&s_max_nch, mx);
-    __syncthreads();
-    n_pass = min(p.n_pass, (s_max_nch + p.gsplit * CH - 1) / (p.gsplit * CH));
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) mbar_init(&s_bar[k], 1);
   }
-  const int *nch_cache = persistent ? s_nch : nullptr;
-  const int n_units = per_pass * n_pass;
+  __syncthreads();
   unsigned phase = 0;
-
-  auto stage = [&](const CUtensorMap *tm, const PropUnit &un) {   // one thread
-    mbar_expect_tx(&s_bar[0], (unsigned)(un.live * kNear * kFS * sizeof(float)));
-    mbar_expect_tx(&s_bar[1], (unsigned)(un.live * kFar * kFS * sizeof(float)));
-    const int gx = p.li.off + un.x0 - kFH, gz = un.b * p.c_stride + un.c0;
-    for (int r = kFNear0; r < kFNear1; r += kBoxRows)
-      for (int k = 0; k < un.live; ++k) tma_load_box(s_tile + (k * kFS + r) * kFS, tm, gx, un.y0 - kFH + r, gz + k, &s_bar[0]);
-    for (int k = 0; k < un.live; ++k) {
-      tma_load_box(s_tile + (k * kFS) * kFS, tm, gx, un.y0 - kFH, gz + k, &s_bar[1]);
-      tma_load_box(s_tile + (k * kFS + kFNear1) * kFS, tm, gx, un.y0 - kFH + kFNear1, gz + k, &s_bar[1]);
-    }
-  };
-  auto aff_ptr = [&](const PropUnit &un) {
-    return p.aff + (size_t)un.b * 48 * plane + (size_t)min(un.y0 + tr, p.h - 1) * p.w + min(un.x0 + (tq << 2), p.w - 4);
-  };
-
-  for (int it = p.it_begin; it < p.it_end; ++it) {
-    const CUtensorMap *tm = it == 0 ? &tm_src0 : (((it - 1) & 1) ? &tm_b : &tm_a);
-    const bool last = it == p.num_iter - 1;
-    float *out = last ? p.out_final : ((it & 1) ? p.out_b : p.out_a);
-    const MaskLayout lo = last ? p.lo_final : p.li;
-    const size_t oplane = (size_t)p.h * lo.pitch;
-
-    PropUnit cur = prop_find_unit<CH>(p, nch_cache, n_pass, blockIdx.x);
-    float4 a0[8], a1[8], a2[8];
-    const float *Ap = aff_ptr(cur);
-    if (cur.u < n_units) {
-      if (threadIdx.x == 0) stage(tm, cur);
-      load_aff8(a0, Ap, plane);
-      load_aff8(a1, Ap, plane);
-    }
-    while (cur.u < n_units) {
-      const int live = cur.live;
-      // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
-      const int r_lo = max(0, kFH - cur.y0), r_hi = min(kFS, p.h - cur.y0 + kFH);
-      const bool edge = r_lo > 0 || r_hi < kFS;
-      float4 acc[CH];
-#pragma unroll
-      for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_wait(&s_bar[0], phase);
-      if (edge) {
-        mbar_wait(&s_bar[1], phase);
-        replicate_border_rows(s_tile, live, r_lo, r_hi);
-      }
-      load_aff8(a2, Ap, plane);
-      tile_dilation<1, CH>(acc, a0, q, live);
-      load_aff8(a0, Ap, plane);
-      tile_dilation<2, CH>(acc, a1, q, live);
-      load_aff8(a1, Ap, plane);
-      tile_dilation<4, CH>(acc, a2, q, live);
-      load_aff8(a2, Ap, plane);
-      tile_dilation<8, CH>(acc, a0, q, live);
-      if (!edge) mbar_wait(&s_bar[1], phase);
-      phase ^= 1;
-      // the next unit's first affinity quads travel while the far dilations of this one are computed
-      const PropUnit nxt = prop_find_unit<CH>(p, nch_cache, n_pass, cur.u + gridDim.x);
-      const bool more = nxt.u < n_units;
-      Ap = aff_ptr(nxt);
-      if (more) load_aff8(a0, Ap, plane);
-      tile_dilation<12, CH>(acc, a1, q, live);
-      if (more) load_aff8(a1, Ap, plane);
-      tile_dilation<24, CH>(acc, a2, q, live);
-      __syncthreads();                       // every shared-memory read of this tile has retired
-      if (more && threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        stage(tm, nxt);
-      }
-      const int xq = (cur.x0 >> 2) + tq, y = cur.y0 + tr;
-      if (xq < wq && y < p.h) {
-        float *dst = out + ((size_t)cur.b * p.c_stride + cur.c0) * oplane + (size_t)y * lo.pitch + lo.off + (xq << 2);
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-          if (k < live) {
-            float *o = dst + (size_t)k * oplane;
-            *reinterpret_cast<float4 *>(o) = acc[k];
-            if (lo.padn) {   // replicate the edge pixels into the column pads for the next step
-              if (xq == 0) {
-                const float4 e = make_float4(acc[k].x, acc[k].x, acc[k].x, acc[k].x);
-                for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o - i) = e;
-              }
-              if (xq == wq - 1) {
-                const float4 e = make_float4(acc[k].w, acc[k].w, acc[k].w, acc[k].w);
-                for (int i = 4; i <= lo.padn; i += 4) *reinterpret_cast<float4 *>(o + i) = e;
-              }
+  for (int c0 = 0; c0 < nch; c0 += chunk) {
+    const int live = min(chunk, nch - c0);
+    if (threadIdx.x < 32) {
+      if (c0 == 0 && it > 0) {
+        // lanes 0..8: one neighbour tile each (the tile itself included)
+        const int lane = threadIdx.x;
+        if (lane < 9) {
+          const int ny = tyi + lane / 3 - 1, nx = txi + lane % 3 - 1;
+          if (ny >= 0 && ny < p.tiles_y && nx >= 0 && nx < p.tiles_x) {
+            const int *f = done + (size_t)b * tiles + ny * p.tiles_x + nx;
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(f) < it) {
+              __nanosleep(40);
+              if (clock64() - t0 > (1LL << 33)) __trap();   // seconds: the dispatch-order assumption failed - fail loudly
             }
           }
         }
+        __syncwarp();
       }
-      cur = nxt;
+      if (threadIdx.x == 0) {
+        // the neighbours' generic-proxy stores (acquired above) precede this CTA's async-proxy (TMA) reads
+        asm volatile("fence.proxy.async;" ::: "memory");
+        stage_tiles(s_tile, tm, p.li.off + x0 - kFH, y0 - kFH, b * p.c_stride + c0, live, s_bar);
+      }
     }
-    if (it + 1 < p.it_end) {   // next step reads (through the async proxy) what every CTA wrote in this one
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __threadfence();
-      cooperative_groups::this_grid().sync();
-      asm volatile("fence.proxy.async;" ::: "memory");
-    }
+    float4 acc[CH];
+    tile_pass<CH>(acc, A, plane, q, live, s_tile, s_bar, phase, r_lo, r_hi);
+    phase ^= 1;
+    if (active) store_quads<CH>(acc, dst, oplane, c0, live, lo, xq, wq);
+    __syncthreads();   // every shared-memory read and every output store of this pass has been issued
+    if (c0 + chunk < nch && threadIdx.x == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (!last && threadIdx.x == 0) {
+    // publish: this tile has completed step `it` (bar.sync above + release: its outputs are visible before the
+    // counter is; the consumers read them through the async proxy)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    st_release_gpu(done + (size_t)b * tiles + t, it + 1);
   }
 }
+
 
 // plain [planes, h, w] -> padded layout (interior + replicated column pads)
 __global__ void par_pack_kernel(const float *__restrict__ src, float *__restrict__ dst, MaskLayout l, int planes,
@@ -1080,25 +1038,31 @@ int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, in
 // Step-kernel selection (cosa_par_set_step_mode; process-wide, meant for A/B runs and tests - results are identical):
 //   tile (default)  TMA-tile kernel, one CTA per tile and channel split, one launch per step (steps 2..T as
 //                   programmatic dependent launches)
-//   coop            persistent TMA-tile kernel, every step in ONE cooperative launch (grid barriers)
+//   chain           TMA-tile kernel, every step in ONE launch, tile-level dependencies through step counters
+//                   ("chain<G>": G images per group, default 8): north_star's single launch.  The kernel alone is as
+//                   fast as ten tile launches; the whole step is slower (the lattice build on the second stream
+//                   does not interleave with one long grid): DESIGN.md section 4
 //   smem            the generic per-step kernel (what non-reference dilation sets use)
-enum { kStepTile = 0, kStepCoop = 1, kStepSmem = 2 };
+enum { kStepTile = 0, kStepSmem = 2, kStepChain = 3 };
 static std::atomic<int> g_step_mode{kStepTile};
+static std::atomic<int> g_chain_group{0};   // images per group of the chained kernel, 0 = automatic (A/B knob)
 static int parse_step_mode(const char *e) {
   if (!e) return -1;
   switch (e[0]) {
     case 't': return kStepTile;
-    case 'c': return kStepCoop;
+    case 'c': return kStepChain;
     case 's': return kStepSmem;
     default: return -1;
   }
 }
 
-constexpr int kStepCH = 3;   // channels per CTA pass of the tile kernels
+constexpr int kStepCH = 3;    // channels per CTA pass of the per-step tile kernels
+constexpr int kChainCH = 4;   // channels per CTA pass of the chained kernel
 
 static int par_launch_propagate(const float *aff, const float *src0, float *scratch_a, float *scratch_b, MaskLayout lay,
                                 float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                                int c_stride, int B, int h, int w, int num_iter, int mode, cudaStream_t stream) {
+                                int c_stride, int B, int h, int w, int num_iter, int mode, int *tile_flags,
+                                cudaStream_t stream) {
   constexpr int CH = kStepCH;
   PropArgs a;
   a.aff = aff;
@@ -1109,40 +1073,39 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
   a.tiles_x = ceil_div(w, kTileW); a.tiles_y = ceil_div(h, kTileH);
   a.num_iter = num_iter;
   const long long planes = (long long)B * c_stride;
-  CUtensorMap t0, ta, tb;
-  COSA_CHECK(make_tmap3(&t0, src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
-  COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
-  COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kBoxRows, 1));
-  const int max_nch = nch_dev ? c_stride : nch_uniform;
-  const size_t smem = (size_t)CH * kFS * kFS * sizeof(float);
-  // two CTAs per tile share the channels of an image with more than CH live ones (the kernel keeps <= CH channels in
-  // one CTA, where the affinity quads are loaded once)
-  a.gsplit = 2;
-  a.n_pass = ceil_div(max_nch, a.gsplit * CH);
-  if (mode == kStepCoop && num_iter > 1) {   // every step in one cooperative launch
-    static std::atomic<unsigned long long> done{0};
-    COSA_CHECK(opt_in_smem(par_propagate_kernel<CH>, (int)smem, done));
-    int dev = 0, occ = 0, coop_ok = 0;
-    COSA_CUDA(cudaGetDevice(&dev));
-    COSA_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
-    COSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, par_propagate_kernel<CH>, 256, smem));
-    if (coop_ok && occ >= 1) {
-      const long long per_pass = (long long)a.B * a.tiles_x * a.tiles_y * a.gsplit;
-      const int grid = (int)max(1LL, min(per_pass, (long long)occ * sm_count()));
-      a.it_begin = 0;
-      a.it_end = a.num_iter;
-      void *args[] = {(void *)&a, (void *)&t0, (void *)&ta, (void *)&tb};
-      if (g_prof_on) prof_mark("par_propagate_kernel", stream, true);
-      const cudaError_t e = cudaLaunchCooperativeKernel((const void *)par_propagate_kernel<CH>, dim3(grid), dim3(256),
-                                                        args, smem, stream);
-      ++g_launches;
-      if (g_prof_on) prof_mark("par_propagate_kernel", stream, false);
-      return e == cudaSuccess ? 0 : (int)e;
+  CUtensorMap t0, ta, tb;   // one box = the whole (32+48)^2 halo tile of one channel
+  COSA_CHECK(make_tmap3(&t0, src0, planes, h, lay.pitch, kFS, kFS, 1));
+  COSA_CHECK(make_tmap3(&ta, scratch_a ? scratch_a : src0, planes, h, lay.pitch, kFS, kFS, 1));
+  COSA_CHECK(make_tmap3(&tb, scratch_b ? scratch_b : src0, planes, h, lay.pitch, kFS, kFS, 1));
+  if (mode == kStepChain && tile_flags) {   // every step in one launch, tile-level dependencies
+    constexpr int CC = kChainCH;
+    const size_t smem_c = (size_t)CC * kTileBytes;
+    static std::atomic<unsigned long long> done_chain{0};
+    COSA_CHECK(opt_in_smem(par_chain_kernel<CC>, (int)smem_c, done_chain));
+    const int tiles = a.tiles_x * a.tiles_y;
+    const long long ctas = (long long)a.num_iter * a.B * tiles;
+    if (ctas <= 0x7fffffffLL) {
+      COSA_CUDA(cudaMemsetAsync(tile_flags, 0, (size_t)a.B * tiles * sizeof(int), stream));
+      // a tile's consecutive steps must be further apart in the grid than the CTAs resident at once
+      // (a closer pair still completes - the later CTA waits for the earlier one - it only idles a slot meanwhile)
+      int group = g_chain_group.load(std::memory_order_relaxed);
+      if (group <= 0) {   // automatic: 8 images (77 MB of affinity planes at 224^2) or as many as the distance needs
+        const int resident = 2 * sm_count();
+        group = 8;
+        while (group < a.B && (long long)group * tiles < resident + 2 * a.tiles_x + 2) ++group;
+      }
+      group = min(group, a.B);
+      COSA_LAUNCH(par_chain_kernel<CC>, dim3((unsigned)ctas), 256, smem_c, stream, a, t0, ta, tb, tile_flags, group);
+      return 0;
     }
   }
+  // two CTAs per tile share the channels of an image with more than CH live ones (the kernel keeps <= CH channels in
+  // one CTA, where the affinity quads are loaded once)
+  const int gsplit = 2;
+  const size_t smem = (size_t)CH * kTileBytes;
   static std::atomic<unsigned long long> done_tile{0};
   COSA_CHECK(opt_in_smem(par_iterate_tile_kernel<CH>, (int)smem, done_tile));
-  const dim3 grid(a.tiles_x, a.tiles_y, a.B * a.gsplit);
+  const dim3 grid(a.tiles_x, a.tiles_y, a.B * gsplit);
   for (int it = 0; it < a.num_iter; ++it) {
     const bool last = it == a.num_iter - 1;
     const CUtensorMap &tm = it == 0 ? t0 : (((it - 1) & 1) ? tb : ta);
@@ -1162,7 +1125,7 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
     cfg.numAttrs = (it > 0 && !g_prof_on) ? 1 : 0;
     if (g_prof_on) prof_mark("par_iterate_tile_kernel", stream, true);
     const cudaError_t e = cudaLaunchKernelEx(&cfg, par_iterate_tile_kernel<CH>, a.aff, tm, a.li, dst, lo_it, a.nch_dev,
-                                             a.nch_uniform, a.c_stride, a.h, a.w, a.gsplit);
+                                             a.nch_uniform, a.c_stride, a.h, a.w, gsplit);
     ++g_launches;
     if (g_prof_on) prof_mark("par_iterate_tile_kernel", stream, false);
     if (e != cudaSuccess) return (int)e;
@@ -1172,7 +1135,7 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
 
 int par_launch_iterations(const ParConst &pc, const float *aff, const float *src0, float *scratch_a, float *scratch_b,
                           MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev, int nch_uniform,
-                          int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
+                          int c_stride, int B, int h, int w, int num_iter, int *tile_flags, cudaStream_t stream) {
   if (num_iter <= 0) return COSA_E_ARG;   // callers handle the zero-iteration copy themselves
   const int n_dil = pc.n_dil;
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
@@ -1180,7 +1143,7 @@ int par_launch_iterations(const ParConst &pc, const float *aff, const float *src
   const int mode = g_step_mode.load(std::memory_order_relaxed);
   if (vec && pc.std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) && mode != kStepSmem)
     return par_launch_propagate(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
-                                c_stride, B, h, w, num_iter, mode, stream);
+                                c_stride, B, h, w, num_iter, mode, tile_flags, stream);
   const float *src = src0;
   for (int it = 0; it < num_iter; ++it) {
     const bool last = it == num_iter - 1;
@@ -1219,10 +1182,11 @@ int par_launch_iterations(const ParConst &pc, const float *aff, const float *src
 // neighbour loads, not by the affinity stream - see profiles/README.md.)
 int par_refine_batch(const ParConst &pc, const float *imgs, float *aff, const float *src0, float *scratch_a,
                      float *scratch_b, MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev,
-                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, cudaStream_t stream) {
+                     int nch_uniform, int c_stride, int B, int h, int w, int num_iter, int *tile_flags,
+                     cudaStream_t stream) {
   COSA_CHECK(par_launch_affinity(pc, imgs, aff, B, h, w, stream));
   return par_launch_iterations(pc, aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
-                               c_stride, B, h, w, num_iter, stream);
+                               c_stride, B, h, w, num_iter, tile_flags, stream);
 }
 
 }  // namespace cosa
@@ -1235,12 +1199,19 @@ extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
   const size_t plane = (size_t)h * w;
   const size_t pitch = (size_t)max_padded_pitch(w);
   return align_up((size_t)B * 8 * n_dil * plane * sizeof(float), 256) +
-         2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256);
+         2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256) + align_up(par_tile_flag_ints(B, h, w) * sizeof(int), 256);
 }
 
 extern "C" int cosa_par_set_step_mode(const char *name) {
   const int m = parse_step_mode(name);
   if (m < 0) return COSA_E_ARG;
+  if (m == kStepChain) {   // "chain" or "chain<images per group>"
+    const char *d = name;
+    while (*d && (*d < '0' || *d > '9')) ++d;
+    const int grp = *d ? atoi(d) : 0;
+    if (grp < 0) return COSA_E_ARG;
+    g_chain_group.store(grp, std::memory_order_relaxed);
+  }
   g_step_mode.store(m, std::memory_order_relaxed);
   return 0;
 }
@@ -1270,6 +1241,7 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
   float *aff = arena.take<float>((size_t)B * 8 * n_dil * plane);
   float *buf_a = arena.take<float>(layout_floats(lay, B, C, h));
   float *buf_b = arena.take<float>(layout_floats(lay, B, C, h));
+  int *tile_flags = arena.take<int>(par_tile_flag_ints(B, h, w));
   const bool resize = (hm != h || wm != w);
   const long long total = (long long)B * C * plane;
   const int blocks = (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(total, 256)));
@@ -1297,5 +1269,6 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
   }
   // step 0 reads src0 (buf_b or the caller's tensor) and writes buf_a, step 1 writes buf_b, ...
   // (src0 is the caller's tensor only in the plain layout, whose strides equal the scratch strides)
-  return par_refine_batch(pc, imgs, aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, num_iter, s);
+  return par_refine_batch(pc, imgs, aff, src0, buf_a, buf_b, lay, masks_out, plain, nullptr, C, C, B, h, w, num_iter,
+                          tile_flags, s);
 }

@@ -14,8 +14,9 @@ from . import _lib
 
 
 def set_step_mode(name):
-    """Select the propagation kernel: "tile" (default), "coop" (all steps in one cooperative launch) or "smem" (the
-    generic per-step kernel); process-wide, for A/B runs and tests - see cosa_par_set_step_mode."""
+    """Select the propagation kernel: "tile" (default: one launch per step), "chain" (all steps in one launch,
+    tile-level step counters; "chain<G>" sets the images per group) or "smem" (the generic per-step kernel);
+    process-wide, for A/B runs and tests - see cosa_par_set_step_mode."""
     _lib.check(_lib.load().cosa_par_set_step_mode(name.encode()))
 
 

@@ -124,10 +124,11 @@ def test_par_tile_path_shapes(cosa, port, shape):
     assert_close(aff, port.par_affinity(imgs)[:, 0], "affinity %s" % (shape,))
 
 
-@pytest.mark.parametrize("mode", ["coop", "smem", "tile"])
+@pytest.mark.parametrize("mode", ["smem", "tile", "chain", "chain1", "chain2"])
 def test_par_step_kernels_agree(cosa, port, mode):
-    """Every propagation kernel (single cooperative launch, the generic per-step kernel, and the default one CTA
-    per tile) against the oracle, on a
+    """Every propagation kernel (the generic per-step kernel, the default - one launch per step with one CTA per tile -
+    and all steps in one launch chained by tile-level step counters, also with image groups so small that a tile's
+    consecutive steps are resident together and really wait) against the oracle, on a
     ragged batch shape (partial tiles in both directions) and on the cam2mask path with per-image channel counts."""
     from cosa_b200 import par as par_mod
     g = torch.Generator().manual_seed(11)
