@@ -50,8 +50,8 @@ def parse_args():
     ap.add_argument("--aux-labelling", action="store_true",
                     help="also label the auxiliary CAMs of the batch (main.py:171-199, the reference's default); "
                          "reported as a separate workload")
-    ap.add_argument("--par-step", default="tile",
-                    help="PAR step kernel (cosa_b200.par.set_step_mode): tile (default), chain[<images per group>], smem")
+    ap.add_argument("--par-step", default="chain",
+                    help="PAR step kernel (cosa_b200.par.set_step_mode): chain[<images per group>] (default), tile, smem")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement")
@@ -257,11 +257,9 @@ def run_reference_arm(args):
 # the CUDA arm
 # ----------------------------------------------------------------------------------------------------
 PAR_STEP_NOTE = {
-    "chain": "1 affinity launch + ONE launch for all 10 propagation steps (par_chain_kernel: one CTA per step x image "
-             "tile, tile-level step counters instead of grid barriers)",
-    "tile": "1 affinity launch + 10 step launches (programmatic dependent launches); north_star's single launch "
-            "exists (--par-step chain: par_chain_kernel, tile-level step counters) - its kernel time equals the ten "
-            "launches', the whole step is slower",
+    "chain": "1 affinity launch + ONE launch for all 10 propagation steps (north_star's single launch; "
+             "par_chain_kernel: one CTA per step x image tile, tile-level step counters instead of grid barriers)",
+    "tile": "1 affinity launch + 10 step launches (programmatic dependent launches)",
     "smem": "1 affinity launch + 10 launches of the generic step kernel",
 }
 
@@ -350,9 +348,10 @@ def run_cosa_arm(args):
 
     def step(t, overlap=True, aux=args.aux_labelling, img_box=None):
         boxes = host["img_box"] if img_box is None else img_box
-        if overlap:
-            # the CRF lattice needs only the image: DenseEnergyLoss.prebuild_lattice starts it on a second stream so
-            # that the build runs under cam2mask; get_energy_loss below picks it up (same kernels, same results)
+        if overlap and cosa_b200.par.overlap_lattice_build():
+            # the CRF lattice needs only the image: with the per-step PAR kernel, DenseEnergyLoss.prebuild_lattice
+            # starts it on a second stream so that the build runs under cam2mask; get_energy_loss below picks it up
+            # (same kernels, same results)
             layer.prebuild_lattice(t["simg"], C)
         img_denorm = cosa_b200.denormalize_img(t["simg"])                       # main.py:117
         cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
@@ -609,8 +608,9 @@ def run_cosa_arm(args):
                        "fused_producers": "denormalize_img and cam_validation are folded into cam2mask's first kernel "
                                           "(cosa_cam2mask_ex); their tensors are never written",
                        "streams": ("CRF lattice build (image-only) on a second stream under cam2mask "
-                                   "(DenseEnergyLoss.prebuild_lattice)" if os.environ.get("COSA_NO_PREBUILD") != "1"
-                                   else "single stream (COSA_NO_PREBUILD=1)"),
+                                   "(DenseEnergyLoss.prebuild_lattice)"
+                                   if os.environ.get("COSA_NO_PREBUILD") != "1" and cosa_b200.par.overlap_lattice_build()
+                                   else "single stream"),
                        "parallelism": "batch-sharded, %d image(s)/GPU x %d GPU, no data-path collective" % (B, world),
                        "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
                                 % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),

@@ -1093,7 +1093,7 @@ extern "C" size_t cosa_cam2mask_ws_bytes_ex(int B, int C1, int H, int W, int dow
   bytes += n_mask_bufs * align_up((size_t)B * cstride * g.h * pitch * sizeof(float), 256);
   if (use_par) {
     bytes += align_up((size_t)B * 3 * hw * sizeof(float), 256);
-    bytes += align_up((size_t)B * 8 * n_dil * hw * sizeof(float), 256);
+    bytes += align_up(par_affinity_floats(B, n_dil, g.h, g.w) * sizeof(float), 256);
     bytes += align_up(par_tile_flag_ints(B, g.h, g.w) * sizeof(int), 256);
   }
   return bytes;
@@ -1176,7 +1176,7 @@ extern "C" int cosa_cam2mask_ex(const float *images, const int *boxes, const flo
     sb = arena.take<float>(mfloats);
     fin = arena.take<float>(mfloats);
     img_small = arena.take<float>((size_t)B * 3 * hw);
-    aff = arena.take<float>((size_t)B * 8 * n_dil * hw);
+    aff = arena.take<float>(par_affinity_floats(B, n_dil, g.h, g.w));
     tile_flags = arena.take<int>(par_tile_flag_ints(B, g.h, g.w));
   }
   // COSA_CAM2MASK_REUSE_AFFINITY: the previous call on this workspace had the same images, geometry and dilations

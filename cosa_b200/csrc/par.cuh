@@ -19,8 +19,14 @@ struct ParConst {
 };
 int par_make_constants(const int *dilations, int n_dil, ParConst *pc);
 
-// aff [B, 8*n_dil, h, w] from imgs [B,3,h,w].
-int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, cudaStream_t stream);
+// aff from imgs [B,3,h,w]: plain [B, 8*n_dil, h, w], or - tile_permuted, what the tile step kernels read (the
+// reference dilation set only) - [B, 48, tiles, 32 x 32] with the pixels of a tile in aff_tile_offset order.
+int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, bool tile_permuted,
+                        cudaStream_t stream);
+// floats of an affinity buffer in either layout (planes padded to whole 32 x 32 tiles)
+inline size_t par_affinity_floats(int B, int n_dil, int h, int w) {
+  return (size_t)B * 8 * n_dil * (((h + 31) / 32) * 32) * (((w + 31) / 32) * 32);
+}
 
 // Row layout of a mask buffer [B, c_stride, h, pitch]: the w interior columns start at column `off`; `padn`
 // replicated columns on either side make every neighbour load of the vectorised kernel an unclamped, 16-byte

@@ -530,11 +530,27 @@ __device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&
   }
 }
 
-// the 8 affinity quads of one dilation; A walks through the planes (one live 64-bit address instead of 48)
+// Tile-permuted affinity layout of the tile step kernels: [B][48][tiles][8 warps][4 j][32 lanes], the value of pixel
+// (4 tq + j, 4 wi + r) of a 32 x 32 tile at wi*128 + j*32 + (r*8 + tq) - the j-th pixel of the quad that lane r*8 + tq
+// of warp wi owns.  A warp then fetches one neighbour plane of its 32 quads with FOUR fully coalesced 128-byte
+// LDG.32 (one L1 wavefront each) instead of one LDG.128 that spans four lines: the L1 pipeline replays a multi-line
+// request at half rate (8.3 against 4 cycles per 512 bytes), and the 48 affinity loads of a pass were as expensive
+// on that pipeline as its 100 shared-memory loads.
+__host__ __device__ __forceinline__ int aff_tile_offset(int px, int py) {
+  return (py >> 2) * 128 + (px & 3) * 32 + (py & 3) * 8 + (px >> 2);
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// the 8 affinity quads of one dilation; A (this lane's slot in the tile-permuted plane) walks through the planes
+// with one live 64-bit address instead of 48
 __device__ __forceinline__ void load_aff8(float4 (&a)[8], const float *&A, size_t plane) {
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    a[m] = ldg_stream4(A);
+    a[m] = make_float4(ldg_stream1(A), ldg_stream1(A + 32), ldg_stream1(A + 64), ldg_stream1(A + 96));
     // opaque increment: keeps ptxas from materialising (and spilling) all 48 plane addresses up front
     asm volatile("add.u64 %0, %0, %1;" : "+l"(A) : "l"(plane * sizeof(float)));
   }
@@ -604,6 +620,7 @@ __device__ __forceinline__ void replicate_border(float *tile, int planes, int r_
   if (r_lo > 0 || r_hi < kFS) replicate_border_rows(tile, planes, r_lo, r_hi);
 }
 
+template <bool PERM>
 __global__ void __launch_bounds__(256, 2)
     par_affinity_tile_kernel(const __grid_constant__ CUtensorMap tm_img, float *__restrict__ aff, int h, int w,
                              const ParConst pc) {
@@ -690,13 +707,17 @@ __global__ void __launch_bounds__(256, 2)
       den += logit[n];
     }
     const float rden = 1.0f / den;
-    float *out = aff + (size_t)b * ND * plane + (size_t)y * w + x;
+    // PERM: the tile-permuted layout the tile step kernels read (aff_tile_offset); else plain [B, 48, h, w]
+    const size_t stride = PERM ? (size_t)gridDim.x * gridDim.y * (kTileW * kTileH) : plane;
+    float *out = PERM ? aff + ((size_t)b * ND * gridDim.x * gridDim.y + (size_t)blockIdx.y * gridDim.x + blockIdx.x) *
+                                  (kTileW * kTileH) + aff_tile_offset(tx, yl)
+                      : aff + (size_t)b * ND * plane + (size_t)y * w + x;
 #pragma unroll
     for (int n = 0; n < ND; ++n) {
       *out = fmaf(logit[n], rden, pc.pos_term[n]);
       // walk the planes with one opaque 64-bit add: `out[n * plane]` costs a wide multiply and four more integer
       // instructions per store in a kernel that is bound by instruction issue
-      asm volatile("add.u64 %0, %0, %1;" : "+l"(out) : "l"(plane * sizeof(float)));
+      asm volatile("add.u64 %0, %0, %1;" : "+l"(out) : "l"(stride * sizeof(float)));
     }
   }
 }
@@ -784,9 +805,10 @@ __global__ void __launch_bounds__(256, 2)
   const int n_groups = nch <= CH ? 1 : gsplit * ((nch + gsplit * CH - 1) / (gsplit * CH));
   const int chunk = (nch + n_groups - 1) / n_groups;
   if (g * chunk >= nch) return;
-  const size_t plane = (size_t)h * w;
+  const size_t plane = (size_t)gridDim.x * gridDim.y * (kTileW * kTileH);   // tile-permuted affinity (aff_tile_offset)
   const size_t oplane = (size_t)h * lo.pitch;
-  const float *A = aff + (size_t)b * 48 * plane + (size_t)min(y, h - 1) * w + min(x, w - 4);
+  const float *A = aff + ((size_t)b * 48 * gridDim.x * gridDim.y + (size_t)blockIdx.y * gridDim.x + blockIdx.x) *
+                             (kTileW * kTileH) + (threadIdx.x >> 5) * 128 + (threadIdx.x & 31);
   float *dst = out + (size_t)b * c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
   // staged rows [r_lo, r_hi) exist in the image; the others replicate the border row (PAR.py:44)
   const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
@@ -885,9 +907,9 @@ __global__ void __launch_bounds__(256, 2)
   const int x0 = txi * kTileW, y0 = tyi * kTileH;
   const int xq = (x0 >> 2) + tq, y = y0 + tr, x = x0 + (tq << 2);
   const bool active = xq < wq && y < h;
-  const size_t plane = (size_t)h * w;
+  const size_t plane = (size_t)tiles * (kTileW * kTileH);   // tile-permuted affinity (aff_tile_offset)
   const size_t oplane = (size_t)h * lo.pitch;
-  const float *A = p.aff + (size_t)b * 48 * plane + (size_t)min(y, h - 1) * w + min(x, w - 4);
+  const float *A = p.aff + ((size_t)b * 48 * tiles + t) * (kTileW * kTileH) + (threadIdx.x >> 5) * 128 + (threadIdx.x & 31);
   float *dst = out + (size_t)b * p.c_stride * oplane + (size_t)y * lo.pitch + lo.off + x;
   const int r_lo = max(0, kFH - y0), r_hi = min(kFS, h - y0 + kFH);
   const float *q = s_tile + (tr + kFH) * kFS + (tq << 2) + kFH;   // this thread's quad in staged channel 0
@@ -1009,17 +1031,50 @@ MaskLayout padded_layout(int w, const int *dilations, int n_dil) {
   return l;
 }
 
-int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, cudaStream_t stream) {
+// Step-kernel selection (cosa_par_set_step_mode; process-wide, meant for A/B runs and tests - results are identical):
+//   chain (default) TMA-tile kernel, every step in ONE launch (north_star's single launch), tile-level dependencies
+//                   through step counters, <= 4 channels per CTA pass ("chain<G>": G images per group, default 8)
+//   tile            TMA-tile kernel, one CTA per tile and channel split (<= 3 channels per pass), one launch per
+//                   step (steps 2..T as programmatic dependent launches)
+//   smem            the generic per-step kernel (what non-reference dilation sets use)
+enum { kStepTile = 0, kStepSmem = 2, kStepChain = 3 };
+static std::atomic<int> g_step_mode{kStepChain};
+static std::atomic<int> g_chain_group{0};   // images per group of the chained kernel, 0 = automatic (A/B knob)
+static int parse_step_mode(const char *e) {
+  if (!e) return -1;
+  switch (e[0]) {
+    case 't': return kStepTile;
+    case 'c': return kStepChain;
+    case 's': return kStepSmem;
+    default: return -1;
+  }
+}
+
+bool par_tile_path(const ParConst &pc, const MaskLayout &lay, const MaskLayout &lay_final) {
+  return lay.padn > 0 && pc.std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) &&
+         g_step_mode.load(std::memory_order_relaxed) != kStepSmem;
+}
+
+int par_launch_affinity(const ParConst &pc, const float *imgs, float *aff, int B, int h, int w, bool tile_permuted,
+                        cudaStream_t stream) {
   dim3 grid(ceil_div(w, 32), ceil_div(h, 4), B), block(128);
   const int n_dil = pc.n_dil;
   if (pc.std_dilations && w % 4 == 0) {
     static std::atomic<unsigned long long> done{0};
     const int smem = 3 * kFS * kFS * (int)sizeof(float);
-    COSA_CHECK(opt_in_smem(par_affinity_tile_kernel, smem, done));
     CUtensorMap tm;
     COSA_CHECK(make_tmap3(&tm, imgs, (long long)B * 3, h, w, kFS, kBoxRows, 1));
-    COSA_LAUNCH(par_affinity_tile_kernel, dim3(ceil_div(w, kTileW), ceil_div(h, kTileH), B), 256, smem, stream, tm, aff,
-                h, w, pc);
+    const dim3 tgrid(ceil_div(w, kTileW), ceil_div(h, kTileH), B);
+    if (tile_permuted) {
+      static std::atomic<unsigned long long> done_p{0};
+      COSA_CHECK(opt_in_smem(par_affinity_tile_kernel<true>, smem, done_p));
+      COSA_LAUNCH_T("par_affinity_tile_kernel", par_affinity_tile_kernel<true>, tgrid, 256, smem, stream, tm, aff, h, w, pc);
+    } else {
+      COSA_CHECK(opt_in_smem(par_affinity_tile_kernel<false>, smem, done));
+      COSA_LAUNCH_T("par_affinity_tile_kernel", par_affinity_tile_kernel<false>, tgrid, 256, smem, stream, tm, aff, h, w, pc);
+    }
+  } else if (tile_permuted) {
+    return COSA_E_ARG;   // the tile step kernels exist for the reference dilation set only
   } else if (n_dil == 6) {
     COSA_LAUNCH(par_affinity_kernel<6>, grid, block, 0, stream, imgs, aff, h, w, pc);
   } else {
@@ -1033,27 +1088,6 @@ int par_launch_pack(const float *src, float *dst, MaskLayout lay, int planes, in
   const int blocks = (int)max(1LL, min((long long)sm_count() * 8, ceil_div_ll(total, 256)));
   COSA_LAUNCH(par_pack_kernel, blocks, 256, 0, stream, src, dst, lay, planes, h, w);
   return 0;
-}
-
-// Step-kernel selection (cosa_par_set_step_mode; process-wide, meant for A/B runs and tests - results are identical):
-//   tile (default)  TMA-tile kernel, one CTA per tile and channel split, one launch per step (steps 2..T as
-//                   programmatic dependent launches)
-//   chain           TMA-tile kernel, every step in ONE launch, tile-level dependencies through step counters
-//                   ("chain<G>": G images per group, default 8): north_star's single launch.  The kernel alone is as
-//                   fast as ten tile launches; the whole step is slower (the lattice build on the second stream
-//                   does not interleave with one long grid): DESIGN.md section 4
-//   smem            the generic per-step kernel (what non-reference dilation sets use)
-enum { kStepTile = 0, kStepSmem = 2, kStepChain = 3 };
-static std::atomic<int> g_step_mode{kStepTile};
-static std::atomic<int> g_chain_group{0};   // images per group of the chained kernel, 0 = automatic (A/B knob)
-static int parse_step_mode(const char *e) {
-  if (!e) return -1;
-  switch (e[0]) {
-    case 't': return kStepTile;
-    case 'c': return kStepChain;
-    case 's': return kStepSmem;
-    default: return -1;
-  }
 }
 
 constexpr int kStepCH = 3;    // channels per CTA pass of the per-step tile kernels
@@ -1141,7 +1175,7 @@ int par_launch_iterations(const ParConst &pc, const float *aff, const float *src
   const bool wide = nch_dev ? (c_stride > 4) : (nch_uniform > 4);
   const bool vec = lay.padn > 0;
   const int mode = g_step_mode.load(std::memory_order_relaxed);
-  if (vec && pc.std_dilations && lay.padn == kFH && (lay_final.padn == 0 || lay_final.padn == kFH) && mode != kStepSmem)
+  if (par_tile_path(pc, lay, lay_final))   // `aff` is in the tile-permuted layout (par_launch_affinity)
     return par_launch_propagate(aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
                                 c_stride, B, h, w, num_iter, mode, tile_flags, stream);
   const float *src = src0;
@@ -1184,7 +1218,7 @@ int par_refine_batch(const ParConst &pc, const float *imgs, float *aff, const fl
                      float *scratch_b, MaskLayout lay, float *final_dst, MaskLayout lay_final, const int *nch_dev,
                      int nch_uniform, int c_stride, int B, int h, int w, int num_iter, int *tile_flags,
                      cudaStream_t stream) {
-  COSA_CHECK(par_launch_affinity(pc, imgs, aff, B, h, w, stream));
+  COSA_CHECK(par_launch_affinity(pc, imgs, aff, B, h, w, par_tile_path(pc, lay, lay_final), stream));
   return par_launch_iterations(pc, aff, src0, scratch_a, scratch_b, lay, final_dst, lay_final, nch_dev, nch_uniform,
                                c_stride, B, h, w, num_iter, tile_flags, stream);
 }
@@ -1198,7 +1232,7 @@ using namespace cosa;
 extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
   const size_t plane = (size_t)h * w;
   const size_t pitch = (size_t)max_padded_pitch(w);
-  return align_up((size_t)B * 8 * n_dil * plane * sizeof(float), 256) +
+  return align_up(par_affinity_floats(B, n_dil, h, w) * sizeof(float), 256) +
          2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256) + align_up(par_tile_flag_ints(B, h, w) * sizeof(int), 256);
 }
 
@@ -1221,7 +1255,7 @@ extern "C" int cosa_par_affinity(const float *imgs, float *aff, int B, int h, in
   if (!imgs || !aff || B < 1 || h < 1 || w < 1) return COSA_E_ARG;
   ParConst pc;
   COSA_CHECK(par_make_constants(dilations, n_dil, &pc));
-  return par_launch_affinity(pc, imgs, aff, B, h, w, (cudaStream_t)stream);
+  return par_launch_affinity(pc, imgs, aff, B, h, w, false, (cudaStream_t)stream);
 }
 
 extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out, int B, int C, int h, int w,
@@ -1238,7 +1272,7 @@ extern "C" int cosa_par_forward(const float *imgs, const float *masks_in, float 
   if (lay.padn > 24) lay = plain_layout(w);   // keeps the scratch within cosa_par_ws_bytes
   const MaskLayout plain = plain_layout(w);
   Arena arena(ws);
-  float *aff = arena.take<float>((size_t)B * 8 * n_dil * plane);
+  float *aff = arena.take<float>(par_affinity_floats(B, n_dil, h, w));
   float *buf_a = arena.take<float>(layout_floats(lay, B, C, h));
   float *buf_b = arena.take<float>(layout_floats(lay, B, C, h));
   int *tile_flags = arena.take<int>(par_tile_flag_ints(B, h, w));

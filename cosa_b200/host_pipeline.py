@@ -35,6 +35,7 @@ import copy
 import torch
 
 from . import _lib, seg_helper
+from . import par as par_mod
 
 _FULL = ("simg", "cls_label", "logits")
 
@@ -139,7 +140,8 @@ class HostPipeline:
             return s["graph"]()
         d, boxes = s["dev"], batch["img_box"]
         H, W = s["shapes"]["simg"][2:]
-        self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # overlaps cam2mask
+        if par_mod.overlap_lattice_build():
+            self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # overlaps cam2mask
         img_denorm = seg_helper.denormalize_img(d["simg"])
         if s["native"]:
             # seg_helper.py:250-270 + cam_validation (main.py:137), absent classes' planes zero-filled
@@ -265,8 +267,10 @@ class GraphedStep:
         thr = (float(threshold_high), float(threshold_low))
 
         def body():
-            # the lattice needs only the image: built on a second stream (a forked branch of the graph) under cam2mask
-            loss_layer.prebuild_lattice(self.simg, C)
+            # the lattice needs only the image: with the per-step PAR kernel it is built on a second stream (a forked
+            # branch of the graph) under cam2mask
+            if par_mod.overlap_lattice_build():
+                loss_layer.prebuild_lattice(self.simg, C)
             img_denorm = seg_helper.denormalize_img(self.simg)
             if self.native:
                 # seg_helper.py:250-270 + cam_validation (main.py:137), absent classes' planes zero-filled

@@ -13,11 +13,29 @@ import torch.nn as nn
 from . import _lib
 
 
+_STEP_MODE = "chain"
+
+
 def set_step_mode(name):
-    """Select the propagation kernel: "tile" (default: one launch per step), "chain" (all steps in one launch,
-    tile-level step counters; "chain<G>" sets the images per group) or "smem" (the generic per-step kernel);
+    """Select the propagation kernel: "chain" (default: all steps in one launch, tile-level step counters;
+    "chain<G>" sets the images per group), "tile" (one launch per step) or "smem" (the generic per-step kernel);
     process-wide, for A/B runs and tests - see cosa_par_set_step_mode."""
+    global _STEP_MODE
     _lib.check(_lib.load().cosa_par_set_step_mode(name.encode()))
+    _STEP_MODE = name
+
+
+def step_mode():
+    """The propagation kernel selected by set_step_mode."""
+    return _STEP_MODE
+
+
+def overlap_lattice_build():
+    """Whether a step should start the CRF lattice build on a second stream under cam2mask
+    (DenseEnergyLoss.prebuild_lattice).  Measured on B200 (profiles/README.md): next to the per-step launches of the
+    "tile" kernel the build fills the wave tails (2.20 -> 2.19 ms per step); next to the single long grid of the
+    "chain" kernel it makes the step slower (2.10 -> 2.21 ms), so the default path builds the lattice in stream order."""
+    return _STEP_MODE.startswith("tile")
 
 
 def get_kernel():

@@ -126,9 +126,9 @@ def test_par_tile_path_shapes(cosa, port, shape):
 
 @pytest.mark.parametrize("mode", ["smem", "tile", "chain", "chain1", "chain2"])
 def test_par_step_kernels_agree(cosa, port, mode):
-    """Every propagation kernel (the generic per-step kernel, the default - one launch per step with one CTA per tile -
-    and all steps in one launch chained by tile-level step counters, also with image groups so small that a tile's
-    consecutive steps are resident together and really wait) against the oracle, on a
+    """Every propagation kernel (the generic per-step kernel, one launch per step with one CTA per tile, and the
+    default - all steps in one launch chained by tile-level step counters, also with image groups so small that a
+    tile's consecutive steps are resident together and really wait) against the oracle, on a
     ragged batch shape (partial tiles in both directions) and on the cam2mask path with per-image channel counts."""
     from cosa_b200 import par as par_mod
     g = torch.Generator().manual_seed(11)
@@ -143,7 +143,7 @@ def test_par_step_kernels_agree(cosa, port, mode):
         out = cosa.PAR(DIL, 10).cuda()(imgs.cuda(), masks.cuda())
         lab = cosa.cam2mask(refine_model=cosa.PAR(DIL, 10).cuda(), **args)
     finally:
-        par_mod.set_step_mode("tile")        # the default
+        par_mod.set_step_mode("chain")       # the default
     assert_close(out, want, "PAR, step kernel %s" % mode)
     assert_same(lab, d["out_par"], "cam2mask + PAR, step kernel %s" % mode)
     with pytest.raises(cosa._lib.CosaError):
