@@ -348,10 +348,11 @@ def run_cosa_arm(args):
 
     def step(t, overlap=True, aux=args.aux_labelling, img_box=None):
         boxes = host["img_box"] if img_box is None else img_box
-        if overlap and cosa_b200.par.overlap_lattice_build():
-            # the CRF lattice needs only the image: with the per-step PAR kernel, DenseEnergyLoss.prebuild_lattice
-            # starts it on a second stream so that the build runs under cam2mask; get_energy_loss below picks it up
-            # (same kernels, same results)
+        # the CRF lattice needs only the image: DenseEnergyLoss.prebuild_lattice starts it on a second stream - under
+        # cam2mask next to the per-step PAR kernel, else behind cam2mask, beside the first kernel of get_energy_loss,
+        # which picks it up (same kernels, same results)
+        early = cosa_b200.par.lattice_prebuild_before_cam2mask()
+        if overlap and early:
             layer.prebuild_lattice(t["simg"], C)
         img_denorm = cosa_b200.denormalize_img(t["simg"])                       # main.py:117
         cams = cosa_b200.cam_validation(t["cams"], t["cls_label"])
@@ -367,6 +368,8 @@ def run_cosa_arm(args):
         else:
             label = cosa_b200.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=t["cls_label"],
                                        threshold_high=thr_high, threshold_low=thr_low, refine_model=par)
+        if overlap and not early:
+            layer.prebuild_lattice(t["simg"], C)
         logit = t["logits"].detach().requires_grad_(True)
         loss = cosa_b200.get_energy_loss(img=t["simg"], logit=logit, label=label, img_box=boxes, loss_layer=layer)
         loss.backward()
@@ -607,10 +610,10 @@ def run_cosa_arm(args):
                        "par_step": PAR_STEP_NOTE[args.par_step.rstrip("0123456789")],
                        "fused_producers": "denormalize_img and cam_validation are folded into cam2mask's first kernel "
                                           "(cosa_cam2mask_ex); their tensors are never written",
-                       "streams": ("CRF lattice build (image-only) on a second stream under cam2mask "
-                                   "(DenseEnergyLoss.prebuild_lattice)"
-                                   if os.environ.get("COSA_NO_PREBUILD") != "1" and cosa_b200.par.overlap_lattice_build()
-                                   else "single stream"),
+                       "streams": ("single stream (COSA_NO_PREBUILD=1)" if os.environ.get("COSA_NO_PREBUILD") == "1" else
+                                   "CRF lattice build (image-only) on a second stream (DenseEnergyLoss.prebuild_lattice): "
+                                   + ("under cam2mask" if cosa_b200.par.lattice_prebuild_before_cam2mask() else
+                                      "beside the softmax / gate kernel of get_energy_loss")),
                        "parallelism": "batch-sharded, %d image(s)/GPU x %d GPU, no data-path collective" % (B, world),
                        "cache": "inputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush"
                                 % ((sum(v.numel() * v.element_size() for v in d.values())) / 1e6),

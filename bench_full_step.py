@@ -115,11 +115,14 @@ def main():
                 raw_seg.append(seg_t.float())
         ev[0].record()
         with torch.no_grad():                                   # ---- the path, part 1: pseudo labels ----
-            if cosa_b200.par.overlap_lattice_build():
+            early = cosa_b200.par.lattice_prebuild_before_cam2mask()
+            if early:
                 layer.prebuild_lattice(simg, C)
             cams = cosa_b200.multi_scale_cam_merge(raw_cam, (S, S), cls_label=cls_label)
             label = cosa_b200.cam2mask(images=cosa_b200.denormalize_img(simg), img_boxes=boxes, cams=cams,
                                        cls_labels=cls_label, threshold_high=0.7, threshold_low=0.25, refine_model=par)
+            if not early:
+                layer.prebuild_lattice(simg, C)       # second stream: runs under the student's forward pass
         ev[1].record()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             cls, cls_aux, _, seg, _, _ = model(simg)

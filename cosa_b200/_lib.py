@@ -73,6 +73,8 @@ _SIGNATURES = {
     "cosa_energy_loss_prebuild": (_c_int, [_vp] * 3 + [_c_float] * 2 + [_c_int] * 4 + [_vp, _c_size_t, _vp]),
     "cosa_energy_loss_forward_flags": (_c_int, [_vp] * 6 + [_c_float] * 3 + [_vp, _vp] + [_c_int] * 4 +
                                        [_vp, _c_size_t, _c_int, _vp]),
+    "cosa_energy_loss_forward_ev": (_c_int, [_vp] * 6 + [_c_float] * 3 + [_vp, _vp] + [_c_int] * 4 +
+                                    [_vp, _c_size_t, _c_int, _vp, _vp]),
     "cosa_energy_loss_backward": (_c_int, [_vp] * 3 + [_c_float, _vp] + [_c_int] * 4 + [_vp]),
 }
 

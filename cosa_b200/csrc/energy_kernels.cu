@@ -111,10 +111,12 @@ __global__ void __launch_bounds__(256) energy_prepare_kernel(const float *__rest
   const size_t pix = (size_t)y * w + x;
   const size_t src = (size_t)(2 * y) * W + 2 * x;   // nearest: source index 2i (seg_helper.py:201,203,204)
 
+  if (img_half) {   // null: the prebuilt lattice's owner has written it already
 #pragma unroll
-  for (int c = 0; c < 3; ++c)   // img * std + mean, two roundings like the two tensor ops (:225-227)
-    img_half[((size_t)b * 3 + c) * hw + pix] =
-        __fadd_rn(__fmul_rn(__ldg(simg + ((size_t)b * 3 + c) * HW + src), aff.std[c]), aff.mean[c]);
+    for (int c = 0; c < 3; ++c)   // img * std + mean, two roundings like the two tensor ops (:225-227)
+      img_half[((size_t)b * 3 + c) * hw + pix] =
+          __fadd_rn(__fmul_rn(__ldg(simg + ((size_t)b * 3 + c) * HW + src), aff.std[c]), aff.mean[c]);
+  }
 
   const int *box = boxes + 4 * b;
   const float roi = (2 * y >= box[0] && 2 * y < box[1] && 2 * x >= box[2] && 2 * x < box[3]) ? 1.0f : 0.0f;
@@ -255,11 +257,13 @@ __global__ void __launch_bounds__(256) energy_prepare_vec_kernel(const float *__
     }
     // image (nearest, de-normalised), unlabel flag, gate, ROI for the two half-resolution pixels
     const float4 lab = ldg_stream4(label + (size_t)b * HW + src);
+    if (img_half) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float4 v = ldg_stream4(simg + ((size_t)b * 3 + c) * HW + src);
-      *reinterpret_cast<float2 *>(img_half + ((size_t)b * 3 + c) * hw + pix) =
-          make_float2(__fadd_rn(__fmul_rn(v.x, aff.std[c]), aff.mean[c]), __fadd_rn(__fmul_rn(v.z, aff.std[c]), aff.mean[c]));
+      for (int c = 0; c < 3; ++c) {
+        const float4 v = ldg_stream4(simg + ((size_t)b * 3 + c) * HW + src);
+        *reinterpret_cast<float2 *>(img_half + ((size_t)b * 3 + c) * hw + pix) =
+            make_float2(__fadd_rn(__fmul_rn(v.x, aff.std[c]), aff.mean[c]), __fadd_rn(__fmul_rn(v.z, aff.std[c]), aff.mean[c]));
+      }
     }
     float g0 = __fsub_rn(roi0, smax0), g1 = __fsub_rn(roi1, smax1);
     if (((int)lab.x & 255) == 255) g0 = 1.0f;
@@ -393,9 +397,11 @@ __global__ void __launch_bounds__(128, 4) energy_prepare_reg_kernel(const float 
     smax = fmaxf(smax, sv);
     dst[(size_t)c * hw] = __fmul_rn(sv, roi);
   }
+  if (img_half) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-    img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+    for (int c = 0; c < 3; ++c)
+      img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+  }
   float g = __fsub_rn(roi, smax);
   if (((int)lab & 255) == 255) g = 1.0f;
   gate[(size_t)b * hw + pix] = fmaxf(g, 0.0f);
@@ -524,9 +530,11 @@ __global__ void __launch_bounds__(128, 2) energy_prepare_pair_kernel(const float
     }
   }
   if (writer) {
+    if (img_half) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+      for (int c = 0; c < 3; ++c)
+        img_half[((size_t)b * 3 + c) * hw + pix] = __fadd_rn(__fmul_rn(im[c], aff.std[c]), aff.mean[c]);
+    }
     float g = __fsub_rn(roi, smax);
     if (((int)lab & 255) == 255) g = 1.0f;
     gate[(size_t)b * hw + pix] = fmaxf(g, 0.0f);
@@ -756,7 +764,17 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
                                               const int *boxes, const float *mean, const float *std, float weight,
                                               float sigmargb, float sigmaxy_scaled, float *loss_out, void *saved, int B,
                                               int C, int H, int W, void *ws, size_t ws_bytes, int flags, void *stream) {
+  return cosa_energy_loss_forward_ev(simg, logit, label, boxes, mean, std, weight, sigmargb, sigmaxy_scaled, loss_out,
+                                     saved, B, C, H, W, ws, ws_bytes, flags, nullptr, stream);
+}
+
+extern "C" int cosa_energy_loss_forward_ev(const float *simg, const float *logit, const float *label, const int *boxes,
+                                           const float *mean, const float *std, float weight, float sigmargb,
+                                           float sigmaxy_scaled, float *loss_out, void *saved, int B, int C, int H,
+                                           int W, void *ws, size_t ws_bytes, int flags, void *lattice_ready,
+                                           void *stream) {
   if (flags & ~(COSA_ENERGY_LATTICE_PREBUILT | COSA_ENERGY_VERTEX_BUDGET_MASK)) return COSA_E_ARG;
+  if (lattice_ready && !(flags & COSA_ENERGY_LATTICE_PREBUILT)) return COSA_E_ARG;
   if (!simg || !logit || !label || !boxes || !mean || !std || !loss_out || !saved || !ws || B < 1 || C < 1)
     return COSA_E_ARG;
   if (H < 2 || W < 2 || (H & 1) || (W & 1)) return COSA_E_ARG;
@@ -768,11 +786,14 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
   float *as_out = sv.take<float>((size_t)B * C * hw);
   float *roi_half = sv.take<float>((size_t)B * hw);
   Arena a(ws);
-  float *img_half = a.take<float>((size_t)B * 3 * hw);
+  float *img_half_ws = a.take<float>((size_t)B * 3 * hw);
   float *s_roi = a.take<float>((size_t)B * C * hw);
   float *gate = a.take<float>((size_t)B * hw);
   double *acc = a.take<double>(1);
   void *lws = a.base + a.off;
+  // a prebuilt lattice comes with its half-resolution image: the prepare kernel leaves it alone, so it may run while
+  // the build is still in flight on another stream (lattice_ready)
+  float *img_half = (flags & COSA_ENERGY_LATTICE_PREBUILT) ? nullptr : img_half_ws;
   Affine3 aff;
   for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
   if (C == 21) {   // VOC: register-resident single pass
@@ -792,8 +813,9 @@ extern "C" int cosa_energy_loss_forward_flags(const float *simg, const float *lo
     COSA_LAUNCH(energy_prepare_kernel, grid, 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi, gate,
                 roi_half, C, H, W);
   }
-  return energy_core(img_half, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1, lws,
-                     s, (flags & COSA_ENERGY_LATTICE_PREBUILT) != 0, budget_of(flags));
+  if (lattice_ready) COSA_CUDA(cudaStreamWaitEvent(s, (cudaEvent_t)lattice_ready, 0));
+  return energy_core(img_half_ws, s_roi, gate, as_out, loss_out, acc, B, C, h, w, sigmargb, sigmaxy_scaled, weight, 1,
+                     lws, s, (flags & COSA_ENERGY_LATTICE_PREBUILT) != 0, budget_of(flags));
 }
 
 extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,

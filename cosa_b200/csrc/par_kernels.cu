@@ -1123,10 +1123,13 @@ static int par_launch_propagate(const float *aff, const float *src0, float *scra
       // a tile's consecutive steps must be further apart in the grid than the CTAs resident at once
       // (a closer pair still completes - the later CTA waits for the earlier one - it only idles a slot meanwhile)
       int group = g_chain_group.load(std::memory_order_relaxed);
-      if (group <= 0) {   // automatic: 8 images (77 MB of affinity planes at 224^2) or as many as the distance needs
+      if (group <= 0) {
+        // automatic: groups of about 8 images (their affinity planes stay close in L2), all of nearly the same size
+        // (a short last group would bring a tile's consecutive steps too close), each large enough for the distance
         const int resident = 2 * sm_count();
-        group = 8;
-        while (group < a.B && (long long)group * tiles < resident + 2 * a.tiles_x + 2) ++group;
+        int n_groups = max(1, a.B / 8);
+        while (n_groups > 1 && (long long)(a.B / n_groups) * tiles < resident + 2 * a.tiles_x + 2) --n_groups;
+        group = ceil_div(a.B, n_groups);
       }
       group = min(group, a.B);
       COSA_LAUNCH(par_chain_kernel<CC>, dim3((unsigned)ctas), 256, smem_c, stream, a, t0, ta, tb, tile_flags, group);

@@ -140,7 +140,8 @@ class HostPipeline:
             return s["graph"]()
         d, boxes = s["dev"], batch["img_box"]
         H, W = s["shapes"]["simg"][2:]
-        if par_mod.overlap_lattice_build():
+        early = par_mod.lattice_prebuild_before_cam2mask()
+        if early:
             self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # overlaps cam2mask
         img_denorm = seg_helper.denormalize_img(d["simg"])
         if s["native"]:
@@ -153,6 +154,8 @@ class HostPipeline:
             leaf = logit = d["logits"].detach().requires_grad_(True)
         label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=d["cls_label"],
                                     threshold_high=self.thr[0], threshold_low=self.thr[1], refine_model=self.par)
+        if not early:
+            self.loss_layer.prebuild_lattice(d["simg"], d["cls_label"].shape[1] + 1)   # beside get_energy_loss's first kernel
         loss = seg_helper.get_energy_loss(img=d["simg"], logit=logit, label=label, img_box=boxes,
                                           loss_layer=self.loss_layer)
         loss.backward()
@@ -267,9 +270,10 @@ class GraphedStep:
         thr = (float(threshold_high), float(threshold_low))
 
         def body():
-            # the lattice needs only the image: with the per-step PAR kernel it is built on a second stream (a forked
-            # branch of the graph) under cam2mask
-            if par_mod.overlap_lattice_build():
+            # the lattice needs only the image: it is built on a second stream (a forked branch of the graph), under
+            # cam2mask next to the per-step PAR kernel, else beside the first kernel of get_energy_loss
+            early = par_mod.lattice_prebuild_before_cam2mask()
+            if early:
                 loss_layer.prebuild_lattice(self.simg, C)
             img_denorm = seg_helper.denormalize_img(self.simg)
             if self.native:
@@ -282,6 +286,8 @@ class GraphedStep:
                 leaf = logit = self.logits
             label = seg_helper.cam2mask(images=img_denorm, img_boxes=boxes, cams=cams, cls_labels=self.cls_label,
                                         threshold_high=thr[0], threshold_low=thr[1], refine_model=par)
+            if not early:
+                loss_layer.prebuild_lattice(self.simg, C)
             loss = seg_helper.get_energy_loss(img=self.simg, logit=logit, label=label, img_box=boxes,
                                               loss_layer=loss_layer)
             grad, = torch.autograd.grad(loss, leaf)

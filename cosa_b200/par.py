@@ -30,11 +30,12 @@ def step_mode():
     return _STEP_MODE
 
 
-def overlap_lattice_build():
-    """Whether a step should start the CRF lattice build on a second stream under cam2mask
-    (DenseEnergyLoss.prebuild_lattice).  Measured on B200 (profiles/README.md): next to the per-step launches of the
-    "tile" kernel the build fills the wave tails (2.20 -> 2.19 ms per step); next to the single long grid of the
-    "chain" kernel it makes the step slower (2.10 -> 2.21 ms), so the default path builds the lattice in stream order."""
+def lattice_prebuild_before_cam2mask():
+    """Where a step should start the CRF lattice build on the second stream (DenseEnergyLoss.prebuild_lattice): True =
+    before cam2mask, False = between cam2mask and get_energy_loss.  Measured on B200 (profiles/README.md): next to the
+    per-step launches of the "tile" kernel the build fills the wave tails of PAR; next to the single long grid of the
+    "chain" kernel it makes the step slower (2.10 -> 2.21 ms), so there it is started behind cam2mask and runs beside
+    the HBM-bound softmax / gate kernel of get_energy_loss (the hand-over is inside cosa_energy_loss_forward_ev)."""
     return _STEP_MODE.startswith("tile")
 
 

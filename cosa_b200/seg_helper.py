@@ -561,17 +561,21 @@ class _FusedEnergyLoss(Function):
         with torch.cuda.device(dev):
             saved = torch.empty(lib.cosa_energy_loss_saved_bytes(B, C, H, W), dtype=torch.uint8, device=dev)
             nbytes = lib.cosa_energy_loss_ws_bytes_ex(B, C, H, W, int(bflags))
+            ready = None
             if pre is not None:       # DenseEnergyLoss.prebuild_lattice: the lattice is in the layer's own workspace
-                torch.cuda.current_stream(dev).wait_event(pre["done"])
-                ws, flags = pre["ws"], 1 | int(bflags)   # COSA_ENERGY_LATTICE_PREBUILT
+                # the build may still be running on the layer's side stream: the library waits for its event between
+                # the softmax / gate kernel and the first kernel that reads the lattice
+                ws, flags, ready = pre["ws"], 1 | int(bflags), pre["done"].cuda_event   # COSA_ENERGY_LATTICE_PREBUILT
                 _LAST_ENERGY_WS[dev.index] = ws
             else:
                 ws, flags = _lib.workspace(nbytes, dev), int(bflags)
                 _LAST_ENERGY_WS.pop(dev.index, None)
-            _lib.check(lib.cosa_energy_loss_forward_flags(
+            _lib.check(lib.cosa_energy_loss_forward_ev(
                 _lib.ptr(simg), _lib.ptr(logit), _lib.ptr(label), _lib.ptr(boxes), mean_c, std_c, float(weight),
                 float(sigma_rgb), float(sigma_xy_scaled), _lib.ptr(loss), _lib.ptr(saved), B, C, H, W, _lib.ptr(ws),
-                nbytes, flags, _lib.stream_ptr()))
+                nbytes, flags, ready, _lib.stream_ptr()))
+            if pre is not None:       # the side stream's workspace is read by this stream from here on
+                pre["ws"].record_stream(torch.cuda.current_stream(dev))
         ctx.save_for_backward(logit)
         ctx.saved_blob = saved
         ctx.weight = float(weight)

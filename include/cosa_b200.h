@@ -256,6 +256,14 @@ int cosa_energy_loss_forward_flags(const float *simg, const float *logit, const 
                                    const float *mean, const float *std, float weight, float sigmargb,
                                    float sigmaxy_scaled, float *loss_out, void *saved, int B, int C, int H, int W,
                                    void *ws, size_t ws_bytes, int flags, void *stream);
+/* The same, with the hand-over of a lattice prebuilt on ANOTHER stream made inside the call: `lattice_ready`
+ * (a cudaEvent_t recorded behind cosa_energy_loss_prebuild on that stream; needs COSA_ENERGY_LATTICE_PREBUILT) is
+ * waited for on `stream` AFTER the softmax / gate kernel has been enqueued, so that HBM-bound kernel runs beside the
+ * latency-bound build instead of behind it.  NULL: plain cosa_energy_loss_forward_flags. */
+int cosa_energy_loss_forward_ev(const float *simg, const float *logit, const float *label, const int *boxes,
+                                const float *mean, const float *std, float weight, float sigmargb, float sigmaxy_scaled,
+                                float *loss_out, void *saved, int B, int C, int H, int W, void *ws, size_t ws_bytes,
+                                int flags, void *lattice_ready, void *stream);
 int cosa_energy_loss_backward(const float *logit, const void *saved, const float *grad_out, float weight,
                               float *grad_logit, int B, int C, int H, int W, void *stream);
 
