@@ -211,7 +211,8 @@ def cpu_kind():
             else "port (torch-CPU PAR/labelling port + C lattice port)")
 
 
-REF_SAMPLE_IMAGES = 4      # images per step of the CPU arms: the same at every N (one host runs them)
+REF_SAMPLE_IMAGES = 4      # images per step of the --impl reference arm: the same at every N (one host runs it)
+CPU_LEG_IMAGES = 32        # images of the cosa arm's cpu_baseline / parity leg (about 7 s of CPU work at VOC shape)
 
 
 def run_reference_arm(args):
@@ -385,7 +386,7 @@ def run_cosa_arm(args):
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_img = min(REF_SAMPLE_IMAGES, B)
+        n_img = min(CPU_LEG_IMAGES, B)
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_path_step(host, 1)
         t0 = time.perf_counter()
