@@ -796,15 +796,18 @@ extern "C" int cosa_energy_loss_forward_ev(const float *simg, const float *logit
   float *img_half = (flags & COSA_ENERGY_LATTICE_PREBUILT) ? nullptr : img_half_ws;
   Affine3 aff;
   for (int c = 0; c < 3; ++c) { aff.mean[c] = mean[c]; aff.std[c] = std[c]; }
-  if (C == 21) {   // VOC: register-resident single pass
+  // the vector kernels read 8 / 16 bytes at a time: a tensor view that starts at an odd element takes the scalar kernel
+  const uintptr_t in_bits = (uintptr_t)simg | (uintptr_t)logit | (uintptr_t)label;
+  const bool al8 = in_bits % 8 == 0, al16 = in_bits % 16 == 0;
+  if (C == 21 && al8) {   // VOC: register-resident single pass
     const long long threads = (long long)B * h * w;
     COSA_LAUNCH(energy_prepare_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label, boxes,
                 aff, img_half, s_roi, gate, roi_half, B, H, W);
-  } else if (C == 81 && W % 32 == 0) {   // COCO: register-resident, two pixels per thread
+  } else if (C == 81 && W % 32 == 0 && al8) {   // COCO: register-resident, two pixels per thread
     const long long threads = (long long)B * h * (W / 32) * 32;
     COSA_LAUNCH(energy_prepare_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, simg, logit, label,
                 boxes, aff, img_half, s_roi, gate, roi_half, B, H, W);
-  } else if (W % 4 == 0) {
+  } else if (W % 4 == 0 && al16) {
     const long long threads = (long long)B * h * (W / 4);
     COSA_LAUNCH(energy_prepare_vec_kernel, grid1d(threads), 256, 0, s, simg, logit, label, boxes, aff, img_half, s_roi,
                 gate, roi_half, B, C, H, W);
@@ -828,15 +831,17 @@ extern "C" int cosa_energy_loss_backward(const float *logit, const void *saved, 
   const float *roi_half = sv.take<float>((size_t)B * hw);
   dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B);
   cudaStream_t s = (cudaStream_t)stream;
-  if (C == 21 && W % 4 == 0) {
+  const uintptr_t io_bits = (uintptr_t)logit | (uintptr_t)grad_logit;
+  const bool al8 = io_bits % 8 == 0, al16 = io_bits % 16 == 0;
+  if (C == 21 && W % 4 == 0 && al16) {
     const long long threads = (long long)B * H * (W / 4);
     COSA_LAUNCH(energy_logit_grad_reg_kernel<21>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
                 roi_half, grad_out, weight, grad_logit, B, H, W);
-  } else if (C == 81) {
+  } else if (C == 81 && al8) {
     const long long threads = (long long)B * H * (W / 2);
     COSA_LAUNCH(energy_logit_grad_pair_kernel<81>, (unsigned)ceil_div_ll(threads, 128), 128, 0, s, logit, as_saved,
                 roi_half, grad_out, weight, grad_logit, B, H, W);
-  } else if (W % 4 == 0) {
+  } else if (W % 4 == 0 && al16) {
     const long long threads = (long long)B * H * (W / 4);
     COSA_LAUNCH(energy_logit_grad_vec_kernel, grid1d(threads), 256, 0, s, logit, as_saved, roi_half, grad_out, weight,
                 grad_logit, B, C, H, W);

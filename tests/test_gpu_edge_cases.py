@@ -493,3 +493,31 @@ def test_cam2mask_class_budget(cosa):
         over = cosa.cam2mask(refine_model=refine, max_classes=2, **kw)          # three classes present, budget two
         assert bool(torch.isnan(over).all())
         assert torch.equal(cosa.cam2mask(refine_model=refine, **kw), want)       # the next call is unaffected
+
+
+@pytest.mark.parametrize("C", [21, 81, 5])
+def test_energy_loss_on_unaligned_tensor_views(cosa, C):
+    """Tensor views that start at an odd element (4-byte aligned only): the vectorised energy kernels read 8 / 16 bytes
+    at a time, so the dispatch must fall back to the scalar kernels - same loss and gradient as on aligned copies."""
+    d = to_cuda(batch(B=2, C=C, H=64, W=96, n_fg=2, seed=311))
+    label = cosa.cam_to_label(d["cams"], d["cls_label"], img_box=d["img_box"], bkg_thre=0.35, high_thre=0.55,
+                              low_thre=0.35, ignore_mid=True, ignore_index=255)[1].float()
+
+    def off1(t):                      # the same values, one float past a 256-byte aligned allocation
+        buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.is_contiguous() and v.data_ptr() % 8 == 4
+        return v
+
+    def run(simg, logits, lab):
+        layer = cosa.DenseEnergyLoss(weight=1e-7, sigma_rgb=15, sigma_xy=100, scale_factor=0.5)
+        logit = logits.detach().requires_grad_(True)
+        loss = cosa.get_energy_loss(img=simg, logit=logit, label=lab, img_box=d["img_box"], loss_layer=layer)
+        loss.backward()
+        return loss.detach(), logit.grad
+
+    loss0, grad0 = run(d["simg"], d["logits"], label)
+    loss1, grad1 = run(off1(d["simg"]), off1(d["logits"]), off1(label))
+    assert_close(loss1, loss0, "loss on unaligned views", tol=1e-5)
+    assert_close(grad1, grad0, "gradient on unaligned views", tol=1e-5)
