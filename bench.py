@@ -522,7 +522,7 @@ def run_cosa_arm(args):
     if top["kernel"] in ("par_iterate_tile_kernel", "par_chain_kernel"):
         # The PAR step is bound on the SM side, not by HBM: every FMA consumes one neighbour value
         # through the 128 B/clk shared-memory / L1 load path.  Bytes through that path per launch: per pixel and moved
-        # channel 50 LDS.128 per quad (200 B), plus the 48 affinity quads (192 B per pixel) once per CTA of a tile
+        # channel 45 LDS.128 per quad (180 B), plus the 48 affinity quads (192 B per pixel) once per CTA of a tile
         # (two CTAs share a tile's channels).  Peak = SMs x 128 B/clk x the SM clock seen during the run.
         h2, w2 = H // 2, W // 2
         ncm = 2 * nc if os.environ.get("COSA_CAM2MASK_ALL_CHANNELS") else 2 * (nc - 1)
@@ -530,14 +530,14 @@ def run_cosa_arm(args):
             n_groups, steps_in_launch = (ncm + 3) // 4, NUM_ITER / max(1.0, top["launches_per_step"])
         else:                                                  # channel groups of a tile: each loads the affinity quads
             n_groups, steps_in_launch = (1 if ncm <= 3 else 2 * ((ncm + 5) // 6)), 1
-        lsu_bytes = int(B * h2 * w2 * (ncm * 200 + n_groups * 192) * steps_in_launch)
+        lsu_bytes = int(B * h2 * w2 * (ncm * 180 + n_groups * 192) * steps_in_launch)
         sm_mhz = (clocks.summary_peek() or {}).get("sm_mhz") or 1965.0
         lsu_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128 * sm_mhz * 1e6 / 1e9
         lsu_gbs = lsu_bytes / 1e9 / (top["avg_ms"] / 1e3)
         roofline["secondary"] = {"bound": "shared-memory / L1 load path (LSU)", "achieved": round(lsu_gbs, 1),
                                  "peak": round(lsu_peak, 1), "unit": "GB/s", "frac": round(lsu_gbs / lsu_peak, 4),
                                  "bytes_per_launch": lsu_bytes,
-                                 "note": "per pixel: 200 B of mask quads per moved channel + 192 B of affinity quads per "
+                                 "note": "per pixel: 180 B of mask quads per moved channel + 192 B of affinity quads per "
                                          "channel group of its tile, per propagation step; peak = SMs x 128 B/clk x SM clock"}
 
     # ---- end to end through the host-buffer API (cosa_b200.HostPipeline): pinned host tensors in, labels + loss in

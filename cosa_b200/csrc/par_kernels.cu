@@ -530,6 +530,50 @@ __device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&
   }
 }
 
+// Rows -D and +D of dilation D (plane group a[0..5] = (-,-) (-,0) (-,+) (+,-) (+,0) (+,+)); D = 1, 2, 4.
+// WAIT: channel k's tile is awaited right before its first use (the first group of a pass).
+template <int D, int CH, bool WAIT>
+__device__ __forceinline__ void tile_rows(float4 (&acc)[CH], const float4 (&a)[8], const float *q, int live,
+                                          unsigned long long *bars, unsigned phase) {
+  constexpr int R = D * kFS;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < live) {
+      if constexpr (WAIT) mbar_wait(&bars[k], phase);
+      const float *p = q + k * (kFS * kFS);
+      if constexpr (D == 4) {
+        fma4(acc[k], a[0], lds4(p - R - 4)); fma4(acc[k], a[1], lds4(p - R)); fma4(acc[k], a[2], lds4(p - R + 4));
+        fma4(acc[k], a[3], lds4(p + R - 4)); fma4(acc[k], a[4], lds4(p + R)); fma4(acc[k], a[5], lds4(p + R + 4));
+      } else {
+        float4 m, pl, C;
+        C = lds4(p - R); shifted_quads(lds4(p - R - 4), C, lds4(p - R + 4), D, m, pl);
+        fma4(acc[k], a[0], m); fma4(acc[k], a[1], C); fma4(acc[k], a[2], pl);
+        C = lds4(p + R); shifted_quads(lds4(p + R - 4), C, lds4(p + R + 4), D, m, pl);
+        fma4(acc[k], a[3], m); fma4(acc[k], a[4], C); fma4(acc[k], a[5], pl);
+      }
+    }
+  }
+}
+
+// The centre-row taps of d = 1, 2, 4 (plane group a[0..5] = d1 (0,-) (0,+), d2 (0,-) (0,+), d4 (0,-) (0,+)) from ONE
+// read of the aligned quads p - 4, p, p + 4.
+template <int CH>
+__device__ __forceinline__ void tile_centre(float4 (&acc)[CH], const float4 (&a)[8], const float *q, int live) {
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    if (k < live) {
+      const float *p = q + k * (kFS * kFS);
+      const float4 L = lds4(p - 4), C = lds4(p), Rr = lds4(p + 4);
+      float4 m, pl;
+      shifted_quads(L, C, Rr, 1, m, pl);
+      fma4(acc[k], a[0], m); fma4(acc[k], a[1], pl);
+      shifted_quads(L, C, Rr, 2, m, pl);
+      fma4(acc[k], a[2], m); fma4(acc[k], a[3], pl);
+      fma4(acc[k], a[4], L); fma4(acc[k], a[5], Rr);
+    }
+  }
+}
+
 // Tile-permuted affinity layout of the tile step kernels: [B][48][tiles][8 warps][4 j][32 lanes], the value of pixel
 // (4 tq + j, 4 wi + r) of a 32 x 32 tile at wi*128 + j*32 + (r*8 + tq) - the j-th pixel of the quad that lane r*8 + tq
 // of warp wi owns.  A warp then fetches one neighbour plane of its 32 quads with FOUR fully coalesced 128-byte
@@ -539,17 +583,30 @@ __device__ __forceinline__ void tile_dilation(float4 (&acc)[CH], const float4 (&
 __host__ __device__ __forceinline__ int aff_tile_offset(int px, int py) {
   return (py >> 2) * 128 + (px & 3) * 32 + (py & 3) * 8 + (px >> 2);
 }
+// Plane order of the tile-permuted layout: the neighbour (8 * dilation + direction, PAR.py:10-24) stored in plane m.
+// The centre-row taps (0, -d) and (0, +d) of d = 1, 2, 4 all read the aligned quads p - 4, p, p + 4 of the mask tile, so
+// they form a group of their own and those three loads are made once instead of three times (45 instead of 50
+// shared-memory loads per pixel quad and channel):
+//   planes  0.. 5  d = 1, rows -1 / +1     6..11  d = 2, rows -2 / +2     12..17  d = 4, rows -4 / +4
+//   planes 18..23  the centre-row taps of d = 1, 2, 4                      24..47  d = 8, 12, 24 in neighbour order
+__host__ __device__ constexpr int aff_plane_neighbour(int m) {
+  return m >= 24 ? m
+         : m >= 18 ? 8 * ((m - 18) >> 1) + 3 + ((m - 18) & 1)
+                   : 8 * (m / 6) + (m % 6 < 3 ? m % 6 : m % 6 + 2);
+}
+
 __device__ __forceinline__ float ldg_stream1(const float *p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 
-// the 8 affinity quads of one dilation; A (this lane's slot in the tile-permuted plane) walks through the planes
-// with one live 64-bit address instead of 48
-__device__ __forceinline__ void load_aff8(float4 (&a)[8], const float *&A, size_t plane) {
+// the affinity quads of one plane group (N = 6 or 8 planes); A (this lane's slot in the tile-permuted plane) walks
+// through the planes with one live 64-bit address instead of 48
+template <int N>
+__device__ __forceinline__ void load_aff(float4 (&a)[8], const float *&A, size_t plane) {
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
+  for (int m = 0; m < N; ++m) {
     a[m] = make_float4(ldg_stream1(A), ldg_stream1(A + 32), ldg_stream1(A + 64), ldg_stream1(A + 96));
     // opaque increment: keeps ptxas from materialising (and spilling) all 48 plane addresses up front
     asm volatile("add.u64 %0, %0, %1;" : "+l"(A) : "l"(plane * sizeof(float)));
@@ -724,7 +781,8 @@ __global__ void __launch_bounds__(256, 2)
                                   (kTileW * kTileH) + aff_tile_offset(tx, yl)
                       : aff + (size_t)b * ND * plane + (size_t)y * w + x;
 #pragma unroll
-    for (int n = 0; n < ND; ++n) {
+    for (int m = 0; m < ND; ++m) {
+      const int n = PERM ? aff_plane_neighbour(m) : m;   // PERM: planes in the order the tile step kernels consume them
       *out = fmaf(logit[n], rden, pc.pos_term[n]);
       // walk the planes with one opaque 64-bit add: `out[n * plane]` costs a wide multiply and four more integer
       // instructions per store in a kernel that is bound by instruction issue
@@ -741,29 +799,33 @@ __device__ __forceinline__ void tile_pass(float4 (&acc)[CH], const float *A, siz
 #pragma unroll
   for (int k = 0; k < CH; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 a0[8], a1[8];
-  load_aff8(a0, A, plane);   // d = 1
-  load_aff8(a1, A, plane);   // d = 2 (in flight together with d = 1: the first wait drains both)
-  prefetch_aff8(A, plane);               // d = 4
-  prefetch_aff8(A + 8 * plane, plane);   // d = 8
+  load_aff<6>(a0, A, plane);   // rows of d = 1
+  load_aff<6>(a1, A, plane);   // rows of d = 2 (in flight together with the first group: the first wait drains both)
+  prefetch_aff8(A, plane);                // planes 12..19
+  prefetch_aff8(A + 8 * plane, plane);    // planes 20..27
   if (r_lo > 0 || r_hi < kFS) {   // top / bottom tiles: every channel must have landed before the border rows are repaired
     for (int k = 0; k < live; ++k) mbar_wait(&bars[k], phase);
     replicate_border_rows(s_tile, live, r_lo, r_hi);
   }
-  tile_dilation<1, CH, true>(acc, a0, q, live, bars, phase);
-  load_aff8(a0, A, plane);   // d = 4: nothing else is in flight
-  prefetch_aff8(A + 8 * plane, plane);   // d = 12
-  tile_dilation<2, CH>(acc, a1, q, live);
+  tile_rows<1, CH, true>(acc, a0, q, live, bars, phase);
+  load_aff<6>(a0, A, plane);   // rows of d = 4: nothing else is in flight
+  prefetch_aff8(A + 10 * plane, plane);   // planes 28..35
+  tile_rows<2, CH, false>(acc, a1, q, live, bars, phase);
   A = issue_after<CH>(A, a0[0], acc);
-  load_aff8(a1, A, plane);   // d = 8
-  prefetch_aff8(A + 8 * plane, plane);   // d = 24
-  tile_dilation<4, CH>(acc, a0, q, live);
+  load_aff<6>(a1, A, plane);   // centre taps of d = 1, 2, 4
+  prefetch_aff8(A + 12 * plane, plane);   // planes 36..43
+  tile_rows<4, CH, false>(acc, a0, q, live, bars, phase);
   A = issue_after<CH>(A, a1[0], acc);
-  load_aff8(a0, A, plane);   // d = 12
-  tile_dilation<8, CH>(acc, a1, q, live);
+  load_aff<8>(a0, A, plane);   // d = 8
+  prefetch_aff8(A + 12 * plane, plane);   // planes 44..47 (the lanes beyond request the next image's first planes)
+  tile_centre<CH>(acc, a1, q, live);
   A = issue_after<CH>(A, a0[0], acc);
-  load_aff8(a1, A, plane);   // d = 24
-  tile_dilation<12, CH>(acc, a0, q, live);
-  tile_dilation<24, CH>(acc, a1, q, live);
+  load_aff<8>(a1, A, plane);   // d = 12
+  tile_dilation<8, CH>(acc, a0, q, live);
+  A = issue_after<CH>(A, a1[0], acc);
+  load_aff<8>(a0, A, plane);   // d = 24
+  tile_dilation<12, CH>(acc, a1, q, live);
+  tile_dilation<24, CH>(acc, a0, q, live);
 }
 
 // one thread: stage `live` channel tiles (planes gz .. gz + live - 1, origin (gx, gy)), one TMA box and barrier each
