@@ -54,10 +54,11 @@ int cosa_par_forward(const float *imgs, const float *masks_in, float *masks_out,
                      int hm, int wm, const int *dilations, int n_dil, int num_iter, void *ws, size_t ws_bytes,
                      void *stream);
 /* Selects the propagation kernel used by cosa_par_forward / cosa_cam2mask from now on (process-wide, meant for A/B
- * runs and tests; results are identical, only the launch structure differs): "tile" (default; TMA-staged 32x32 tiles,
- * one launch per step, steps 2..T as programmatic dependent launches), "coop" (persistent kernel, ALL steps in one
- * cooperative launch with grid barriers), "smem" (the generic per-step kernel that non-reference dilation sets use).
- * Returns COSA_E_ARG for an unknown name. */
+ * runs and tests; the results agree to the rounding of the fp32 sums): "chain" (default: ALL num_iter steps in ONE
+ * launch - one CTA per step x image tile, tile-level step counters in the workspace instead of grid barriers;
+ * "chain<G>" fixes the number of images per group), "tile" (one launch per step, steps 2..T as programmatic dependent
+ * launches), "smem" (the generic per-step kernel that non-reference dilation sets use).  Returns COSA_E_ARG for an
+ * unknown name. */
 int cosa_par_set_step_mode(const char *name);
 
 /* The affinity alone, [B, 8*n_dil, h, w] (PAR.py:69-85); used by tests and by cam2mask internally. */

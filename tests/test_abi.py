@@ -146,3 +146,21 @@ def test_synthetic_batch_is_seeded_and_shaped():
     assert a["cams"].shape == (2, 20, 64, 64) and a["logits"].shape == (2, 21, 64, 64)
     assert a["cls_label"].sum(1).tolist() == [2.0, 2.0]
     assert float(a["img_denorm"].max()) <= 1.0 and a["img_box"].dtype == torch.int16
+
+
+def test_par_step_mode_switch_and_prebuild_policy():
+    """cosa_par_set_step_mode is host-only: the names, the error for an unknown one, and the policy that follows the
+    mode (where a step starts the second-stream lattice build)."""
+    import cosa_b200
+    from cosa_b200 import par as par_mod
+    assert par_mod.step_mode() == "chain" and par_mod.lattice_prebuild_before_cam2mask() is False
+    try:
+        for name in ("tile", "smem", "chain16", "chain"):
+            par_mod.set_step_mode(name)
+            assert par_mod.step_mode() == name
+            assert par_mod.lattice_prebuild_before_cam2mask() is (name == "tile")
+        with pytest.raises(cosa_b200._lib.CosaError):
+            par_mod.set_step_mode("nonsense")
+        assert par_mod.step_mode() == "chain"          # a refused name changes nothing
+    finally:
+        par_mod.set_step_mode("chain")
