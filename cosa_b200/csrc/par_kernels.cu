@@ -618,10 +618,10 @@ __device__ __forceinline__ void load_aff(float4 (&a)[8], const float *&A, size_t
 // that uses them (register pressure), so without this every dilation starts with a DRAM round trip (chain kernel:
 // 0.757 -> 0.724 ms for the ten steps).
 // A = this lane's slot in the first plane of that dilation.
-__device__ __forceinline__ void prefetch_aff8(const float *A, size_t plane) {
+__device__ __forceinline__ void prefetch_aff8(const float *A, size_t plane, int n_planes = 8) {
   const int lane = threadIdx.x & 31;
   const float *p = A - lane + (size_t)(lane >> 2) * plane + (lane & 3) * 32;
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if ((lane >> 2) < n_planes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Orders the refill of one affinity register set behind (a) the arrival of the OTHER set and (b) the end of the
@@ -817,7 +817,7 @@ __device__ __forceinline__ void tile_pass(float4 (&acc)[CH], const float *A, siz
   tile_rows<4, CH, false>(acc, a0, q, live, bars, phase);
   A = issue_after<CH>(A, a1[0], acc);
   load_aff<8>(a0, A, plane);   // d = 8
-  prefetch_aff8(A + 12 * plane, plane);   // planes 44..47 (the lanes beyond request the next image's first planes)
+  prefetch_aff8(A + 12 * plane, plane, 4);   // planes 44..47: the last ones of this image
   tile_centre<CH>(acc, a1, q, live);
   A = issue_after<CH>(A, a0[0], acc);
   load_aff<8>(a1, A, plane);   // d = 12
