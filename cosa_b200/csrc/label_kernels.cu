@@ -586,6 +586,55 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_kernel(const float *__r
   if (label_lo_out) label_lo_out[out_idx] = lo;
 }
 
+// The two stacks of one 2 x 2 output block: per stack the argmax over the channels of the bilinearly enlarged values.
+// NC > 0: the channel count as a compile-time constant - the loop unrolls, every channel's nine loads are issued up
+// front and ptxas schedules across channels (the generic loop waited on its loads channel by channel: 42 % of the
+// kernel's stalls); NC = 0: run-time count.  DERIVE: the last channel of a stack is total - (sum of the others).
+template <int NC, bool DERIVE>
+__device__ __forceinline__ void finalize_stacks(const float *st, size_t mplane, int nc_rt, const int (&off)[3][3],
+                                                const Tap (&ty)[2], const Tap (&tx)[2], float derive_total,
+                                                int (&arg_hi)[2][2], int (&arg_lo)[2][2]) {
+  const int nc = NC ? NC : nc_rt;
+  const int nload = DERIVE ? nc - 1 : nc;            // channels of a stack that exist in memory
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {                       // high stack, low stack
+    const float *stack = st + (size_t)s * nload * mplane;
+    float best[2][2];
+    int arg[2][2] = {{0, 0}, {0, 0}};
+    float sum[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll(NC ? NC : 1)
+    for (int j = 0; j < nc; ++j) {
+      const float *p = stack + (size_t)j * mplane;
+      float v[3][3];
+      if (DERIVE && j == nc - 1) {   // the channel that was not propagated
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) v[a][e] = derive_total - sum[a][e];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            v[a][e] = __ldg(p + off[a][e]);
+            sum[a][e] += v[a][e];
+          }
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float val = bilerp_up(ty[dy], tx[dx], v[dy][dx], v[dy][dx + 1], v[dy + 1][dx], v[dy + 1][dx + 1]);
+          if (j == 0 || val > best[dy][dx]) { best[dy][dx] = val; arg[dy][dx] = j; }
+        }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) (s == 0 ? arg_hi : arg_lo)[dy][dx] = arg[dy][dx];
+  }
+}
+
 // Exact 2x enlargement (H = 2h, W = 2w): one thread per half-resolution cell produces the 2x2 block of labels
 // from ONE 3x3 neighbourhood per channel (9 loads instead of 16, index arithmetic shared by the four outputs).
 // Output row 2y' interpolates source rows (y'-1, y'), row 2y'+1 rows (y', y'+1); the weights come from the same
@@ -629,44 +678,33 @@ __global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *
     const size_t r[3] = {(size_t)max(ys - 1, 0) * ml.pitch, (size_t)ys * ml.pitch, (size_t)min(ys + 1, g.h - 1) * ml.pitch};
     const int c[3] = {max(xs - 1, 0), xs, min(xs + 1, g.w - 1)};
     const float *st = refined + (size_t)b * cstride * mplane + ml.off;
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {                       // high stack, low stack
-      const bool derive = derive_total > 0.0f;
-      const float *stack = st + (size_t)s * (derive ? nc - 1 : nc) * mplane;
-      float best[2][2];
-      int arg[2][2] = {{0, 0}, {0, 0}};
-      float sum[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      for (int j = 0; j < nc; ++j) {
-        const float *p = stack + (size_t)j * mplane;
-        float v[3][3];
-        if (derive && j == nc - 1) {   // the channel that was not propagated: total - (sum of the others)
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int e = 0; e < 3; ++e) v[a][e] = derive_total - sum[a][e];
-        } else {
-#pragma unroll
-          for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-              v[a][e] = __ldg(p + r[a] + c[e]);
-              sum[a][e] += v[a][e];
-            }
-        }
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const float val = bilerp_up(ty[dy], tx[dx], v[dy][dx], v[dy][dx + 1], v[dy + 1][dx], v[dy + 1][dx + 1]);
-            if (j == 0 || val > best[dy][dx]) { best[dy][dx] = val; arg[dy][dx] = j; }
-          }
+    const int off[3][3] = {{(int)r[0] + c[0], (int)r[0] + c[1], (int)r[0] + c[2]},
+                           {(int)r[1] + c[0], (int)r[1] + c[1], (int)r[1] + c[2]},
+                           {(int)r[2] + c[0], (int)r[2] + c[1], (int)r[2] + c[2]}};
+    int arg_hi[2][2], arg_lo[2][2];
+    if (derive_total > 0.0f) {
+      switch (nc) {
+        case 2: finalize_stacks<2, true>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        case 3: finalize_stacks<3, true>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        case 4: finalize_stacks<4, true>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        default: finalize_stacks<0, true>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo);
       }
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx)
-          if (in[dy][dx]) (s == 0 ? hi : lo)[dy][dx] = (float)key[arg[dy][dx]];
+    } else {
+      switch (nc) {
+        case 2: finalize_stacks<2, false>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        case 3: finalize_stacks<3, false>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        case 4: finalize_stacks<4, false>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo); break;
+        default: finalize_stacks<0, false>(st, mplane, nc, off, ty, tx, derive_total, arg_hi, arg_lo);
+      }
     }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        if (in[dy][dx]) {
+          hi[dy][dx] = (float)key[arg_hi[dy][dx]];
+          lo[dy][dx] = (float)key[arg_lo[dy][dx]];
+        }
   }
   const bool poisoned = *err != 0;      // class budget exceeded: fail loudly
 #pragma unroll
