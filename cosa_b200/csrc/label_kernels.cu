@@ -639,7 +639,7 @@ __device__ __forceinline__ void finalize_stacks(const float *st, size_t mplane, 
 // from ONE 3x3 neighbourhood per channel (9 loads instead of 16, index arithmetic shared by the four outputs).
 // Output row 2y' interpolates source rows (y'-1, y'), row 2y'+1 rows (y', y'+1); the weights come from the same
 // tap function as the general kernel (at the borders they degenerate to (1, 0), so clamped loads are exact).
-__global__ void __launch_bounds__(256) cam2mask_finalize_x2_kernel(const float *__restrict__ refined,
+__global__ void __launch_bounds__(256, 4) cam2mask_finalize_x2_kernel(const float *__restrict__ refined,
                                                                    const int *__restrict__ keys,
                                                                    const int *__restrict__ nc_dev,
                                                                    const int *__restrict__ boxes,
