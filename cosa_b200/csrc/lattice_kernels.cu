@@ -207,7 +207,7 @@ __device__ __forceinline__ void point_features(float f[D], const float *img, int
 constexpr int kPairFirst = 1 << 11;    // plist code: (pixel in tile << 3) | r, bit 11 = first pair of its vertex
 
 template <int D>
-__global__ void __launch_bounds__(kTilePix) lattice_tile_build_kernel(LatticeBufs L, const float *__restrict__ images,
+__global__ void __launch_bounds__(kTilePix, 5) lattice_tile_build_kernel(LatticeBufs L, const float *__restrict__ images,
                                                                       EmbedConst ec, int H, int W, int n_pad,
                                                                       float sigmargb, float sigmaxy) {
   constexpr int kLatD = D;                           // (shadows the path's default inside this kernel)
