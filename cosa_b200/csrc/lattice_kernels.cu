@@ -472,7 +472,8 @@ __global__ void lattice_zero_values_kernel(LatticeBufs L) {
     v0[i] = z;
 }
 
-constexpr int kChunk = 24;                       // channels per pass (K = 21 -> one pass)
+constexpr int kChunk = 24;                       // channels per pass of the K = 21 instantiations (one pass)
+constexpr int kChunkWide = 28;                   // ... of the run-time-K instantiations (K = 81 -> 84 = three passes)
 constexpr int kPlane = kTilePix + 1;             // odd plane pitch: channel-strided reads hit distinct banks
 
 // Splat (permutohedral.cpp:526-534), one CTA per tile.  The tile's pair list (bucketed by vertex in the build), the
@@ -480,15 +481,15 @@ constexpr int kPlane = kTilePix + 1;             // odd plane pitch: channel-str
 // kPairBlock consecutive pairs of the list - the same amount of work whatever the vertex degrees - and lane cl sums
 // channels cl, cl + 8, cl + 16; a quarter-warp flushes its partial sum with one reduction per vertex row whenever the
 // list moves on to the next vertex (kPairFirst).  KT > 0: compile-time channel count (one pass); 0: run-time K.
-template <int KT, int D>
+template <int KT, int D, int CHUNK>
 __global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBufs L, const float *__restrict__ ins,
                                                                       int Krt, int H, int W) {
-  static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
+  static_assert(KT <= CHUNK, "a compile-time channel count must fit one pass");
   constexpr int kLatD = D;
   constexpr int kTilePairs = tile_pairs(D), kPairBlock = pair_block(D), kTileListStride = list_stride(D);
   extern __shared__ __align__(16) unsigned char s_raw[];
-  float *in_s = reinterpret_cast<float *>(s_raw);                         // [kChunk][kPlane]
-  float *bary_s = in_s + kChunk * kPlane;                                 // [D + 1][256]
+  float *in_s = reinterpret_cast<float *>(s_raw);                         // [CHUNK][kPlane]
+  float *bary_s = in_s + CHUNK * kPlane;                                 // [D + 1][256]
   int *vid_s = reinterpret_cast<int *>(bary_s + (D + 1) * kTilePix);      // [kTilePairs]
   unsigned short *plist_s = reinterpret_cast<unsigned short *>(vid_s + kTilePairs);   // [kTileListStride], 16-byte aligned
 
@@ -515,31 +516,34 @@ __global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBuf
   const int j = ly * 4 + sub;                     // this quarter-warp's block of the pair list
   const int e0 = j * kPairBlock, e1 = min(e0 + kPairBlock, pairs);
   const float *src0 = ins + (size_t)b * K * n + (size_t)y * W + x;
-  for (int c0 = 0; c0 < Kp; c0 += kChunk) {
-    const int kc = min(kChunk, Kp - c0);
+  for (int c0 = 0; c0 < Kp; c0 += CHUNK) {
+    const int kc = min(CHUNK, Kp - c0);
     if (c0) __syncthreads();   // the previous pass has read in_s
     {
-      float v[kChunk];
+      float v[CHUNK];
       const float *sp = src0 + (size_t)c0 * n;
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) {
+      for (int c = 0; c < CHUNK; ++c) {
         v[c] = (ok && c0 + c < K) ? __ldg(sp) : 0.0f;
         sp += n;
       }
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) in_s[c * kPlane + tid] = v[c];
+      for (int c = 0; c < CHUNK; ++c) in_s[c * kPlane + tid] = v[c];
     }
     __syncthreads();
     if (e0 < e1) {
       int u = plist_s[kTilePairs + j];
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+      constexpr int NA = (CHUNK + 7) / 8;      // channels cl, cl + 8, ... of the pass
+      float acc[NA];
+#pragma unroll
+      for (int i = 0; i < NA; ++i) acc[i] = 0.0f;
       auto flush = [&]() {
         const int vid = vid_s[u];
         if (vid > 0) {
           float *dst = L.val0 + (size_t)vid * Kp + c0 + cl;
-          if (cl < kc) atomicAdd(dst, a0);
-          if (cl + 8 < kc) atomicAdd(dst + 8, a1);
-          if (cl + 16 < kc) atomicAdd(dst + 16, a2);
+#pragma unroll
+          for (int i = 0; i < NA; ++i)
+            if (cl + 8 * i < kc) atomicAdd(dst + 8 * i, acc[i]);
         }
       };
       const float *inl = in_s + cl * kPlane;
@@ -549,13 +553,14 @@ __global__ void __launch_bounds__(kTilePix) lattice_splat_tile_kernel(LatticeBuf
         if ((code & kPairFirst) && e != e0) {
           flush();
           ++u;
-          a0 = a1 = a2 = 0.0f;
+#pragma unroll
+          for (int i = 0; i < NA; ++i) acc[i] = 0.0f;
         }
         const int pix = (code >> 3) & 0xff;
         const float wv = bary_s[(code & 7) * kTilePix + pix];
-        a0 = fmaf(wv, inl[pix], a0);
-        a1 = fmaf(wv, inl[8 * kPlane + pix], a1);
-        a2 = fmaf(wv, inl[16 * kPlane + pix], a2);
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+          if (8 * i + 7 < CHUNK || cl + 8 * i < CHUNK) acc[i] = fmaf(wv, inl[8 * i * kPlane + pix], acc[i]);
       }
       flush();
     }
@@ -593,8 +598,8 @@ __global__ void __launch_bounds__(256) lattice_blur_kernel(LatticeBufs L, const 
 // in shared memory once per channel pass and the pixels gather from there through their 16-bit list indices.
 // KT > 0: compile-time channel count; 0: run-time K.
 constexpr int kSliceRows = 512;
-constexpr int kRowPitch = kChunk + 4;             // 28 floats: row starts fall on 8 different bank quads
-template <bool ENERGY, int KT, int D>
+constexpr int kRowPitch = 28;                     // >= both chunk sizes; 7 quads: row starts fall on 8 different bank quads
+template <bool ENERGY, int KT, int D, int CHUNK>
 __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(LatticeBufs L, const float *__restrict__ values,
                                                                          const float *__restrict__ ins,
                                                                          const float *__restrict__ gate, double *loss_acc,
@@ -603,7 +608,7 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
   float *rows = reinterpret_cast<float *>(s_raw);   // [kSliceRows][kRowPitch]
   __shared__ int vid_s[kSliceRows];
   __shared__ float s_part[kTilePix / 32];
-  static_assert(KT <= kChunk, "a compile-time channel count must fit one pass");
+  static_assert(KT <= CHUNK, "a compile-time channel count must fit one pass");
   constexpr int kLatD = D;
   constexpr int KQ = KT ? (KT + 3) / 4 : 1;       // row quads per vertex (compile-time form of kq)
   const int K = KT ? KT : Krt, Kp = (K + 3) & ~3;
@@ -632,8 +637,8 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
   const float gt = (ENERGY && ok) ? __ldg(gate + gp) : 1.0f;
   const size_t at0 = (size_t)b * K * n + (size_t)y * W + x;
   float local = 0.0f;
-  for (int c0 = 0; c0 < Kp; c0 += kChunk) {
-    const int kc = min(kChunk, Kp - c0), kq = kc >> 2;
+  for (int c0 = 0; c0 < Kp; c0 += CHUNK) {
+    const int kc = min(CHUNK, Kp - c0), kq = kc >> 2;
     __syncthreads();                     // vid_s is complete / the previous pass has read `rows`
     for (int i0 = tid; i0 < Us * kq; i0 += 4 * kTilePix) {   // four row quads in flight per thread
       float4 v[4];
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(kTilePix, 3) lattice_slice_tile_kernel(Lattice
           if (c0 + k < K) nxt[k] = __ldg(ip + (size_t)k * n);
       }
 #pragma unroll
-      for (int q = 0; q < kChunk / 4; ++q) {
+      for (int q = 0; q < CHUNK / 4; ++q) {
         if (q >= kq) break;
         float cur[4];
 #pragma unroll
@@ -836,8 +841,8 @@ int lattice_build(const LatticeBufs &L, const float *images, int N, int H, int W
   return 0;
 }
 
-static size_t splat_smem_bytes(int d) {
-  return (size_t)kChunk * kPlane * 4 + (size_t)(d + 1) * kTilePix * 4 + (size_t)tile_pairs(d) * 4 +
+static size_t splat_smem_bytes(int d, int chunk) {
+  return (size_t)chunk * kPlane * 4 + (size_t)(d + 1) * kTilePix * 4 + (size_t)tile_pairs(d) * 4 +
          (size_t)list_stride(d) * 2;
 }
 
@@ -846,13 +851,13 @@ int lattice_splat_blur(const LatticeBufs &L, const float *ins, int N, int K, int
   COSA_LAUNCH(lattice_zero_values_kernel, sm_count() * 8, 256, 0, stream, L);
   const dim3 grid(L.tiles_x, L.tiles_y, N);
   if (L.d == 2) {
-    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 2>), grid, kTilePix, splat_smem_bytes(2),
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 2, kChunkWide>), grid, kTilePix, splat_smem_bytes(2, kChunkWide),
                   stream, L, ins, K, H, W);
   } else if (K == 21) {
-    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<21, 5>), grid, kTilePix, splat_smem_bytes(5),
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<21, 5, kChunk>), grid, kTilePix, splat_smem_bytes(5, kChunk),
                   stream, L, ins, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 5>), grid, kTilePix, splat_smem_bytes(5),
+    COSA_LAUNCH_T("lattice_splat_tile_kernel", (lattice_splat_tile_kernel<0, 5, kChunkWide>), grid, kTilePix, splat_smem_bytes(5, kChunkWide),
                   stream, L, ins, K, H, W);
   }
   float *src = L.val0, *dst = L.val1;
@@ -872,10 +877,10 @@ int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, dou
   COSA_CUDA(cudaGetDevice(&dev));
   const unsigned long long bit = 1ULL << (dev & 63);
   if (dev >= 64 || !(attr_done.load(std::memory_order_acquire) & bit)) {
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 21, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 21, 5, kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<true, 0, 5, kChunkWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 5, kChunkWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    COSA_CUDA(cudaFuncSetAttribute(lattice_slice_tile_kernel<false, 0, 2, kChunkWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (dev < 64) attr_done.fetch_or(bit, std::memory_order_release);
   }
   const dim3 grid(L.tiles_x, L.tiles_y, N);
@@ -883,16 +888,16 @@ int lattice_slice(const LatticeBufs &L, const float *ins, const float *gate, dou
   const float *values = ((L.d + 1) & 1) ? L.val1 : L.val0;
   if (L.d == 2) {
     if (gate) return COSA_E_ARG;   // the energy epilogue belongs to the bilateral (d = 5) filter
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 2>), grid, kTilePix, smem, stream, L,
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 2, kChunkWide>), grid, kTilePix, smem, stream, L,
                   values, ins, gate, loss_acc, outs, K, H, W);
   } else if (gate && K == 21) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 21, 5>), grid, kTilePix, smem, stream, L,
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 21, 5, kChunk>), grid, kTilePix, smem, stream, L,
                   values, ins, gate, loss_acc, outs, K, H, W);
   } else if (gate) {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 0, 5>), grid, kTilePix, smem, stream, L,
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<true, 0, 5, kChunkWide>), grid, kTilePix, smem, stream, L,
                   values, ins, gate, loss_acc, outs, K, H, W);
   } else {
-    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 5>), grid, kTilePix, smem, stream, L,
+    COSA_LAUNCH_T("lattice_slice_tile_kernel", (lattice_slice_tile_kernel<false, 0, 5, kChunkWide>), grid, kTilePix, smem, stream, L,
                   values, ins, gate, loss_acc, outs, K, H, W);
   }
   return 0;
