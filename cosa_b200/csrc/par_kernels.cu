@@ -1323,7 +1323,6 @@ using namespace cosa;
 // scratch: affinity [B,8*n_dil,h,w] + two mask buffers in the widest layout cosa_par_forward uses
 // (column pads of at most 24: wider dilations take the plain layout and the generic kernel)
 extern "C" size_t cosa_par_ws_bytes(int B, int C, int h, int w, int n_dil) {
-  const size_t plane = (size_t)h * w;
   const size_t pitch = (size_t)max_padded_pitch(w);
   return align_up(par_affinity_floats(B, n_dil, h, w) * sizeof(float), 256) +
          2 * align_up((size_t)B * C * h * pitch * sizeof(float), 256) + align_up(par_tile_flag_ints(B, h, w) * sizeof(int), 256);
