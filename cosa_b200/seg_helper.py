@@ -15,6 +15,7 @@ kernels of ``csrc/`` through the C-ABI (``include/cosa_b200.h``).  Inputs must b
 """
 import ctypes
 import os
+import warnings
 
 import torch
 import torch.nn.functional as F
@@ -280,6 +281,9 @@ def cam2mask(
     b, _, h, w = images.shape
     c1 = cams.shape[1]
     if generic:
+        _warn_once("cam2mask", "cosa_b200.cam2mask: refine_model is %s, not cosa_b200.PAR - the reference's per-image "
+                               "control flow in torch ops is used around it (the fused sm_100a kernels serve "
+                               "cosa_b200.PAR and refine_model=None)" % type(refine_model).__name__)
         return _cam2mask_generic(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model,
                                  ignore_index, downscale)
     use_par = isinstance(refine_model, PAR)
@@ -337,6 +341,16 @@ def _refine_cams(refine_model, images, cams, valid_key, orig_size):
         _lib.check(lib.cosa_upsample_argmax(_lib.ptr(refined), _lib.ptr(key), _lib.ptr(out), b, nc, h, w, H, W,
                                             _lib.stream_ptr()))
     return out
+
+
+_WARNED = set()
+
+
+def _warn_once(key, message):
+    """The paths that leave the fused kernels say so, once per process (they are correct, only slower)."""
+    if key not in _WARNED:
+        _WARNED.add(key)
+        warnings.warn(message, RuntimeWarning, stacklevel=3)
 
 
 def _cam2mask_generic(images, img_boxes, cams, cls_labels, threshold_high, threshold_low, refine_model, ignore_index,
@@ -623,6 +637,10 @@ def get_energy_loss(img,
         return _FusedEnergyLoss.apply(logit.contiguous(), simg, _lib.dev_f32(label.to(dev), "label"), boxes, mean, std,
                                       loss_layer.weight, loss_layer.sigma_rgb,
                                       loss_layer.sigma_xy * loss_layer.scale_factor, pre, loss_layer._budget_flags())
+    _warn_once("get_energy_loss", "cosa_b200.get_energy_loss: %s (scale_factor=%s, %dx%d) takes the reference's "
+                                  "composition in torch ops around loss_layer - the fused kernels serve "
+                                  "cosa_b200.DenseEnergyLoss itself at scale_factor=0.5 and even H, W"
+               % (type(loss_layer).__name__, getattr(loss_layer, "scale_factor", "?"), H, W))
     pred_prob = F.softmax(logit, dim=1)
     crop_mask = torch.zeros_like(pred_prob[:, 0, ...])
     boxes = _lib.resolve_boxes(img_box, B, H, W, torch.device("cpu")).tolist()
